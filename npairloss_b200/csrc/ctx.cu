@@ -1,0 +1,690 @@
+// ctx.cu -- host side of libnpair_b200.so: the context behind the C ABI of include/npair_b200.h.
+// Owns all device scratch (the reference keeps ~31 member Blobs, npair_multi_class_loss.hpp:59-78 / .cpp:44-154),
+// builds the TMA tensor maps, enqueues the kernels of Forward_gpu (.cu:207-402) and Backward_gpu (.cu:420-499)
+// on the caller's stream, and talks to NCCL (dlopen'ed, so the library loads on machines without it).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+#include <dlfcn.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/npair_b200.h"
+#include "gemm_tcgen05.cuh"
+#include "kernels.cuh"
+
+namespace npair {
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_create_err;
+
+static std::string fmt(const char* f, ...) {
+  char buf[1024];
+  va_list ap; va_start(ap, f); vsnprintf(buf, sizeof(buf), f, ap); va_end(ap);
+  return std::string(buf);
+}
+
+// ------------------------------------------------------------------------------------------------ NCCL (dlopen)
+struct NcclId { char internal[128]; };
+typedef int (*fn_ncclGetUniqueId)(NcclId*);
+typedef int (*fn_ncclCommInitRank)(void**, int, NcclId, int);
+typedef int (*fn_ncclCommDestroy)(void*);
+typedef int (*fn_ncclAllGather)(const void*, void*, size_t, int, void*, cudaStream_t);
+typedef int (*fn_ncclReduceScatter)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*fn_ncclGroup)(void);
+typedef const char* (*fn_ncclGetErrorString)(int);
+struct NcclApi {
+  void* h = nullptr;
+  fn_ncclGetUniqueId GetUniqueId = nullptr;
+  fn_ncclCommInitRank CommInitRank = nullptr;
+  fn_ncclCommDestroy CommDestroy = nullptr;
+  fn_ncclAllGather AllGather = nullptr;
+  fn_ncclReduceScatter ReduceScatter = nullptr;
+  fn_ncclGroup GroupStart = nullptr, GroupEnd = nullptr;
+  fn_ncclGetErrorString GetErrorString = nullptr;
+  std::string err;
+};
+static NcclApi* nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return &api;
+  tried = true;
+  const char* env = getenv("NPAIR_NCCL_LIB");
+  const char* names[] = {env, "libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    if (!n) continue;
+    api.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (api.h) break;
+  }
+  if (!api.h) { api.err = "libnccl.so.2 not found (set NPAIR_NCCL_LIB)"; return &api; }
+#define NPAIR_SYM(name) api.name = reinterpret_cast<decltype(api.name)>(dlsym(api.h, "nccl" #name)); if (!api.name) api.err = "missing symbol nccl" #name;
+  NPAIR_SYM(GetUniqueId) NPAIR_SYM(CommInitRank) NPAIR_SYM(CommDestroy) NPAIR_SYM(AllGather) NPAIR_SYM(ReduceScatter)
+  NPAIR_SYM(GroupStart) NPAIR_SYM(GroupEnd) NPAIR_SYM(GetErrorString)
+#undef NPAIR_SYM
+  return &api;
+}
+enum { NCCL_FLOAT32 = 7, NCCL_SUM = 0 };
+
+// ------------------------------------------------------------------------------------------------ TMA maps
+static PFN_cuTensorMapEncodeTiled_v12000 tmap_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+// 3-D map over NSPLIT stacked 2-byte matrices [piece][rows][ld]; inner extent `cols` (<= ld), box {bk, box_rows, 1}
+static bool make_tmap_pieces(CUtensorMap* m, const void* base, int cols, int rows, int pieces, long long ld_elems,
+                             long long piece_stride_elems, int bk, int box_rows, std::string* err) {
+  auto fn = tmap_encode_fn();
+  if (!fn) { *err = "cuTensorMapEncodeTiled entry point not available"; return false; }
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(pieces)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld_elems) * 2ull, static_cast<cuuint64_t>(piece_stride_elems) * 2ull};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(bk), static_cast<cuuint32_t>(box_rows), 1u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  const CUtensorMapSwizzle sw = (bk * 2 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { *err = fmt("cuTensorMapEncodeTiled failed (%d): cols=%d rows=%d pieces=%d ld=%lld", (int)r, cols, rows, pieces, ld_elems); return false; }
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------ GEMM launchers
+static inline int nsplit_of_prec(int prec) { return prec == PREC_BF16 ? 1 : (prec == PREC_FP16X2 ? 2 : 3); }
+static inline int bk_of_prec(int prec) { return prec == PREC_BF16X3 ? 32 : 64; }
+
+template <int NSPLIT, bool BF16, int EPI>
+static cudaError_t launch_split_gemm_t(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, int sms, cudaStream_t st) {
+  using Cfg = GemmCfg<NSPLIT>;
+  auto kern = split_gemm_kernel<NSPLIT, BF16, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int tiles = p.tiles_m * p.tiles_n;
+  const int grid = tiles < sms ? tiles : sms;
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a, b, p);
+  return cudaGetLastError();
+}
+static cudaError_t launch_split_gemm(int prec, int epi, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, int sms, cudaStream_t st) {
+  if (prec == PREC_BF16) return epi == EPI_SIM ? launch_split_gemm_t<1, true, EPI_SIM>(a, b, p, sms, st) : launch_split_gemm_t<1, true, EPI_OUT>(a, b, p, sms, st);
+  if (prec == PREC_FP16X2) return epi == EPI_SIM ? launch_split_gemm_t<2, false, EPI_SIM>(a, b, p, sms, st) : launch_split_gemm_t<2, false, EPI_OUT>(a, b, p, sms, st);
+  return epi == EPI_SIM ? launch_split_gemm_t<3, true, EPI_SIM>(a, b, p, sms, st) : launch_split_gemm_t<3, true, EPI_OUT>(a, b, p, sms, st);
+}
+
+// SIMT cross-check of the same contraction on the same split operands (tests only; NPAIR_GEMM_SIMT_CHECK).
+template <int PREC>
+__device__ __forceinline__ float piece_sum(const uint16_t* base, long long off, long long ps) {
+  if (PREC == PREC_BF16) return __bfloat162float(__ushort_as_bfloat16(base[off]));
+  if (PREC == PREC_FP16X2) return __half2float(__ushort_as_half(base[off])) + __half2float(__ushort_as_half(base[ps + off]));
+  return __bfloat162float(__ushort_as_bfloat16(base[off])) + __bfloat162float(__ushort_as_bfloat16(base[ps + off])) +
+         __bfloat162float(__ushort_as_bfloat16(base[2 * ps + off]));
+}
+template <int PREC, int EPI>
+__global__ void __launch_bounds__(256) simt_gemm_kernel(const uint16_t* __restrict__ A, long long lda, long long psA,
+                                                        const uint16_t* __restrict__ B, long long ldb, long long psB, int K, GemmParams p) {
+  __shared__ float As[16][65], Bs[16][65];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int e = threadIdx.x; e < 64 * 16; e += 256) {
+      const int r = e >> 4, kk = e & 15;
+      const int gm = m0 + r, gn = n0 + r, gk = k0 + kk;
+      As[kk][r] = (gm < p.M && gk < K) ? piece_sum<PREC>(A, static_cast<long long>(gm) * lda + gk, psA) : 0.f;
+      Bs[kk][r] = (gn < p.Nn && gk < K) ? piece_sum<PREC>(B, static_cast<long long>(gn) * ldb + gk, psB) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  const float inv = p.dev_scale ? *p.dev_scale : 1.f;
+  for (int i = 0; i < 4; ++i) {
+    const int row = m0 + ty * 4 + i;
+    if (row >= p.M) continue;
+    for (int j = 0; j < 4; ++j) {
+      const int col = n0 + tx * 4 + j;
+      if (col >= p.Nn) continue;
+      if (EPI == EPI_SIM) p.S[static_cast<long long>(row) * p.ldS + col] = acc[i][j] * inv * inv;
+      else {
+        float* d = p.out + static_cast<long long>(row) * p.ldo + col;
+        float o = p.alpha * inv * acc[i][j];
+        if (p.beta != 0.f) o += p.beta * *d;
+        *d = o;
+      }
+    }
+  }
+}
+static cudaError_t launch_simt_gemm(int prec, int epi, const uint16_t* A, long long lda, long long psA, const uint16_t* B, long long ldb,
+                                    long long psB, int K, const GemmParams& p, cudaStream_t st) {
+  dim3 grid((p.Nn + 63) / 64, (p.M + 63) / 64);
+#define NPAIR_SIMT(P)                                                                                   \
+  do {                                                                                                  \
+    if (epi == EPI_SIM) simt_gemm_kernel<P, EPI_SIM><<<grid, 256, 0, st>>>(A, lda, psA, B, ldb, psB, K, p); \
+    else simt_gemm_kernel<P, EPI_OUT><<<grid, 256, 0, st>>>(A, lda, psA, B, ldb, psB, K, p);                \
+  } while (0)
+  if (prec == PREC_BF16) NPAIR_SIMT(PREC_BF16);
+  else if (prec == PREC_FP16X2) NPAIR_SIMT(PREC_FP16X2);
+  else NPAIR_SIMT(PREC_BF16X3);
+#undef NPAIR_SIMT
+  return cudaGetLastError();
+}
+
+static inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
+
+}  // namespace npair
+
+using namespace npair;
+
+// ------------------------------------------------------------------------------------------------ context
+struct npair_ctx {
+  npair_config cfg;
+  int Q, N, D, world, rank, prec, nsplit, bk, sms, device;
+  long long Dp, Np, Qp, ldS;
+  // device scratch
+  float* Xtot_buf = nullptr;     // world > 1: all-gather target
+  float* labtot_buf = nullptr;
+  float* S = nullptr;
+  uint16_t *Xs = nullptr, *XsT = nullptr, *XlT = nullptr, *H = nullptr, *HT = nullptr;
+  float* OUT2 = nullptr;         // world > 1: N x D transposed-term product before the reduce-scatter
+  void* row_block = nullptr;     // backing store of RowArrays
+  RowArrays ra;
+  BlockScalars* bs = nullptr;
+  float* partial = nullptr;
+  unsigned long long* ghist = nullptr;
+  float* tops_pinned = nullptr;  // host-mapped: 5 tops + err(int) + inv_scale
+  float* tops_dev = nullptr;
+  CUtensorMap tm_simA, tm_simB, tm_b1A, tm_b1B, tm_b2A, tm_b2B;
+  // nccl
+  void* comm = nullptr; bool own_comm = false;
+  // per-step state
+  const float* cur_feat = nullptr; const float* cur_label = nullptr;
+  const float *x_total = nullptr, *lab_total = nullptr;
+  bool fwd_done = false;
+  cudaStream_t last_stream = nullptr;
+  size_t bytes = 0;
+  std::string err;
+};
+
+#define CUDA_TRY(ctx, call)                                                                              \
+  do {                                                                                                   \
+    cudaError_t e__ = (call);                                                                            \
+    if (e__ != cudaSuccess) {                                                                            \
+      (ctx)->err = fmt("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__);      \
+      return NPAIR_E_CUDA;                                                                               \
+    }                                                                                                    \
+  } while (0)
+
+static int validate(const npair_config* c, std::string* err) {
+  if (!c) { *err = "null config"; return NPAIR_E_ARG; }
+  if (c->Q < 1 || c->D < 1) { *err = "Q and D must be >= 1"; return NPAIR_E_ARG; }
+  if (c->world < 1 || c->rank < 0 || c->rank >= c->world) { *err = "bad world/rank"; return NPAIR_E_ARG; }
+  if (c->num_tops < 1 || c->num_tops > 5) { *err = "num_tops must be 1..5 (npair_multi_class_loss.hpp:32-34)"; return NPAIR_E_ARG; }
+  if (c->ap_region < 0 || c->ap_region > 1 || c->an_region < 0 || c->an_region > 1) { *err = "bad mining region"; return NPAIR_E_ARG; }
+  if (c->ap_method < 0 || c->ap_method > 4 || c->an_method < 0 || c->an_method > 4) { *err = "bad mining method"; return NPAIR_E_ARG; }
+  if (c->sim_precision < 0 || c->sim_precision > 2) { *err = "bad sim_precision"; return NPAIR_E_ARG; }
+  if (c->gemm_backend < 0 || c->gemm_backend > 1) { *err = "bad gemm_backend"; return NPAIR_E_ARG; }
+  if (static_cast<long long>(c->Q) * c->world > 0x7fffffffLL) { *err = "N = Q*world exceeds int32"; return NPAIR_E_ARG; }
+  return NPAIR_OK;
+}
+
+struct Sizes { long long N, Dp, Np, Qp, ldS; int ns; size_t total; };
+static Sizes sizes_of(const npair_config* c) {
+  Sizes s;
+  s.N = static_cast<long long>(c->Q) * c->world;
+  s.Dp = round_up(c->D, 64); s.Np = round_up(s.N, 64); s.Qp = round_up(c->Q, 64); s.ldS = round_up(s.N, 32);
+  s.ns = nsplit_of_prec(c->sim_precision);
+  size_t t = 0;
+  if (c->world > 1) t += sizeof(float) * (s.N * c->D + s.N);
+  t += sizeof(float) * c->Q * s.ldS;                       // S
+  t += 2ull * s.ns * s.N * s.Dp;                            // Xs
+  t += 2ull * s.ns * c->D * s.Np;                           // XsT
+  t += 2ull * s.ns * c->Q * s.Np;                           // H
+  if (c->world > 1) { t += 2ull * s.ns * c->D * s.Qp; t += 2ull * s.ns * s.N * s.Qp; t += sizeof(float) * s.N * c->D; }
+  t += 64ull * c->Q + 65536;                                // row arrays + scalars
+  s.total = t;
+  return s;
+}
+
+extern "C" {
+
+const char* npair_version(void) { return "npairloss_b200 0.1 (abi 1; sm_100a tcgen05/TMA)"; }
+
+void npair_config_default(npair_config* c, int32_t Q, int32_t D) {
+  if (!c) return;
+  memset(c, 0, sizeof(*c));
+  c->Q = Q; c->D = D; c->world = 1; c->rank = 0; c->num_tops = 5;
+  c->margin_ident = 0.f; c->margin_diff = 0.f; c->identsn = -1.f; c->diffsn = -1.f;       // caffe.proto:4-7
+  c->ap_region = NPAIR_LOCAL; c->ap_method = NPAIR_RAND; c->an_region = NPAIR_LOCAL; c->an_method = NPAIR_RAND;   // :19-22
+  c->sim_precision = NPAIR_PREC_FP32_FP16X2; c->gemm_backend = NPAIR_GEMM_TCGEN05; c->device = -1;
+}
+
+size_t npair_workspace_bytes(const npair_config* cfg) {
+  std::string e;
+  if (validate(cfg, &e) != NPAIR_OK) return 0;
+  return sizes_of(cfg).total;
+}
+
+const char* npair_last_error(const npair_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int npair_nccl_unique_id(void* out) {
+  if (!out) return NPAIR_E_ARG;
+  NcclApi* api = nccl_api();
+  if (!api->h || !api->err.empty()) { g_create_err = api->err; return NPAIR_E_NCCL; }
+  NcclId id;
+  int r = api->GetUniqueId(&id);
+  if (r != 0) { g_create_err = fmt("ncclGetUniqueId: %s", api->GetErrorString(r)); return NPAIR_E_NCCL; }
+  memcpy(out, &id, 128);
+  return NPAIR_OK;
+}
+
+void npair_destroy(npair_ctx* c) {
+  if (!c) return;
+  if (c->device >= 0) cudaSetDevice(c->device);
+  if (c->comm && c->own_comm) { NcclApi* api = nccl_api(); if (api->CommDestroy) api->CommDestroy(c->comm); }
+  cudaFree(c->Xtot_buf); cudaFree(c->labtot_buf); cudaFree(c->S); cudaFree(c->Xs); cudaFree(c->XsT); cudaFree(c->XlT);
+  cudaFree(c->H); cudaFree(c->HT); cudaFree(c->OUT2); cudaFree(c->row_block); cudaFree(c->bs); cudaFree(c->partial); cudaFree(c->ghist);
+  if (c->tops_pinned) cudaFreeHost(c->tops_pinned);
+  delete c;
+}
+
+static int create_impl(const npair_config* cfg, const void* id128, void* ext_comm, npair_ctx** out) {
+  if (!out) { g_create_err = "null out"; return NPAIR_E_ARG; }
+  *out = nullptr;
+  std::string e;
+  int rc = validate(cfg, &e);
+  if (rc != NPAIR_OK) { g_create_err = e; return rc; }
+  npair_ctx* c = new npair_ctx();
+  c->cfg = *cfg;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+    g_create_err = "no CUDA device: libnpair_b200 has no CPU fallback (the oracle under oracle/ is test-only)";
+    delete c; return NPAIR_E_CUDA;
+  }
+#define CREATE_TRY(call)                                                                                  \
+  do {                                                                                                    \
+    cudaError_t e__ = (call);                                                                             \
+    if (e__ != cudaSuccess) {                                                                             \
+      g_create_err = fmt("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__);     \
+      npair_destroy(c); return NPAIR_E_CUDA;                                                              \
+    }                                                                                                     \
+  } while (0)
+  if (cfg->device >= 0) CREATE_TRY(cudaSetDevice(cfg->device));
+  CREATE_TRY(cudaGetDevice(&c->device));
+  cudaDeviceProp prop;
+  CREATE_TRY(cudaGetDeviceProperties(&prop, c->device));
+  if (prop.major != 10) {
+    g_create_err = fmt("device %d is sm_%d%d; this library contains sm_100a code only", c->device, prop.major, prop.minor);
+    npair_destroy(c); return NPAIR_E_CUDA;
+  }
+  c->sms = prop.multiProcessorCount;
+  const Sizes sz = sizes_of(cfg);
+  c->Q = cfg->Q; c->D = cfg->D; c->world = cfg->world; c->rank = cfg->rank; c->N = static_cast<int>(sz.N);
+  c->prec = cfg->sim_precision; c->nsplit = sz.ns; c->bk = bk_of_prec(c->prec);
+  c->Dp = sz.Dp; c->Np = sz.Np; c->Qp = sz.Qp; c->ldS = sz.ldS; c->bytes = sz.total;
+  const int Q = c->Q, D = c->D, N = c->N, ns = c->nsplit;
+  if (c->world > 1) {
+    CREATE_TRY(cudaMalloc(&c->Xtot_buf, sizeof(float) * static_cast<size_t>(N) * D));
+    CREATE_TRY(cudaMalloc(&c->labtot_buf, sizeof(float) * N));
+  }
+  CREATE_TRY(cudaMalloc(&c->S, sizeof(float) * static_cast<size_t>(Q) * c->ldS));
+  CREATE_TRY(cudaMemset(c->S, 0, sizeof(float) * static_cast<size_t>(Q) * c->ldS));
+  CREATE_TRY(cudaMalloc(&c->Xs, 2ull * ns * N * c->Dp));
+  CREATE_TRY(cudaMemset(c->Xs, 0, 2ull * ns * N * c->Dp));
+  CREATE_TRY(cudaMalloc(&c->XsT, 2ull * ns * D * c->Np));
+  CREATE_TRY(cudaMemset(c->XsT, 0, 2ull * ns * D * c->Np));
+  CREATE_TRY(cudaMalloc(&c->H, 2ull * ns * Q * c->Np));
+  CREATE_TRY(cudaMemset(c->H, 0, 2ull * ns * Q * c->Np));
+  if (c->world > 1) {
+    CREATE_TRY(cudaMalloc(&c->XlT, 2ull * ns * D * c->Qp));
+    CREATE_TRY(cudaMemset(c->XlT, 0, 2ull * ns * D * c->Qp));
+    CREATE_TRY(cudaMalloc(&c->HT, 2ull * ns * N * c->Qp));
+    CREATE_TRY(cudaMemset(c->HT, 0, 2ull * ns * N * c->Qp));
+    CREATE_TRY(cudaMalloc(&c->OUT2, sizeof(float) * static_cast<size_t>(N) * D));
+  }
+  // row arrays: 5 uint32/int stats, 2 thr, 3 fwd, 3 hits, 5 row scalars = 18 arrays of Q 4-byte words
+  CREATE_TRY(cudaMalloc(&c->row_block, 4ull * 18 * Q));
+  CREATE_TRY(cudaMemset(c->row_block, 0, 4ull * 18 * Q));
+  {
+    uint32_t* w = static_cast<uint32_t*>(c->row_block);
+    RowArrays& ra = c->ra;
+    ra.st_minw = w; w += Q; ra.st_maxw = w; w += Q; ra.st_maxb = w; w += Q; ra.st_maxall = w; w += Q;
+    ra.cnt_same = reinterpret_cast<int*>(w); w += Q;
+    ra.posi_thr = reinterpret_cast<float*>(w); w += Q; ra.nega_thr = reinterpret_cast<float*>(w); w += Q;
+    ra.A = reinterpret_cast<float*>(w); w += Q; ra.T = reinterpret_cast<float*>(w); w += Q; ra.logv = reinterpret_cast<float*>(w); w += Q;
+    ra.hits = reinterpret_cast<int*>(w); w += 3 * Q;
+    ra.rs_maxall = reinterpret_cast<float*>(w); w += Q; ra.rs_tp = reinterpret_cast<float*>(w); w += Q; ra.rs_tn = reinterpret_cast<float*>(w); w += Q;
+    ra.rs_cA = reinterpret_cast<float*>(w); w += Q; ra.rs_cT = reinterpret_cast<float*>(w); w += Q;
+  }
+  CREATE_TRY(cudaMalloc(&c->bs, sizeof(BlockScalars)));
+  CREATE_TRY(cudaMemset(c->bs, 0, sizeof(BlockScalars)));
+  CREATE_TRY(cudaMalloc(&c->partial, sizeof(float) * 2048));
+  CREATE_TRY(cudaMalloc(&c->ghist, sizeof(unsigned long long) * 2048));
+  CREATE_TRY(cudaMemset(c->ghist, 0, sizeof(unsigned long long) * 2048));
+  CREATE_TRY(cudaHostAlloc(&c->tops_pinned, 64, cudaHostAllocMapped));
+  memset(c->tops_pinned, 0, 64);
+  CREATE_TRY(cudaHostGetDevicePointer(&c->tops_dev, c->tops_pinned, 0));
+  // ---- TMA tensor maps (K-major boxes of one swizzle span) ----
+  if (cfg->gemm_backend == NPAIR_GEMM_TCGEN05) {
+    std::string te;
+    const int bk = c->bk;
+    bool ok = true;
+    // similarity: A = local rows of Xs, B = all rows of Xs; K = D
+    ok = ok && make_tmap_pieces(&c->tm_simA, c->Xs + static_cast<long long>(c->rank) * Q * c->Dp, D, Q, ns, c->Dp, static_cast<long long>(N) * c->Dp, bk, 128, &te);
+    ok = ok && make_tmap_pieces(&c->tm_simB, c->Xs, D, N, ns, c->Dp, static_cast<long long>(N) * c->Dp, bk, 256, &te);
+    // gradient 1: A = H [Q x N], B = XsT [D x N]; K = N
+    ok = ok && make_tmap_pieces(&c->tm_b1A, c->H, N, Q, ns, c->Np, static_cast<long long>(Q) * c->Np, bk, 128, &te);
+    ok = ok && make_tmap_pieces(&c->tm_b1B, c->XsT, N, D, ns, c->Np, static_cast<long long>(D) * c->Np, bk, 256, &te);
+    if (c->world > 1) {   // gradient 2: A = HT [N x Q], B = XlT [D x Q]; K = Q
+      ok = ok && make_tmap_pieces(&c->tm_b2A, c->HT, Q, N, ns, c->Qp, static_cast<long long>(N) * c->Qp, bk, 128, &te);
+      ok = ok && make_tmap_pieces(&c->tm_b2B, c->XlT, Q, D, ns, c->Qp, static_cast<long long>(D) * c->Qp, bk, 256, &te);
+    }
+    if (!ok) { g_create_err = te; npair_destroy(c); return NPAIR_E_CUDA; }
+  }
+  // ---- NCCL ----
+  if (c->world > 1 && (id128 || ext_comm)) {
+    NcclApi* api = nccl_api();
+    if (!api->h || !api->err.empty()) { g_create_err = api->err; npair_destroy(c); return NPAIR_E_NCCL; }
+    if (ext_comm) { c->comm = ext_comm; c->own_comm = false; }
+    else {
+      NcclId id; memcpy(&id, id128, 128);
+      int r = api->CommInitRank(&c->comm, c->world, id, c->rank);
+      if (r != 0) { g_create_err = fmt("ncclCommInitRank: %s", api->GetErrorString(r)); c->comm = nullptr; npair_destroy(c); return NPAIR_E_NCCL; }
+      c->own_comm = true;
+    }
+  }
+#undef CREATE_TRY
+  *out = c;
+  return NPAIR_OK;
+}
+
+int npair_create(const npair_config* cfg, const void* id128, npair_ctx** out) { return create_impl(cfg, id128, nullptr, out); }
+int npair_create_with_comm(const npair_config* cfg, void* comm, npair_ctx** out) {
+  if (cfg && cfg->world > 1 && !comm) { g_create_err = "null communicator"; return NPAIR_E_ARG; }
+  return create_impl(cfg, nullptr, comm, out);
+}
+
+static MiningParams mining_of(const npair_config& c) {
+  MiningParams mp;
+  mp.ap_region = c.ap_region; mp.ap_method = c.ap_method; mp.an_region = c.an_region; mp.an_method = c.an_method;
+  mp.margin_ident = c.margin_ident; mp.margin_diff = c.margin_diff; mp.identsn = c.identsn; mp.diffsn = c.diffsn;
+  return mp;
+}
+static inline bool is_rel_m(int m) { return m == NPAIR_RELATIVE_HARD || m == NPAIR_RELATIVE_EASY; }
+static inline bool sn_max(float sn) { return sn >= 0.f && static_cast<int>(sn) == 0; }
+
+static int forward_impl(npair_ctx* c, const float* d_feat, const float* d_label, float tops_host[5], cudaStream_t st);
+
+int npair_forward(npair_ctx* c, const float* d_feat, const float* d_label, float tops_host[5], void* stream) {
+  if (!c) return NPAIR_E_ARG;
+  if (!d_feat || !d_label || !tops_host) { c->err = "null pointer argument"; return NPAIR_E_ARG; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  c->fwd_done = false; c->last_stream = st;
+  const int Q = c->Q, D = c->D;
+  // ---- GatherFeatureAndLabel (.cu:17-43): one NCCL group, device to device over NVLink ----
+  if (c->world > 1) {
+    if (!c->comm) { c->err = "context was created without a communicator: use npair_forward_gathered"; return NPAIR_E_STATE; }
+    NcclApi* api = nccl_api();
+    int r = api->GroupStart();
+    if (r == 0) r = api->AllGather(d_feat, c->Xtot_buf, static_cast<size_t>(Q) * D, NCCL_FLOAT32, c->comm, st);
+    if (r == 0) r = api->AllGather(d_label, c->labtot_buf, static_cast<size_t>(Q), NCCL_FLOAT32, c->comm, st);
+    int r2 = api->GroupEnd();
+    if (r == 0) r = r2;
+    if (r != 0) { c->err = fmt("ncclAllGather: %s", api->GetErrorString(r)); return NPAIR_E_NCCL; }
+    c->x_total = c->Xtot_buf; c->lab_total = c->labtot_buf;
+  } else { c->x_total = d_feat; c->lab_total = d_label; }
+  return forward_impl(c, d_feat, d_label, tops_host, st);
+}
+
+/* External-collectives variant: the caller already holds the all-gathered N x D features and N labels (rank r's rows are
+ * [r*Q,(r+1)*Q)).  Lets a host framework keep its own communication layer, and lets tests emulate every rank on one GPU. */
+int npair_forward_gathered(npair_ctx* c, const float* d_feat_total, const float* d_label_total, float tops_host[5], void* stream) {
+  if (!c) return NPAIR_E_ARG;
+  if (!d_feat_total || !d_label_total || !tops_host) { c->err = "null pointer argument"; return NPAIR_E_ARG; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  c->fwd_done = false; c->last_stream = st;
+  c->x_total = d_feat_total; c->lab_total = d_label_total;
+  return forward_impl(c, d_feat_total + static_cast<long long>(c->rank) * c->Q * c->D, d_label_total + static_cast<long long>(c->rank) * c->Q, tops_host, st);
+}
+
+static int forward_impl(npair_ctx* c, const float* d_feat, const float* d_label, float tops_host[5], cudaStream_t st) {
+  const int Q = c->Q, N = c->N, D = c->D;
+  const MiningParams mp = mining_of(c->cfg);
+  c->cur_feat = d_feat; c->cur_label = d_label;
+  const int self_off = c->rank * Q;
+  // ---- operand preparation: |x| sum (top asum, .cu:400), power-of-two pre-scale, split to tensor-core pieces ----
+  launch_absmax_asum(d_feat, static_cast<long long>(Q) * D, c->x_total, static_cast<long long>(N) * D, c->partial, c->bs,
+                     c->prec == PREC_FP16X2 ? 1 : 0, st);
+  launch_split(c->x_total, N, D, c->prec, c->bs, c->Xs, c->Dp, c->XsT, c->Np, c->XlT, c->Qp, self_off, Q, st);
+  launch_init_stats(c->ra, Q, c->bs, st);
+  // ---- S = X_local . X_total^T (.cu:218) with fused masks + row statistics (.cu:44-66, :225-265) ----
+  GemmParams gp; memset(&gp, 0, sizeof(gp));
+  gp.M = Q; gp.Nn = N; gp.num_kblocks = static_cast<int>((D + c->bk - 1) / c->bk);
+  gp.tiles_m = (Q + 127) / 128; gp.tiles_n = (N + 255) / 256;
+  gp.S = c->S; gp.ldS = c->ldS; gp.dev_scale = &c->bs->x_inv_scale;
+  gp.lab_rows = d_label; gp.lab_cols = c->lab_total; gp.self_offset = self_off;
+  gp.st_minw = c->ra.st_minw; gp.st_maxw = c->ra.st_maxw; gp.st_maxb = c->ra.st_maxb; gp.st_maxall = c->ra.st_maxall; gp.cnt_same = c->ra.cnt_same;
+  if (c->cfg.gemm_backend == NPAIR_GEMM_TCGEN05) {
+    CUDA_TRY(c, launch_split_gemm(c->prec, EPI_SIM, c->tm_simA, c->tm_simB, gp, c->sms, st));
+  } else {
+    CUDA_TRY(c, launch_simt_gemm(c->prec, EPI_SIM, c->Xs + static_cast<long long>(self_off) * c->Dp, c->Dp, static_cast<long long>(N) * c->Dp,
+                                 c->Xs, c->Dp, static_cast<long long>(N) * c->Dp, D, gp, st));
+    launch_row_stats_ref(c->S, c->ldS, Q, N, d_label, c->lab_total, self_off, c->ra, st);
+  }
+  // ---- thresholds (.cu:275-337) ----
+  launch_thresholds(c->ra, Q, N, mp, c->bs, st);
+  if (is_rel_m(mp.ap_method) && !sn_max(mp.identsn)) {
+    if (mp.ap_region == NPAIR_LOCAL) launch_local_select(c->S, c->ldS, Q, N, d_label, c->lab_total, self_off, 0, mp.identsn, c->ra, c->bs, st);
+    else launch_global_select(c->S, c->ldS, Q, N, d_label, c->lab_total, self_off, 0, mp.identsn, c->ra, c->ghist, c->bs, st);
+  }
+  if (is_rel_m(mp.an_method) && !sn_max(mp.diffsn)) {
+    if (mp.an_region == NPAIR_LOCAL) launch_local_select(c->S, c->ldS, Q, N, d_label, c->lab_total, self_off, 1, mp.diffsn, c->ra, c->bs, st);
+    else launch_global_select(c->S, c->ldS, Q, N, d_label, c->lab_total, self_off, 1, mp.diffsn, c->ra, c->ghist, c->bs, st);
+  }
+  // ---- selection + counts + exp + masked sums + log + retrieval in one pass (.cu:343-398) ----
+  launch_lse_rows(c->S, c->ldS, Q, N, d_label, c->lab_total, self_off, mp, c->ra, st);
+  launch_finalize(c->ra, Q, c->cfg.num_tops, c->bs, c->tops_dev, st);
+  CUDA_TRY(c, cudaGetLastError());
+  CUDA_TRY(c, cudaStreamSynchronize(st));          // the reference also blocks here (host reads of loss/asum, .cu:384,400)
+  const int derr = reinterpret_cast<int*>(c->tops_pinned)[5];
+  if (derr & DERR_EMPTY_LIST) { c->err = "an empty same/diff list was indexed (undefined behaviour in the reference, .cu:296/:327/:288)"; return NPAIR_E_EMPTY_LIST; }
+  if (derr & DERR_POS_RANGE) { c->err = "identsn/diffsn select a position outside the list (undefined behaviour in the reference, .cu:285-288)"; return NPAIR_E_POS_RANGE; }
+  for (int t = 0; t < 5; ++t) tops_host[t] = t < c->cfg.num_tops ? c->tops_pinned[t] : 0.f;
+  c->fwd_done = true;
+  return NPAIR_OK;
+}
+
+static int backward_impl(npair_ctx* c, float loss_weight, float* d_diff, float* d_total_ext, cudaStream_t st);
+
+int npair_backward(npair_ctx* c, float loss_weight, float* d_diff, void* stream) {
+  if (!c) return NPAIR_E_ARG;
+  if (!d_diff) { c->err = "null gradient pointer"; return NPAIR_E_ARG; }
+  if (!c->fwd_done) { c->err = "npair_backward called without a successful npair_forward"; return NPAIR_E_STATE; }
+  if (c->world > 1 && !c->comm) { c->err = "context was created without a communicator: use npair_backward_partial"; return NPAIR_E_STATE; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  c->last_stream = st;
+  return backward_impl(c, loss_weight, d_diff, nullptr, st);
+}
+
+/* External-collectives variant of Backward_gpu up to the all-reduce (.cu:420-460):
+ *   d_local_half : Q x D  = (1/2)(lw/Q) G . X_total
+ *   d_total_half : N x D  = (1/2)(1/world)(lw/Q) G^T . X_local        (this rank's addend of the all-reduce)
+ * so that bottom.diff of rank r = d_local_half + sum over ranks of d_total_half[rows of r]  (.cu:462-497).
+ * world == 1: d_total_half may be NULL and d_local_half receives the complete gradient. */
+int npair_backward_partial(npair_ctx* c, float loss_weight, float* d_local_half, float* d_total_half, void* stream) {
+  if (!c) return NPAIR_E_ARG;
+  if (!d_local_half || (c->world > 1 && !d_total_half)) { c->err = "null gradient pointer"; return NPAIR_E_ARG; }
+  if (!c->fwd_done) { c->err = "npair_backward_partial called without a successful forward"; return NPAIR_E_STATE; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  c->last_stream = st;
+  return backward_impl(c, loss_weight, d_local_half, c->world > 1 ? d_total_half : nullptr, st);
+}
+
+static int backward_impl(npair_ctx* c, float loss_weight, float* d_diff, float* d_total_ext, cudaStream_t st) {
+  const int Q = c->Q, N = c->N, D = c->D;
+  const MiningParams mp = mining_of(c->cfg);
+  const int self_off = c->rank * Q;
+  const float lw_over_q = loss_weight / static_cast<float>(Q);     // loss_weight / dot_normalizer (.cu:427,448)
+  launch_build_weights(c->S, c->ldS, Q, N, c->cur_label, c->lab_total, self_off, c->world, mp, c->ra, c->prec, c->H, c->Np, c->HT, c->Qp, st);
+  GemmParams gp; memset(&gp, 0, sizeof(gp));
+  gp.dev_scale = &c->bs->x_inv_scale;
+  const bool tc = c->cfg.gemm_backend == NPAIR_GEMM_TCGEN05;
+  if (c->world > 1) {
+    // total = (1/2)(1/k)(lw/Q) * G^T . X_local  (N x D)  -> reduce-scatter (== all-reduce + own slice, .cu:462-497)
+    gp.M = N; gp.Nn = D; gp.num_kblocks = static_cast<int>((Q + c->bk - 1) / c->bk);
+    gp.tiles_m = (N + 127) / 128; gp.tiles_n = (D + 255) / 256;
+    gp.out = d_total_ext ? d_total_ext : c->OUT2; gp.ldo = D; gp.alpha = 0.5f * (1.f / static_cast<float>(c->world)) * lw_over_q; gp.beta = 0.f;
+    if (tc) CUDA_TRY(c, launch_split_gemm(c->prec, EPI_OUT, c->tm_b2A, c->tm_b2B, gp, c->sms, st));
+    else CUDA_TRY(c, launch_simt_gemm(c->prec, EPI_OUT, c->HT, c->Qp, static_cast<long long>(N) * c->Qp, c->XlT, c->Qp, static_cast<long long>(D) * c->Qp, Q, gp, st));
+    if (!d_total_ext) {
+      NcclApi* api = nccl_api();
+      int r = api->ReduceScatter(c->OUT2, d_diff, static_cast<size_t>(Q) * D, NCCL_FLOAT32, NCCL_SUM, c->comm, st);
+      if (r != 0) { c->err = fmt("ncclReduceScatter: %s", api->GetErrorString(r)); return NPAIR_E_NCCL; }
+    }
+  }
+  // local = (1/2)(lw/Q) * G . X_total, accumulated onto the scattered transposed term when world > 1
+  gp.M = Q; gp.Nn = D; gp.num_kblocks = static_cast<int>((N + c->bk - 1) / c->bk);
+  gp.tiles_m = (Q + 127) / 128; gp.tiles_n = (D + 255) / 256;
+  gp.out = d_diff; gp.ldo = D; gp.alpha = 0.5f * lw_over_q; gp.beta = (c->world > 1 && !d_total_ext) ? 1.f : 0.f;
+  if (tc) CUDA_TRY(c, launch_split_gemm(c->prec, EPI_OUT, c->tm_b1A, c->tm_b1B, gp, c->sms, st));
+  else CUDA_TRY(c, launch_simt_gemm(c->prec, EPI_OUT, c->H, c->Np, static_cast<long long>(Q) * c->Np, c->XsT, c->Np, static_cast<long long>(D) * c->Np, N, gp, st));
+  CUDA_TRY(c, cudaGetLastError());
+  return NPAIR_OK;
+}
+
+__global__ void decode_ord_kernel(const uint32_t* __restrict__ in, float* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = ord2f(in[i]);
+}
+__global__ void int_to_float_kernel(const int* __restrict__ in, float* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = static_cast<float>(in[i]);
+}
+
+int npair_debug_read(npair_ctx* c, int which, float* dst, size_t n) {
+  if (!c || !dst) return NPAIR_E_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  CUDA_TRY(c, cudaStreamSynchronize(c->last_stream));
+  const int Q = c->Q, N = c->N;
+  if (which == 0) {
+    if (n < static_cast<size_t>(Q) * N) { c->err = "buffer too small"; return NPAIR_E_ARG; }
+    CUDA_TRY(c, cudaMemcpy2D(dst, sizeof(float) * N, c->S, sizeof(float) * c->ldS, sizeof(float) * N, Q, cudaMemcpyDeviceToHost));
+    return NPAIR_OK;
+  }
+  if (which == 10) {
+    if (n < 1) return NPAIR_E_ARG;
+    CUDA_TRY(c, cudaMemcpy(dst, &c->bs->x_scale, sizeof(float), cudaMemcpyDeviceToHost));
+    return NPAIR_OK;
+  }
+  if (n < static_cast<size_t>(Q)) { c->err = "buffer too small"; return NPAIR_E_ARG; }
+  const float* src = nullptr; const uint32_t* osrc = nullptr; const int* isrc = nullptr;
+  switch (which) {
+    case 1: src = c->ra.posi_thr; break;
+    case 2: src = c->ra.nega_thr; break;
+    case 3: osrc = c->ra.st_minw; break;
+    case 4: osrc = c->ra.st_maxb; break;
+    case 5: osrc = c->ra.st_maxall; break;
+    case 6: src = c->ra.A; break;
+    case 7: src = c->ra.T; break;
+    case 8: isrc = c->ra.cnt_same; break;
+    case 9: osrc = c->ra.st_maxw; break;
+    default: c->err = "unknown debug selector"; return NPAIR_E_ARG;
+  }
+  if (src) { CUDA_TRY(c, cudaMemcpy(dst, src, sizeof(float) * Q, cudaMemcpyDeviceToHost)); return NPAIR_OK; }
+  float* tmp = nullptr;
+  CUDA_TRY(c, cudaMalloc(&tmp, sizeof(float) * Q));
+  if (osrc) decode_ord_kernel<<<(Q + 255) / 256, 256>>>(osrc, tmp, Q);
+  else int_to_float_kernel<<<(Q + 255) / 256, 256>>>(isrc, tmp, Q);
+  cudaError_t e = cudaMemcpy(dst, tmp, sizeof(float) * Q, cudaMemcpyDeviceToHost);
+  cudaFree(tmp);
+  CUDA_TRY(c, e);
+  return NPAIR_OK;
+}
+
+int npair_debug_gemm(int precision, int backend, int M, int Nn, int K, const float* dA, const float* dB, float* dC, void* stream) {
+  if (M < 1 || Nn < 1 || K < 1 || !dA || !dB || !dC || precision < 0 || precision > 2) { g_create_err = "bad argument"; return NPAIR_E_ARG; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int ns = nsplit_of_prec(precision), bk = bk_of_prec(precision);
+  const long long Kp = round_up(K, 64);
+  uint16_t *As = nullptr, *Bs = nullptr, *dummyT = nullptr;
+  BlockScalars* bs = nullptr; float* partial = nullptr;
+  int rc = NPAIR_OK;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+#define DG_TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { g_create_err = fmt("%s: %s", #call, cudaGetErrorString(e__)); rc = NPAIR_E_CUDA; goto done; } } while (0)
+  {
+    const long long Mt = round_up(M, 64), Nt = round_up(Nn, 64);
+    const long long tmax = Mt > Nt ? Mt : Nt;
+    DG_TRY(cudaMalloc(&As, 2ull * ns * M * Kp)); DG_TRY(cudaMalloc(&Bs, 2ull * ns * Nn * Kp));
+    DG_TRY(cudaMalloc(&dummyT, 2ull * ns * K * tmax));
+    DG_TRY(cudaMalloc(&bs, sizeof(BlockScalars))); DG_TRY(cudaMemset(bs, 0, sizeof(BlockScalars)));
+    DG_TRY(cudaMalloc(&partial, sizeof(float) * 2048));
+    // one common power-of-two scale over both operands (the layer multiplies X by X^T, i.e. a single matrix)
+    launch_absmax_asum(dA, static_cast<long long>(M) * K, dA, static_cast<long long>(M) * K, partial, bs, precision == PREC_FP16X2, st);
+    float sA = 1.f, sB = 1.f;
+    if (precision == PREC_FP16X2) {
+      DG_TRY(cudaStreamSynchronize(st));
+      float mA = 0.f, mB = 0.f;
+      DG_TRY(cudaMemcpy(&mA, &bs->x_absmax, 4, cudaMemcpyDeviceToHost));
+      launch_absmax_asum(dB, static_cast<long long>(Nn) * K, dB, static_cast<long long>(Nn) * K, partial, bs, 1, st);
+      DG_TRY(cudaStreamSynchronize(st));
+      DG_TRY(cudaMemcpy(&mB, &bs->x_absmax, 4, cudaMemcpyDeviceToHost));
+      const float mx = mA > mB ? mA : mB;
+      int e = 0; if (mx > 0.f) frexpf(mx, &e);
+      sA = ldexpf(1.f, -e); sB = ldexpf(1.f, e);
+      float sc[2] = {sA, sB};
+      DG_TRY(cudaMemcpy(&bs->x_scale, sc, 8, cudaMemcpyHostToDevice));
+    } else {
+      float sc[2] = {1.f, 1.f};
+      DG_TRY(cudaMemcpy(&bs->x_scale, sc, 8, cudaMemcpyHostToDevice));
+    }
+    launch_split(dA, M, K, precision, bs, As, Kp, dummyT, tmax, nullptr, 0, 0, 0, st);
+    launch_split(dB, Nn, K, precision, bs, Bs, Kp, dummyT, tmax, nullptr, 0, 0, 0, st);
+    GemmParams gp; memset(&gp, 0, sizeof(gp));
+    gp.M = M; gp.Nn = Nn; gp.num_kblocks = (K + bk - 1) / bk; gp.tiles_m = (M + 127) / 128; gp.tiles_n = (Nn + 255) / 256;
+    gp.out = dC; gp.ldo = Nn; gp.alpha = 1.f; gp.beta = 0.f;
+    // EPI_OUT applies the inverse scale once; both operands were scaled -> fold the second factor into alpha
+    gp.alpha = sB; gp.dev_scale = &bs->x_inv_scale;
+    if (backend == NPAIR_GEMM_TCGEN05) {
+      CUtensorMap ta, tb; std::string te;
+      if (!make_tmap_pieces(&ta, As, K, M, ns, Kp, static_cast<long long>(M) * Kp, bk, 128, &te) ||
+          !make_tmap_pieces(&tb, Bs, K, Nn, ns, Kp, static_cast<long long>(Nn) * Kp, bk, 256, &te)) { g_create_err = te; rc = NPAIR_E_CUDA; goto done; }
+      DG_TRY(launch_split_gemm(precision, EPI_OUT, ta, tb, gp, sms, st));
+    } else {
+      DG_TRY(launch_simt_gemm(precision, EPI_OUT, As, Kp, static_cast<long long>(M) * Kp, Bs, Kp, static_cast<long long>(Nn) * Kp, K, gp, st));
+    }
+    DG_TRY(cudaStreamSynchronize(st));
+  }
+done:
+  cudaFree(As); cudaFree(Bs); cudaFree(dummyT); cudaFree(bs); cudaFree(partial);
+#undef DG_TRY
+  return rc;
+}
+
+}  // extern "C"

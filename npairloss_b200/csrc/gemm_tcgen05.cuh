@@ -1,0 +1,292 @@
+// gemm_tcgen05.cuh -- persistent, warp-specialised split-operand GEMM for sm_100a.
+//
+//   C[M x Nn] = sum over passes (sa,sb) of  A_sa[M x K] . B_sb[Nn x K]^T      (both operands K-major, 2-byte elements)
+//
+// "Split operand": an fp32 matrix is stored as NSPLIT 2-byte pieces whose sum reproduces it
+//   NSPLIT=1 bf16            1 pass  (hi.hi)                                  -- throughput mode
+//   NSPLIT=2 fp16 hi+lo      3 passes (hh, hl, lh)      ~2^-22 relative       -- fp32-faithful, pre-scaled inputs
+//   NSPLIT=3 bf16 hi+mid+lo  6 passes (hh,hm,mh,mm,hl,lh) ~2^-24 relative     -- fp32-faithful, any dynamic range
+// All passes accumulate into the same fp32 TMEM accumulator, so the tensor pipe sees one long K loop.
+//
+// Structure (one CTA per SM, 256 threads):
+//   warp 0   TMA producer: cp.async.bulk.tensor 3-D boxes {BK, rows, 1 piece} -> 128B/64B-swizzled smem ring
+//   warp 1   MMA issuer  : one thread issues tcgen05.mma.cta_group::1.kind::f16 (128 x 256 x 16), fp32 accum in TMEM
+//   warp 2   TMEM allocator (512 columns = two 128x256 fp32 accumulators, double buffered)
+//   warps 4-7 epilogue   : tcgen05.ld 32x32b -> registers -> fused epilogue (similarity store + row statistics,
+//                          or scaled store of a gradient tile), overlapped with the next tile's MMAs
+// Replaces the reference's cublasSgemm calls: sim GEMM npair_multi_class_loss.cu:218 and the six backward
+// GEMMs .cu:448-460; the EPI_SIM epilogue also replaces GetLabelDiffMtx (.cu:44-66) and the host statistics loop
+// (.cu:225-265: min_within / max_between / max_all) -- they are computed while the tile is in registers.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cfloat>
+#include <stdint.h>
+
+#include "ptx.cuh"
+
+namespace npair {
+
+enum { EPI_SIM = 0, EPI_OUT = 1 };
+
+// order-preserving float <-> uint32 map so atomicMin/atomicMax work on floats of either sign
+__host__ __device__ __forceinline__ uint32_t f2ord(float f) {
+#ifdef __CUDA_ARCH__
+  uint32_t b = __float_as_uint(f);
+#else
+  union { float f; uint32_t u; } c; c.f = f; uint32_t b = c.u;
+#endif
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ord2f(uint32_t u) {
+  uint32_t b = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(b);
+#else
+  union { float f; uint32_t u; } c; c.u = b; return c.f;
+#endif
+}
+
+struct GemmParams {
+  int M, Nn;           // logical output extent
+  int num_kblocks;     // K_pad / BK
+  int tiles_m, tiles_n;
+  // ---- EPI_SIM ----
+  float* S;            // [M x ldS] fp32 similarities
+  long long ldS;       // multiple of 32
+  const float* dev_scale;  // device scalar: inverse operand pre-scale (power of two) or NULL.  EPI_SIM multiplies the
+                           // accumulators by its square (both operands were pre-scaled), EPI_OUT multiplies alpha by it
+  const float* lab_rows;   // [M]  labels of this rank's rows
+  const float* lab_cols;   // [Nn] labels of all columns
+  int self_offset;         // rank * Q : column index of row 0's self pair
+  uint32_t* st_minw;       // ordered-uint per-row statistics, pre-initialised
+  uint32_t* st_maxw;
+  uint32_t* st_maxb;
+  uint32_t* st_maxall;
+  int* cnt_same;           // per-row number of same-label non-self columns
+  // ---- EPI_OUT ----
+  float* out;          // [M x ldo]
+  long long ldo;
+  float alpha, beta;   // out = alpha*acc + beta*out
+};
+
+template <int NSPLIT>
+struct GemmCfg {
+  static constexpr int BM = 128, BN = 256;
+  static constexpr int BK = (NSPLIT == 3) ? 32 : 64;          // elements; one swizzle span per row
+  static constexpr int ROW_BYTES = BK * 2;                    // 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
+  static constexpr uint32_t LAYOUT = (ROW_BYTES == 128) ? 2u : 4u;
+  static constexpr uint32_t SBO = 8 * ROW_BYTES;              // byte distance between 8-row groups
+  static constexpr int A_PIECE = BM * ROW_BYTES;
+  static constexpr int B_PIECE = BN * ROW_BYTES;
+  static constexpr int STAGE_BYTES = NSPLIT * (A_PIECE + B_PIECE);
+  static constexpr int STAGES = (NSPLIT == 1) ? 4 : (NSPLIT == 2 ? 2 : 3);
+  static constexpr int NPASS = (NSPLIT == 1) ? 1 : (NSPLIT == 2 ? 3 : 6);
+  static constexpr int SMEM_AUX = 2048;                       // barriers + tmem ptr + column labels
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + SMEM_AUX + 1024 /*alignment slack*/;
+  static constexpr int THREADS = 256;
+};
+
+__device__ __forceinline__ void pass_pieces(int nsplit, int p, int& sa, int& sb) {
+  // (A piece, B piece) of pass p; largest terms first
+  if (nsplit == 1) { sa = 0; sb = 0; return; }
+  if (nsplit == 2) { sa = (p == 2) ? 1 : 0; sb = (p == 1) ? 1 : 0; return; }
+  // nsplit == 3: hh, hm, mh, mm, hl, lh
+  const int A[6] = {0, 0, 1, 1, 0, 2};
+  const int B[6] = {0, 1, 0, 1, 2, 0};
+  sa = A[p]; sb = B[p];
+}
+
+template <int NSPLIT, bool BF16, int EPI>
+__global__ void __launch_bounds__(256, 1)
+split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const GemmParams p) {
+  using Cfg = GemmCfg<NSPLIT>;
+  constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* aux = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);            // [STAGES]
+  uint64_t* empty_bar = full_bar + STAGES;                           // [STAGES]
+  uint64_t* tfull_bar = empty_bar + STAGES;                          // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;                              // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_lab = reinterpret_cast<float*>(aux + 256);                // [256] column labels of the current tile (EPI_SIM)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = p.tiles_m * p.tiles_n;
+  const float inv_scale = p.dev_scale ? *p.dev_scale : 1.f;
+  const float out_scale = (EPI == EPI_SIM) ? inv_scale * inv_scale : 1.f;
+  const float alpha = p.alpha * inv_scale;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmapA);
+    ptx::prefetch_tmap(&tmapB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 4); }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc<512>(tmem_ptr);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+        for (int kb = 0; kb < p.num_kblocks; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
+#pragma unroll
+          for (int s = 0; s < NSPLIT; ++s) {
+            ptx::tma_load_3d(st + s * Cfg::A_PIECE, &tmapA, &full_bar[stage], kb * BK, m_blk * BM, s);
+            ptx::tma_load_3d(st + NSPLIT * Cfg::A_PIECE + s * Cfg::B_PIECE, &tmapB, &full_bar[stage], kb * BK, n_blk * BN, s);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =====================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_f16(BF16, BM, BN);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.num_kblocks; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t a0 = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t b0 = a0 + NSPLIT * Cfg::A_PIECE;
+#pragma unroll
+          for (int ps = 0; ps < Cfg::NPASS; ++ps) {
+            int sa, sb;
+            pass_pieces(NSPLIT, ps, sa, sb);
+#pragma unroll
+            for (int k4 = 0; k4 < BK / 16; ++k4) {
+              const uint64_t ad = ptx::make_kmajor_desc(a0 + sa * Cfg::A_PIECE + k4 * 32, Cfg::SBO, Cfg::LAYOUT);
+              const uint64_t bd = ptx::make_kmajor_desc(b0 + sb * Cfg::B_PIECE + k4 * 32, Cfg::SBO, Cfg::LAYOUT);
+              ptx::mma_f16_ss(d_tmem, ad, bd, idesc, (kb | ps | k4) != 0 ? 1u : 0u);
+            }
+          }
+          ptx::mma_commit(&empty_bar[stage]);   // smem slot reusable once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        ptx::mma_commit(&tfull_bar[acc]);        // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================== epilogue =====================================
+    const int ew = warp - 4;                     // TMEM lane group = warp % 4
+    const int et = threadIdx.x - 128;            // 0..127
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int row = m_blk * BM + ew * 32 + lane;
+      const int col_base = n_blk * BN;
+      float lab_i = 0.f;
+      if (EPI == EPI_SIM) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // previous tile's readers are done with s_lab
+        for (int c = et; c < BN; c += 128) s_lab[c] = (col_base + c < p.Nn) ? p.lab_cols[col_base + c] : 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (row < p.M) lab_i = p.lab_rows[row];
+      }
+      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
+
+      float minw = FLT_MAX, maxw = -FLT_MAX, maxb = -FLT_MAX, maxall = -FLT_MAX;
+      int cnt = 0;
+      const int self_col = row + p.self_offset;
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(t_row + ch * 32, r);
+        ptx::tmem_ld_wait();
+        const int col0 = col_base + ch * 32;
+        if (EPI == EPI_SIM) {
+          float v[32];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(r[c]) * out_scale;
+          if (row < p.M && col0 < p.Nn) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const int col = col0 + c;
+              const bool valid = (col < p.Nn) && (col != self_col);
+              const bool same = (s_lab[ch * 32 + c] == lab_i);
+              if (valid) {
+                maxall = fmaxf(maxall, v[c]);
+                if (same) { minw = fminf(minw, v[c]); maxw = fmaxf(maxw, v[c]); ++cnt; }
+                else      { maxb = fmaxf(maxb, v[c]); }
+              }
+            }
+          }
+          if (row < p.M && col0 < p.ldS) {
+            float4* dst = reinterpret_cast<float4*>(p.S + static_cast<long long>(row) * p.ldS + col0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          }
+        } else {
+          if (row < p.M) {
+            float* dst = p.out + static_cast<long long>(row) * p.ldo + col0;
+            if (col0 + 32 <= p.Nn && (p.ldo & 3) == 0) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                float4 o = make_float4(alpha * __uint_as_float(r[4 * q]), alpha * __uint_as_float(r[4 * q + 1]),
+                                       alpha * __uint_as_float(r[4 * q + 2]), alpha * __uint_as_float(r[4 * q + 3]));
+                if (p.beta != 0.f) {
+                  const float4 old = reinterpret_cast<float4*>(dst)[q];
+                  o.x += p.beta * old.x; o.y += p.beta * old.y; o.z += p.beta * old.z; o.w += p.beta * old.w;
+                }
+                reinterpret_cast<float4*>(dst)[q] = o;
+              }
+            } else {
+#pragma unroll
+              for (int c = 0; c < 32; ++c)
+                if (col0 + c < p.Nn) {
+                  float o = alpha * __uint_as_float(r[c]);
+                  if (p.beta != 0.f) o += p.beta * dst[c];
+                  dst[c] = o;
+                }
+            }
+          }
+        }
+      }
+      // accumulator drained -> MMA warp may overwrite it
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+      if (EPI == EPI_SIM && row < p.M) {
+        atomicMin(&p.st_minw[row], f2ord(minw));
+        atomicMax(&p.st_maxw[row], f2ord(maxw));
+        atomicMax(&p.st_maxb[row], f2ord(maxb));
+        atomicMax(&p.st_maxall[row], f2ord(maxall));
+        if (cnt) atomicAdd(&p.cnt_same[row], cnt);
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace npair

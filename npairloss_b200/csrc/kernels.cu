@@ -1,0 +1,682 @@
+// kernels.cu -- HBM-bound kernels of the N-pair hot path (everything except the two tensor-core contractions).
+// Each kernel cites the reference code it replaces (paths relative to /root/reference).
+#include "kernels.cuh"
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cfloat>
+
+#include "gemm_tcgen05.cuh"   // f2ord / ord2f
+
+namespace npair {
+
+// --------------------------------------------------------------------------------------------
+// small helpers
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// split an fp32 value into 2-byte pieces (see gemm_tcgen05.cuh header)
+template <int PREC>
+__device__ __forceinline__ void split3(float v, uint16_t& p0, uint16_t& p1, uint16_t& p2) {
+  if (PREC == PREC_BF16) {
+    p0 = __bfloat16_as_ushort(__float2bfloat16_rn(v)); p1 = 0; p2 = 0;
+  } else if (PREC == PREC_FP16X2) {
+    const __half h = __float2half_rn(v);
+    const float r = v - __half2float(h);
+    p0 = __half_as_ushort(h); p1 = __half_as_ushort(__float2half_rn(r)); p2 = 0;
+  } else {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(h);
+    const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(m);
+    p0 = __bfloat16_as_ushort(h); p1 = __bfloat16_as_ushort(m); p2 = __bfloat16_as_ushort(__float2bfloat16_rn(r2));
+  }
+}
+__host__ __device__ inline int nsplit_of(int prec) { return prec == PREC_BF16 ? 1 : (prec == PREC_FP16X2 ? 2 : 3); }
+
+// pos(SN,size) of npair_multi_class_loss.cu:285-287: size_t arithmetic for SN>=0, un-fused fp32 otherwise.
+__device__ __forceinline__ bool pos_index(float sn, unsigned long long size, unsigned long long& pos) {
+  if (size == 0) return false;
+  if (sn >= 0.f) {                                    // -0.0f >= 0 is true
+    const unsigned long long p = size - 1ull - static_cast<unsigned long long>(static_cast<long long>(static_cast<int>(sn)));
+    if (p >= size) return false;
+    pos = p; return true;
+  }
+  const float a = __ull2float_rn(size - 1ull);
+  const float b = __fmul_rn(sn, __ull2float_rn(size));
+  const float c = __fadd_rn(a, b);
+  if (!(c > -2147483648.f && c < 2147483648.f)) return false;
+  const int ip = static_cast<int>(c);                 // truncation toward zero
+  if (ip < 0 || static_cast<unsigned long long>(ip) >= size) return false;
+  pos = static_cast<unsigned long long>(ip); return true;
+}
+__device__ __forceinline__ float clamp_thr(float v) { return v >= 0.f ? v : -FLT_MAX; }   // .cu:288,303,319,334
+
+__device__ __forceinline__ bool sel_ap(float s, float tp, int m) {   // .cu:79-98
+  switch (m) {
+    case M_HARD: return s < tp;
+    case M_EASY: return s >= tp;
+    case M_RAND: return true;
+    case M_RELATIVE_HARD: return s <= tp;
+    default: return s >= tp;
+  }
+}
+__device__ __forceinline__ bool sel_an(float s, float tn, int m) {   // .cu:100-119
+  switch (m) {
+    case M_HARD: return s > tn;
+    case M_EASY: return s <= tn;
+    case M_RAND: return true;
+    case M_RELATIVE_HARD: return s >= tn;
+    default: return s <= tn;
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// absmax / asum  (caffe_gpu_asum .cu:400; operand pre-scale for PREC_FP16X2)
+// --------------------------------------------------------------------------------------------
+__global__ void absmax_asum_partial_kernel(const float* __restrict__ xl, long long nl, const float* __restrict__ xt, long long ntot,
+                                           float* __restrict__ partial, int want_scale) {
+  __shared__ float s_sum[32], s_max[32];
+  float sum = 0.f, mx = 0.f;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nl; i += stride) sum += fabsf(xl[i]);
+  if (want_scale)
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < ntot; i += stride) mx = fmaxf(mx, fabsf(xt[i]));
+  sum = warp_sum(sum); mx = warp_max(mx);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { s_sum[w] = sum; s_max[w] = mx; }
+  __syncthreads();
+  if (w == 0) {
+    sum = (l < (blockDim.x >> 5)) ? s_sum[l] : 0.f;
+    mx = (l < (blockDim.x >> 5)) ? s_max[l] : 0.f;
+    sum = warp_sum(sum); mx = warp_max(mx);
+    if (l == 0) { partial[blockIdx.x] = sum; partial[1024 + blockIdx.x] = mx; }
+  }
+}
+__global__ void absmax_asum_final_kernel(const float* __restrict__ partial, int nb, BlockScalars* bs, int want_scale) {
+  if (threadIdx.x == 0) {
+    double s = 0.0; float mx = 0.f;
+    for (int b = 0; b < nb; ++b) { s += partial[b]; mx = fmaxf(mx, partial[1024 + b]); }
+    bs->asum = static_cast<float>(s);
+    bs->x_absmax = mx;
+    float sc = 1.f, inv = 1.f;
+    if (want_scale && mx > 0.f && isfinite(mx)) {
+      int e; frexpf(mx, &e);                 // mx = m * 2^e, m in [0.5,1)
+      sc = ldexpf(1.f, -e); inv = ldexpf(1.f, e);
+    }
+    bs->x_scale = sc; bs->x_inv_scale = inv;
+  }
+}
+void launch_absmax_asum(const float* x_local, long long n_local, const float* x_total, long long n_total,
+                        float* partial, BlockScalars* bs, int want_scale, cudaStream_t st) {
+  long long nmax = n_local > n_total ? n_local : n_total;
+  int nb = static_cast<int>((nmax + 256 * 8 - 1) / (256 * 8));
+  if (nb < 1) nb = 1; if (nb > 1024) nb = 1024;
+  absmax_asum_partial_kernel<<<nb, 256, 0, st>>>(x_local, n_local, x_total, n_total, partial, want_scale);
+  absmax_asum_final_kernel<<<1, 32, 0, st>>>(partial, nb, bs, want_scale);
+}
+
+// --------------------------------------------------------------------------------------------
+// operand split: x_total fp32 [N x D] -> Xs[s][N][ldXs] (K-major for the similarity GEMM) and the transposed
+// XsT[s][D][ldXsT] (K-major for the gradient GEMM whose K is the sample index); XlT = local columns only.
+// --------------------------------------------------------------------------------------------
+template <int PREC>
+__global__ void split_kernel(const float* __restrict__ x, int N, int D, const BlockScalars* __restrict__ bs,
+                             uint16_t* __restrict__ Xs, long long ldXs, uint16_t* __restrict__ XsT, long long ldXsT,
+                             uint16_t* __restrict__ XlT, long long ldXlT, int row0, int Q) {
+  constexpr int NS = (PREC == PREC_BF16) ? 1 : (PREC == PREC_FP16X2 ? 2 : 3);
+  __shared__ uint16_t tile[NS][32][34];
+  const float sc = (PREC == PREC_FP16X2) ? bs->x_scale : 1.f;
+  const int n0 = blockIdx.y * 32, d0 = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
+  const long long ps = static_cast<long long>(N) * ldXs;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int n = n0 + ty + 8 * r, d = d0 + tx;
+    uint16_t p[3] = {0, 0, 0};
+    if (n < N && d < D) split3<PREC>(x[static_cast<long long>(n) * D + d] * sc, p[0], p[1], p[2]);
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      tile[s][ty + 8 * r][tx] = p[s];
+      if (n < N && d < D) Xs[s * ps + static_cast<long long>(n) * ldXs + d] = p[s];
+    }
+  }
+  __syncthreads();
+  const long long pt = static_cast<long long>(D) * ldXsT;
+  const long long pl = static_cast<long long>(D) * ldXlT;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int d = d0 + ty + 8 * r, n = n0 + tx;
+    if (d < D && n < N) {
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        const uint16_t v = tile[s][tx][ty + 8 * r];
+        XsT[s * pt + static_cast<long long>(d) * ldXsT + n] = v;
+        if (XlT && n >= row0 && n < row0 + Q) XlT[s * pl + static_cast<long long>(d) * ldXlT + (n - row0)] = v;
+      }
+    }
+  }
+}
+void launch_split(const float* x_total, int N, int D, int prec, const BlockScalars* bs, uint16_t* Xs, long long ldXs,
+                  uint16_t* XsT, long long ldXsT, uint16_t* XlT, long long ldXlT, int row0_local, int Q, cudaStream_t st) {
+  dim3 grid((D + 31) / 32, (N + 31) / 32), block(32, 8);
+  if (prec == PREC_BF16) split_kernel<PREC_BF16><<<grid, block, 0, st>>>(x_total, N, D, bs, Xs, ldXs, XsT, ldXsT, XlT, ldXlT, row0_local, Q);
+  else if (prec == PREC_FP16X2) split_kernel<PREC_FP16X2><<<grid, block, 0, st>>>(x_total, N, D, bs, Xs, ldXs, XsT, ldXsT, XlT, ldXlT, row0_local, Q);
+  else split_kernel<PREC_BF16X3><<<grid, block, 0, st>>>(x_total, N, D, bs, Xs, ldXs, XsT, ldXsT, XlT, ldXlT, row0_local, Q);
+}
+
+// --------------------------------------------------------------------------------------------
+// statistics init / reference row statistics (caffe_set of the three stat blobs, .cu:230-236)
+// --------------------------------------------------------------------------------------------
+__global__ void init_stats_kernel(RowArrays ra, int Q, BlockScalars* bs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Q) {
+    ra.st_minw[i] = f2ord(FLT_MAX); ra.st_maxw[i] = f2ord(-FLT_MAX);
+    ra.st_maxb[i] = f2ord(-FLT_MAX); ra.st_maxall[i] = f2ord(-FLT_MAX);
+    ra.cnt_same[i] = 0;
+  }
+  if (i == 0) {
+    bs->err = 0; bs->sel_active[0] = 0; bs->sel_active[1] = 0;
+    bs->n_same = 0; bs->n_diff = 0;
+  }
+}
+void launch_init_stats(RowArrays ra, int Q, BlockScalars* bs, cudaStream_t st) {
+  init_stats_kernel<<<(Q + 255) / 256, 256, 0, st>>>(ra, Q, bs);
+}
+
+// One block per row; same outputs as the sim-GEMM epilogue.  Used by the SIMT cross-check backend and by tests.
+__global__ void row_stats_ref_kernel(const float* __restrict__ S, long long ldS, int Q, int N, const float* __restrict__ lab_rows,
+                                     const float* __restrict__ lab_cols, int self_offset, RowArrays ra) {
+  const int i = blockIdx.x;
+  const float li = lab_rows[i];
+  const int self_col = i + self_offset;
+  float minw = FLT_MAX, maxw = -FLT_MAX, maxb = -FLT_MAX, maxall = -FLT_MAX;
+  int cnt = 0;
+  const float* row = S + static_cast<long long>(i) * ldS;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    if (j == self_col) continue;
+    const float v = row[j];
+    maxall = fmaxf(maxall, v);
+    if (lab_cols[j] == li) { minw = fminf(minw, v); maxw = fmaxf(maxw, v); ++cnt; } else maxb = fmaxf(maxb, v);
+  }
+  minw = warp_min(minw); maxw = warp_max(maxw); maxb = warp_max(maxb); maxall = warp_max(maxall); cnt = warp_sum_i(cnt);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(&ra.st_minw[i], f2ord(minw)); atomicMax(&ra.st_maxw[i], f2ord(maxw));
+    atomicMax(&ra.st_maxb[i], f2ord(maxb)); atomicMax(&ra.st_maxall[i], f2ord(maxall));
+    if (cnt) atomicAdd(&ra.cnt_same[i], cnt);
+  }
+}
+void launch_row_stats_ref(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
+                          int self_offset, RowArrays ra, cudaStream_t st) {
+  row_stats_ref_kernel<<<Q, 256, 0, st>>>(S, ldS, Q, N, lab_rows, lab_cols, self_offset, ra);
+}
+
+// --------------------------------------------------------------------------------------------
+// thresholds (.cu:275-337).  One block.  Non-relative modes and the pos==size-1 relative shortcut are
+// closed forms of the row statistics; general relative modes arm the radix selects below.
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool is_rel(int m) { return m == M_RELATIVE_HARD || m == M_RELATIVE_EASY; }
+__host__ __device__ inline bool sn_is_max(float sn) { return sn >= 0.f && static_cast<int>(sn) == 0; }   // pos = size-1
+
+__global__ void thresholds_kernel(RowArrays ra, int Q, int N, MiningParams mp, BlockScalars* bs) {
+  __shared__ unsigned long long s_ns[32];
+  __shared__ float s_mn[32], s_mxw[32], s_mxb[32];
+  __shared__ int s_err;
+  if (threadIdx.x == 0) s_err = 0;
+  unsigned long long ns = 0; float mn = FLT_MAX, mxw = -FLT_MAX, mxb = -FLT_MAX;
+  for (int i = threadIdx.x; i < Q; i += blockDim.x) {
+    ns += static_cast<unsigned long long>(ra.cnt_same[i]);
+    mn = fminf(mn, ord2f(ra.st_minw[i])); mxw = fmaxf(mxw, ord2f(ra.st_maxw[i])); mxb = fmaxf(mxb, ord2f(ra.st_maxb[i]));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ns += __shfl_xor_sync(0xffffffffu, ns, o);
+  mn = warp_min(mn); mxw = warp_max(mxw); mxb = warp_max(mxb);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { s_ns[w] = ns; s_mn[w] = mn; s_mxw[w] = mxw; s_mxb[w] = mxb; }
+  __syncthreads();
+  if (w == 0) {
+    const int nw = blockDim.x >> 5;
+    ns = l < nw ? s_ns[l] : 0ull; mn = l < nw ? s_mn[l] : FLT_MAX; mxw = l < nw ? s_mxw[l] : -FLT_MAX; mxb = l < nw ? s_mxb[l] : -FLT_MAX;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ns += __shfl_xor_sync(0xffffffffu, ns, o);
+    mn = warp_min(mn); mxw = warp_max(mxw); mxb = warp_max(mxb);
+    if (l == 0) { s_ns[0] = ns; s_mn[0] = mn; s_mxw[0] = mxw; s_mxb[0] = mxb; }
+  }
+  __syncthreads();
+  const unsigned long long n_same = s_ns[0];
+  const unsigned long long n_diff = static_cast<unsigned long long>(Q) * static_cast<unsigned long long>(N - 1) - n_same;
+  const float gmin_w = s_mn[0], gmax_w = s_mxw[0], gmax_b = s_mxb[0];
+  int err = 0;
+  float posi_g = 0.f, nega_g = 0.f;
+  bool arm_ap = false, arm_an = false;
+  // ---- AP side ----
+  if (mp.ap_region == REGION_GLOBAL) {
+    if (!is_rel(mp.ap_method)) { if (n_diff == 0) err |= DERR_EMPTY_LIST; posi_g = gmax_b; }              // .cu:296
+    else if (sn_is_max(mp.identsn)) { if (n_same == 0) err |= DERR_EMPTY_LIST; posi_g = clamp_thr(gmax_w); }   // pos = size-1
+    else arm_ap = true;                                                                                    // .cu:300-304
+  }
+  // ---- AN side ----
+  if (mp.an_region == REGION_GLOBAL) {
+    if (!is_rel(mp.an_method)) { if (n_same == 0) err |= DERR_EMPTY_LIST; nega_g = gmin_w; }               // .cu:327
+    else if (sn_is_max(mp.diffsn)) { if (n_diff == 0) err |= DERR_EMPTY_LIST; nega_g = clamp_thr(gmax_b); }
+    else arm_an = true;                                                                                    // .cu:331-335
+  }
+  for (int i = threadIdx.x; i < Q; i += blockDim.x) {
+    const int cs = ra.cnt_same[i];
+    const int cd = N - 1 - cs;
+    if (mp.ap_region == REGION_LOCAL) {
+      if (!is_rel(mp.ap_method)) ra.posi_thr[i] = ord2f(ra.st_maxb[i]);                                    // .cu:279
+      else if (sn_is_max(mp.identsn)) { if (cs == 0) atomicOr(&s_err, DERR_EMPTY_LIST); ra.posi_thr[i] = clamp_thr(ord2f(ra.st_maxw[i])); }
+    } else if (!arm_ap) ra.posi_thr[i] = posi_g;
+    if (mp.an_region == REGION_LOCAL) {
+      if (!is_rel(mp.an_method)) ra.nega_thr[i] = ord2f(ra.st_minw[i]);                                    // .cu:310
+      else if (sn_is_max(mp.diffsn)) { if (cd == 0) atomicOr(&s_err, DERR_EMPTY_LIST); ra.nega_thr[i] = clamp_thr(ord2f(ra.st_maxb[i])); }
+    } else if (!arm_an) ra.nega_thr[i] = nega_g;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    err |= s_err;
+    bs->n_same = n_same; bs->n_diff = n_diff;
+    bs->gmin_within = gmin_w; bs->gmax_within = gmax_w; bs->gmax_between = gmax_b;
+    bs->posi_global = posi_g; bs->nega_global = nega_g;
+    for (int side = 0; side < 2; ++side) {
+      const bool arm = side == 0 ? arm_ap : arm_an;
+      bs->sel_active[side] = 0;
+      if (arm) {
+        unsigned long long pos = 0;
+        const unsigned long long size = side == 0 ? n_same : n_diff;
+        if (size == 0) err |= DERR_EMPTY_LIST;
+        else if (!pos_index(side == 0 ? mp.identsn : mp.diffsn, size, pos)) err |= DERR_POS_RANGE;
+        else { bs->sel_active[side] = 1; bs->sel_rank[side] = pos; bs->sel_prefix[side] = 0; bs->sel_mask[side] = 0; }
+      }
+    }
+    bs->err |= err;
+  }
+}
+void launch_thresholds(RowArrays ra, int Q, int N, MiningParams mp, BlockScalars* bs, cudaStream_t st) {
+  thresholds_kernel<<<1, 1024, 0, st>>>(ra, Q, N, mp, bs);
+}
+
+// --------------------------------------------------------------------------------------------
+// LOCAL relative thresholds: k-th smallest masked element of each row by 4 x 8-bit MSB radix select
+// (replaces the per-row std::sort + index of .cu:270-273, :282-290, :313-321).  One block per row; the
+// row is re-read from L1/L2, HBM sees it once.
+// --------------------------------------------------------------------------------------------
+__global__ void local_select_kernel(const float* __restrict__ S, long long ldS, int Q, int N, const float* __restrict__ lab_rows,
+                                    const float* __restrict__ lab_cols, int self_offset, int side, float sn, RowArrays ra,
+                                    BlockScalars* bs) {
+  __shared__ unsigned int hist[256];
+  __shared__ uint32_t s_prefix, s_mask;
+  __shared__ unsigned int s_rank;
+  __shared__ int s_ok;
+  const int i = blockIdx.x;
+  const float li = lab_rows[i];
+  const int self_col = i + self_offset;
+  const float* row = S + static_cast<long long>(i) * ldS;
+  float* out = side == 0 ? ra.posi_thr : ra.nega_thr;
+  if (threadIdx.x == 0) {
+    const int cs = ra.cnt_same[i];
+    const unsigned long long size = side == 0 ? cs : (N - 1 - cs);
+    unsigned long long pos = 0;
+    s_ok = 1;
+    if (size == 0) { atomicOr(&bs->err, DERR_EMPTY_LIST); s_ok = 0; }
+    else if (!pos_index(sn, size, pos)) { atomicOr(&bs->err, DERR_POS_RANGE); s_ok = 0; }
+    s_rank = static_cast<unsigned int>(pos); s_prefix = 0; s_mask = 0;
+  }
+  __syncthreads();
+  if (!s_ok) { if (threadIdx.x == 0) out[i] = 0.f; return; }
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int b = threadIdx.x; b < 256; b += blockDim.x) hist[b] = 0;
+    __syncthreads();
+    const uint32_t prefix = s_prefix, mask = s_mask;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+      if (j == self_col) continue;
+      const bool same = lab_cols[j] == li;
+      if (same != (side == 0)) continue;
+      const uint32_t key = f2ord(row[j]);
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned int r = s_rank, cum = 0; int d = 0;
+      for (; d < 256; ++d) { if (cum + hist[d] > r) break; cum += hist[d]; }
+      s_rank = r - cum; s_prefix = prefix | (static_cast<uint32_t>(d) << shift); s_mask = mask | (255u << shift);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[i] = clamp_thr(ord2f(s_prefix));
+}
+void launch_local_select(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
+                         int self_offset, int side, float sn, RowArrays ra, BlockScalars* bs, cudaStream_t st) {
+  local_select_kernel<<<Q, 256, 0, st>>>(S, ldS, Q, N, lab_rows, lab_cols, self_offset, side, sn, ra, bs);
+}
+
+// --------------------------------------------------------------------------------------------
+// GLOBAL relative thresholds: k-th smallest of ALL same (or diff) similarities of this rank's Q x N block
+// (replaces the std::sort of ident/diff_prod_global_list, .cu:267-268, and the index at .cu:300-304/:331-335).
+// Three digit passes (11/11/10 bits) of a multi-block histogram radix select with 64-bit counts.
+// --------------------------------------------------------------------------------------------
+__global__ void global_hist_kernel(const float* __restrict__ S, long long ldS, int Q, int N, const float* __restrict__ lab_rows,
+                                   const float* __restrict__ lab_cols, int self_offset, int side, int shift, int nbits,
+                                   unsigned long long* __restrict__ ghist, const BlockScalars* __restrict__ bs) {
+  __shared__ unsigned int hist[2048];
+  if (!bs->sel_active[side]) return;
+  const uint32_t prefix = bs->sel_prefix[side], mask = bs->sel_mask[side];
+  const uint32_t dmask = (1u << nbits) - 1u;
+  for (int b = threadIdx.x; b < 2048; b += blockDim.x) hist[b] = 0;
+  __syncthreads();
+  for (int i = blockIdx.x; i < Q; i += gridDim.x) {
+    const float li = lab_rows[i];
+    const int self_col = i + self_offset;
+    const float* row = S + static_cast<long long>(i) * ldS;
+    for (int j4 = threadIdx.x * 4; j4 < N; j4 += blockDim.x * 4) {
+      const float4 v = *reinterpret_cast<const float4*>(row + j4);
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int j = j4 + c;
+        if (j >= N || j == self_col) continue;
+        const bool same = lab_cols[j] == li;
+        if (same != (side == 0)) continue;
+        const uint32_t key = f2ord(vv[c]);
+        if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & dmask], 1u);
+      }
+    }
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < 2048; b += blockDim.x)
+    if (hist[b]) atomicAdd(&ghist[b], static_cast<unsigned long long>(hist[b]));
+}
+__global__ void global_pick_kernel(unsigned long long* __restrict__ ghist, int side, int shift, int nbits, int last,
+                                   RowArrays ra, int Q, BlockScalars* bs) {
+  __shared__ float s_thr;
+  __shared__ int s_done;
+  if (threadIdx.x == 0) {
+    s_done = 0;
+    if (bs->sel_active[side]) {
+      const int nb = 1 << nbits;
+      unsigned long long r = bs->sel_rank[side], cum = 0; int d = 0;
+      for (; d < nb; ++d) { if (cum + ghist[d] > r) break; cum += ghist[d]; }
+      if (d == nb) { bs->err |= DERR_POS_RANGE; bs->sel_active[side] = 0; d = 0; }
+      bs->sel_rank[side] = r - cum;
+      bs->sel_prefix[side] |= static_cast<uint32_t>(d) << shift;
+      bs->sel_mask[side] |= ((1u << nbits) - 1u) << shift;
+      if (last) {
+        const float thr = clamp_thr(ord2f(bs->sel_prefix[side]));
+        if (side == 0) bs->posi_global = thr; else bs->nega_global = thr;
+        s_thr = thr; s_done = 1;
+      }
+    }
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < 2048; b += blockDim.x) ghist[b] = 0ull;
+  if (s_done) {
+    float* out = side == 0 ? ra.posi_thr : ra.nega_thr;
+    for (int i = threadIdx.x; i < Q; i += blockDim.x) out[i] = s_thr;
+  }
+}
+void launch_global_select(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
+                          int self_offset, int side, float sn, RowArrays ra, unsigned long long* hist, BlockScalars* bs,
+                          cudaStream_t st) {
+  (void)sn;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int grid = sms * 4; if (grid > Q) grid = Q;
+  const int shifts[3] = {21, 10, 0}, bits[3] = {11, 11, 10};
+  for (int p = 0; p < 3; ++p) {
+    global_hist_kernel<<<grid, 512, 0, st>>>(S, ldS, Q, N, lab_rows, lab_cols, self_offset, side, shifts[p], bits[p], hist, bs);
+    global_pick_kernel<<<1, 1024, 0, st>>>(hist, side, shifts[p], bits[p], p == 2, ra, Q, bs);
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// The forward row pass: one streaming read of S per row computes everything the reference spreads over
+// GetSampledPairMtx (.cu:69-122), the count gemvs (.cu:355-360), Minus_Querywise_Maxval (.cu:124-156), the
+// masked sums (.cu:373-380), ManipulateDIVandLOG (.cu:158-171) and GetRetrivePerformance (.cu:173-206).
+// Retrieval uses the sort-free equivalence of SURVEY.md 9.4 Q11: with p* = max E over same-label non-self
+// columns and c = #{non-self j : E_j >= p*},  hit_k  <=>  c <= min(k, N-2).
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) lse_rows_kernel(const float* __restrict__ S, long long ldS, int Q, int N,
+                                                       const float* __restrict__ lab_rows, const float* __restrict__ lab_cols,
+                                                       int self_offset, MiningParams mp, RowArrays ra) {
+  __shared__ float s_A[8], s_B[8];
+  __shared__ int s_c[8], s_id[8], s_df[8];
+  const int i = blockIdx.x;
+  const float li = lab_rows[i];
+  const int self_col = i + self_offset;
+  const float max_all = ord2f(ra.st_maxall[i]);
+  const float tp = ra.posi_thr[i] + mp.margin_ident;          // fp32 add as in .cu:81
+  const float tn = ra.nega_thr[i] + mp.margin_diff;           // .cu:102
+  const int cs = ra.cnt_same[i];
+  const float pstar = cs > 0 ? expf(ord2f(ra.st_maxw[i]) - max_all) : FLT_MAX;
+  const float* row = S + static_cast<long long>(i) * ldS;
+  float A = 0.f, B = 0.f; int c = 0, idn = 0, dfn = 0;
+  for (int j4 = threadIdx.x * 4; j4 < N; j4 += 256 * 4) {
+    const float4 v = *reinterpret_cast<const float4*>(row + j4);
+    const float4 lc = (j4 + 3 < N) ? *reinterpret_cast<const float4*>(lab_cols + j4)
+                                   : make_float4(lab_cols[j4], j4 + 1 < N ? lab_cols[j4 + 1] : 0.f, j4 + 2 < N ? lab_cols[j4 + 2] : 0.f, 0.f);
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+    const float ll[4] = {lc.x, lc.y, lc.z, lc.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int j = j4 + q;
+      if (j >= N || j == self_col) continue;
+      const float s = vv[q];
+      const float e = expf(s - max_all);                      // .cu:130-131 (fp32 subtract, then expf)
+      c += (e >= pstar) ? 1 : 0;
+      if (ll[q] == li) { if (sel_ap(s, tp, mp.ap_method)) { A += e; ++idn; } }
+      else             { if (sel_an(s, tn, mp.an_method)) { B += e; ++dfn; } }
+    }
+  }
+  A = warp_sum(A); B = warp_sum(B); c = warp_sum_i(c); idn = warp_sum_i(idn); dfn = warp_sum_i(dfn);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { s_A[w] = A; s_B[w] = B; s_c[w] = c; s_id[w] = idn; s_df[w] = dfn; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    A = 0.f; B = 0.f; c = 0; idn = 0; dfn = 0;
+    for (int k = 0; k < 8; ++k) { A += s_A[k]; B += s_B[k]; c += s_c[k]; idn += s_id[k]; dfn += s_df[k]; }
+    const float T = A + B;                                    // .cu:380
+    ra.A[i] = A; ra.T[i] = T;
+    ra.logv[i] = (A == 0.f || T == 0.f) ? 0.f : logf(A / T);  // .cu:162-169
+    const int lim = N - 2;
+    ra.hits[i] = (cs > 0 && c <= min(1, lim)) ? 1 : 0;
+    ra.hits[Q + i] = (cs > 0 && c <= min(5, lim)) ? 1 : 0;
+    ra.hits[2 * Q + i] = (cs > 0 && c <= min(10, lim)) ? 1 : 0;
+    const float invA = A == 0.f ? 0.f : 1.f / A;              // Get_Query_Diff_Part zero rules (.cu:410-415)
+    const float invT = T == 0.f ? 0.f : 1.f / T;
+    ra.rs_maxall[i] = max_all; ra.rs_tp[i] = tp; ra.rs_tn[i] = tn;
+    ra.rs_cA[i] = invT - invA;                                // same-label weight:  -1/A + 1/T
+    ra.rs_cT[i] = invT;                                       // diff-label weight:   1/T
+  }
+}
+void launch_lse_rows(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
+                     int self_offset, MiningParams mp, RowArrays ra, cudaStream_t st) {
+  lse_rows_kernel<<<Q, 256, 0, st>>>(S, ldS, Q, N, lab_rows, lab_cols, self_offset, mp, ra);
+}
+
+// --------------------------------------------------------------------------------------------
+// finalize: loss = -sum(log)/Q (.cu:384-385), retrieval ratios (.cu:205), feature asum / num (.cu:400-401),
+// top layout of .cu:388-401 (last top is always the asum).
+// --------------------------------------------------------------------------------------------
+__global__ void finalize_kernel(RowArrays ra, int Q, int num_tops, const BlockScalars* __restrict__ bs, float* __restrict__ tops) {
+  __shared__ double s_l[32];
+  __shared__ int s_h[3][32];
+  double ls = 0.0; int h[3] = {0, 0, 0};
+  for (int i = threadIdx.x; i < Q; i += blockDim.x) {
+    ls += ra.logv[i];
+    h[0] += ra.hits[i]; h[1] += ra.hits[Q + i]; h[2] += ra.hits[2 * Q + i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ls += __shfl_xor_sync(0xffffffffu, ls, o);
+    h[0] += __shfl_xor_sync(0xffffffffu, h[0], o); h[1] += __shfl_xor_sync(0xffffffffu, h[1], o); h[2] += __shfl_xor_sync(0xffffffffu, h[2], o);
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { s_l[w] = ls; s_h[0][w] = h[0]; s_h[1][w] = h[1]; s_h[2][w] = h[2]; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ls = 0.0; h[0] = h[1] = h[2] = 0;
+    for (int k = 0; k < (blockDim.x >> 5); ++k) { ls += s_l[k]; h[0] += s_h[0][k]; h[1] += s_h[1][k]; h[2] += s_h[2][k]; }
+    float out[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    out[0] = static_cast<float>(ls) / static_cast<float>(-Q);
+    for (int t = 1; t <= num_tops - 2 && t <= 3; ++t) out[t] = static_cast<float>(h[t - 1]) / static_cast<float>(Q);
+    out[num_tops - 1] = bs->asum / static_cast<float>(Q);
+    for (int t = 0; t < 5; ++t) tops[t] = out[t];
+    reinterpret_cast<int*>(tops)[5] = bs->err;
+    __threadfence_system();
+  }
+}
+void launch_finalize(RowArrays ra, int Q, int num_tops, const BlockScalars* bs, float* tops_dev, cudaStream_t st) {
+  finalize_kernel<<<1, 1024, 0, st>>>(ra, Q, num_tops, bs, tops_dev);
+}
+
+// --------------------------------------------------------------------------------------------
+// Backward weight builder: replaces Get_Query_Diff_Part x3 (.cu:405-419, :438-446).  The reference
+// materialises W1,W2,W3 in fp32 and runs six GEMMs; here one pass over S produces the unit gradient
+// weight   g'(i,c) = sel(i,c) * expf(S[i,c]-max_all_i) * (same ? 1/T_i - 1/A_i : 1/T_i)     ( = -W1+W2+W3 )
+// directly as split 2-byte operand tiles for the tensor-core GEMM:
+//   world == 1 :  H[j][m]  = g'(j,m) + g'(m,j)            dX = (lw/Q)/2 * H . X        (.cu:448-497 folded)
+//   world  > 1 :  H[j][m]  = g'(j,m)  and  HT[m][j] = g'(j,m)
+//                 local = H . X_total ,  total = HT . X_local , then reduce-scatter and blend (.cu:462-497)
+// --------------------------------------------------------------------------------------------
+struct RowScal { float maxall, tp, tn, cA, cT, lab; };
+
+__device__ __forceinline__ float gprime(float s, bool same, const RowScal& r, int apM, int anM) {
+  const bool sel = same ? sel_ap(s, r.tp, apM) : sel_an(s, r.tn, anM);
+  return sel ? expf(s - r.maxall) * (same ? r.cA : r.cT) : 0.f;
+}
+
+template <int PREC, bool FUSED>
+__global__ void __launch_bounds__(256) build_weights_kernel(const float* __restrict__ S, long long ldS, int Q, int N,
+                                                            const float* __restrict__ lab_rows, const float* __restrict__ lab_cols,
+                                                            int self_offset, MiningParams mp, RowArrays ra,
+                                                            uint16_t* __restrict__ H, long long ldH, uint16_t* __restrict__ HT, long long ldHT) {
+  constexpr int NS = (PREC == PREC_BF16) ? 1 : (PREC == PREC_FP16X2 ? 2 : 3);
+  constexpr int TS = 64;
+  __shared__ float G[TS][TS + 1];
+  __shared__ RowScal sc_j[TS], sc_m[TS];
+  __shared__ float lab_m[TS];
+  const int j0 = blockIdx.y * TS, m0 = blockIdx.x * TS;        // rows j (local), columns m (global)
+  const int t = threadIdx.x;
+  const int cp = t & 31, rg = t >> 5;
+  if (t < TS) {
+    const int j = j0 + t;
+    RowScal r = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (j < Q) { r.maxall = ra.rs_maxall[j]; r.tp = ra.rs_tp[j]; r.tn = ra.rs_tn[j]; r.cA = ra.rs_cA[j]; r.cT = ra.rs_cT[j]; r.lab = lab_rows[j]; }
+    sc_j[t] = r;
+  } else if (t < 2 * TS) {
+    const int mm = t - TS, m = m0 + mm;
+    lab_m[mm] = m < N ? lab_cols[m] : 0.f;
+    if (FUSED) {   // world == 1: column m is also a local row
+      RowScal r = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (m < Q) { r.maxall = ra.rs_maxall[m]; r.tp = ra.rs_tp[m]; r.tn = ra.rs_tn[m]; r.cA = ra.rs_cA[m]; r.cT = ra.rs_cT[m]; r.lab = lab_rows[m]; }
+      sc_m[mm] = r;
+    }
+  }
+  __syncthreads();
+  if (FUSED) {
+    // phase 1: G[a][b] = g'(row m0+a, col j0+b)   (the transposed contribution), coalesced along b
+#pragma unroll
+    for (int r8 = 0; r8 < 8; ++r8) {
+      const int a = rg + 8 * r8, m = m0 + a;
+      const int b = 2 * cp, jc = j0 + b;
+      float g0 = 0.f, g1 = 0.f;
+      if (m < Q && jc < N) {
+        const float2 v = *reinterpret_cast<const float2*>(S + static_cast<long long>(m) * ldS + jc);
+        const RowScal rs = sc_m[a];
+        if (jc != m + self_offset) g0 = gprime(v.x, sc_j[b].lab == rs.lab, rs, mp.ap_method, mp.an_method);
+        if (jc + 1 < N && jc + 1 != m + self_offset) g1 = gprime(v.y, sc_j[b + 1].lab == rs.lab, rs, mp.ap_method, mp.an_method);
+      }
+      G[a][b] = g0; G[a][b + 1] = g1;
+    }
+    __syncthreads();
+  }
+  // phase 2: direct contribution, add the transposed one, split and store (packed pairs along m)
+  const long long psH = static_cast<long long>(Q) * ldH;
+#pragma unroll
+  for (int r8 = 0; r8 < 8; ++r8) {
+    const int a = rg + 8 * r8, j = j0 + a;
+    const int b = 2 * cp, m = m0 + b;
+    float g0 = 0.f, g1 = 0.f;
+    if (j < Q && m < N) {
+      const float2 v = *reinterpret_cast<const float2*>(S + static_cast<long long>(j) * ldS + m);
+      const RowScal rs = sc_j[a];
+      if (m != j + self_offset) g0 = gprime(v.x, lab_m[b] == rs.lab, rs, mp.ap_method, mp.an_method);
+      if (m + 1 < N && m + 1 != j + self_offset) g1 = gprime(v.y, lab_m[b + 1] == rs.lab, rs, mp.ap_method, mp.an_method);
+    }
+    if (FUSED) { g0 += G[b][a]; g1 += G[b + 1][a]; }
+    else { G[a][b] = g0; G[a][b + 1] = g1; }
+    if (j < Q && m < ldH) {
+      uint16_t p0[3], p1[3];
+      split3<PREC>(g0, p0[0], p0[1], p0[2]);
+      split3<PREC>(g1, p1[0], p1[1], p1[2]);
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+        *reinterpret_cast<uint32_t*>(H + s * psH + static_cast<long long>(j) * ldH + m) = static_cast<uint32_t>(p0[s]) | (static_cast<uint32_t>(p1[s]) << 16);
+    }
+  }
+  if (!FUSED) {
+    // transposed copy HT[m][j] = g'(j,m), packed pairs along j
+    __syncthreads();
+    const long long psT = static_cast<long long>(N) * ldHT;
+#pragma unroll
+    for (int r8 = 0; r8 < 8; ++r8) {
+      const int a = rg + 8 * r8, m = m0 + a;      // row of HT
+      const int b = 2 * cp, j = j0 + b;           // column pair of HT
+      if (m < N && j < ldHT) {
+        const float g0 = (j < Q) ? G[b][a] : 0.f, g1 = (j + 1 < Q) ? G[b + 1][a] : 0.f;
+        uint16_t p0[3], p1[3];
+        split3<PREC>(g0, p0[0], p0[1], p0[2]);
+        split3<PREC>(g1, p1[0], p1[1], p1[2]);
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+          *reinterpret_cast<uint32_t*>(HT + s * psT + static_cast<long long>(m) * ldHT + j) = static_cast<uint32_t>(p0[s]) | (static_cast<uint32_t>(p1[s]) << 16);
+      }
+    }
+  }
+}
+void launch_build_weights(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
+                          int self_offset, int world, MiningParams mp, RowArrays ra, int prec, uint16_t* H, long long ldH,
+                          uint16_t* HT, long long ldHT, cudaStream_t st) {
+  dim3 grid((N + 63) / 64, (Q + 63) / 64);
+#define NPAIR_LAUNCH_BW(P)                                                                                                   \
+  do {                                                                                                                       \
+    if (world == 1) build_weights_kernel<P, true><<<grid, 256, 0, st>>>(S, ldS, Q, N, lab_rows, lab_cols, self_offset, mp, ra, H, ldH, HT, ldHT); \
+    else build_weights_kernel<P, false><<<grid, 256, 0, st>>>(S, ldS, Q, N, lab_rows, lab_cols, self_offset, mp, ra, H, ldH, HT, ldHT);           \
+  } while (0)
+  if (prec == PREC_BF16) NPAIR_LAUNCH_BW(PREC_BF16);
+  else if (prec == PREC_FP16X2) NPAIR_LAUNCH_BW(PREC_FP16X2);
+  else NPAIR_LAUNCH_BW(PREC_BF16X3);
+#undef NPAIR_LAUNCH_BW
+}
+
+__global__ void axpy_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n, float a) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] += a * src[i];
+}
+void launch_axpy_rows(float* dst, const float* src, long long n, float a, cudaStream_t st) {
+  int nb = static_cast<int>((n + 255) / 256); if (nb > 148 * 8) nb = 148 * 8; if (nb < 1) nb = 1;
+  axpy_kernel<<<nb, 256, 0, st>>>(dst, src, n, a);
+}
+
+}  // namespace npair

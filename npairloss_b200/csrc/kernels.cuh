@@ -1,0 +1,77 @@
+// kernels.cuh -- device-side data structures shared by the memory-bound kernels and the host context.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace npair {
+
+// mining enums: caffe.proto:8-18
+enum { REGION_GLOBAL = 0, REGION_LOCAL = 1 };
+enum { M_HARD = 0, M_EASY = 1, M_RAND = 2, M_RELATIVE_HARD = 3, M_RELATIVE_EASY = 4 };
+
+// device error bits (the reference has undefined behaviour in these cases: SURVEY.md 9.4 Q5)
+enum { DERR_EMPTY_LIST = 1, DERR_POS_RANGE = 2 };
+
+// operand split formats (see gemm_tcgen05.cuh)
+enum { PREC_BF16X3 = 0, PREC_BF16 = 1, PREC_FP16X2 = 2 };
+
+// Global (per-rank-block) scalars living in device memory.
+struct BlockScalars {
+  unsigned long long n_same, n_diff;       // sizes of ident_global / diff_global (.cu:225-265)
+  float gmin_within, gmax_within;          // min / max over all same-label pairs of the block
+  float gmax_between;                      // max over all diff-label pairs (diff_global.back(), .cu:296)
+  float posi_global, nega_global;          // GLOBAL-region thresholds (valid when the region is GLOBAL)
+  int err;                                 // DERR_* bits
+  // radix-select state, one per side (0 = AP over same pairs, 1 = AN over diff pairs)
+  unsigned long long sel_rank[2];          // remaining 0-based rank inside the current prefix bucket
+  uint32_t sel_prefix[2];                  // ordered-uint prefix decided so far
+  uint32_t sel_mask[2];                    // which bits of the prefix are decided
+  int sel_active[2];                       // 1 while a GLOBAL relative select is in flight
+  float asum;                              // sum |x| over the local features (.cu:400)
+  float x_absmax;                          // max |x| over x_total (operand pre-scale for PREC_FP16X2)
+  float x_scale, x_inv_scale;              // power of two s.t. max|x*scale| in [0.5,1]; 1 for other precisions
+};
+
+struct MiningParams {
+  int ap_region, ap_method, an_region, an_method;
+  float margin_ident, margin_diff, identsn, diffsn;
+};
+
+struct RowArrays {
+  // statistics written by the sim-GEMM epilogue (ordered-uint encoded)
+  uint32_t *st_minw, *st_maxw, *st_maxb, *st_maxall;
+  int* cnt_same;
+  // thresholds WITHOUT margin (posi_thr / nega_thr of .cu:275-337)
+  float *posi_thr, *nega_thr;
+  // forward row results
+  float *A, *T, *logv;
+  int* hits;                 // [3][Q] retrieval hit flags for k=1,5,10
+  // row scalars consumed by the backward weight builder
+  float *rs_maxall, *rs_tp, *rs_tn, *rs_cA, *rs_cT;
+};
+
+// launchers (kernels.cu)
+void launch_absmax_asum(const float* x_local, long long n_local, const float* x_total, long long n_total,
+                        float* partial /*[2*1024]*/, BlockScalars* bs, int want_scale, cudaStream_t st);
+void launch_split(const float* x_total, int N, int D, int prec, const BlockScalars* bs,
+                  uint16_t* Xs, long long ldXs /*Dp*/, uint16_t* XsT, long long ldXsT /*Np*/,
+                  uint16_t* XlT, long long ldXlT /*Qp, or 0*/, int row0_local, int Q, cudaStream_t st);
+void launch_init_stats(RowArrays ra, int Q, BlockScalars* bs, cudaStream_t st);
+void launch_row_stats_ref(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
+                          int self_offset, RowArrays ra, cudaStream_t st);
+void launch_thresholds(RowArrays ra, int Q, int N, MiningParams mp, BlockScalars* bs, cudaStream_t st);
+void launch_local_select(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
+                         int self_offset, int side /*0 AP same, 1 AN diff*/, float sn, RowArrays ra, BlockScalars* bs,
+                         cudaStream_t st);
+void launch_global_select(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
+                          int self_offset, int side, float sn, RowArrays ra, unsigned long long* hist /*[2048]*/,
+                          BlockScalars* bs, cudaStream_t st);
+void launch_lse_rows(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
+                     int self_offset, MiningParams mp, RowArrays ra, cudaStream_t st);
+void launch_finalize(RowArrays ra, int Q, int num_tops, const BlockScalars* bs, float* tops_dev /*[5]+err*/, cudaStream_t st);
+void launch_build_weights(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
+                          int self_offset, int world, MiningParams mp, RowArrays ra, int prec,
+                          uint16_t* H, long long ldH /*Np*/, uint16_t* HT, long long ldHT /*Qp*/, cudaStream_t st);
+void launch_axpy_rows(float* dst, const float* src, long long n, float a, cudaStream_t st);
+
+}  // namespace npair

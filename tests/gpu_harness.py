@@ -1,0 +1,81 @@
+"""Shared helpers for the GPU parity tests: run the CUDA path through the C ABI and compare with the oracle.
+
+Two-level parity (SURVEY.md section 7 "hard parts"): mining is discontinuous in S, so
+  L1: the GPU similarity matrix vs. the oracle's (tolerance by operand precision), and
+  L2: the oracle re-run on the GPU's OWN S (S_inject) must give the same thresholds / loss / tops / gradient.
+"""
+import numpy as np
+import torch
+
+from npairloss_b200 import capi
+
+# |S_gpu - S_oracle| bound for unit-norm rows, per operand precision
+S_TOL = {capi.PREC_FP32_BF16X3: 2e-6, capi.PREC_FP32_FP16X2: 2e-6, capi.PREC_BF16: 2e-2}
+# normwise relative gradient bound at level 2
+G_TOL = {capi.PREC_FP32_BF16X3: 1e-5, capi.PREC_FP32_FP16X2: 1e-5, capi.PREC_BF16: 2e-2}
+
+
+def gpu_step_world(x, lab, Q, world, mining, prec, backend, loss_weight=1.0, num_tops=5, want_grad=True):
+    """Emulates every rank on one GPU through the external-collectives API.
+    Returns dict(tops[world,5], dx[N,D], S[N,N], posi[N], nega[N])."""
+    N, D = x.shape
+    dev = torch.device("cuda:0")
+    xt = torch.from_numpy(x).to(dev).contiguous()
+    lt = torch.from_numpy(lab).to(dev).contiguous()
+    tops = np.zeros((world, 5), dtype=np.float32)
+    S = np.zeros((N, N), dtype=np.float32)
+    posi = np.zeros(N, dtype=np.float32)
+    nega = np.zeros(N, dtype=np.float32)
+    local = torch.zeros((N, D), dtype=torch.float32, device=dev)
+    total = torch.zeros((N, D), dtype=torch.float32, device=dev)
+    for r in range(world):
+        cfg = capi.make_config(Q, D, world=world, rank=r, num_tops=num_tops, sim_precision=prec, gemm_backend=backend, **mining)
+        ctx = capi.Context(cfg)
+        try:
+            tops[r] = ctx.forward_gathered(xt, lt)
+            S[r * Q:(r + 1) * Q] = ctx.debug_read(0, Q * N).reshape(Q, N)
+            posi[r * Q:(r + 1) * Q] = ctx.debug_read(1, Q)
+            nega[r * Q:(r + 1) * Q] = ctx.debug_read(2, Q)
+            if want_grad:
+                lh = torch.full((Q, D), float("nan"), dtype=torch.float32, device=dev)
+                if world > 1:
+                    th = torch.full((N, D), float("nan"), dtype=torch.float32, device=dev)
+                    ctx.backward_partial(loss_weight, lh, th)
+                    total += th
+                else:
+                    ctx.backward_partial(loss_weight, lh, None)
+                local[r * Q:(r + 1) * Q] = lh
+        finally:
+            ctx.close()
+    torch.cuda.synchronize()
+    dx = (local + total).cpu().numpy() if want_grad else None
+    return dict(tops=tops, dx=dx, S=S, posi=posi, nega=nega)
+
+
+def check_parity(oracle, x, lab, Q, world, mining, prec, backend, loss_weight=1.0, num_tops=5, tag=""):
+    N, D = x.shape
+    g = gpu_step_world(x, lab, Q, world, mining, prec, backend, loss_weight, num_tops)
+    cfg = oracle.make_config(Q, D, world=world, num_tops=num_tops, faithful_sorts=0, **mining)
+    # ---- level 1: similarities ----
+    S_ref = (x.astype(np.float64) @ x.astype(np.float64).T).astype(np.float32)
+    s_err = float(np.abs(g["S"] - S_ref).max())
+    assert s_err <= S_TOL[prec], f"{tag} L1 S error {s_err:.3e}"
+    # ---- level 2: oracle on the GPU's own S ----
+    tops_o, dx_o = oracle.step_world(x, lab, cfg, loss_weight, S_inject_all=g["S"])
+    for r in range(world):
+        _, st = oracle.forward(x, lab, oracle.make_config(Q, D, world=world, rank=r, num_tops=num_tops, faithful_sorts=0, **mining),
+                               S_inject=g["S"][r * Q:(r + 1) * Q])
+        np.testing.assert_array_equal(g["posi"][r * Q:(r + 1) * Q], st["posi_thr"], err_msg=f"{tag} posi_thr rank {r}")
+        np.testing.assert_array_equal(g["nega"][r * Q:(r + 1) * Q], st["nega_thr"], err_msg=f"{tag} nega_thr rank {r}")
+    # loss: 1e-5 relative (north star); retrieval counters: discrete, allow one expf-rounding tie flip per 1000 rows
+    np.testing.assert_allclose(g["tops"][:, 0], tops_o[:, 0], rtol=1e-5, atol=1e-6, err_msg=f"{tag} loss")
+    n_ret = max(0, num_tops - 2)
+    if n_ret:
+        d = np.abs(g["tops"][:, 1:1 + n_ret] - tops_o[:, 1:1 + n_ret]) * Q
+        assert d.max() <= max(1.0, Q / 1000.0) + 1e-3, f"{tag} retrieval counters differ by {d.max()} rows"
+    np.testing.assert_allclose(g["tops"][:, num_tops - 1], tops_o[:, num_tops - 1], rtol=2e-6, err_msg=f"{tag} asum")
+    gn = float(np.linalg.norm(dx_o))
+    ge = float(np.linalg.norm(g["dx"] - dx_o))
+    assert np.isfinite(g["dx"]).all(), f"{tag} non-finite gradient"
+    assert ge <= G_TOL[prec] * max(gn, 1e-20), f"{tag} gradient normwise error {ge / max(gn, 1e-20):.3e}"
+    return dict(s_err=s_err, g_rel=ge / max(gn, 1e-20), loss=float(g["tops"][0, 0]))

@@ -1,0 +1,143 @@
+"""GPU parity tests (run on a B200 via `pytest -m gpu`): the CUDA path through the C ABI vs the CPU oracle."""
+import itertools
+
+import numpy as np
+import pytest
+
+from npairloss_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+PRECS = [capi.PREC_FP32_FP16X2, capi.PREC_FP32_BF16X3, capi.PREC_BF16]
+PREC_NAME = {0: "bf16x3", 1: "bf16", 2: "fp16x2"}
+
+
+@pytest.fixture(scope="module")
+def cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a B200"
+    assert torch.cuda.get_device_capability(0)[0] == 10
+    return torch
+
+
+@pytest.mark.parametrize("backend", [capi.GEMM_SIMT_CHECK, capi.GEMM_TCGEN05])
+@pytest.mark.parametrize("prec", PRECS)
+def test_split_gemm_vs_fp64(cuda, prec, backend):
+    torch = cuda
+    tol = {capi.PREC_FP32_BF16X3: 3e-6, capi.PREC_FP32_FP16X2: 3e-6, capi.PREC_BF16: 3e-2}[prec]
+    g = torch.Generator(device="cpu").manual_seed(5)
+    for (M, Nn, K) in [(128, 256, 64), (128, 256, 128), (256, 512, 512), (120, 120, 100), (1, 7, 3), (300, 1000, 1024), (129, 257, 65)]:
+        A = torch.randn(M, K, generator=g)
+        B = torch.randn(Nn, K, generator=g)
+        A = A / A.norm(dim=1, keepdim=True)
+        B = B / B.norm(dim=1, keepdim=True)
+        C = capi.debug_gemm(prec, backend, A.cuda(), B.cuda()).cpu()
+        ref = (A.double() @ B.double().T)
+        err = (C.double() - ref).abs().max().item()
+        assert err <= tol, f"prec={PREC_NAME[prec]} backend={backend} shape={(M, Nn, K)} err={err:.3e}"
+
+
+def test_split_gemm_large_dynamic_range(cuda):
+    """bf16x3 keeps fp32 accuracy for un-normalised operands; fp16x2 relies on the power-of-two pre-scale."""
+    torch = cuda
+    g = torch.Generator(device="cpu").manual_seed(9)
+    A = torch.randn(256, 256, generator=g) * 37.0
+    B = torch.randn(512, 256, generator=g) * 37.0
+    ref = A.double() @ B.double().T
+    scale = ref.abs().max().item()
+    for prec in (capi.PREC_FP32_BF16X3, capi.PREC_FP32_FP16X2):
+        C = capi.debug_gemm(prec, capi.GEMM_TCGEN05, A.cuda(), B.cuda()).cpu().double()
+        assert (C - ref).abs().max().item() <= 4e-6 * scale
+
+
+@pytest.mark.parametrize("backend", [capi.GEMM_SIMT_CHECK, capi.GEMM_TCGEN05])
+def test_kat_survey_9_3(cuda, oracle, backend):
+    from gpu_harness import gpu_step_world
+    x = np.array([[1, 0], [1, 0], [0, 1], [0, 1]], dtype=np.float32)
+    lab = np.array([0, 0, 1, 1], dtype=np.float32)
+    g = gpu_step_world(x, lab, 4, 1, synth.DEFAULT_MINING, capi.PREC_FP32_BF16X3, backend)
+    assert g["tops"][0, 0] == pytest.approx(0.5514447139, rel=1e-6)
+    assert list(g["tops"][0, 1:4]) == [1.0, 1.0, 1.0]
+    assert g["tops"][0, 4] == pytest.approx(1.0, rel=1e-6)
+    gg = 0.1059707788
+    np.testing.assert_allclose(g["dx"], np.array([[-gg, gg], [-gg, gg], [gg, -gg], [gg, -gg]], dtype=np.float32), rtol=1e-5)
+
+
+@pytest.mark.parametrize("backend", [capi.GEMM_SIMT_CHECK, capi.GEMM_TCGEN05])
+@pytest.mark.parametrize("world", [1, 2])
+def test_all_mining_modes_small(cuda, oracle, world, backend):
+    """Every (region, method) combination, both GEMM engines, emulated ranks."""
+    from gpu_harness import check_parity
+    Q, D = 48, 40
+    x, lab = synth.make_inputs(Q * world, D, seed=100 + world, imgs_per_class=3, noise=0.7)
+    for apR, apM, anR, anM in itertools.product([0, 1], range(5), [0, 1], range(5)):
+        mining = dict(margin_ident=0.02, margin_diff=-0.03, identsn=-0.4, diffsn=-0.3,
+                      ap_region=apR, ap_method=apM, an_region=anR, an_method=anM)
+        check_parity(oracle, x, lab, Q, world, mining, capi.PREC_FP32_FP16X2, backend, loss_weight=0.7,
+                     tag=f"w{world} b{backend} {apR}{apM}{anR}{anM}")
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("name", ["C1", "C2"])
+def test_baseline_configs_small(cuda, oracle, name, prec):
+    from gpu_harness import check_parity
+    c = synth.CONFIGS[name]
+    x, lab = synth.config_inputs(name)
+    r = check_parity(oracle, x, lab, c["B"], 1, c["mining"], prec, capi.GEMM_TCGEN05, tag=f"{name} {PREC_NAME[prec]}")
+    print(name, PREC_NAME[prec], r)
+
+
+@pytest.mark.parametrize("mining_name", ["usage", "default", "local_rel"])
+@pytest.mark.parametrize("shape", [(120, 1, 1024), (30, 2, 64), (256, 4, 128), (1000, 1, 200)])
+def test_odd_shapes_and_usage_block(cuda, oracle, shape, mining_name):
+    """Reference batch sizes (usage/def.prototxt: 120 and 30 per rank), ragged tiles, the usage-block mining."""
+    from gpu_harness import check_parity
+    Q, world, D = shape
+    mining = {"usage": synth.USAGE_MINING, "default": synth.DEFAULT_MINING,
+              "local_rel": dict(synth.DEFAULT_MINING, ap_method=3, an_method=3, identsn=0.0, diffsn=-0.3, margin_diff=-0.01)}[mining_name]
+    x, lab = synth.make_inputs(Q * world, D, seed=Q + world + D, imgs_per_class=2)
+    check_parity(oracle, x, lab, Q, world, mining, capi.PREC_FP32_FP16X2, capi.GEMM_TCGEN05, tag=f"{shape} {mining_name}")
+
+
+def test_num_tops_layout(cuda, oracle):
+    from gpu_harness import gpu_step_world
+    Q, D = 64, 32
+    x, lab = synth.make_inputs(Q, D, seed=4)
+    t5 = gpu_step_world(x, lab, Q, 1, synth.DEFAULT_MINING, capi.PREC_FP32_FP16X2, capi.GEMM_TCGEN05, want_grad=False)["tops"][0]
+    for nt in (1, 2, 3, 4):
+        t = gpu_step_world(x, lab, Q, 1, synth.DEFAULT_MINING, capi.PREC_FP32_FP16X2, capi.GEMM_TCGEN05, num_tops=nt, want_grad=False)["tops"][0]
+        exp = np.zeros(5, dtype=np.float32)
+        exp[0] = t5[0]
+        for k in range(1, nt - 1):
+            exp[k] = t5[k]
+        exp[nt - 1] = t5[4]          # last top is always the asum (overwrites the loss when nt == 1)
+        np.testing.assert_allclose(t, exp, rtol=1e-6)
+
+
+def test_error_codes(cuda):
+    import torch
+    Q, D = 16, 8
+    x, lab = synth.make_inputs(Q, D, seed=1)
+    xt, lt = torch.from_numpy(x).cuda(), torch.from_numpy(lab).cuda()
+    ctx = capi.Context(capi.make_config(Q, D, ap_method=capi.RELATIVE_HARD))      # identsn=-1 -> pos=-1
+    with pytest.raises(capi.NpairError) as e:
+        ctx.forward(xt, lt)
+    assert e.value.code == -5
+    ctx.close()
+    ctx = capi.Context(capi.make_config(Q, D, an_region=capi.GLOBAL, an_method=capi.HARD))
+    with pytest.raises(capi.NpairError) as e:
+        ctx.forward(xt, torch.arange(Q, dtype=torch.float32).cuda())                 # no positive pair
+    assert e.value.code == -4
+    with pytest.raises(capi.NpairError) as e:
+        ctx.backward(1.0, torch.empty_like(xt))                                      # no successful forward
+    assert e.value.code == -6
+    ctx.close()
+
+
+def test_medium_headline_mining_fp32_faithful(cuda, oracle):
+    """B=2048, D=512 with the usage-block mining in both fp32-faithful modes."""
+    from gpu_harness import check_parity
+    x, lab = synth.make_inputs(2048, 512, seed=20171225 + 5)
+    for prec in (capi.PREC_FP32_FP16X2, capi.PREC_FP32_BF16X3):
+        r = check_parity(oracle, x, lab, 2048, 1, synth.USAGE_MINING, prec, capi.GEMM_TCGEN05, tag=f"B2048 {PREC_NAME[prec]}")
+        print("B2048", PREC_NAME[prec], r)
