@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- N-pair fwd+bwd samples/sec at B=8192, D=512 on 1/2/4/8 B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp16x2|bf16x3|bf16]
+
+One "step" = Forward_gpu + Backward_gpu of the NPairMultiClassLoss layer over one batch of synthetic L2-normalised
+embeddings (B/2 classes x 2 images, usage-block mining of usage/def.prototxt:137-146), the global batch B=8192
+sharded by anchor over the N ranks (strong scaling: Q = B/N rows per rank, all N columns).
+
+  value    : whole-job samples/sec with the inputs resident in HBM, through the C ABI (npair_forward + npair_backward,
+             includes the all-gather / reduce-scatter and the five host scalars), CUDA-event timed, max over ranks.
+  e2e      : same metric through the reference-facing plugin surface (the Caffe-style layer in npairloss_b200/caffe_shim)
+             with HOST bottoms: H2D of features+labels from pinned memory and D2H of the gradient and tops inside
+             the timed region.
+  roofline : dominant kernel (similarity GEMM with fused statistics), live CUDA-event duration from a profiled pass.
+  cpu_baseline : the oracle (a "port": the reference has no CPU path and cannot be compiled here) on a bounded sample.
+
+--impl reference times the CPU oracle (faithful sorts, all host threads) on the same config; rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "N-pair fwd+bwd samples/sec at B=8192,D=512"
+PRECS = {"bf16x3": 0, "bf16": 1, "fp16x2": 2}
+MMA_PASSES = {"bf16x3": 6, "bf16": 1, "fp16x2": 3}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    sm_max_mhz=d.get("sm_max_mhz"), source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, sm_max_mhz=1965.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+
+
+def run_reference(args, B, D, mining, noise):
+    """CPU baseline arm: the oracle with the reference's unconditional sorts on all host threads.  Each step is the
+    rank-0 block of the 8-way anchor sharding (1024 anchors x 8192 database), a bounded sample of the same workload."""
+    from npairloss_b200 import synth
+    from oracle import oracle_lib as o
+    o.build()
+    x, lab = synth.make_inputs(B, D, 20171225 + 5, noise=noise)
+    world_s = 8
+    Qs = B // world_s
+    cores = os.cpu_count() or 1
+    cfg = o.make_config(Qs, D, world=world_s, rank=0, accum_double=0, faithful_sorts=1, num_threads=0, **mining)
+    L = o.lib()
+    buf = np.zeros(L.npo_state_floats(C.byref(cfg)), dtype=np.float32)
+    st = o.NpoState()
+    L.npo_state_bind(C.byref(cfg), o._fp(buf), C.byref(st))
+    tops = np.zeros(5, np.float32)
+    ld = np.zeros((Qs, D), np.float32)
+    td = np.zeros((B, D), np.float32)
+
+    def step():
+        e = L.npo_forward(C.byref(cfg), o._fp(x), o._fp(lab), None, C.byref(st), o._fp(tops))
+        e2 = L.npo_backward_partial(C.byref(cfg), o._fp(x), C.byref(st), C.c_float(1.0), o._fp(ld), o._fp(td))
+        assert e == 0 and e2 == 0
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = Qs / dt
+    sample = f"rank-0 block of the 8-way anchor sharding: {Qs} anchors x {B} database x D={D}, faithful sorts, fp32 accumulate"
+    out = {"metric": METRIC, "impl": "reference", "value": val, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"HL: B={B}, D={D}, {B // 2} classes x 2, usage-block mining (AP GLOBAL RELATIVE_HARD, AN LOCAL HARD -0.05)",
+                      "global_batch": B, "feature_dim": D, "noise": noise},
+           "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="fp16x2", choices=list(PRECS))
+    ap.add_argument("--batch", type=int, default=8192)
+    ap.add_argument("--dim", type=int, default=512)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    from npairloss_b200 import synth
+    B, D = args.batch, args.dim
+    mining = dict(synth.USAGE_MINING)
+    noise = synth.CONFIGS["HL"]["noise"]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if args.steps == 50 and args.warmup == 10:      # defaults are sized for the GPU arm; keep the CPU arm to minutes
+            args.steps, args.warmup = 3, 1
+        if rank == 0:
+            run_reference(args, B, D, mining, noise)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from npairloss_b200 import capi
+
+    assert torch.cuda.is_available(), "bench.py needs a B200 (the product path has no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    assert B % world == 0
+    Q = B // world
+    peaks = load_peaks()
+
+    # identical bytes on every rank; each rank keeps its own row block
+    x, lab = synth.make_inputs(B, D, 20171225 + 5, noise=noise)
+    xl = np.ascontiguousarray(x[rank * Q:(rank + 1) * Q])
+    ll = np.ascontiguousarray(lab[rank * Q:(rank + 1) * Q])
+
+    nccl_id = None
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(capi.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        nccl_id = bytes(idt.cpu().numpy().tobytes())
+    cfg = capi.make_config(Q, D, world=world, rank=rank, sim_precision=PRECS[args.precision], device=local_rank, **mining)
+    ctx = capi.Context(cfg, nccl_id)
+
+    stream = torch.cuda.current_stream()
+    d_x = torch.from_numpy(xl).to(dev)
+    d_l = torch.from_numpy(ll).to(dev)
+    d_g = torch.empty_like(d_x)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        tops = ctx.forward(d_x, d_l)
+        ctx.backward(1.0, d_g)
+        return tops
+
+    # ---------------- device-resident timed region ----------------
+    for _ in range(args.warmup):
+        tops = step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        tops = step_device()
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms_step = ms_t.item() / args.steps
+    value = B / (ms_step * 1e-3)
+
+    # ---------------- end-to-end through the plugin surface with host buffers ----------------
+    h_x = torch.from_numpy(xl).pin_memory()
+    h_l = torch.from_numpy(ll).pin_memory()
+    h_g = torch.empty((Q, D), dtype=torch.float32).pin_memory()
+    e2e_api = "C ABI + pinned cudaMemcpyAsync"
+    layer = None
+    try:
+        from npairloss_b200 import caffe_layer
+        layer = caffe_layer.Layer(Q, D, world=world, rank=rank, mining=mining, precision=PRECS[args.precision],
+                                  nccl_ctx=ctx, device=local_rank)
+        e2e_api = "caffe_shim NPairMultiClassLossLayer::Forward/Backward on host Blobs"
+    except Exception:
+        layer = None
+
+    def step_e2e():
+        if layer is not None:
+            return layer.step_host(h_x, h_l, h_g)
+        d_x.copy_(h_x, non_blocking=True)
+        d_l.copy_(h_l, non_blocking=True)
+        t = ctx.forward(d_x, d_l)
+        ctx.backward(1.0, d_g)
+        h_g.copy_(d_g, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return t
+
+    for _ in range(max(3, args.warmup // 2)):
+        tops_e = step_e2e()
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        tops_e = step_e2e()
+    e1.record(stream)
+    barrier()
+    ms_e = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
+    e2e_value = B / (ms_e.item() / args.steps * 1e-3)
+    h2d = Q * D * 4 + Q * 4
+    d2h = Q * D * 4 + 5 * 4
+
+    # ---------------- profiled pass: per-phase CUDA events (roofline of the dominant kernel) ----------------
+    ctx.profile_enable(True)
+    phases = np.zeros(8)
+    nprof = min(args.steps, 10)
+    for _ in range(nprof):
+        step_device()
+        phases += np.array(ctx.profile_read())
+    phases /= nprof
+    ctx.profile_enable(False)
+    N = B
+    sim_ms = float(phases[2])
+    flops_alg = 2.0 * Q * N * D                                   # one similarity contraction per launch
+    achieved_tf = flops_alg / (sim_ms * 1e-3) / 1e12 if sim_ms > 0 else 0.0
+    peak_tf = peaks["tf_sustained"]
+    roofline = {"kernel": "split_gemm_kernel<EPI_SIM> (tcgen05 similarity GEMM + fused row statistics)", "bound": "tensor",
+                "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                "mma_passes": MMA_PASSES[args.precision], "frac_of_issued_mma": achieved_tf * MMA_PASSES[args.precision] / peak_tf,
+                "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
+                "duration_ms": sim_ms, "traffic": None,
+                "note": "achieved = algorithmic 2*Q*N*D flops / live CUDA-event duration; the fp32-faithful modes issue mma_passes "
+                        "bf16-rate MMA passes per algorithmic flop, frac_of_issued_mma counts them"}
+    phase_names = ["collectives", "operand_prep", "sim_gemm", "thresholds_select", "row_pass_finalize", "weight_build", "grad_gemm", "grad_gemm_T"]
+    phase_ms = {n: float(v) for n, v in zip(phase_names, phases)}
+    # memory-bound kernels: algorithmic bytes = one fp32 pass over the Q x N block
+    sbytes = 4.0 * Q * N
+    hbm = {"row_pass_GBs": sbytes / (phases[4] * 1e-3) / 1e9 if phases[4] > 0 else None,
+           "weight_build_GBs": sbytes / (phases[5] * 1e-3) / 1e9 if phases[5] > 0 else None,
+           "hbm_peak_GBs": peaks["hbm_gbs"]}
+
+    # kernels launched per step by OUR library (counted from the launch sequence in ctx.cu)
+    launches = 2 + 1 + 1 + 1 + 1 + 1 + 1 + 1 + 1           # absmax x2, split, init, sim gemm, thresholds, row pass, finalize, build, grad gemm
+    if world > 1:
+        launches += 1                                       # transposed gradient GEMM
+    gpu_launches = launches * args.steps
+
+    # ---------------- CPU baseline (rank 0, bounded sample) ----------------
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import oracle_lib as o
+        o.build()
+        world_s = 8
+        Qs = B // world_s
+        ocfg = o.make_config(Qs, D, world=world_s, rank=0, accum_double=0, faithful_sorts=1, num_threads=0, **mining)
+        L = o.lib()
+        buf = np.zeros(L.npo_state_floats(C.byref(ocfg)), dtype=np.float32)
+        st = o.NpoState()
+        L.npo_state_bind(C.byref(ocfg), o._fp(buf), C.byref(st))
+        t5 = np.zeros(5, np.float32)
+        ld = np.zeros((Qs, D), np.float32)
+        td = np.zeros((B, D), np.float32)
+        reps, t0 = 0, time.perf_counter()
+        while reps < 2 or (time.perf_counter() - t0 < 10 and reps < 8):
+            assert L.npo_forward(C.byref(ocfg), o._fp(x), o._fp(lab), None, C.byref(st), o._fp(t5)) == 0
+            assert L.npo_backward_partial(C.byref(ocfg), o._fp(x), C.byref(st), C.c_float(1.0), o._fp(ld), o._fp(td)) == 0
+            reps += 1
+        dt = (time.perf_counter() - t0) / reps
+        cpu = {"value": Qs / dt, "unit": "samples/s", "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": f"rank-0 block of the 8-way anchor sharding: {Qs} anchors x {B} database x D={D}, {reps} reps, "
+                         "faithful unconditional sorts, fp32 accumulate, OpenMP on all cores"}
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+               "dtype": {"fp16x2": "f32 (3-pass fp16-split tcgen05, f32 accumulate)", "bf16x3": "f32 (6-pass bf16-split tcgen05, f32 accumulate)",
+                         "bf16": "bf16 (f32 accumulate)"}[args.precision],
+               "data": "synthetic",
+               "config": {"workload": f"HL: B={B}, D={D}, {B // 2} classes x 2, usage-block mining (AP GLOBAL RELATIVE_HARD identsn -0.0, "
+                                      "AN LOCAL HARD margin_diff -0.05), loss_weight 1", "global_batch": B, "feature_dim": D,
+                          "rows_per_rank": Q, "sharding": f"anchor-sharded x{world}", "precision": args.precision, "noise": noise,
+                          "l2": f"not flushed: per-step working set (S {4 * Q * N / 1e6:.0f} MB fp32 + split weights) exceeds the 126 MB L2"},
+               "clocks": clocks, "roofline": roofline, "phase_ms": phase_ms, "hbm_kernels": hbm,
+               "cpu_baseline": cpu,
+               "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": e2e_api},
+               "gpu_launches": gpu_launches,
+               "tops": {"loss": tops[0], "top1": tops[1], "top5": tops[2], "top10": tops[3], "feature_asum": tops[4]}}
+        print(json.dumps(out))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

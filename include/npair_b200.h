@@ -119,6 +119,12 @@ int npair_backward_partial(npair_ctx* ctx, float loss_weight, float* d_local_hal
 const char* npair_last_error(const npair_ctx* ctx);   /* ctx may be NULL: last create() error of this thread */
 const char* npair_version(void);
 
+/* Per-phase CUDA-event timing on the caller's stream (used by bench.py for the roofline of the dominant kernel).
+ * ms_out[8]: 0 collectives  1 operand prep  2 similarity GEMM (+fused statistics)  3 thresholds / radix selects
+ *            4 forward row pass + finalize  5 backward weight builder  6 gradient GEMM  7 transposed gradient GEMM */
+int npair_profile_enable(npair_ctx* ctx, int on);
+int npair_profile_read(npair_ctx* ctx, float ms_out[8]);
+
 /* Introspection for parity tests (copies device scratch to host; synchronises the context's last stream).
  * which: 0 = S (Q x N similarities, row-major, ld = N)      1 = posi_thr[Q]   2 = nega_thr[Q]
  *        3 = min_within[Q]  4 = max_between[Q]  5 = max_all[Q]  6 = A[Q]  7 = T[Q]  8 = same-label count[Q]

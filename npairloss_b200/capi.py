@@ -25,7 +25,7 @@ class NpairConfig(C.Structure):
 
 
 EXPORTS = ["npair_config_default", "npair_workspace_bytes", "npair_nccl_unique_id", "npair_create", "npair_create_with_comm",
-           "npair_destroy", "npair_forward", "npair_backward", "npair_forward_gathered", "npair_backward_partial", "npair_last_error", "npair_version", "npair_debug_read",
+           "npair_destroy", "npair_forward", "npair_backward", "npair_forward_gathered", "npair_backward_partial", "npair_profile_enable", "npair_profile_read", "npair_last_error", "npair_version", "npair_debug_read",
            "npair_debug_gemm"]
 
 _LIB = None
@@ -58,6 +58,8 @@ def lib():
         L.npair_backward.argtypes = [vp, C.c_float, vp, vp]
         L.npair_forward_gathered.argtypes = [vp, vp, vp, fp, vp]
         L.npair_backward_partial.argtypes = [vp, C.c_float, vp, vp, vp]
+        L.npair_profile_enable.argtypes = [vp, C.c_int]
+        L.npair_profile_read.argtypes = [vp, fp]
         L.npair_last_error.argtypes = [vp]
         L.npair_last_error.restype = C.c_char_p
         L.npair_version.restype = C.c_char_p
@@ -142,6 +144,14 @@ class Context:
         self._check(lib().npair_backward_partial(self._h, C.c_float(loss_weight), local_half.data_ptr(),
                                                  total_half.data_ptr() if total_half is not None else None,
                                                  torch.cuda.current_stream().cuda_stream))
+
+    def profile_enable(self, on=True):
+        self._check(lib().npair_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self):
+        ms = (C.c_float * 8)()
+        self._check(lib().npair_profile_read(self._h, ms))
+        return [ms[i] for i in range(8)]
 
     def debug_read(self, which: int, n: int):
         import numpy as np

@@ -198,6 +198,8 @@ static inline long long round_up(long long v, long long m) { return (v + m - 1) 
 
 using namespace npair;
 
+#define NPAIR_PROF_PHASES 8
+
 // ------------------------------------------------------------------------------------------------ context
 struct npair_ctx {
   npair_config cfg;
@@ -226,6 +228,21 @@ struct npair_ctx {
   cudaStream_t last_stream = nullptr;
   size_t bytes = 0;
   std::string err;
+  // optional per-phase CUDA-event timing (npair_profile_enable)
+  bool prof = false;
+  cudaEvent_t ev[NPAIR_PROF_PHASES + 1][2];
+  bool ev_made = false;
+  bool ev_used[NPAIR_PROF_PHASES] = {};
+};
+
+struct PhaseTimer {
+  npair_ctx* c; int ph; cudaStream_t st;
+  PhaseTimer(npair_ctx* c_, int ph_, cudaStream_t st_) : c(c_), ph(ph_), st(st_) {
+    if (c->prof) { cudaEventRecord(c->ev[ph][0], st); }
+  }
+  ~PhaseTimer() {
+    if (c->prof) { cudaEventRecord(c->ev[ph][1], st); c->ev_used[ph] = true; }
+  }
 };
 
 #define CUDA_TRY(ctx, call)                                                                              \
@@ -307,6 +324,7 @@ void npair_destroy(npair_ctx* c) {
   cudaFree(c->Xtot_buf); cudaFree(c->labtot_buf); cudaFree(c->S); cudaFree(c->Xs); cudaFree(c->XsT); cudaFree(c->XlT);
   cudaFree(c->H); cudaFree(c->HT); cudaFree(c->OUT2); cudaFree(c->row_block); cudaFree(c->bs); cudaFree(c->partial); cudaFree(c->ghist);
   if (c->tops_pinned) cudaFreeHost(c->tops_pinned);
+  if (c->ev_made) for (int i = 0; i < NPAIR_PROF_PHASES; ++i) { cudaEventDestroy(c->ev[i][0]); cudaEventDestroy(c->ev[i][1]); }
   delete c;
 }
 
@@ -447,6 +465,7 @@ int npair_forward(npair_ctx* c, const float* d_feat, const float* d_label, float
   // ---- GatherFeatureAndLabel (.cu:17-43): one NCCL group, device to device over NVLink ----
   if (c->world > 1) {
     if (!c->comm) { c->err = "context was created without a communicator: use npair_forward_gathered"; return NPAIR_E_STATE; }
+    PhaseTimer pt(c, 0, st);
     NcclApi* api = nccl_api();
     int r = api->GroupStart();
     if (r == 0) r = api->AllGather(d_feat, c->Xtot_buf, static_cast<size_t>(Q) * D, NCCL_FLOAT32, c->comm, st);
@@ -477,10 +496,13 @@ static int forward_impl(npair_ctx* c, const float* d_feat, const float* d_label,
   c->cur_feat = d_feat; c->cur_label = d_label;
   const int self_off = c->rank * Q;
   // ---- operand preparation: |x| sum (top asum, .cu:400), power-of-two pre-scale, split to tensor-core pieces ----
-  launch_absmax_asum(d_feat, static_cast<long long>(Q) * D, c->x_total, static_cast<long long>(N) * D, c->partial, c->bs,
-                     c->prec == PREC_FP16X2 ? 1 : 0, st);
-  launch_split(c->x_total, N, D, c->prec, c->bs, c->Xs, c->Dp, c->XsT, c->Np, c->XlT, c->Qp, self_off, Q, st);
-  launch_init_stats(c->ra, Q, c->bs, st);
+  {
+    PhaseTimer pt(c, 1, st);
+    launch_absmax_asum(d_feat, static_cast<long long>(Q) * D, c->x_total, static_cast<long long>(N) * D, c->partial, c->bs,
+                       c->prec == PREC_FP16X2 ? 1 : 0, st);
+    launch_split(c->x_total, N, D, c->prec, c->bs, c->Xs, c->Dp, c->XsT, c->Np, c->XlT, c->Qp, self_off, Q, st);
+    launch_init_stats(c->ra, Q, c->bs, st);
+  }
   // ---- S = X_local . X_total^T (.cu:218) with fused masks + row statistics (.cu:44-66, :225-265) ----
   GemmParams gp; memset(&gp, 0, sizeof(gp));
   gp.M = Q; gp.Nn = N; gp.num_kblocks = static_cast<int>((D + c->bk - 1) / c->bk);
@@ -489,6 +511,7 @@ static int forward_impl(npair_ctx* c, const float* d_feat, const float* d_label,
   gp.lab_rows = d_label; gp.lab_cols = c->lab_total; gp.self_offset = self_off;
   gp.st_minw = c->ra.st_minw; gp.st_maxw = c->ra.st_maxw; gp.st_maxb = c->ra.st_maxb; gp.st_maxall = c->ra.st_maxall; gp.cnt_same = c->ra.cnt_same;
   if (c->cfg.gemm_backend == NPAIR_GEMM_TCGEN05) {
+    PhaseTimer pt(c, 2, st);
     CUDA_TRY(c, launch_split_gemm(c->prec, EPI_SIM, c->tm_simA, c->tm_simB, gp, c->sms, st));
   } else {
     CUDA_TRY(c, launch_simt_gemm(c->prec, EPI_SIM, c->Xs + static_cast<long long>(self_off) * c->Dp, c->Dp, static_cast<long long>(N) * c->Dp,
@@ -496,6 +519,8 @@ static int forward_impl(npair_ctx* c, const float* d_feat, const float* d_label,
     launch_row_stats_ref(c->S, c->ldS, Q, N, d_label, c->lab_total, self_off, c->ra, st);
   }
   // ---- thresholds (.cu:275-337) ----
+  {
+  PhaseTimer pt(c, 3, st);
   launch_thresholds(c->ra, Q, N, mp, c->bs, st);
   if (is_rel_m(mp.ap_method) && !sn_max(mp.identsn)) {
     if (mp.ap_region == NPAIR_LOCAL) launch_local_select(c->S, c->ldS, Q, N, d_label, c->lab_total, self_off, 0, mp.identsn, c->ra, c->bs, st);
@@ -505,9 +530,13 @@ static int forward_impl(npair_ctx* c, const float* d_feat, const float* d_label,
     if (mp.an_region == NPAIR_LOCAL) launch_local_select(c->S, c->ldS, Q, N, d_label, c->lab_total, self_off, 1, mp.diffsn, c->ra, c->bs, st);
     else launch_global_select(c->S, c->ldS, Q, N, d_label, c->lab_total, self_off, 1, mp.diffsn, c->ra, c->ghist, c->bs, st);
   }
+  }
   // ---- selection + counts + exp + masked sums + log + retrieval in one pass (.cu:343-398) ----
-  launch_lse_rows(c->S, c->ldS, Q, N, d_label, c->lab_total, self_off, mp, c->ra, st);
-  launch_finalize(c->ra, Q, c->cfg.num_tops, c->bs, c->tops_dev, st);
+  {
+    PhaseTimer pt(c, 4, st);
+    launch_lse_rows(c->S, c->ldS, Q, N, d_label, c->lab_total, self_off, mp, c->ra, st);
+    launch_finalize(c->ra, Q, c->cfg.num_tops, c->bs, c->tops_dev, st);
+  }
   CUDA_TRY(c, cudaGetLastError());
   CUDA_TRY(c, cudaStreamSynchronize(st));          // the reference also blocks here (host reads of loss/asum, .cu:384,400)
   const int derr = reinterpret_cast<int*>(c->tops_pinned)[5];
@@ -551,7 +580,10 @@ static int backward_impl(npair_ctx* c, float loss_weight, float* d_diff, float* 
   const MiningParams mp = mining_of(c->cfg);
   const int self_off = c->rank * Q;
   const float lw_over_q = loss_weight / static_cast<float>(Q);     // loss_weight / dot_normalizer (.cu:427,448)
-  launch_build_weights(c->S, c->ldS, Q, N, c->cur_label, c->lab_total, self_off, c->world, mp, c->ra, c->prec, c->H, c->Np, c->HT, c->Qp, st);
+  {
+    PhaseTimer pt(c, 5, st);
+    launch_build_weights(c->S, c->ldS, Q, N, c->cur_label, c->lab_total, self_off, c->world, mp, c->ra, c->prec, c->H, c->Np, c->HT, c->Qp, st);
+  }
   GemmParams gp; memset(&gp, 0, sizeof(gp));
   gp.dev_scale = &c->bs->x_inv_scale;
   const bool tc = c->cfg.gemm_backend == NPAIR_GEMM_TCGEN05;
@@ -560,9 +592,13 @@ static int backward_impl(npair_ctx* c, float loss_weight, float* d_diff, float* 
     gp.M = N; gp.Nn = D; gp.num_kblocks = static_cast<int>((Q + c->bk - 1) / c->bk);
     gp.tiles_m = (N + 127) / 128; gp.tiles_n = (D + 255) / 256;
     gp.out = d_total_ext ? d_total_ext : c->OUT2; gp.ldo = D; gp.alpha = 0.5f * (1.f / static_cast<float>(c->world)) * lw_over_q; gp.beta = 0.f;
-    if (tc) CUDA_TRY(c, launch_split_gemm(c->prec, EPI_OUT, c->tm_b2A, c->tm_b2B, gp, c->sms, st));
-    else CUDA_TRY(c, launch_simt_gemm(c->prec, EPI_OUT, c->HT, c->Qp, static_cast<long long>(N) * c->Qp, c->XlT, c->Qp, static_cast<long long>(D) * c->Qp, Q, gp, st));
+    {
+      PhaseTimer pt(c, 7, st);
+      if (tc) CUDA_TRY(c, launch_split_gemm(c->prec, EPI_OUT, c->tm_b2A, c->tm_b2B, gp, c->sms, st));
+      else CUDA_TRY(c, launch_simt_gemm(c->prec, EPI_OUT, c->HT, c->Qp, static_cast<long long>(N) * c->Qp, c->XlT, c->Qp, static_cast<long long>(D) * c->Qp, Q, gp, st));
+    }
     if (!d_total_ext) {
+      PhaseTimer pt(c, 0, st);
       NcclApi* api = nccl_api();
       int r = api->ReduceScatter(c->OUT2, d_diff, static_cast<size_t>(Q) * D, NCCL_FLOAT32, NCCL_SUM, c->comm, st);
       if (r != 0) { c->err = fmt("ncclReduceScatter: %s", api->GetErrorString(r)); return NPAIR_E_NCCL; }
@@ -572,9 +608,40 @@ static int backward_impl(npair_ctx* c, float loss_weight, float* d_diff, float* 
   gp.M = Q; gp.Nn = D; gp.num_kblocks = static_cast<int>((N + c->bk - 1) / c->bk);
   gp.tiles_m = (Q + 127) / 128; gp.tiles_n = (D + 255) / 256;
   gp.out = d_diff; gp.ldo = D; gp.alpha = 0.5f * lw_over_q; gp.beta = (c->world > 1 && !d_total_ext) ? 1.f : 0.f;
-  if (tc) CUDA_TRY(c, launch_split_gemm(c->prec, EPI_OUT, c->tm_b1A, c->tm_b1B, gp, c->sms, st));
-  else CUDA_TRY(c, launch_simt_gemm(c->prec, EPI_OUT, c->H, c->Np, static_cast<long long>(Q) * c->Np, c->XsT, c->Np, static_cast<long long>(D) * c->Np, N, gp, st));
+  {
+    PhaseTimer pt(c, 6, st);
+    if (tc) CUDA_TRY(c, launch_split_gemm(c->prec, EPI_OUT, c->tm_b1A, c->tm_b1B, gp, c->sms, st));
+    else CUDA_TRY(c, launch_simt_gemm(c->prec, EPI_OUT, c->H, c->Np, static_cast<long long>(Q) * c->Np, c->XsT, c->Np, static_cast<long long>(D) * c->Np, N, gp, st));
+  }
   CUDA_TRY(c, cudaGetLastError());
+  return NPAIR_OK;
+}
+
+/* Per-phase CUDA-event timing on the caller's stream (bench.py's roofline leg).  Phases:
+ * 0 collectives (all-gather, reduce-scatter; the backward one overwrites the forward one)  1 operand prep (asum/absmax, split, stat init)
+ * 2 similarity GEMM + fused statistics   3 thresholds + radix selects   4 forward row pass + finalize
+ * 5 backward weight builder   6 gradient GEMM (G . X_total)   7 transposed gradient GEMM (G^T . X_local, world > 1) */
+int npair_profile_enable(npair_ctx* c, int on) {
+  if (!c) return NPAIR_E_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  if (on && !c->ev_made) {
+    for (int i = 0; i < NPAIR_PROF_PHASES; ++i) { CUDA_TRY(c, cudaEventCreate(&c->ev[i][0])); CUDA_TRY(c, cudaEventCreate(&c->ev[i][1])); }
+    c->ev_made = true;
+  }
+  c->prof = on != 0;
+  for (int i = 0; i < NPAIR_PROF_PHASES; ++i) c->ev_used[i] = false;
+  return NPAIR_OK;
+}
+/* milliseconds of each phase of the most recent forward+backward; synchronises the stream.  ms_out[8]. */
+int npair_profile_read(npair_ctx* c, float* ms_out) {
+  if (!c || !ms_out) return NPAIR_E_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  CUDA_TRY(c, cudaStreamSynchronize(c->last_stream));
+  for (int i = 0; i < NPAIR_PROF_PHASES; ++i) {
+    ms_out[i] = 0.f;
+    if (c->ev_made && c->ev_used[i]) { float ms = 0.f; CUDA_TRY(c, cudaEventElapsedTime(&ms, c->ev[i][0], c->ev[i][1])); ms_out[i] = ms; }
+    c->ev_used[i] = false;
+  }
   return NPAIR_OK;
 }
 

@@ -9,8 +9,11 @@ import torch
 
 from npairloss_b200 import capi
 
-# |S_gpu - S_oracle| bound for unit-norm rows, per operand precision
-S_TOL = {capi.PREC_FP32_BF16X3: 2e-6, capi.PREC_FP32_FP16X2: 2e-6, capi.PREC_BF16: 2e-2}
+# |S_gpu - S_ref| <= S_ABS + S_REL*|S_ref| for unit-norm rows.  The fp32-faithful operand splits are exact to ~2^-22, but
+# the tensor core's fp32 accumulator truncates on every MMA (measured on B200: a bias of about n_mma * 2^-24 * |acc|,
+# n_mma = passes * K/16), hence the relative term.
+S_ABS = {capi.PREC_FP32_BF16X3: 1e-6, capi.PREC_FP32_FP16X2: 1e-6, capi.PREC_BF16: 2e-2}
+S_REL = {capi.PREC_FP32_BF16X3: 3e-5, capi.PREC_FP32_FP16X2: 1.5e-5, capi.PREC_BF16: 2e-2}
 # normwise relative gradient bound at level 2
 G_TOL = {capi.PREC_FP32_BF16X3: 1e-5, capi.PREC_FP32_FP16X2: 1e-5, capi.PREC_BF16: 2e-2}
 
@@ -58,8 +61,10 @@ def check_parity(oracle, x, lab, Q, world, mining, prec, backend, loss_weight=1.
     cfg = oracle.make_config(Q, D, world=world, num_tops=num_tops, faithful_sorts=0, **mining)
     # ---- level 1: similarities ----
     S_ref = (x.astype(np.float64) @ x.astype(np.float64).T).astype(np.float32)
-    s_err = float(np.abs(g["S"] - S_ref).max())
-    assert s_err <= S_TOL[prec], f"{tag} L1 S error {s_err:.3e}"
+    s_abs = np.abs(g["S"] - S_ref)
+    s_err = float(s_abs.max())
+    viol = s_abs - (S_ABS[prec] + S_REL[prec] * np.abs(S_ref))
+    assert viol.max() <= 0, f"{tag} L1 S error {s_err:.3e} (worst excess {viol.max():.3e} at |S|={np.abs(S_ref).flat[viol.argmax()]:.3f})"
     # ---- level 2: oracle on the GPU's own S ----
     tops_o, dx_o = oracle.step_world(x, lab, cfg, loss_weight, S_inject_all=g["S"])
     for r in range(world):
