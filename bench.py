@@ -231,44 +231,46 @@ def main():
     value = B / (ms_step * 1e-3)
 
     # ---------------- end-to-end through the plugin surface with host buffers ----------------
-    h_x = torch.from_numpy(xl).pin_memory()
-    h_l = torch.from_numpy(ll).pin_memory()
-    h_g = torch.empty((Q, D), dtype=torch.float32).pin_memory()
-    e2e_api = "C ABI + pinned cudaMemcpyAsync"
-    layer = None
-    try:
-        from npairloss_b200 import caffe_layer
-        layer = caffe_layer.Layer(Q, D, world=world, rank=rank, mining=mining, precision=PRECS[args.precision],
-                                  nccl_ctx=ctx, device=local_rank)
-        e2e_api = "caffe_shim NPairMultiClassLossLayer::Forward/Backward on host Blobs"
-    except Exception:
-        layer = None
-
-    def step_e2e():
-        if layer is not None:
-            return layer.step_host(h_x, h_l, h_g)
-        d_x.copy_(h_x, non_blocking=True)
-        d_l.copy_(h_l, non_blocking=True)
-        t = ctx.forward(d_x, d_l)
-        ctx.backward(1.0, d_g)
-        h_g.copy_(d_g, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return t
+    # The Caffe-style layer (npairloss_b200/caffe_shim) on HOST blobs: every step a data layer hands a new batch through
+    # mutable_cpu_data() (-> H2D of features + labels from pinned memory inside Blob::gpu_data()), Forward, Backward, and the
+    # solver reads bottom diff on the host (-> D2H inside Blob::cpu_diff()); the five tops land on the host as well.
+    from npairloss_b200 import caffe_layer
+    nccl_id2 = None
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(capi.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        nccl_id2 = bytes(idt.cpu().numpy().tobytes())
+    layer = caffe_layer.Layer(caffe_layer.layer_prototxt(mining, 5), Q, D, 1, 1, world=world, rank=rank, nccl_id=nccl_id2,
+                              sim_precision=PRECS[args.precision])
+    layer.bottom_data(0)[:] = xl.ravel()
+    layer.bottom_data(1)[:] = ll
+    e2e_api = "caffe_shim NPairMultiClassLossLayer: Layer::Forward + Layer::Backward on host Blobs (prototxt-configured)"
 
     for _ in range(max(3, args.warmup // 2)):
-        tops_e = step_e2e()
+        tops_e = layer.step_host()
     barrier()
     e0.record(stream)
+    t_host0 = time.perf_counter()
     for _ in range(args.steps):
-        tops_e = step_e2e()
+        tops_e = layer.step_host()
     e1.record(stream)
     barrier()
-    ms_e = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    t_host = time.perf_counter() - t_host0
+    # the shim's Blob copies are synchronous on the legacy stream; CUDA events on torch's stream still bracket them because
+    # every step ends with a blocking D2H.  Use the larger of event time and host wall time.
+    ms_e = torch.tensor([max(e0.elapsed_time(e1), t_host * 1e3)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
     e2e_value = B / (ms_e.item() / args.steps * 1e-3)
     h2d = Q * D * 4 + Q * 4
     d2h = Q * D * 4 + 5 * 4
+    grad_e2e = layer.bottom_diff().copy()
+    layer.close()
+    torch.cuda.synchronize()
+    grad_dev = d_g.cpu().numpy()
+    e2e_consistent = bool(np.linalg.norm(grad_e2e - grad_dev) <= 1e-6 * max(np.linalg.norm(grad_dev), 1e-30))
 
     # ---------------- profiled pass: per-phase CUDA events (roofline of the dominant kernel) ----------------
     ctx.profile_enable(True)
@@ -342,7 +344,8 @@ def main():
                           "l2": f"not flushed: per-step working set (S {4 * Q * N / 1e6:.0f} MB fp32 + split weights) exceeds the 126 MB L2"},
                "clocks": clocks, "roofline": roofline, "phase_ms": phase_ms, "hbm_kernels": hbm,
                "cpu_baseline": cpu,
-               "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": e2e_api},
+               "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": e2e_api,
+                       "gradient_matches_device_path": e2e_consistent},
                "gpu_launches": gpu_launches,
                "tops": {"loss": tops[0], "top1": tops[1], "top5": tops[2], "top10": tops[3], "feature_asum": tops[4]}}
         print(json.dumps(out))

@@ -125,6 +125,11 @@ const char* npair_version(void);
 int npair_profile_enable(npair_ctx* ctx, int on);
 int npair_profile_read(npair_ctx* ctx, float ms_out[8]);
 
+/* Device-side dtype bridges for the Dtype=double instantiation of the Caffe layer (INSTANTIATE_CLASS, reference
+ * npair_multi_class_loss.cpp:190); the reference's arithmetic is fp32 there too (expf/logf/FLT_MAX). */
+int npair_util_f64_to_f32(const double* d_src, float* d_dst, size_t n, void* stream);
+int npair_util_f32_to_f64(const float* d_src, double* d_dst, size_t n, void* stream);
+
 /* Introspection for parity tests (copies device scratch to host; synchronises the context's last stream).
  * which: 0 = S (Q x N similarities, row-major, ld = N)      1 = posi_thr[Q]   2 = nega_thr[Q]
  *        3 = min_within[Q]  4 = max_between[Q]  5 = max_all[Q]  6 = A[Q]  7 = T[Q]  8 = same-label count[Q]

@@ -100,12 +100,26 @@ static bool make_tmap_pieces(CUtensorMap* m, const void* base, int cols, int row
   return true;
 }
 
+// 2-D fp32 map over the similarity matrix [rows x ld], inner extent `cols`, box {32, 32}, 128B swizzle (TMA stores)
+static bool make_tmap_f32_store(CUtensorMap* m, const void* base, int cols, int rows, long long ld_elems, std::string* err) {
+  auto fn = tmap_encode_fn();
+  if (!fn) { *err = "cuTensorMapEncodeTiled entry point not available"; return false; }
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld_elems) * 4ull};
+  cuuint32_t box[2] = {32u, 32u};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { *err = fmt("cuTensorMapEncodeTiled(S) failed (%d): cols=%d rows=%d ld=%lld", (int)r, cols, rows, ld_elems); return false; }
+  return true;
+}
+
 // ------------------------------------------------------------------------------------------------ GEMM launchers
 static inline int nsplit_of_prec(int prec) { return prec == PREC_BF16 ? 1 : (prec == PREC_FP16X2 ? 2 : 3); }
 static inline int bk_of_prec(int prec) { return prec == PREC_BF16X3 ? 32 : 64; }
 
 template <int NSPLIT, bool BF16, int EPI>
-static cudaError_t launch_split_gemm_t(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, int sms, cudaStream_t st) {
+static cudaError_t launch_split_gemm_t(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& sm, const GemmParams& p, int sms, cudaStream_t st) {
   using Cfg = GemmCfg<NSPLIT>;
   auto kern = split_gemm_kernel<NSPLIT, BF16, EPI>;
   static bool attr_set = false;
@@ -116,13 +130,14 @@ static cudaError_t launch_split_gemm_t(const CUtensorMap& a, const CUtensorMap& 
   }
   const int tiles = p.tiles_m * p.tiles_n;
   const int grid = tiles < sms ? tiles : sms;
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a, b, p);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a, b, sm, p);
   return cudaGetLastError();
 }
-static cudaError_t launch_split_gemm(int prec, int epi, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, int sms, cudaStream_t st) {
-  if (prec == PREC_BF16) return epi == EPI_SIM ? launch_split_gemm_t<1, true, EPI_SIM>(a, b, p, sms, st) : launch_split_gemm_t<1, true, EPI_OUT>(a, b, p, sms, st);
-  if (prec == PREC_FP16X2) return epi == EPI_SIM ? launch_split_gemm_t<2, false, EPI_SIM>(a, b, p, sms, st) : launch_split_gemm_t<2, false, EPI_OUT>(a, b, p, sms, st);
-  return epi == EPI_SIM ? launch_split_gemm_t<3, true, EPI_SIM>(a, b, p, sms, st) : launch_split_gemm_t<3, true, EPI_OUT>(a, b, p, sms, st);
+// `sm`: fp32 tensor map of the similarity matrix for EPI_SIM's TMA stores (ignored by EPI_OUT: pass any valid map)
+static cudaError_t launch_split_gemm(int prec, int epi, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& sm, const GemmParams& p, int sms, cudaStream_t st) {
+  if (prec == PREC_BF16) return epi == EPI_SIM ? launch_split_gemm_t<1, true, EPI_SIM>(a, b, sm, p, sms, st) : launch_split_gemm_t<1, true, EPI_OUT>(a, b, sm, p, sms, st);
+  if (prec == PREC_FP16X2) return epi == EPI_SIM ? launch_split_gemm_t<2, false, EPI_SIM>(a, b, sm, p, sms, st) : launch_split_gemm_t<2, false, EPI_OUT>(a, b, sm, p, sms, st);
+  return epi == EPI_SIM ? launch_split_gemm_t<3, true, EPI_SIM>(a, b, sm, p, sms, st) : launch_split_gemm_t<3, true, EPI_OUT>(a, b, sm, p, sms, st);
 }
 
 // SIMT cross-check of the same contraction on the same split operands (tests only; NPAIR_GEMM_SIMT_CHECK).
@@ -218,7 +233,7 @@ struct npair_ctx {
   unsigned long long* ghist = nullptr;
   float* tops_pinned = nullptr;  // host-mapped: 5 tops + err(int) + inv_scale
   float* tops_dev = nullptr;
-  CUtensorMap tm_simA, tm_simB, tm_b1A, tm_b1B, tm_b2A, tm_b2B;
+  CUtensorMap tm_simA, tm_simB, tm_S, tm_b1A, tm_b1B, tm_b2A, tm_b2B;
   // nccl
   void* comm = nullptr; bool own_comm = false;
   // per-step state
@@ -412,6 +427,7 @@ static int create_impl(const npair_config* cfg, const void* id128, void* ext_com
     // similarity: A = local rows of Xs, B = all rows of Xs; K = D
     ok = ok && make_tmap_pieces(&c->tm_simA, c->Xs + static_cast<long long>(c->rank) * Q * c->Dp, D, Q, ns, c->Dp, static_cast<long long>(N) * c->Dp, bk, 128, &te);
     ok = ok && make_tmap_pieces(&c->tm_simB, c->Xs, D, N, ns, c->Dp, static_cast<long long>(N) * c->Dp, bk, 256, &te);
+    ok = ok && make_tmap_f32_store(&c->tm_S, c->S, N, Q, c->ldS, &te);
     // gradient 1: A = H [Q x N], B = XsT [D x N]; K = N
     ok = ok && make_tmap_pieces(&c->tm_b1A, c->H, N, Q, ns, c->Np, static_cast<long long>(Q) * c->Np, bk, 128, &te);
     ok = ok && make_tmap_pieces(&c->tm_b1B, c->XsT, N, D, ns, c->Np, static_cast<long long>(D) * c->Np, bk, 256, &te);
@@ -512,7 +528,7 @@ static int forward_impl(npair_ctx* c, const float* d_feat, const float* d_label,
   gp.st_minw = c->ra.st_minw; gp.st_maxw = c->ra.st_maxw; gp.st_maxb = c->ra.st_maxb; gp.st_maxall = c->ra.st_maxall; gp.cnt_same = c->ra.cnt_same;
   if (c->cfg.gemm_backend == NPAIR_GEMM_TCGEN05) {
     PhaseTimer pt(c, 2, st);
-    CUDA_TRY(c, launch_split_gemm(c->prec, EPI_SIM, c->tm_simA, c->tm_simB, gp, c->sms, st));
+    CUDA_TRY(c, launch_split_gemm(c->prec, EPI_SIM, c->tm_simA, c->tm_simB, c->tm_S, gp, c->sms, st));
   } else {
     CUDA_TRY(c, launch_simt_gemm(c->prec, EPI_SIM, c->Xs + static_cast<long long>(self_off) * c->Dp, c->Dp, static_cast<long long>(N) * c->Dp,
                                  c->Xs, c->Dp, static_cast<long long>(N) * c->Dp, D, gp, st));
@@ -594,7 +610,7 @@ static int backward_impl(npair_ctx* c, float loss_weight, float* d_diff, float* 
     gp.out = d_total_ext ? d_total_ext : c->OUT2; gp.ldo = D; gp.alpha = 0.5f * (1.f / static_cast<float>(c->world)) * lw_over_q; gp.beta = 0.f;
     {
       PhaseTimer pt(c, 7, st);
-      if (tc) CUDA_TRY(c, launch_split_gemm(c->prec, EPI_OUT, c->tm_b2A, c->tm_b2B, gp, c->sms, st));
+      if (tc) CUDA_TRY(c, launch_split_gemm(c->prec, EPI_OUT, c->tm_b2A, c->tm_b2B, c->tm_S, gp, c->sms, st));
       else CUDA_TRY(c, launch_simt_gemm(c->prec, EPI_OUT, c->HT, c->Qp, static_cast<long long>(N) * c->Qp, c->XlT, c->Qp, static_cast<long long>(D) * c->Qp, Q, gp, st));
     }
     if (!d_total_ext) {
@@ -610,7 +626,7 @@ static int backward_impl(npair_ctx* c, float loss_weight, float* d_diff, float* 
   gp.out = d_diff; gp.ldo = D; gp.alpha = 0.5f * lw_over_q; gp.beta = (c->world > 1 && !d_total_ext) ? 1.f : 0.f;
   {
     PhaseTimer pt(c, 6, st);
-    if (tc) CUDA_TRY(c, launch_split_gemm(c->prec, EPI_OUT, c->tm_b1A, c->tm_b1B, gp, c->sms, st));
+    if (tc) CUDA_TRY(c, launch_split_gemm(c->prec, EPI_OUT, c->tm_b1A, c->tm_b1B, c->tm_S, gp, c->sms, st));
     else CUDA_TRY(c, launch_simt_gemm(c->prec, EPI_OUT, c->H, c->Np, static_cast<long long>(Q) * c->Np, c->XsT, c->Np, static_cast<long long>(D) * c->Np, N, gp, st));
   }
   CUDA_TRY(c, cudaGetLastError());
@@ -694,6 +710,31 @@ int npair_debug_read(npair_ctx* c, int which, float* dst, size_t n) {
   return NPAIR_OK;
 }
 
+__global__ void cvt_d2f_kernel(const double* __restrict__ in, float* __restrict__ out, size_t n) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = static_cast<float>(in[i]);
+}
+__global__ void cvt_f2d_kernel(const float* __restrict__ in, double* __restrict__ out, size_t n) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = static_cast<double>(in[i]);
+}
+/* Device-side dtype bridges for the Dtype=double instantiation of the Caffe layer (INSTANTIATE_CLASS, reference .cpp:190):
+ * the reference's arithmetic is fp32 there too (expf/logf/FLT_MAX). */
+int npair_util_f64_to_f32(const double* d_src, float* d_dst, size_t n, void* stream) {
+  if (!d_src || !d_dst) return NPAIR_E_ARG;
+  if (n == 0) return NPAIR_OK;
+  int nb = static_cast<int>((n + 255) / 256); if (nb > 148 * 16) nb = 148 * 16;
+  cvt_d2f_kernel<<<nb, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_src, d_dst, n);
+  return cudaGetLastError() == cudaSuccess ? NPAIR_OK : NPAIR_E_CUDA;
+}
+int npair_util_f32_to_f64(const float* d_src, double* d_dst, size_t n, void* stream) {
+  if (!d_src || !d_dst) return NPAIR_E_ARG;
+  if (n == 0) return NPAIR_OK;
+  int nb = static_cast<int>((n + 255) / 256); if (nb > 148 * 16) nb = 148 * 16;
+  cvt_f2d_kernel<<<nb, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_src, d_dst, n);
+  return cudaGetLastError() == cudaSuccess ? NPAIR_OK : NPAIR_E_CUDA;
+}
+
 int npair_debug_gemm(int precision, int backend, int M, int Nn, int K, const float* dA, const float* dB, float* dC, void* stream) {
   if (M < 1 || Nn < 1 || K < 1 || !dA || !dB || !dC || precision < 0 || precision > 2) { g_create_err = "bad argument"; return NPAIR_E_ARG; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -742,7 +783,7 @@ int npair_debug_gemm(int precision, int backend, int M, int Nn, int K, const flo
       CUtensorMap ta, tb; std::string te;
       if (!make_tmap_pieces(&ta, As, K, M, ns, Kp, static_cast<long long>(M) * Kp, bk, 128, &te) ||
           !make_tmap_pieces(&tb, Bs, K, Nn, ns, Kp, static_cast<long long>(Nn) * Kp, bk, 256, &te)) { g_create_err = te; rc = NPAIR_E_CUDA; goto done; }
-      DG_TRY(launch_split_gemm(precision, EPI_OUT, ta, tb, gp, sms, st));
+      DG_TRY(launch_split_gemm(precision, EPI_OUT, ta, tb, ta, gp, sms, st));
     } else {
       DG_TRY(launch_simt_gemm(precision, EPI_OUT, As, Kp, static_cast<long long>(M) * Kp, Bs, Kp, static_cast<long long>(Nn) * Kp, K, gp, st));
     }

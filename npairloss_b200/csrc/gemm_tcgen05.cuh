@@ -80,10 +80,11 @@ struct GemmCfg {
   static constexpr int A_PIECE = BM * ROW_BYTES;
   static constexpr int B_PIECE = BN * ROW_BYTES;
   static constexpr int STAGE_BYTES = NSPLIT * (A_PIECE + B_PIECE);
-  static constexpr int STAGES = (NSPLIT == 1) ? 4 : (NSPLIT == 2 ? 2 : 3);
+  static constexpr int STAGES = (NSPLIT == 1) ? 4 : 2;
   static constexpr int NPASS = (NSPLIT == 1) ? 1 : (NSPLIT == 2 ? 3 : 6);
+  static constexpr int STORE_STAGE_BYTES = 4 * 4096;          // one 32x32 fp32 TMA-store staging tile per epilogue warp
   static constexpr int SMEM_AUX = 2048;                       // barriers + tmem ptr + column labels
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + SMEM_AUX + 1024 /*alignment slack*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STORE_STAGE_BYTES + SMEM_AUX + 1024 /*alignment slack*/;
   static constexpr int THREADS = 256;
 };
 
@@ -99,12 +100,15 @@ __device__ __forceinline__ void pass_pieces(int nsplit, int p, int& sa, int& sb)
 
 template <int NSPLIT, bool BF16, int EPI>
 __global__ void __launch_bounds__(256, 1)
-split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const GemmParams p) {
+split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
+                  const __grid_constant__ CUtensorMap tmapS, const GemmParams p) {
   using Cfg = GemmCfg<NSPLIT>;
   constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* aux = smem + STAGES * Cfg::STAGE_BYTES;
+  // keep the pointer in the shared address space (offset arithmetic, no integer round trip): LDS/STS, not generic LD/ST
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* store_stage = smem + STAGES * Cfg::STAGE_BYTES;          // [4 warps][32 rows][128 B], 128B-swizzled
+  uint8_t* aux = store_stage + Cfg::STORE_STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);            // [STAGES]
   uint64_t* empty_bar = full_bar + STAGES;                           // [STAGES]
   uint64_t* tfull_bar = empty_bar + STAGES;                          // [2]
@@ -121,6 +125,7 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmapA);
     ptx::prefetch_tmap(&tmapB);
+    if (EPI == EPI_SIM) ptx::prefetch_tmap(&tmapS);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
@@ -225,22 +230,44 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
 #pragma unroll
           for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(r[c]) * out_scale;
           if (row < p.M && col0 < p.Nn) {
+            const float* lab = s_lab + ch * 32;
+            if (col0 + 32 <= p.Nn && (self_col < col0 || self_col >= col0 + 32)) {
+              // interior chunk: no bounds / self-pair checks, branch-free (predicated) statistics
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              const int col = col0 + c;
-              const bool valid = (col < p.Nn) && (col != self_col);
-              const bool same = (s_lab[ch * 32 + c] == lab_i);
-              if (valid) {
-                maxall = fmaxf(maxall, v[c]);
-                if (same) { minw = fminf(minw, v[c]); maxw = fmaxf(maxw, v[c]); ++cnt; }
-                else      { maxb = fmaxf(maxb, v[c]); }
+              for (int q = 0; q < 8; ++q) {
+                const float4 l4 = *reinterpret_cast<const float4*>(lab + 4 * q);
+                const float ll[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float x = v[4 * q + e];
+                  if (ll[e] == lab_i) { minw = fminf(minw, x); maxw = fmaxf(maxw, x); ++cnt; }
+                  else maxb = fmaxf(maxb, x);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) {
+                const int col = col0 + c;
+                const bool valid = (col < p.Nn) && (col != self_col);
+                const bool same = (lab[c] == lab_i);
+                if (valid && same) { minw = fminf(minw, v[c]); maxw = fmaxf(maxw, v[c]); ++cnt; }
+                if (valid && !same) maxb = fmaxf(maxb, v[c]);
               }
             }
           }
-          if (row < p.M && col0 < p.ldS) {
-            float4* dst = reinterpret_cast<float4*>(p.S + static_cast<long long>(row) * p.ldS + col0);
+          // registers -> 128B-swizzled staging tile -> one TMA store of a 32x32 fp32 box (full 128-byte lines;
+          // rows >= M and columns >= Nn are clipped by the tensor map)
+          if (m_blk * BM + ew * 32 < p.M && col0 < p.Nn) {          // warp-uniform
+            uint8_t* stg = store_stage + ew * 4096;
+            if (lane == 0) ptx::tma_store_wait_read<0>();             // previous box has been read out of smem
+            __syncwarp();
+            uint8_t* srow = stg + lane * 128;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<float4*>(srow + ((q ^ (lane & 7)) << 4)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) { ptx::tma_store_2d(&tmapS, stg, col0, m_blk * BM + ew * 32); ptx::tma_store_commit(); }
           }
         } else {
           if (row < p.M) {
@@ -273,14 +300,18 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
       if (EPI == EPI_SIM && row < p.M) {
-        atomicMin(&p.st_minw[row], f2ord(minw));
-        atomicMax(&p.st_maxw[row], f2ord(maxw));
+        maxall = fmaxf(maxw, maxb);                       // every valid column is either same- or diff-label
+        if (cnt) {
+          atomicMin(&p.st_minw[row], f2ord(minw));
+          atomicMax(&p.st_maxw[row], f2ord(maxw));
+          atomicAdd(&p.cnt_same[row], cnt);
+        }
         atomicMax(&p.st_maxb[row], f2ord(maxb));
         atomicMax(&p.st_maxall[row], f2ord(maxall));
-        if (cnt) atomicAdd(&p.cnt_same[row], cnt);
       }
     }
   }
+  if (EPI == EPI_SIM && warp >= 4 && lane == 0) ptx::tma_store_wait<0>();   // bulk stores complete before exit
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 2) {

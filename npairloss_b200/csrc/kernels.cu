@@ -71,6 +71,31 @@ __device__ __forceinline__ bool pos_index(float sn, unsigned long long size, uns
 }
 __device__ __forceinline__ float clamp_thr(float v) { return v >= 0.f ? v : -FLT_MAX; }   // .cu:288,303,319,334
 
+// Every selection rule of .cu:79-120 is rewritten as ONE compare  sgn*s <= thr'  with a per-row transformed threshold:
+//   s <  t  <=>   s <= nextbelow(t)         s <= t  <=>   s <= t
+//   s >= t  <=>  -s <= -t                   s >  t  <=>  -s <= nextbelow(-t)          ALL  <=>  s <= +inf
+// (exact for every float incl. +-0 and the -FLT_MAX / FLT_MAX sentinels; NaN compares false on both sides).
+__host__ __device__ __forceinline__ float ap_sign(int m) { return (m == M_EASY || m == M_RELATIVE_EASY) ? -1.f : 1.f; }
+__host__ __device__ __forceinline__ float an_sign(int m) { return (m == M_HARD || m == M_RELATIVE_HARD) ? -1.f : 1.f; }
+__device__ __forceinline__ float ap_thr(float t, int m) {     // same-label rule on t = posi_thr + margin_ident
+  switch (m) {
+    case M_HARD: return nextafterf(t, -INFINITY);            // s <  t
+    case M_EASY: return -t;                                  // s >= t
+    case M_RAND: return INFINITY;
+    case M_RELATIVE_HARD: return t;                          // s <= t
+    default: return -t;                                      // RELATIVE_EASY: s >= t
+  }
+}
+__device__ __forceinline__ float an_thr(float t, int m) {     // diff-label rule on t = nega_thr + margin_diff
+  switch (m) {
+    case M_HARD: return nextafterf(-t, -INFINITY);           // s >  t
+    case M_EASY: return t;                                   // s <= t
+    case M_RAND: return INFINITY;
+    case M_RELATIVE_HARD: return -t;                         // s >= t
+    default: return t;                                       // RELATIVE_EASY: s <= t
+  }
+}
+
 __device__ __forceinline__ bool sel_ap(float s, float tp, int m) {   // .cu:79-98
   switch (m) {
     case M_HARD: return s < tp;
@@ -113,10 +138,19 @@ __global__ void absmax_asum_partial_kernel(const float* __restrict__ xl, long lo
   }
 }
 __global__ void absmax_asum_final_kernel(const float* __restrict__ partial, int nb, BlockScalars* bs, int want_scale) {
+  __shared__ double s_sum[32];
+  __shared__ float s_max[32];
+  double sum = 0.0; float mx = 0.f;
+  for (int b = threadIdx.x; b < nb; b += blockDim.x) { sum += partial[b]; mx = fmaxf(mx, partial[1024 + b]); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { s_sum[w] = sum; s_max[w] = mx; }
+  __syncthreads();
   if (threadIdx.x == 0) {
-    double s = 0.0; float mx = 0.f;
-    for (int b = 0; b < nb; ++b) { s += partial[b]; mx = fmaxf(mx, partial[1024 + b]); }
-    bs->asum = static_cast<float>(s);
+    sum = 0.0; mx = 0.f;
+    for (int k = 0; k < (blockDim.x >> 5); ++k) { sum += s_sum[k]; mx = fmaxf(mx, s_max[k]); }
+    bs->asum = static_cast<float>(sum);
     bs->x_absmax = mx;
     float sc = 1.f, inv = 1.f;
     if (want_scale && mx > 0.f && isfinite(mx)) {
@@ -132,7 +166,7 @@ void launch_absmax_asum(const float* x_local, long long n_local, const float* x_
   int nb = static_cast<int>((nmax + 256 * 8 - 1) / (256 * 8));
   if (nb < 1) nb = 1; if (nb > 1024) nb = 1024;
   absmax_asum_partial_kernel<<<nb, 256, 0, st>>>(x_local, n_local, x_total, n_total, partial, want_scale);
-  absmax_asum_final_kernel<<<1, 32, 0, st>>>(partial, nb, bs, want_scale);
+  absmax_asum_final_kernel<<<1, 256, 0, st>>>(partial, nb, bs, want_scale);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -456,45 +490,83 @@ void launch_global_select(const float* S, long long ldS, int Q, int N, const flo
 // Retrieval uses the sort-free equivalence of SURVEY.md 9.4 Q11: with p* = max E over same-label non-self
 // columns and c = #{non-self j : E_j >= p*},  hit_k  <=>  c <= min(k, N-2).
 // --------------------------------------------------------------------------------------------
+// Smallest float s (as an ordered key) with expf(s - max_all) >= pstar, searched downward from the best positive.
+// Lets the retrieval count compare similarities instead of exponentials, so expf is only evaluated for SELECTED pairs.
+__device__ __forceinline__ float retrieval_cut(float maxw, float max_all, int lane) {
+  const float pstar = expf(maxw - max_all);
+  if (!(pstar > 0.f)) return -INFINITY;                         // underflow: every entry ties with the best positive
+  uint32_t base = f2ord(maxw), last_ok = base;
+  for (int it = 0; it < 8; ++it) {                             // 256 ulps cover the flat steps of expf for |s-max| < ~80
+    const uint32_t kc = base - static_cast<uint32_t>(lane);
+    const bool ok = (kc <= base) && (expf(ord2f(kc) - max_all) >= pstar);
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    const int T = (bal == 0xffffffffu) ? 32 : (__ffs(~bal) - 1);
+    if (T > 0) last_ok = base - static_cast<uint32_t>(T - 1);
+    if (T < 32) return ord2f(last_ok);
+    if (base < 64u) return ord2f(last_ok);
+    base -= 32u;
+  }
+  // long flat step (denormal exponentials): bisection on the ordered keys, monotone expf assumed
+  uint32_t lo = f2ord(-FLT_MAX), hi = last_ok;                 // invariant: hi satisfies
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    if (expf(ord2f(mid) - max_all) >= pstar) hi = mid; else lo = mid + 1u;
+  }
+  return ord2f(hi);
+}
+
+// One warp per anchor row.
 __global__ void __launch_bounds__(256) lse_rows_kernel(const float* __restrict__ S, long long ldS, int Q, int N,
                                                        const float* __restrict__ lab_rows, const float* __restrict__ lab_cols,
                                                        int self_offset, MiningParams mp, RowArrays ra) {
-  __shared__ float s_A[8], s_B[8];
-  __shared__ int s_c[8], s_id[8], s_df[8];
-  const int i = blockIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= Q) return;
   const float li = lab_rows[i];
   const int self_col = i + self_offset;
   const float max_all = ord2f(ra.st_maxall[i]);
   const float tp = ra.posi_thr[i] + mp.margin_ident;          // fp32 add as in .cu:81
   const float tn = ra.nega_thr[i] + mp.margin_diff;           // .cu:102
+  const float sgn_p = ap_sign(mp.ap_method), sgn_n = an_sign(mp.an_method);
+  const float thr_p = ap_thr(tp, mp.ap_method), thr_n = an_thr(tn, mp.an_method);
   const int cs = ra.cnt_same[i];
-  const float pstar = cs > 0 ? expf(ord2f(ra.st_maxw[i]) - max_all) : FLT_MAX;
+  const float scut = cs > 0 ? retrieval_cut(ord2f(ra.st_maxw[i]), max_all, lane) : INFINITY;
   const float* row = S + static_cast<long long>(i) * ldS;
-  float A = 0.f, B = 0.f; int c = 0, idn = 0, dfn = 0;
-  for (int j4 = threadIdx.x * 4; j4 < N; j4 += 256 * 4) {
-    const float4 v = *reinterpret_cast<const float4*>(row + j4);
-    const float4 lc = (j4 + 3 < N) ? *reinterpret_cast<const float4*>(lab_cols + j4)
-                                   : make_float4(lab_cols[j4], j4 + 1 < N ? lab_cols[j4 + 1] : 0.f, j4 + 2 < N ? lab_cols[j4 + 2] : 0.f, 0.f);
-    const float vv[4] = {v.x, v.y, v.z, v.w};
-    const float ll[4] = {lc.x, lc.y, lc.z, lc.w};
+  float A = 0.f, B = 0.f; int c = 0;
+  for (int base = 0; base < N; base += 512) {
+    float4 v[4], l[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int j = j4 + q;
-      if (j >= N || j == self_col) continue;
-      const float s = vv[q];
-      const float e = expf(s - max_all);                      // .cu:130-131 (fp32 subtract, then expf)
-      c += (e >= pstar) ? 1 : 0;
-      if (ll[q] == li) { if (sel_ap(s, tp, mp.ap_method)) { A += e; ++idn; } }
-      else             { if (sel_an(s, tn, mp.an_method)) { B += e; ++dfn; } }
+    for (int u = 0; u < 4; ++u) {
+      const int j4 = base + u * 128 + lane * 4;
+      if (j4 < N) {
+        v[u] = *reinterpret_cast<const float4*>(row + j4);
+        l[u] = (j4 + 3 < N) ? *reinterpret_cast<const float4*>(lab_cols + j4)
+                            : make_float4(lab_cols[j4], j4 + 1 < N ? lab_cols[j4 + 1] : 0.f, j4 + 2 < N ? lab_cols[j4 + 2] : 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j4 = base + u * 128 + lane * 4;
+      if (j4 >= N) continue;
+      const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+      const float ll[4] = {l[u].x, l[u].y, l[u].z, l[u].w};
+      const bool interior = (j4 + 3 < N) && (self_col < j4 || self_col > j4 + 3);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (!interior && (j4 + q >= N || j4 + q == self_col)) continue;
+        const float sv = vv[q];
+        c += (sv >= scut) ? 1 : 0;                            // == (expf(sv-max_all) >= expf(maxw-max_all)), SURVEY Q11
+        const bool same = ll[q] == li;
+        const bool sel = (same ? sgn_p * sv : sgn_n * sv) <= (same ? thr_p : thr_n);   // .cu:79-120 as one compare
+        if (sel) {
+          const float e = expf(sv - max_all);                 // .cu:130-131 (fp32 subtract, then expf)
+          if (same) A += e; else B += e;
+        }
+      }
     }
   }
-  A = warp_sum(A); B = warp_sum(B); c = warp_sum_i(c); idn = warp_sum_i(idn); dfn = warp_sum_i(dfn);
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  if (l == 0) { s_A[w] = A; s_B[w] = B; s_c[w] = c; s_id[w] = idn; s_df[w] = dfn; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    A = 0.f; B = 0.f; c = 0; idn = 0; dfn = 0;
-    for (int k = 0; k < 8; ++k) { A += s_A[k]; B += s_B[k]; c += s_c[k]; idn += s_id[k]; dfn += s_df[k]; }
+  A = warp_sum(A); B = warp_sum(B); c = warp_sum_i(c);
+  if (lane == 0) {
     const float T = A + B;                                    // .cu:380
     ra.A[i] = A; ra.T[i] = T;
     ra.logv[i] = (A == 0.f || T == 0.f) ? 0.f : logf(A / T);  // .cu:162-169
@@ -504,14 +576,16 @@ __global__ void __launch_bounds__(256) lse_rows_kernel(const float* __restrict__
     ra.hits[2 * Q + i] = (cs > 0 && c <= min(10, lim)) ? 1 : 0;
     const float invA = A == 0.f ? 0.f : 1.f / A;              // Get_Query_Diff_Part zero rules (.cu:410-415)
     const float invT = T == 0.f ? 0.f : 1.f / T;
-    ra.rs_maxall[i] = max_all; ra.rs_tp[i] = tp; ra.rs_tn[i] = tn;
+    ra.rs_maxall[i] = max_all; ra.rs_tp[i] = thr_p; ra.rs_tn[i] = thr_n;   // transformed thresholds (see ap_thr/an_thr)
     ra.rs_cA[i] = invT - invA;                                // same-label weight:  -1/A + 1/T
     ra.rs_cT[i] = invT;                                       // diff-label weight:   1/T
   }
 }
 void launch_lse_rows(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
                      int self_offset, MiningParams mp, RowArrays ra, cudaStream_t st) {
-  lse_rows_kernel<<<Q, 256, 0, st>>>(S, ldS, Q, N, lab_rows, lab_cols, self_offset, mp, ra);
+  int wpb = 8;
+  while (wpb > 1 && (Q + wpb - 1) / wpb < 296) wpb >>= 1;     // keep >= 2 blocks per SM when the rank has few rows
+  lse_rows_kernel<<<(Q + wpb - 1) / wpb, wpb * 32, 0, st>>>(S, ldS, Q, N, lab_rows, lab_cols, self_offset, mp, ra);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -559,99 +633,125 @@ void launch_finalize(RowArrays ra, int Q, int num_tops, const BlockScalars* bs, 
 //   world  > 1 :  H[j][m]  = g'(j,m)  and  HT[m][j] = g'(j,m)
 //                 local = H . X_total ,  total = HT . X_local , then reduce-scatter and blend (.cu:462-497)
 // --------------------------------------------------------------------------------------------
-struct RowScal { float maxall, tp, tn, cA, cT, lab; };
+struct RowScal { float maxall, tp, tn, cA, cT, lab; };   // tp/tn: transformed thresholds of ap_thr/an_thr
 
-__device__ __forceinline__ float gprime(float s, bool same, const RowScal& r, int apM, int anM) {
-  const bool sel = same ? sel_ap(s, r.tp, apM) : sel_an(s, r.tn, anM);
-  return sel ? expf(s - r.maxall) * (same ? r.cA : r.cT) : 0.f;
+__device__ __forceinline__ float gprime(float sv, bool same, const RowScal& r, float sgn_p, float sgn_n) {
+  const bool sel = (same ? sgn_p * sv : sgn_n * sv) <= (same ? r.tp : r.tn);
+  return sel ? expf(sv - r.maxall) * (same ? r.cA : r.cT) : 0.f;
 }
 
+template <int PREC>
+__device__ __forceinline__ void store_pair(uint16_t* __restrict__ base, long long piece_stride, long long off, float g0, float g1) {
+  constexpr int NS = (PREC == PREC_BF16) ? 1 : (PREC == PREC_FP16X2 ? 2 : 3);
+  uint16_t p0[3], p1[3];
+  split3<PREC>(g0, p0[0], p0[1], p0[2]);
+  split3<PREC>(g1, p1[0], p1[1], p1[2]);
+#pragma unroll
+  for (int s = 0; s < NS; ++s)
+    *reinterpret_cast<uint32_t*>(base + s * piece_stride + off) = static_cast<uint32_t>(p0[s]) | (static_cast<uint32_t>(p1[s]) << 16);
+}
+
+// 64 x 64 tiles, 256 threads: thread (rg = t/32, cp = t%32) owns rows rg+8i (i<8) and the column pair (2cp, 2cp+1).
+// FUSED (world == 1): H = G + G^T is symmetric, so a block handles the tile PAIR (a,b), a <= b: it reads S tiles
+//   (a,b) and (b,a) once, evaluates g' once per element, and writes H tiles (a,b) and (b,a).
+// !FUSED (world > 1): a block handles tile (a = local row block, b = global column block), writes H tile and HT tile.
 template <int PREC, bool FUSED>
 __global__ void __launch_bounds__(256) build_weights_kernel(const float* __restrict__ S, long long ldS, int Q, int N,
                                                             const float* __restrict__ lab_rows, const float* __restrict__ lab_cols,
                                                             int self_offset, MiningParams mp, RowArrays ra,
                                                             uint16_t* __restrict__ H, long long ldH, uint16_t* __restrict__ HT, long long ldHT) {
-  constexpr int NS = (PREC == PREC_BF16) ? 1 : (PREC == PREC_FP16X2 ? 2 : 3);
   constexpr int TS = 64;
-  __shared__ float G[TS][TS + 1];
-  __shared__ RowScal sc_j[TS], sc_m[TS];
-  __shared__ float lab_m[TS];
-  const int j0 = blockIdx.y * TS, m0 = blockIdx.x * TS;        // rows j (local), columns m (global)
-  const int t = threadIdx.x;
-  const int cp = t & 31, rg = t >> 5;
+  const int ta = blockIdx.y, tb = blockIdx.x;
+  if (FUSED && ta > tb) return;
+  __shared__ float G1[TS][TS + 1];
+  __shared__ float G2[FUSED ? TS : 1][TS + 1];
+  __shared__ RowScal sc_a[TS], sc_b[FUSED ? TS : 1];
+  __shared__ float lab_b[TS];
+  const int a0 = ta * TS, b0 = tb * TS;
+  const int t = threadIdx.x, cp = t & 31, rg = t >> 5;
+  const float sgn_p = ap_sign(mp.ap_method), sgn_n = an_sign(mp.an_method);
   if (t < TS) {
-    const int j = j0 + t;
-    RowScal r = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int j = a0 + t;
+    RowScal r = {0.f, -INFINITY, -INFINITY, 0.f, 0.f, 0.f};
     if (j < Q) { r.maxall = ra.rs_maxall[j]; r.tp = ra.rs_tp[j]; r.tn = ra.rs_tn[j]; r.cA = ra.rs_cA[j]; r.cT = ra.rs_cT[j]; r.lab = lab_rows[j]; }
-    sc_j[t] = r;
+    sc_a[t] = r;
   } else if (t < 2 * TS) {
-    const int mm = t - TS, m = m0 + mm;
-    lab_m[mm] = m < N ? lab_cols[m] : 0.f;
+    const int mm = t - TS, m = b0 + mm;
+    lab_b[mm] = m < N ? lab_cols[m] : 0.f;
     if (FUSED) {   // world == 1: column m is also a local row
-      RowScal r = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      RowScal r = {0.f, -INFINITY, -INFINITY, 0.f, 0.f, 0.f};
       if (m < Q) { r.maxall = ra.rs_maxall[m]; r.tp = ra.rs_tp[m]; r.tn = ra.rs_tn[m]; r.cA = ra.rs_cA[m]; r.cT = ra.rs_cT[m]; r.lab = lab_rows[m]; }
-      sc_m[mm] = r;
+      sc_b[mm] = r;
     }
   }
   __syncthreads();
-  if (FUSED) {
-    // phase 1: G[a][b] = g'(row m0+a, col j0+b)   (the transposed contribution), coalesced along b
+  float g1[8][2], g2[8][2];
+  const int c0 = 2 * cp;
+  // ---- g'(a_r, b_c) from S tile (a,b) ----
 #pragma unroll
-    for (int r8 = 0; r8 < 8; ++r8) {
-      const int a = rg + 8 * r8, m = m0 + a;
-      const int b = 2 * cp, jc = j0 + b;
-      float g0 = 0.f, g1 = 0.f;
-      if (m < Q && jc < N) {
-        const float2 v = *reinterpret_cast<const float2*>(S + static_cast<long long>(m) * ldS + jc);
-        const RowScal rs = sc_m[a];
-        if (jc != m + self_offset) g0 = gprime(v.x, sc_j[b].lab == rs.lab, rs, mp.ap_method, mp.an_method);
-        if (jc + 1 < N && jc + 1 != m + self_offset) g1 = gprime(v.y, sc_j[b + 1].lab == rs.lab, rs, mp.ap_method, mp.an_method);
-      }
-      G[a][b] = g0; G[a][b + 1] = g1;
-    }
-    __syncthreads();
-  }
-  // phase 2: direct contribution, add the transposed one, split and store (packed pairs along m)
-  const long long psH = static_cast<long long>(Q) * ldH;
-#pragma unroll
-  for (int r8 = 0; r8 < 8; ++r8) {
-    const int a = rg + 8 * r8, j = j0 + a;
-    const int b = 2 * cp, m = m0 + b;
-    float g0 = 0.f, g1 = 0.f;
+  for (int i8 = 0; i8 < 8; ++i8) {
+    const int r = rg + 8 * i8, j = a0 + r, m = b0 + c0;
+    float x0 = 0.f, x1 = 0.f;
     if (j < Q && m < N) {
       const float2 v = *reinterpret_cast<const float2*>(S + static_cast<long long>(j) * ldS + m);
-      const RowScal rs = sc_j[a];
-      if (m != j + self_offset) g0 = gprime(v.x, lab_m[b] == rs.lab, rs, mp.ap_method, mp.an_method);
-      if (m + 1 < N && m + 1 != j + self_offset) g1 = gprime(v.y, lab_m[b + 1] == rs.lab, rs, mp.ap_method, mp.an_method);
+      const RowScal rs = sc_a[r];
+      if (m != j + self_offset) x0 = gprime(v.x, lab_b[c0] == rs.lab, rs, sgn_p, sgn_n);
+      if (m + 1 < N && m + 1 != j + self_offset) x1 = gprime(v.y, lab_b[c0 + 1] == rs.lab, rs, sgn_p, sgn_n);
     }
-    if (FUSED) { g0 += G[b][a]; g1 += G[b + 1][a]; }
-    else { G[a][b] = g0; G[a][b + 1] = g1; }
-    if (j < Q && m < ldH) {
-      uint16_t p0[3], p1[3];
-      split3<PREC>(g0, p0[0], p0[1], p0[2]);
-      split3<PREC>(g1, p1[0], p1[1], p1[2]);
+    g1[i8][0] = x0; g1[i8][1] = x1;
+    G1[r][c0] = x0; G1[r][c0 + 1] = x1;
+  }
+  const bool diag = FUSED && (ta == tb);
+  if (FUSED && !diag) {
+    // ---- g'(b_r, a_c) from S tile (b,a) ----
 #pragma unroll
-      for (int s = 0; s < NS; ++s)
-        *reinterpret_cast<uint32_t*>(H + s * psH + static_cast<long long>(j) * ldH + m) = static_cast<uint32_t>(p0[s]) | (static_cast<uint32_t>(p1[s]) << 16);
+    for (int i8 = 0; i8 < 8; ++i8) {
+      const int r = rg + 8 * i8, j = b0 + r, m = a0 + c0;
+      float x0 = 0.f, x1 = 0.f;
+      if (j < Q && m < N) {
+        const float2 v = *reinterpret_cast<const float2*>(S + static_cast<long long>(j) * ldS + m);
+        const RowScal rs = sc_b[r];
+        if (m != j + self_offset) x0 = gprime(v.x, sc_a[c0].lab == rs.lab, rs, sgn_p, sgn_n);
+        if (m + 1 < N && m + 1 != j + self_offset) x1 = gprime(v.y, sc_a[c0 + 1].lab == rs.lab, rs, sgn_p, sgn_n);
+      }
+      g2[i8][0] = x0; g2[i8][1] = x1;
+      G2[r][c0] = x0; G2[r][c0 + 1] = x1;
     }
   }
-  if (!FUSED) {
+  __syncthreads();
+  const long long psH = static_cast<long long>(Q) * ldH;
+  if (FUSED) {
+    // H[a_r, b_c] = g'(a_r,b_c) + g'(b_c,a_r)
+#pragma unroll
+    for (int i8 = 0; i8 < 8; ++i8) {
+      const int r = rg + 8 * i8, j = a0 + r, m = b0 + c0;
+      if (j < Q && m < ldH) {
+        const float t0 = diag ? G1[c0][r] : G2[c0][r], t1 = diag ? G1[c0 + 1][r] : G2[c0 + 1][r];
+        store_pair<PREC>(H, psH, static_cast<long long>(j) * ldH + m, g1[i8][0] + t0, g1[i8][1] + t1);
+      }
+    }
+    if (!diag) {
+      // H[b_r, a_c] = g'(b_r,a_c) + g'(a_c,b_r)
+#pragma unroll
+      for (int i8 = 0; i8 < 8; ++i8) {
+        const int r = rg + 8 * i8, j = b0 + r, m = a0 + c0;
+        if (j < Q && m < ldH)
+          store_pair<PREC>(H, psH, static_cast<long long>(j) * ldH + m, g2[i8][0] + G1[c0][r], g2[i8][1] + G1[c0 + 1][r]);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i8 = 0; i8 < 8; ++i8) {
+      const int r = rg + 8 * i8, j = a0 + r, m = b0 + c0;
+      if (j < Q && m < ldH) store_pair<PREC>(H, psH, static_cast<long long>(j) * ldH + m, g1[i8][0], g1[i8][1]);
+    }
     // transposed copy HT[m][j] = g'(j,m), packed pairs along j
-    __syncthreads();
     const long long psT = static_cast<long long>(N) * ldHT;
 #pragma unroll
-    for (int r8 = 0; r8 < 8; ++r8) {
-      const int a = rg + 8 * r8, m = m0 + a;      // row of HT
-      const int b = 2 * cp, j = j0 + b;           // column pair of HT
-      if (m < N && j < ldHT) {
-        const float g0 = (j < Q) ? G[b][a] : 0.f, g1 = (j + 1 < Q) ? G[b + 1][a] : 0.f;
-        uint16_t p0[3], p1[3];
-        split3<PREC>(g0, p0[0], p0[1], p0[2]);
-        split3<PREC>(g1, p1[0], p1[1], p1[2]);
-#pragma unroll
-        for (int s = 0; s < NS; ++s)
-          *reinterpret_cast<uint32_t*>(HT + s * psT + static_cast<long long>(m) * ldHT + j) = static_cast<uint32_t>(p0[s]) | (static_cast<uint32_t>(p1[s]) << 16);
-      }
+    for (int i8 = 0; i8 < 8; ++i8) {
+      const int r = rg + 8 * i8, m = b0 + r, j = a0 + c0;
+      if (m < N && j < ldHT)
+        store_pair<PREC>(HT, psT, static_cast<long long>(m) * ldHT + j, (j < Q) ? G1[c0][r] : 0.f, (j + 1 < Q) ? G1[c0 + 1][r] : 0.f);
     }
   }
 }
