@@ -58,7 +58,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -134,10 +134,24 @@ def run_reference(args, B, D, mining, noise):
            "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out))
+    emit(out)
+
+
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """The contract is ONE JSON line on stdout; libraries (NCCL's version banner, torchrun) also write to fd 1, so the
+    process's stdout is pointed at stderr for the whole run and the result goes to the saved descriptor."""
+    line = (json.dumps(obj) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, line)
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -209,12 +223,13 @@ def main():
         return tops
 
     # ---------------- device-resident timed region ----------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()            # nvidia-smi takes ~0.1 s to produce its first line: start it ahead of the warm-up
     for _ in range(args.warmup):
         tops = step_device()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    n_before = len(sampler.rows)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
@@ -223,7 +238,17 @@ def main():
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = None
+    if rank == 0:
+        in_region = len(sampler.rows) - n_before
+        # a 50-step timed region lasts ~30 ms, shorter than nvidia-smi's sampling period: keep the SAME load running
+        # (untimed) until a handful of samples exist, and say how many fell inside the timed region itself
+        t_top = time.perf_counter()
+        while len(sampler.rows) - n_before < 6 and time.perf_counter() - t_top < 2.0 and world == 1:
+            step_device()
+        clocks = sampler.stop()
+        clocks["samples_in_timed_region"] = in_region
+        clocks["note"] = "sampled with nvidia-smi -lms 25 from warm-up through the timed region and an untimed continuation of the same load"
     ms_t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
@@ -348,7 +373,7 @@ def main():
                        "gradient_matches_device_path": e2e_consistent},
                "gpu_launches": gpu_launches,
                "tops": {"loss": tops[0], "top1": tops[1], "top5": tops[2], "top10": tops[3], "feature_asum": tops[4]}}
-        print(json.dumps(out))
+        emit(out)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

@@ -128,7 +128,7 @@ static cudaError_t launch_split_gemm_t(const CUtensorMap& a, const CUtensorMap& 
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  const int tiles = p.tiles_m * p.tiles_n;
+  const int tiles = p.tiles_m * p.tiles_n * p.splits;
   const int grid = tiles < sms ? tiles : sms;
   kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a, b, sm, p);
   return cudaGetLastError();
@@ -207,6 +207,38 @@ static cudaError_t launch_simt_gemm(int prec, int epi, const uint16_t* A, long l
   return cudaGetLastError();
 }
 
+// out = sum_s part[s] + beta*out, fixed summation order (deterministic split-K)
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, long long n, float* __restrict__ out, float beta) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 4;
+  for (long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    if (i + 3 < n) {
+      float4 a = *reinterpret_cast<const float4*>(part + i);
+      for (int s = 1; s < splits; ++s) { const float4 b = *reinterpret_cast<const float4*>(part + s * n + i); a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+      if (beta != 0.f) { const float4 o = *reinterpret_cast<const float4*>(out + i); a.x += beta * o.x; a.y += beta * o.y; a.z += beta * o.z; a.w += beta * o.w; }
+      *reinterpret_cast<float4*>(out + i) = a;
+    } else {
+      for (long long j = i; j < n; ++j) {
+        float a = part[j];
+        for (int s = 1; s < splits; ++s) a += part[s * n + j];
+        if (beta != 0.f) a += beta * out[j];
+        out[j] = a;
+      }
+    }
+  }
+}
+// choose a split-K factor that fills the SMs when the output has few tiles (strong scaling: Q = B/world shrinks)
+static void plan_splits(GemmParams* gp, int sms, long long max_part_floats) {
+  const int tiles = gp->tiles_m * gp->tiles_n;
+  int splits = sms / (tiles > 0 ? tiles : 1);
+  if (splits > 16) splits = 16;
+  if (splits > gp->num_kblocks / 4) splits = gp->num_kblocks / 4;       // keep >= 4 k-blocks per split
+  while (splits > 1 && static_cast<long long>(splits) * gp->M * gp->ldo > max_part_floats) --splits;
+  if (splits < 1) splits = 1;
+  int kpb = (gp->num_kblocks + splits - 1) / splits;
+  splits = (gp->num_kblocks + kpb - 1) / kpb;                            // no empty split
+  gp->splits = splits; gp->kb_per_split = kpb;
+}
+
 static inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
 
 }  // namespace npair
@@ -226,6 +258,8 @@ struct npair_ctx {
   float* S = nullptr;
   uint16_t *Xs = nullptr, *XsT = nullptr, *XlT = nullptr, *H = nullptr, *HT = nullptr;
   float* OUT2 = nullptr;         // world > 1: N x D transposed-term product before the reduce-scatter
+  float* part = nullptr;         // split-K partial products of the gradient GEMM
+  long long part_floats = 0;
   void* row_block = nullptr;     // backing store of RowArrays
   RowArrays ra;
   BlockScalars* bs = nullptr;
@@ -337,7 +371,7 @@ void npair_destroy(npair_ctx* c) {
   if (c->device >= 0) cudaSetDevice(c->device);
   if (c->comm && c->own_comm) { NcclApi* api = nccl_api(); if (api->CommDestroy) api->CommDestroy(c->comm); }
   cudaFree(c->Xtot_buf); cudaFree(c->labtot_buf); cudaFree(c->S); cudaFree(c->Xs); cudaFree(c->XsT); cudaFree(c->XlT);
-  cudaFree(c->H); cudaFree(c->HT); cudaFree(c->OUT2); cudaFree(c->row_block); cudaFree(c->bs); cudaFree(c->partial); cudaFree(c->ghist);
+  cudaFree(c->H); cudaFree(c->HT); cudaFree(c->OUT2); cudaFree(c->part); cudaFree(c->row_block); cudaFree(c->bs); cudaFree(c->partial); cudaFree(c->ghist);
   if (c->tops_pinned) cudaFreeHost(c->tops_pinned);
   if (c->ev_made) for (int i = 0; i < NPAIR_PROF_PHASES; ++i) { cudaEventDestroy(c->ev[i][0]); cudaEventDestroy(c->ev[i][1]); }
   delete c;
@@ -396,6 +430,15 @@ static int create_impl(const npair_config* cfg, const void* id128, void* ext_com
     CREATE_TRY(cudaMalloc(&c->HT, 2ull * ns * N * c->Qp));
     CREATE_TRY(cudaMemset(c->HT, 0, 2ull * ns * N * c->Qp));
     CREATE_TRY(cudaMalloc(&c->OUT2, sizeof(float) * static_cast<size_t>(N) * D));
+  }
+  {
+    // split-K workspace for the gradient GEMM: at most (SMs / tiles) partial Q x D products, capped at 16
+    const int tiles = ((Q + 127) / 128) * ((D + 255) / 256);
+    int smax = c->sms / (tiles > 0 ? tiles : 1); if (smax > 16) smax = 16;
+    if (smax > 1) {
+      c->part_floats = static_cast<long long>(smax) * Q * D;
+      CREATE_TRY(cudaMalloc(&c->part, sizeof(float) * c->part_floats));
+    }
   }
   // row arrays: 5 uint32/int stats, 2 thr, 3 fwd, 3 hits, 5 row scalars = 18 arrays of Q 4-byte words
   CREATE_TRY(cudaMalloc(&c->row_block, 4ull * 18 * Q));
@@ -522,7 +565,7 @@ static int forward_impl(npair_ctx* c, const float* d_feat, const float* d_label,
   // ---- S = X_local . X_total^T (.cu:218) with fused masks + row statistics (.cu:44-66, :225-265) ----
   GemmParams gp; memset(&gp, 0, sizeof(gp));
   gp.M = Q; gp.Nn = N; gp.num_kblocks = static_cast<int>((D + c->bk - 1) / c->bk);
-  gp.tiles_m = (Q + 127) / 128; gp.tiles_n = (N + 255) / 256;
+  gp.tiles_m = (Q + 127) / 128; gp.tiles_n = (N + 255) / 256; gp.splits = 1; gp.kb_per_split = gp.num_kblocks;
   gp.S = c->S; gp.ldS = c->ldS; gp.dev_scale = &c->bs->x_inv_scale;
   gp.lab_rows = d_label; gp.lab_cols = c->lab_total; gp.self_offset = self_off;
   gp.st_minw = c->ra.st_minw; gp.st_maxw = c->ra.st_maxw; gp.st_maxb = c->ra.st_maxb; gp.st_maxall = c->ra.st_maxall; gp.cnt_same = c->ra.cnt_same;
@@ -606,7 +649,7 @@ static int backward_impl(npair_ctx* c, float loss_weight, float* d_diff, float* 
   if (c->world > 1) {
     // total = (1/2)(1/k)(lw/Q) * G^T . X_local  (N x D)  -> reduce-scatter (== all-reduce + own slice, .cu:462-497)
     gp.M = N; gp.Nn = D; gp.num_kblocks = static_cast<int>((Q + c->bk - 1) / c->bk);
-    gp.tiles_m = (N + 127) / 128; gp.tiles_n = (D + 255) / 256;
+    gp.tiles_m = (N + 127) / 128; gp.tiles_n = (D + 255) / 256; gp.splits = 1; gp.kb_per_split = gp.num_kblocks;
     gp.out = d_total_ext ? d_total_ext : c->OUT2; gp.ldo = D; gp.alpha = 0.5f * (1.f / static_cast<float>(c->world)) * lw_over_q; gp.beta = 0.f;
     {
       PhaseTimer pt(c, 7, st);
@@ -624,10 +667,17 @@ static int backward_impl(npair_ctx* c, float loss_weight, float* d_diff, float* 
   gp.M = Q; gp.Nn = D; gp.num_kblocks = static_cast<int>((N + c->bk - 1) / c->bk);
   gp.tiles_m = (Q + 127) / 128; gp.tiles_n = (D + 255) / 256;
   gp.out = d_diff; gp.ldo = D; gp.alpha = 0.5f * lw_over_q; gp.beta = (c->world > 1 && !d_total_ext) ? 1.f : 0.f;
+  gp.splits = 1; gp.kb_per_split = gp.num_kblocks; gp.part = c->part;
+  if (tc && c->part) plan_splits(&gp, c->sms, c->part_floats);
   {
     PhaseTimer pt(c, 6, st);
     if (tc) CUDA_TRY(c, launch_split_gemm(c->prec, EPI_OUT, c->tm_b1A, c->tm_b1B, c->tm_S, gp, c->sms, st));
     else CUDA_TRY(c, launch_simt_gemm(c->prec, EPI_OUT, c->H, c->Np, static_cast<long long>(Q) * c->Np, c->XsT, c->Np, static_cast<long long>(D) * c->Np, N, gp, st));
+    if (tc && gp.splits > 1) {
+      const long long n = static_cast<long long>(Q) * D;
+      int nb = static_cast<int>((n / 4 + 255) / 256); if (nb > c->sms * 8) nb = c->sms * 8; if (nb < 1) nb = 1;
+      splitk_reduce_kernel<<<nb, 256, 0, st>>>(c->part, gp.splits, n, d_diff, gp.beta);
+    }
   }
   CUDA_TRY(c, cudaGetLastError());
   return NPAIR_OK;
@@ -776,7 +826,7 @@ int npair_debug_gemm(int precision, int backend, int M, int Nn, int K, const flo
     launch_split(dB, Nn, K, precision, bs, Bs, Kp, dummyT, tmax, nullptr, 0, 0, 0, st);
     GemmParams gp; memset(&gp, 0, sizeof(gp));
     gp.M = M; gp.Nn = Nn; gp.num_kblocks = (K + bk - 1) / bk; gp.tiles_m = (M + 127) / 128; gp.tiles_n = (Nn + 255) / 256;
-    gp.out = dC; gp.ldo = Nn; gp.alpha = 1.f; gp.beta = 0.f;
+    gp.out = dC; gp.ldo = Nn; gp.alpha = 1.f; gp.beta = 0.f; gp.splits = 1; gp.kb_per_split = gp.num_kblocks;
     // EPI_OUT applies the inverse scale once; both operands were scaled -> fold the second factor into alpha
     gp.alpha = sB; gp.dev_scale = &bs->x_inv_scale;
     if (backend == NPAIR_GEMM_TCGEN05) {

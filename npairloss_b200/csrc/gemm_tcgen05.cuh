@@ -51,6 +51,8 @@ struct GemmParams {
   int M, Nn;           // logical output extent
   int num_kblocks;     // K_pad / BK
   int tiles_m, tiles_n;
+  int splits, kb_per_split;   // split-K (EPI_OUT only): tile = (m_blk*tiles_n + n_blk)*splits + split, k-blocks [split*kb_per_split, ...)
+  float* part;                // splits > 1: partial products [split][M][ldo]; a reduce kernel sums them in fixed order
   // ---- EPI_SIM ----
   float* S;            // [M x ldS] fp32 similarities
   long long ldS;       // multiple of 32
@@ -117,7 +119,7 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   float* s_lab = reinterpret_cast<float*>(aux + 256);                // [256] column labels of the current tile (EPI_SIM)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int num_tiles = p.tiles_m * p.tiles_n * p.splits;
   const float inv_scale = p.dev_scale ? *p.dev_scale : 1.f;
   const float out_scale = (EPI == EPI_SIM) ? inv_scale * inv_scale : 1.f;
   const float alpha = p.alpha * inv_scale;
@@ -146,8 +148,10 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
-        for (int kb = 0; kb < p.num_kblocks; ++kb) {
+        const int mn = tile / p.splits, split = tile - mn * p.splits;
+        const int m_blk = mn / p.tiles_n, n_blk = mn % p.tiles_n;
+        const int kb0 = split * p.kb_per_split, kb1 = min(p.num_kblocks, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
@@ -172,7 +176,9 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < p.num_kblocks; ++kb) {
+        const int split = tile % p.splits;
+        const int kb0 = split * p.kb_per_split, kb1 = min(p.num_kblocks, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
           const uint32_t a0 = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -185,7 +191,7 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
             for (int k4 = 0; k4 < BK / 16; ++k4) {
               const uint64_t ad = ptx::make_kmajor_desc(a0 + sa * Cfg::A_PIECE + k4 * 32, Cfg::SBO, Cfg::LAYOUT);
               const uint64_t bd = ptx::make_kmajor_desc(b0 + sb * Cfg::B_PIECE + k4 * 32, Cfg::SBO, Cfg::LAYOUT);
-              ptx::mma_f16_ss(d_tmem, ad, bd, idesc, (kb | ps | k4) != 0 ? 1u : 0u);
+              ptx::mma_f16_ss(d_tmem, ad, bd, idesc, ((kb - kb0) | ps | k4) != 0 ? 1u : 0u);
             }
           }
           ptx::mma_commit(&empty_bar[stage]);   // smem slot reusable once these MMAs retire
@@ -200,7 +206,8 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     const int et = threadIdx.x - 128;            // 0..127
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+      const int mn = tile / p.splits, split = tile - mn * p.splits;
+      const int m_blk = mn / p.tiles_n, n_blk = mn % p.tiles_n;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int row = m_blk * BM + ew * 32 + lane;
@@ -271,15 +278,17 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
           }
         } else {
           if (row < p.M) {
-            float* dst = p.out + static_cast<long long>(row) * p.ldo + col0;
+            float* obase = p.splits > 1 ? p.part + static_cast<long long>(split) * p.M * p.ldo : p.out;
+            const float beta = p.splits > 1 ? 0.f : p.beta;
+            float* dst = obase + static_cast<long long>(row) * p.ldo + col0;
             if (col0 + 32 <= p.Nn && (p.ldo & 3) == 0) {
 #pragma unroll
               for (int q = 0; q < 8; ++q) {
                 float4 o = make_float4(alpha * __uint_as_float(r[4 * q]), alpha * __uint_as_float(r[4 * q + 1]),
                                        alpha * __uint_as_float(r[4 * q + 2]), alpha * __uint_as_float(r[4 * q + 3]));
-                if (p.beta != 0.f) {
+                if (beta != 0.f) {
                   const float4 old = reinterpret_cast<float4*>(dst)[q];
-                  o.x += p.beta * old.x; o.y += p.beta * old.y; o.z += p.beta * old.z; o.w += p.beta * old.w;
+                  o.x += beta * old.x; o.y += beta * old.y; o.z += beta * old.z; o.w += beta * old.w;
                 }
                 reinterpret_cast<float4*>(dst)[q] = o;
               }
@@ -288,7 +297,7 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
               for (int c = 0; c < 32; ++c)
                 if (col0 + c < p.Nn) {
                   float o = alpha * __uint_as_float(r[c]);
-                  if (p.beta != 0.f) o += p.beta * dst[c];
+                  if (beta != 0.f) o += beta * dst[c];
                   dst[c] = o;
                 }
             }
