@@ -515,24 +515,31 @@ __device__ __forceinline__ float retrieval_cut(float maxw, float max_all, int la
   return ord2f(hi);
 }
 
-// One warp per anchor row.
-__global__ void __launch_bounds__(256) lse_rows_kernel(const float* __restrict__ S, long long ldS, int Q, int N,
+// One warp per anchor row.  Hot loop per element: retrieval-count compare, label compare, ONE selection compare; the
+// selected diff-label similarities (a few percent under margin mining) are queued per lane in shared memory and
+// exponentiated in dense batches, so expf never runs under divergence.  Same-label pairs are rare and handled inline.
+#define LSE_QCAP 12
+template <bool AN_NEG>
+__global__ void __launch_bounds__(256, 3) lse_rows_kernel(const float* __restrict__ S, long long ldS, int Q, int N,
                                                        const float* __restrict__ lab_rows, const float* __restrict__ lab_cols,
                                                        int self_offset, MiningParams mp, RowArrays ra) {
-  const int lane = threadIdx.x & 31;
-  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  __shared__ float queue[8][LSE_QCAP][32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int i = blockIdx.x * (blockDim.x >> 5) + wib;
   if (i >= Q) return;
   const float li = lab_rows[i];
   const int self_col = i + self_offset;
   const float max_all = ord2f(ra.st_maxall[i]);
   const float tp = ra.posi_thr[i] + mp.margin_ident;          // fp32 add as in .cu:81
   const float tn = ra.nega_thr[i] + mp.margin_diff;           // .cu:102
-  const float sgn_p = ap_sign(mp.ap_method), sgn_n = an_sign(mp.an_method);
+  const float sgn_p = ap_sign(mp.ap_method);
   const float thr_p = ap_thr(tp, mp.ap_method), thr_n = an_thr(tn, mp.an_method);
+  const float bound_n = AN_NEG ? -thr_n : thr_n;              // -s <= t  <=>  s >= -t
   const int cs = ra.cnt_same[i];
   const float scut = cs > 0 ? retrieval_cut(ord2f(ra.st_maxw[i]), max_all, lane) : INFINITY;
   const float* row = S + static_cast<long long>(i) * ldS;
-  float A = 0.f, B = 0.f; int c = 0;
+  float A = 0.f, B = 0.f; int c = 0, qn = 0;
+  float (*myq)[32] = queue[wib];
   for (int base = 0; base < N; base += 512) {
     float4 v[4], l[4];
 #pragma unroll
@@ -547,23 +554,32 @@ __global__ void __launch_bounds__(256) lse_rows_kernel(const float* __restrict__
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int j4 = base + u * 128 + lane * 4;
-      if (j4 >= N) continue;
-      const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-      const float ll[4] = {l[u].x, l[u].y, l[u].z, l[u].w};
-      const bool interior = (j4 + 3 < N) && (self_col < j4 || self_col > j4 + 3);
+      if (j4 < N) {
+        const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+        const float ll[4] = {l[u].x, l[u].y, l[u].z, l[u].w};
+        const bool interior = (j4 + 3 < N) && (self_col < j4 || self_col > j4 + 3);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (!interior && (j4 + q >= N || j4 + q == self_col)) continue;
-        const float sv = vv[q];
-        c += (sv >= scut) ? 1 : 0;                            // == (expf(sv-max_all) >= expf(maxw-max_all)), SURVEY Q11
-        const bool same = ll[q] == li;
-        const bool sel = (same ? sgn_p * sv : sgn_n * sv) <= (same ? thr_p : thr_n);   // .cu:79-120 as one compare
-        if (sel) {
-          const float e = expf(sv - max_all);                 // .cu:130-131 (fp32 subtract, then expf)
-          if (same) A += e; else B += e;
+        for (int q = 0; q < 4; ++q) {
+          if (!interior && (j4 + q >= N || j4 + q == self_col)) continue;
+          const float sv = vv[q];
+          c += (sv >= scut) ? 1 : 0;                          // == (expf(sv-max_all) >= expf(maxw-max_all)), SURVEY Q11
+          if (ll[q] == li) {                                  // same label: rare
+            if (sgn_p * sv <= thr_p) A += expf(sv - max_all); // .cu:79-98 as one compare; .cu:130-131
+          } else if (AN_NEG ? (sv >= bound_n) : (sv <= bound_n)) {   // .cu:100-119 as one compare
+            myq[qn][lane] = sv; ++qn;
+          }
         }
       }
+      if (__any_sync(0xffffffffu, qn > LSE_QCAP - 4)) {       // dense batch of exponentials
+        const int mx = __reduce_max_sync(0xffffffffu, qn);
+        for (int t = 0; t < mx; ++t) if (t < qn) B += expf(myq[t][lane] - max_all);
+        qn = 0;
+      }
     }
+  }
+  {
+    const int mx = __reduce_max_sync(0xffffffffu, qn);
+    for (int t = 0; t < mx; ++t) if (t < qn) B += expf(myq[t][lane] - max_all);
   }
   A = warp_sum(A); B = warp_sum(B); c = warp_sum_i(c);
   if (lane == 0) {
@@ -576,7 +592,7 @@ __global__ void __launch_bounds__(256) lse_rows_kernel(const float* __restrict__
     ra.hits[2 * Q + i] = (cs > 0 && c <= min(10, lim)) ? 1 : 0;
     const float invA = A == 0.f ? 0.f : 1.f / A;              // Get_Query_Diff_Part zero rules (.cu:410-415)
     const float invT = T == 0.f ? 0.f : 1.f / T;
-    ra.rs_maxall[i] = max_all; ra.rs_tp[i] = thr_p; ra.rs_tn[i] = thr_n;   // transformed thresholds (see ap_thr/an_thr)
+    ra.rs_maxall[i] = max_all; ra.rs_tp[i] = thr_p; ra.rs_tn[i] = bound_n;  // transformed thresholds (ap_thr / s-domain bound)
     ra.rs_cA[i] = invT - invA;                                // same-label weight:  -1/A + 1/T
     ra.rs_cT[i] = invT;                                       // diff-label weight:   1/T
   }
@@ -585,7 +601,9 @@ void launch_lse_rows(const float* S, long long ldS, int Q, int N, const float* l
                      int self_offset, MiningParams mp, RowArrays ra, cudaStream_t st) {
   int wpb = 8;
   while (wpb > 1 && (Q + wpb - 1) / wpb < 296) wpb >>= 1;     // keep >= 2 blocks per SM when the rank has few rows
-  lse_rows_kernel<<<(Q + wpb - 1) / wpb, wpb * 32, 0, st>>>(S, ldS, Q, N, lab_rows, lab_cols, self_offset, mp, ra);
+  const int grid = (Q + wpb - 1) / wpb;
+  if (an_sign(mp.an_method) < 0.f) lse_rows_kernel<true><<<grid, wpb * 32, 0, st>>>(S, ldS, Q, N, lab_rows, lab_cols, self_offset, mp, ra);
+  else lse_rows_kernel<false><<<grid, wpb * 32, 0, st>>>(S, ldS, Q, N, lab_rows, lab_cols, self_offset, mp, ra);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -633,29 +651,39 @@ void launch_finalize(RowArrays ra, int Q, int num_tops, const BlockScalars* bs, 
 //   world  > 1 :  H[j][m]  = g'(j,m)  and  HT[m][j] = g'(j,m)
 //                 local = H . X_total ,  total = HT . X_local , then reduce-scatter and blend (.cu:462-497)
 // --------------------------------------------------------------------------------------------
-struct RowScal { float maxall, tp, tn, cA, cT, lab; };   // tp/tn: transformed thresholds of ap_thr/an_thr
+struct RowScal { float maxall, tp, tn, cA, cT, lab; };   // tp: ap_thr-transformed; tn: s-domain bound of the diff rule
 
-__device__ __forceinline__ float gprime(float sv, bool same, const RowScal& r, float sgn_p, float sgn_n) {
-  const bool sel = (same ? sgn_p * sv : sgn_n * sv) <= (same ? r.tp : r.tn);
-  return sel ? expf(sv - r.maxall) * (same ? r.cA : r.cT) : 0.f;
+template <bool AN_NEG>
+__device__ __forceinline__ float gprime(float sv, bool same, const RowScal& r, float sgn_p) {
+  if (same) return (sgn_p * sv <= r.tp) ? expf(sv - r.maxall) * r.cA : 0.f;
+  return (AN_NEG ? (sv >= r.tn) : (sv <= r.tn)) ? expf(sv - r.maxall) * r.cT : 0.f;
 }
 
+// four consecutive weights -> NS pieces, one 8-byte store per piece
 template <int PREC>
-__device__ __forceinline__ void store_pair(uint16_t* __restrict__ base, long long piece_stride, long long off, float g0, float g1) {
+__device__ __forceinline__ void store_quad(uint16_t* __restrict__ base, long long piece_stride, long long off, const float g[4]) {
   constexpr int NS = (PREC == PREC_BF16) ? 1 : (PREC == PREC_FP16X2 ? 2 : 3);
-  uint16_t p0[3], p1[3];
-  split3<PREC>(g0, p0[0], p0[1], p0[2]);
-  split3<PREC>(g1, p1[0], p1[1], p1[2]);
+  if (g[0] == 0.f && g[1] == 0.f && g[2] == 0.f && g[3] == 0.f) {          // the common case under margin mining
+#pragma unroll
+    for (int s = 0; s < NS; ++s) *reinterpret_cast<uint2*>(base + s * piece_stride + off) = make_uint2(0u, 0u);
+    return;
+  }
+  uint16_t p[4][3];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) split3<PREC>(g[e], p[e][0], p[e][1], p[e][2]);
 #pragma unroll
   for (int s = 0; s < NS; ++s)
-    *reinterpret_cast<uint32_t*>(base + s * piece_stride + off) = static_cast<uint32_t>(p0[s]) | (static_cast<uint32_t>(p1[s]) << 16);
+    *reinterpret_cast<uint2*>(base + s * piece_stride + off) =
+        make_uint2(static_cast<uint32_t>(p[0][s]) | (static_cast<uint32_t>(p[1][s]) << 16), static_cast<uint32_t>(p[2][s]) | (static_cast<uint32_t>(p[3][s]) << 16));
 }
 
-// 64 x 64 tiles, 256 threads: thread (rg = t/32, cp = t%32) owns rows rg+8i (i<8) and the column pair (2cp, 2cp+1).
-// FUSED (world == 1): H = G + G^T is symmetric, so a block handles the tile PAIR (a,b), a <= b: it reads S tiles
-//   (a,b) and (b,a) once, evaluates g' once per element, and writes H tiles (a,b) and (b,a).
-// !FUSED (world > 1): a block handles tile (a = local row block, b = global column block), writes H tile and HT tile.
-template <int PREC, bool FUSED>
+// 64 x 64 tiles, 256 threads; thread (tr = t/16, tc = t%16) owns the 4 x 4 micro-tile rows 4tr.., columns 4tc.. .
+// FUSED (world == 1): H = G + G^T is symmetric.  A block handles the tile PAIR (a,b), a <= b; each thread loads its
+//   micro-tile of S tile (a,b) AND the mirrored micro-tile of S tile (b,a) (both sector-exact 16-byte row segments),
+//   evaluates g' for each unordered pair once, and stores the 4 x 4 result to H tile (a,b) and, transposed in
+//   registers, to H tile (b,a): no shared-memory transposition, no block barrier after the scalar preload.
+// !FUSED (world > 1): a block handles tile (a = local row block, b = global column block): H rows and HT rows.
+template <int PREC, bool FUSED, bool AN_NEG>
 __global__ void __launch_bounds__(256) build_weights_kernel(const float* __restrict__ S, long long ldS, int Q, int N,
                                                             const float* __restrict__ lab_rows, const float* __restrict__ lab_cols,
                                                             int self_offset, MiningParams mp, RowArrays ra,
@@ -663,111 +691,98 @@ __global__ void __launch_bounds__(256) build_weights_kernel(const float* __restr
   constexpr int TS = 64;
   const int ta = blockIdx.y, tb = blockIdx.x;
   if (FUSED && ta > tb) return;
-  __shared__ float G1[TS][TS + 1];
-  __shared__ float G2[FUSED ? TS : 1][TS + 1];
-  __shared__ RowScal sc_a[TS], sc_b[FUSED ? TS : 1];
-  __shared__ float lab_b[TS];
+  __shared__ RowScal sc_a[TS], sc_b[TS];
   const int a0 = ta * TS, b0 = tb * TS;
-  const int t = threadIdx.x, cp = t & 31, rg = t >> 5;
-  const float sgn_p = ap_sign(mp.ap_method), sgn_n = an_sign(mp.an_method);
+  const int t = threadIdx.x, tr = t >> 4, tc = t & 15;
+  const float sgn_p = ap_sign(mp.ap_method);
   if (t < TS) {
     const int j = a0 + t;
-    RowScal r = {0.f, -INFINITY, -INFINITY, 0.f, 0.f, 0.f};
+    RowScal r = {0.f, -INFINITY, AN_NEG ? INFINITY : -INFINITY, 0.f, 0.f, 0.f};
     if (j < Q) { r.maxall = ra.rs_maxall[j]; r.tp = ra.rs_tp[j]; r.tn = ra.rs_tn[j]; r.cA = ra.rs_cA[j]; r.cT = ra.rs_cT[j]; r.lab = lab_rows[j]; }
     sc_a[t] = r;
   } else if (t < 2 * TS) {
     const int mm = t - TS, m = b0 + mm;
-    lab_b[mm] = m < N ? lab_cols[m] : 0.f;
+    RowScal r = {0.f, -INFINITY, AN_NEG ? INFINITY : -INFINITY, 0.f, 0.f, 0.f};
     if (FUSED) {   // world == 1: column m is also a local row
-      RowScal r = {0.f, -INFINITY, -INFINITY, 0.f, 0.f, 0.f};
       if (m < Q) { r.maxall = ra.rs_maxall[m]; r.tp = ra.rs_tp[m]; r.tn = ra.rs_tn[m]; r.cA = ra.rs_cA[m]; r.cT = ra.rs_cT[m]; r.lab = lab_rows[m]; }
-      sc_b[mm] = r;
-    }
+    } else if (m < N) r.lab = lab_cols[m];
+    sc_b[mm] = r;
   }
   __syncthreads();
-  float g1[8][2], g2[8][2];
-  const int c0 = 2 * cp;
-  // ---- g'(a_r, b_c) from S tile (a,b) ----
+  const int ja0 = a0 + 4 * tr, mb0 = b0 + 4 * tc;       // my rows of block a, my columns of block b
+  float m1[4][4], m2[4][4];
 #pragma unroll
-  for (int i8 = 0; i8 < 8; ++i8) {
-    const int r = rg + 8 * i8, j = a0 + r, m = b0 + c0;
-    float x0 = 0.f, x1 = 0.f;
-    if (j < Q && m < N) {
-      const float2 v = *reinterpret_cast<const float2*>(S + static_cast<long long>(j) * ldS + m);
-      const RowScal rs = sc_a[r];
-      if (m != j + self_offset) x0 = gprime(v.x, lab_b[c0] == rs.lab, rs, sgn_p, sgn_n);
-      if (m + 1 < N && m + 1 != j + self_offset) x1 = gprime(v.y, lab_b[c0 + 1] == rs.lab, rs, sgn_p, sgn_n);
-    }
-    g1[i8][0] = x0; g1[i8][1] = x1;
-    G1[r][c0] = x0; G1[r][c0 + 1] = x1;
+  for (int i = 0; i < 4; ++i) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ja0 + i < Q && mb0 < N) v = *reinterpret_cast<const float4*>(S + static_cast<long long>(ja0 + i) * ldS + mb0);
+    m1[i][0] = v.x; m1[i][1] = v.y; m1[i][2] = v.z; m1[i][3] = v.w;
   }
-  const bool diag = FUSED && (ta == tb);
-  if (FUSED && !diag) {
-    // ---- g'(b_r, a_c) from S tile (b,a) ----
-#pragma unroll
-    for (int i8 = 0; i8 < 8; ++i8) {
-      const int r = rg + 8 * i8, j = b0 + r, m = a0 + c0;
-      float x0 = 0.f, x1 = 0.f;
-      if (j < Q && m < N) {
-        const float2 v = *reinterpret_cast<const float2*>(S + static_cast<long long>(j) * ldS + m);
-        const RowScal rs = sc_b[r];
-        if (m != j + self_offset) x0 = gprime(v.x, sc_a[c0].lab == rs.lab, rs, sgn_p, sgn_n);
-        if (m + 1 < N && m + 1 != j + self_offset) x1 = gprime(v.y, sc_a[c0 + 1].lab == rs.lab, rs, sgn_p, sgn_n);
-      }
-      g2[i8][0] = x0; g2[i8][1] = x1;
-      G2[r][c0] = x0; G2[r][c0 + 1] = x1;
-    }
-  }
-  __syncthreads();
-  const long long psH = static_cast<long long>(Q) * ldH;
   if (FUSED) {
-    // H[a_r, b_c] = g'(a_r,b_c) + g'(b_c,a_r)
 #pragma unroll
-    for (int i8 = 0; i8 < 8; ++i8) {
-      const int r = rg + 8 * i8, j = a0 + r, m = b0 + c0;
-      if (j < Q && m < ldH) {
-        const float t0 = diag ? G1[c0][r] : G2[c0][r], t1 = diag ? G1[c0 + 1][r] : G2[c0 + 1][r];
-        store_pair<PREC>(H, psH, static_cast<long long>(j) * ldH + m, g1[i8][0] + t0, g1[i8][1] + t1);
-      }
+    for (int e = 0; e < 4; ++e) {                        // mirrored micro-tile: rows of block b, columns of block a
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (mb0 + e < Q && ja0 < N) v = *reinterpret_cast<const float4*>(S + static_cast<long long>(mb0 + e) * ldS + ja0);
+      m2[e][0] = v.x; m2[e][1] = v.y; m2[e][2] = v.z; m2[e][3] = v.w;
     }
-    if (!diag) {
-      // H[b_r, a_c] = g'(b_r,a_c) + g'(a_c,b_r)
+  }
+  RowScal ra4[4], rb4[4];
 #pragma unroll
-      for (int i8 = 0; i8 < 8; ++i8) {
-        const int r = rg + 8 * i8, j = b0 + r, m = a0 + c0;
-        if (j < Q && m < ldH)
-          store_pair<PREC>(H, psH, static_cast<long long>(j) * ldH + m, g2[i8][0] + G1[c0][r], g2[i8][1] + G1[c0 + 1][r]);
+  for (int i = 0; i < 4; ++i) { ra4[i] = sc_a[4 * tr + i]; rb4[i] = sc_b[4 * tc + i]; }
+  float g[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = ja0 + i, m = mb0 + e;
+      float x = 0.f;
+      if (j < Q && m < N && m != j + self_offset) {
+        const bool same = ra4[i].lab == rb4[e].lab;
+        x = gprime<AN_NEG>(m1[i][e], same, ra4[i], sgn_p);
+        if (FUSED) x += gprime<AN_NEG>(m2[e][i], same, rb4[e], sgn_p);
       }
+      g[i][e] = x;
+    }
+  const long long psH = static_cast<long long>(Q) * ldH;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (ja0 + i < Q && mb0 < ldH) store_quad<PREC>(H, psH, static_cast<long long>(ja0 + i) * ldH + mb0, g[i]);
+  if (FUSED) {
+    if (ta != tb) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (mb0 + e < Q && ja0 < ldH) {
+          const float gt[4] = {g[0][e], g[1][e], g[2][e], g[3][e]};
+          store_quad<PREC>(H, psH, static_cast<long long>(mb0 + e) * ldH + ja0, gt);
+        }
     }
   } else {
-#pragma unroll
-    for (int i8 = 0; i8 < 8; ++i8) {
-      const int r = rg + 8 * i8, j = a0 + r, m = b0 + c0;
-      if (j < Q && m < ldH) store_pair<PREC>(H, psH, static_cast<long long>(j) * ldH + m, g1[i8][0], g1[i8][1]);
-    }
-    // transposed copy HT[m][j] = g'(j,m), packed pairs along j
     const long long psT = static_cast<long long>(N) * ldHT;
 #pragma unroll
-    for (int i8 = 0; i8 < 8; ++i8) {
-      const int r = rg + 8 * i8, m = b0 + r, j = a0 + c0;
-      if (m < N && j < ldHT)
-        store_pair<PREC>(HT, psT, static_cast<long long>(m) * ldHT + j, (j < Q) ? G1[c0][r] : 0.f, (j + 1 < Q) ? G1[c0 + 1][r] : 0.f);
-    }
+    for (int e = 0; e < 4; ++e)
+      if (mb0 + e < N && ja0 < ldHT) {
+        const float gt[4] = {g[0][e], g[1][e], g[2][e], g[3][e]};   // rows beyond Q are already zero
+        store_quad<PREC>(HT, psT, static_cast<long long>(mb0 + e) * ldHT + ja0, gt);
+      }
   }
 }
 void launch_build_weights(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
                           int self_offset, int world, MiningParams mp, RowArrays ra, int prec, uint16_t* H, long long ldH,
                           uint16_t* HT, long long ldHT, cudaStream_t st) {
   dim3 grid((N + 63) / 64, (Q + 63) / 64);
-#define NPAIR_LAUNCH_BW(P)                                                                                                   \
-  do {                                                                                                                       \
-    if (world == 1) build_weights_kernel<P, true><<<grid, 256, 0, st>>>(S, ldS, Q, N, lab_rows, lab_cols, self_offset, mp, ra, H, ldH, HT, ldHT); \
-    else build_weights_kernel<P, false><<<grid, 256, 0, st>>>(S, ldS, Q, N, lab_rows, lab_cols, self_offset, mp, ra, H, ldH, HT, ldHT);           \
+  const bool neg = an_sign(mp.an_method) < 0.f;
+#define NPAIR_BW_ARGS S, ldS, Q, N, lab_rows, lab_cols, self_offset, mp, ra, H, ldH, HT, ldHT
+#define NPAIR_LAUNCH_BW(P)                                                                                         \
+  do {                                                                                                             \
+    if (world == 1) { if (neg) build_weights_kernel<P, true, true><<<grid, 256, 0, st>>>(NPAIR_BW_ARGS);           \
+                      else build_weights_kernel<P, true, false><<<grid, 256, 0, st>>>(NPAIR_BW_ARGS); }            \
+    else            { if (neg) build_weights_kernel<P, false, true><<<grid, 256, 0, st>>>(NPAIR_BW_ARGS);          \
+                      else build_weights_kernel<P, false, false><<<grid, 256, 0, st>>>(NPAIR_BW_ARGS); }           \
   } while (0)
   if (prec == PREC_BF16) NPAIR_LAUNCH_BW(PREC_BF16);
   else if (prec == PREC_FP16X2) NPAIR_LAUNCH_BW(PREC_FP16X2);
   else NPAIR_LAUNCH_BW(PREC_BF16X3);
 #undef NPAIR_LAUNCH_BW
+#undef NPAIR_BW_ARGS
 }
 
 __global__ void axpy_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n, float a) {
