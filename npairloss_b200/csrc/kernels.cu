@@ -71,6 +71,16 @@ __device__ __forceinline__ bool pos_index(float sn, unsigned long long size, uns
 }
 __device__ __forceinline__ float clamp_thr(float v) { return v >= 0.f ? v : -FLT_MAX; }   // .cu:288,303,319,334
 
+// exp(x) for x <= 0 as one FMUL + MUFU.EX2 (relative error ~ (2 + 1.44|x|) ulp: 3e-7 for the |x| <= 2 of unit-norm
+// embeddings, 1e-5 only beyond |x| ~ 80 where the terms are ~1e-35 anyway).  Cheap enough to evaluate for EVERY pair,
+// which keeps the row pass and the weight builder branch-free (the reference's expf, .cu:131, under a selection branch
+// costs ~20 instructions per divergent hit).  The same function is used forward and backward, so W = e / A stays consistent.
+__device__ __forceinline__ float fast_exp(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+}
+
 // Every selection rule of .cu:79-120 is rewritten as ONE compare  sgn*s <= thr'  with a per-row transformed threshold:
 //   s <  t  <=>   s <= nextbelow(t)         s <= t  <=>   s <= t
 //   s >= t  <=>  -s <= -t                   s >  t  <=>  -s <= nextbelow(-t)          ALL  <=>  s <= +inf
@@ -515,17 +525,26 @@ __device__ __forceinline__ float retrieval_cut(float maxw, float max_all, int la
   return ord2f(hi);
 }
 
-// One warp per anchor row.  Hot loop per element: retrieval-count compare, label compare, ONE selection compare; the
-// selected diff-label similarities (a few percent under margin mining) are queued per lane in shared memory and
-// exponentiated in dense batches, so expf never runs under divergence.  Same-label pairs are rare and handled inline.
-#define LSE_QCAP 12
+// One warp per anchor row, branch-free hot loop: per element one retrieval-count compare, one label compare, one
+// selection compare per side, one 2-instruction exponential and two predicated accumulations.
 template <bool AN_NEG>
-__global__ void __launch_bounds__(256, 3) lse_rows_kernel(const float* __restrict__ S, long long ldS, int Q, int N,
+__device__ __forceinline__ void lse_elem(float sv, float lab, float li, float scut, float max_all, float sgn_p, float thr_p,
+                                         float bound_n, float& A, float& B, int& c) {
+  c += (sv >= scut) ? 1 : 0;                                  // == (exp(sv-max_all) >= exp(maxw-max_all)), SURVEY Q11
+  const float e = fast_exp(sv - max_all);                     // .cu:130-131
+  const bool same = (lab == li);
+  const bool selp = (sgn_p * sv <= thr_p);                    // .cu:79-98 as one compare
+  const bool seln = AN_NEG ? (sv >= bound_n) : (sv <= bound_n);   // .cu:100-119 as one compare
+  A += (same && selp) ? e : 0.f;
+  B += (!same && seln) ? e : 0.f;
+}
+
+template <bool AN_NEG>
+__global__ void __launch_bounds__(256) lse_rows_kernel(const float* __restrict__ S, long long ldS, int Q, int N,
                                                        const float* __restrict__ lab_rows, const float* __restrict__ lab_cols,
                                                        int self_offset, MiningParams mp, RowArrays ra) {
-  __shared__ float queue[8][LSE_QCAP][32];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int i = blockIdx.x * (blockDim.x >> 5) + wib;
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= Q) return;
   const float li = lab_rows[i];
   const int self_col = i + self_offset;
@@ -538,8 +557,7 @@ __global__ void __launch_bounds__(256, 3) lse_rows_kernel(const float* __restric
   const int cs = ra.cnt_same[i];
   const float scut = cs > 0 ? retrieval_cut(ord2f(ra.st_maxw[i]), max_all, lane) : INFINITY;
   const float* row = S + static_cast<long long>(i) * ldS;
-  float A = 0.f, B = 0.f; int c = 0, qn = 0;
-  float (*myq)[32] = queue[wib];
+  float A = 0.f, B = 0.f; int c = 0;
   for (int base = 0; base < N; base += 512) {
     float4 v[4], l[4];
 #pragma unroll
@@ -554,32 +572,18 @@ __global__ void __launch_bounds__(256, 3) lse_rows_kernel(const float* __restric
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int j4 = base + u * 128 + lane * 4;
-      if (j4 < N) {
-        const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-        const float ll[4] = {l[u].x, l[u].y, l[u].z, l[u].w};
-        const bool interior = (j4 + 3 < N) && (self_col < j4 || self_col > j4 + 3);
+      if (j4 >= N) continue;
+      const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+      const float ll[4] = {l[u].x, l[u].y, l[u].z, l[u].w};
+      if ((j4 + 3 < N) && (self_col < j4 || self_col > j4 + 3)) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (!interior && (j4 + q >= N || j4 + q == self_col)) continue;
-          const float sv = vv[q];
-          c += (sv >= scut) ? 1 : 0;                          // == (expf(sv-max_all) >= expf(maxw-max_all)), SURVEY Q11
-          if (ll[q] == li) {                                  // same label: rare
-            if (sgn_p * sv <= thr_p) A += expf(sv - max_all); // .cu:79-98 as one compare; .cu:130-131
-          } else if (AN_NEG ? (sv >= bound_n) : (sv <= bound_n)) {   // .cu:100-119 as one compare
-            myq[qn][lane] = sv; ++qn;
-          }
-        }
-      }
-      if (__any_sync(0xffffffffu, qn > LSE_QCAP - 4)) {       // dense batch of exponentials
-        const int mx = __reduce_max_sync(0xffffffffu, qn);
-        for (int t = 0; t < mx; ++t) if (t < qn) B += expf(myq[t][lane] - max_all);
-        qn = 0;
+        for (int q = 0; q < 4; ++q) lse_elem<AN_NEG>(vv[q], ll[q], li, scut, max_all, sgn_p, thr_p, bound_n, A, B, c);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (j4 + q < N && j4 + q != self_col) lse_elem<AN_NEG>(vv[q], ll[q], li, scut, max_all, sgn_p, thr_p, bound_n, A, B, c);
       }
     }
-  }
-  {
-    const int mx = __reduce_max_sync(0xffffffffu, qn);
-    for (int t = 0; t < mx; ++t) if (t < qn) B += expf(myq[t][lane] - max_all);
   }
   A = warp_sum(A); B = warp_sum(B); c = warp_sum_i(c);
   if (lane == 0) {
@@ -655,8 +659,11 @@ struct RowScal { float maxall, tp, tn, cA, cT, lab; };   // tp: ap_thr-transform
 
 template <bool AN_NEG>
 __device__ __forceinline__ float gprime(float sv, bool same, const RowScal& r, float sgn_p) {
-  if (same) return (sgn_p * sv <= r.tp) ? expf(sv - r.maxall) * r.cA : 0.f;
-  return (AN_NEG ? (sv >= r.tn) : (sv <= r.tn)) ? expf(sv - r.maxall) * r.cT : 0.f;
+  const float e = fast_exp(sv - r.maxall);
+  const bool selp = (sgn_p * sv <= r.tp);
+  const bool seln = AN_NEG ? (sv >= r.tn) : (sv <= r.tn);
+  const bool sel = same ? selp : seln;
+  return sel ? e * (same ? r.cA : r.cT) : 0.f;
 }
 
 // four consecutive weights -> NS pieces, one 8-byte store per piece
@@ -729,19 +736,33 @@ __global__ void __launch_bounds__(256) build_weights_kernel(const float* __restr
 #pragma unroll
   for (int i = 0; i < 4; ++i) { ra4[i] = sc_a[4 * tr + i]; rb4[i] = sc_b[4 * tc + i]; }
   float g[4][4];
+  // block-uniform fast path: tile fully inside the matrix and not touching the self-pair diagonal
+  const bool interior = (a0 + TS <= Q) && (b0 + TS <= N) && (a0 + self_offset + TS <= b0 || b0 + TS <= a0 + self_offset);
+  if (interior) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int j = ja0 + i, m = mb0 + e;
-      float x = 0.f;
-      if (j < Q && m < N && m != j + self_offset) {
+      for (int e = 0; e < 4; ++e) {
         const bool same = ra4[i].lab == rb4[e].lab;
-        x = gprime<AN_NEG>(m1[i][e], same, ra4[i], sgn_p);
+        float x = gprime<AN_NEG>(m1[i][e], same, ra4[i], sgn_p);
         if (FUSED) x += gprime<AN_NEG>(m2[e][i], same, rb4[e], sgn_p);
+        g[i][e] = x;
       }
-      g[i][e] = x;
-    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = ja0 + i, m = mb0 + e;
+        float x = 0.f;
+        if (j < Q && m < N && m != j + self_offset) {
+          const bool same = ra4[i].lab == rb4[e].lab;
+          x = gprime<AN_NEG>(m1[i][e], same, ra4[i], sgn_p);
+          if (FUSED) x += gprime<AN_NEG>(m2[e][i], same, rb4[e], sgn_p);
+        }
+        g[i][e] = x;
+      }
+  }
   const long long psH = static_cast<long long>(Q) * ldH;
 #pragma unroll
   for (int i = 0; i < 4; ++i)
