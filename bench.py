@@ -327,7 +327,7 @@ def main():
            "hbm_peak_GBs": peaks["hbm_gbs"]}
 
     # kernels launched per step by OUR library (counted from the launch sequence in ctx.cu)
-    launches = 2 + 1 + 1 + 1 + 1 + 1 + 1 + 1 + 1           # absmax x2, split, init, sim gemm, thresholds, row pass, finalize, build, grad gemm
+    launches = 2 + 1 + 1 + 1 + 1 + 1 + 1 + 1               # absmax x2, split, init, sim gemm, thresholds, row pass (+finalize), build, grad gemm
     if world > 1:
         launches += 1                                       # transposed gradient GEMM
     gpu_launches = launches * args.steps

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libnpair_b200.so")
+LIB_PATH = os.environ.get("NPAIR_LIB") or os.path.join(_HERE, "lib", "libnpair_b200.so")   # NPAIR_LIB: tuning builds only
 
 GLOBAL, LOCAL = 0, 1
 HARD, EASY, RAND, RELATIVE_HARD, RELATIVE_EASY = 0, 1, 2, 3, 4

@@ -116,12 +116,17 @@ static bool make_tmap_f32_store(CUtensorMap* m, const void* base, int cols, int 
 
 // ------------------------------------------------------------------------------------------------ GEMM launchers
 static inline int nsplit_of_prec(int prec) { return prec == PREC_BF16 ? 1 : (prec == PREC_FP16X2 ? 2 : 3); }
-static inline int bk_of_prec(int prec) { return prec == PREC_BF16X3 ? 32 : 64; }
+// K-block per (operand format, GEMM role); see GemmCfg
+static inline int bk_of(int prec, int epi) {
+  if (prec == PREC_BF16X3) return 32;
+  if (prec == PREC_FP16X2) return epi == EPI_SIM ? 64 : 32;
+  return 64;
+}
 
-template <int NSPLIT, bool BF16, int EPI>
+template <int NSPLIT, bool BF16, int EPI, int BK>
 static cudaError_t launch_split_gemm_t(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& sm, const GemmParams& p, int sms, cudaStream_t st) {
-  using Cfg = GemmCfg<NSPLIT>;
-  auto kern = split_gemm_kernel<NSPLIT, BF16, EPI>;
+  using Cfg = GemmCfg<NSPLIT, BK>;
+  auto kern = split_gemm_kernel<NSPLIT, BF16, EPI, BK>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -135,9 +140,9 @@ static cudaError_t launch_split_gemm_t(const CUtensorMap& a, const CUtensorMap& 
 }
 // `sm`: fp32 tensor map of the similarity matrix for EPI_SIM's TMA stores (ignored by EPI_OUT: pass any valid map)
 static cudaError_t launch_split_gemm(int prec, int epi, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& sm, const GemmParams& p, int sms, cudaStream_t st) {
-  if (prec == PREC_BF16) return epi == EPI_SIM ? launch_split_gemm_t<1, true, EPI_SIM>(a, b, sm, p, sms, st) : launch_split_gemm_t<1, true, EPI_OUT>(a, b, sm, p, sms, st);
-  if (prec == PREC_FP16X2) return epi == EPI_SIM ? launch_split_gemm_t<2, false, EPI_SIM>(a, b, sm, p, sms, st) : launch_split_gemm_t<2, false, EPI_OUT>(a, b, sm, p, sms, st);
-  return epi == EPI_SIM ? launch_split_gemm_t<3, true, EPI_SIM>(a, b, sm, p, sms, st) : launch_split_gemm_t<3, true, EPI_OUT>(a, b, sm, p, sms, st);
+  if (prec == PREC_BF16) return epi == EPI_SIM ? launch_split_gemm_t<1, true, EPI_SIM, 64>(a, b, sm, p, sms, st) : launch_split_gemm_t<1, true, EPI_OUT, 64>(a, b, sm, p, sms, st);
+  if (prec == PREC_FP16X2) return epi == EPI_SIM ? launch_split_gemm_t<2, false, EPI_SIM, 64>(a, b, sm, p, sms, st) : launch_split_gemm_t<2, false, EPI_OUT, 32>(a, b, sm, p, sms, st);
+  return epi == EPI_SIM ? launch_split_gemm_t<3, true, EPI_SIM, 32>(a, b, sm, p, sms, st) : launch_split_gemm_t<3, true, EPI_OUT, 32>(a, b, sm, p, sms, st);
 }
 
 // SIMT cross-check of the same contraction on the same split operands (tests only; NPAIR_GEMM_SIMT_CHECK).
@@ -250,7 +255,7 @@ using namespace npair;
 // ------------------------------------------------------------------------------------------------ context
 struct npair_ctx {
   npair_config cfg;
-  int Q, N, D, world, rank, prec, nsplit, bk, sms, device;
+  int Q, N, D, world, rank, prec, nsplit, bk_sim, bk_grad, sms, device;
   long long Dp, Np, Qp, ldS;
   // device scratch
   float* Xtot_buf = nullptr;     // world > 1: all-gather target
@@ -409,7 +414,7 @@ static int create_impl(const npair_config* cfg, const void* id128, void* ext_com
   c->sms = prop.multiProcessorCount;
   const Sizes sz = sizes_of(cfg);
   c->Q = cfg->Q; c->D = cfg->D; c->world = cfg->world; c->rank = cfg->rank; c->N = static_cast<int>(sz.N);
-  c->prec = cfg->sim_precision; c->nsplit = sz.ns; c->bk = bk_of_prec(c->prec);
+  c->prec = cfg->sim_precision; c->nsplit = sz.ns; c->bk_sim = bk_of(c->prec, EPI_SIM); c->bk_grad = bk_of(c->prec, EPI_OUT);
   c->Dp = sz.Dp; c->Np = sz.Np; c->Qp = sz.Qp; c->ldS = sz.ldS; c->bytes = sz.total;
   const int Q = c->Q, D = c->D, N = c->N, ns = c->nsplit;
   if (c->world > 1) {
@@ -465,18 +470,18 @@ static int create_impl(const npair_config* cfg, const void* id128, void* ext_com
   // ---- TMA tensor maps (K-major boxes of one swizzle span) ----
   if (cfg->gemm_backend == NPAIR_GEMM_TCGEN05) {
     std::string te;
-    const int bk = c->bk;
+    const int bks = c->bk_sim, bkg = c->bk_grad;
     bool ok = true;
     // similarity: A = local rows of Xs, B = all rows of Xs; K = D
-    ok = ok && make_tmap_pieces(&c->tm_simA, c->Xs + static_cast<long long>(c->rank) * Q * c->Dp, D, Q, ns, c->Dp, static_cast<long long>(N) * c->Dp, bk, 128, &te);
-    ok = ok && make_tmap_pieces(&c->tm_simB, c->Xs, D, N, ns, c->Dp, static_cast<long long>(N) * c->Dp, bk, 256, &te);
+    ok = ok && make_tmap_pieces(&c->tm_simA, c->Xs + static_cast<long long>(c->rank) * Q * c->Dp, D, Q, ns, c->Dp, static_cast<long long>(N) * c->Dp, bks, 128, &te);
+    ok = ok && make_tmap_pieces(&c->tm_simB, c->Xs, D, N, ns, c->Dp, static_cast<long long>(N) * c->Dp, bks, 256, &te);
     ok = ok && make_tmap_f32_store(&c->tm_S, c->S, N, Q, c->ldS, &te);
     // gradient 1: A = H [Q x N], B = XsT [D x N]; K = N
-    ok = ok && make_tmap_pieces(&c->tm_b1A, c->H, N, Q, ns, c->Np, static_cast<long long>(Q) * c->Np, bk, 128, &te);
-    ok = ok && make_tmap_pieces(&c->tm_b1B, c->XsT, N, D, ns, c->Np, static_cast<long long>(D) * c->Np, bk, 256, &te);
+    ok = ok && make_tmap_pieces(&c->tm_b1A, c->H, N, Q, ns, c->Np, static_cast<long long>(Q) * c->Np, bkg, 128, &te);
+    ok = ok && make_tmap_pieces(&c->tm_b1B, c->XsT, N, D, ns, c->Np, static_cast<long long>(D) * c->Np, bkg, 256, &te);
     if (c->world > 1) {   // gradient 2: A = HT [N x Q], B = XlT [D x Q]; K = Q
-      ok = ok && make_tmap_pieces(&c->tm_b2A, c->HT, Q, N, ns, c->Qp, static_cast<long long>(N) * c->Qp, bk, 128, &te);
-      ok = ok && make_tmap_pieces(&c->tm_b2B, c->XlT, Q, D, ns, c->Qp, static_cast<long long>(D) * c->Qp, bk, 256, &te);
+      ok = ok && make_tmap_pieces(&c->tm_b2A, c->HT, Q, N, ns, c->Qp, static_cast<long long>(N) * c->Qp, bkg, 128, &te);
+      ok = ok && make_tmap_pieces(&c->tm_b2B, c->XlT, Q, D, ns, c->Qp, static_cast<long long>(D) * c->Qp, bkg, 256, &te);
     }
     if (!ok) { g_create_err = te; npair_destroy(c); return NPAIR_E_CUDA; }
   }
@@ -564,7 +569,7 @@ static int forward_impl(npair_ctx* c, const float* d_feat, const float* d_label,
   }
   // ---- S = X_local . X_total^T (.cu:218) with fused masks + row statistics (.cu:44-66, :225-265) ----
   GemmParams gp; memset(&gp, 0, sizeof(gp));
-  gp.M = Q; gp.Nn = N; gp.num_kblocks = static_cast<int>((D + c->bk - 1) / c->bk);
+  gp.M = Q; gp.Nn = N; gp.num_kblocks = static_cast<int>((D + c->bk_sim - 1) / c->bk_sim);
   gp.tiles_m = (Q + 127) / 128; gp.tiles_n = (N + 255) / 256; gp.splits = 1; gp.kb_per_split = gp.num_kblocks;
   gp.S = c->S; gp.ldS = c->ldS; gp.dev_scale = &c->bs->x_inv_scale;
   gp.lab_rows = d_label; gp.lab_cols = c->lab_total; gp.self_offset = self_off;
@@ -593,8 +598,7 @@ static int forward_impl(npair_ctx* c, const float* d_feat, const float* d_label,
   // ---- selection + counts + exp + masked sums + log + retrieval in one pass (.cu:343-398) ----
   {
     PhaseTimer pt(c, 4, st);
-    launch_lse_rows(c->S, c->ldS, Q, N, d_label, c->lab_total, self_off, mp, c->ra, st);
-    launch_finalize(c->ra, Q, c->cfg.num_tops, c->bs, c->tops_dev, st);
+    launch_lse_rows(c->S, c->ldS, Q, N, d_label, c->lab_total, self_off, mp, c->ra, c->bs, c->cfg.num_tops, c->tops_dev, st);
   }
   CUDA_TRY(c, cudaGetLastError());
   CUDA_TRY(c, cudaStreamSynchronize(st));          // the reference also blocks here (host reads of loss/asum, .cu:384,400)
@@ -648,7 +652,7 @@ static int backward_impl(npair_ctx* c, float loss_weight, float* d_diff, float* 
   const bool tc = c->cfg.gemm_backend == NPAIR_GEMM_TCGEN05;
   if (c->world > 1) {
     // total = (1/2)(1/k)(lw/Q) * G^T . X_local  (N x D)  -> reduce-scatter (== all-reduce + own slice, .cu:462-497)
-    gp.M = N; gp.Nn = D; gp.num_kblocks = static_cast<int>((Q + c->bk - 1) / c->bk);
+    gp.M = N; gp.Nn = D; gp.num_kblocks = static_cast<int>((Q + c->bk_grad - 1) / c->bk_grad);
     gp.tiles_m = (N + 127) / 128; gp.tiles_n = (D + 255) / 256; gp.splits = 1; gp.kb_per_split = gp.num_kblocks;
     gp.out = d_total_ext ? d_total_ext : c->OUT2; gp.ldo = D; gp.alpha = 0.5f * (1.f / static_cast<float>(c->world)) * lw_over_q; gp.beta = 0.f;
     {
@@ -664,7 +668,7 @@ static int backward_impl(npair_ctx* c, float loss_weight, float* d_diff, float* 
     }
   }
   // local = (1/2)(lw/Q) * G . X_total, accumulated onto the scattered transposed term when world > 1
-  gp.M = Q; gp.Nn = D; gp.num_kblocks = static_cast<int>((N + c->bk - 1) / c->bk);
+  gp.M = Q; gp.Nn = D; gp.num_kblocks = static_cast<int>((N + c->bk_grad - 1) / c->bk_grad);
   gp.tiles_m = (Q + 127) / 128; gp.tiles_n = (D + 255) / 256;
   gp.out = d_diff; gp.ldo = D; gp.alpha = 0.5f * lw_over_q; gp.beta = (c->world > 1 && !d_total_ext) ? 1.f : 0.f;
   gp.splits = 1; gp.kb_per_split = gp.num_kblocks; gp.part = c->part;
@@ -788,7 +792,7 @@ int npair_util_f32_to_f64(const float* d_src, double* d_dst, size_t n, void* str
 int npair_debug_gemm(int precision, int backend, int M, int Nn, int K, const float* dA, const float* dB, float* dC, void* stream) {
   if (M < 1 || Nn < 1 || K < 1 || !dA || !dB || !dC || precision < 0 || precision > 2) { g_create_err = "bad argument"; return NPAIR_E_ARG; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int ns = nsplit_of_prec(precision), bk = bk_of_prec(precision);
+  const int ns = nsplit_of_prec(precision), bk = bk_of(precision, EPI_OUT);
   const long long Kp = round_up(K, 64);
   uint16_t *As = nullptr, *Bs = nullptr, *dummyT = nullptr;
   BlockScalars* bs = nullptr; float* partial = nullptr;

@@ -72,17 +72,20 @@ struct GemmParams {
   float alpha, beta;   // out = alpha*acc + beta*out
 };
 
-template <int NSPLIT>
+// BK_ = K-block in elements = one swizzle span per smem row (64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B).  Measured on B200
+// (gpurun_out/tune1.log): the short-K similarity GEMM (K = D) prefers 64, the long-K gradient GEMM (K = N) with two
+// fp16 pieces prefers 32 (four 48 KB stages hide the TMA latency better than two 96 KB ones: 164 -> 141 us).
+template <int NSPLIT, int BK_>
 struct GemmCfg {
   static constexpr int BM = 128, BN = 256;
-  static constexpr int BK = (NSPLIT == 3) ? 32 : 64;          // elements; one swizzle span per row
+  static constexpr int BK = BK_;
   static constexpr int ROW_BYTES = BK * 2;                    // 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
   static constexpr uint32_t LAYOUT = (ROW_BYTES == 128) ? 2u : 4u;
   static constexpr uint32_t SBO = 8 * ROW_BYTES;              // byte distance between 8-row groups
   static constexpr int A_PIECE = BM * ROW_BYTES;
   static constexpr int B_PIECE = BN * ROW_BYTES;
   static constexpr int STAGE_BYTES = NSPLIT * (A_PIECE + B_PIECE);
-  static constexpr int STAGES = (NSPLIT == 1) ? 4 : 2;
+  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;   // fill 192 KB with operand stages
   static constexpr int NPASS = (NSPLIT == 1) ? 1 : (NSPLIT == 2 ? 3 : 6);
   static constexpr int STORE_STAGE_BYTES = 4 * 4096;          // one 32x32 fp32 TMA-store staging tile per epilogue warp
   static constexpr int SMEM_AUX = 2048;                       // barriers + tmem ptr + column labels
@@ -100,11 +103,11 @@ __device__ __forceinline__ void pass_pieces(int nsplit, int p, int& sa, int& sb)
   sa = A[p]; sb = B[p];
 }
 
-template <int NSPLIT, bool BF16, int EPI>
+template <int NSPLIT, bool BF16, int EPI, int BK_>
 __global__ void __launch_bounds__(256, 1)
 split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
                   const __grid_constant__ CUtensorMap tmapS, const GemmParams p) {
-  using Cfg = GemmCfg<NSPLIT>;
+  using Cfg = GemmCfg<NSPLIT, BK_>;
   constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   // keep the pointer in the shared address space (offset arithmetic, no integer round trip): LDS/STS, not generic LD/ST

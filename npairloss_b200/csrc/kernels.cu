@@ -80,6 +80,13 @@ __device__ __forceinline__ float fast_exp(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
   return y;
 }
+#define NPAIR_LOG2E 1.4426950408889634f
+// exp(s - max) with the row constant pre-multiplied: m2 = max * log2(e)  ->  one FFMA + one MUFU.EX2
+__device__ __forceinline__ float fast_exp_m2(float sv, float m2) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(fmaf(sv, NPAIR_LOG2E, -m2)));
+  return y;
+}
 
 // Every selection rule of .cu:79-120 is rewritten as ONE compare  sgn*s <= thr'  with a per-row transformed threshold:
 //   s <  t  <=>   s <= nextbelow(t)         s <= t  <=>   s <= t
@@ -239,7 +246,7 @@ __global__ void init_stats_kernel(RowArrays ra, int Q, BlockScalars* bs) {
     ra.cnt_same[i] = 0;
   }
   if (i == 0) {
-    bs->err = 0; bs->sel_active[0] = 0; bs->sel_active[1] = 0;
+    bs->err = 0; bs->ticket = 0; bs->sel_active[0] = 0; bs->sel_active[1] = 0;
     bs->n_same = 0; bs->n_diff = 0;
   }
 }
@@ -525,125 +532,125 @@ __device__ __forceinline__ float retrieval_cut(float maxw, float max_all, int la
   return ord2f(hi);
 }
 
-// One warp per anchor row, branch-free hot loop: per element one retrieval-count compare, one label compare, one
-// selection compare per side, one 2-instruction exponential and two predicated accumulations.
-template <bool AN_NEG>
-__device__ __forceinline__ void lse_elem(float sv, float lab, float li, float scut, float max_all, float sgn_p, float thr_p,
-                                         float bound_n, float& A, float& B, int& c) {
+// One warp per anchor row, branch-free hot loop (12 instructions per element): one retrieval-count compare, one label
+// compare, ONE selection compare with sign/threshold picked by the label predicate, a 2-instruction exponential, and two
+// accumulations (T = A + B for every selected pair, A under the same-label predicate).
+__device__ __forceinline__ void lse_elem(float sv, float lab, float li, float scut, float m2, float sgn_p, float thr_p,
+                                         float sgn_n, float thr_n, float& A, float& T, int& c) {
   c += (sv >= scut) ? 1 : 0;                                  // == (exp(sv-max_all) >= exp(maxw-max_all)), SURVEY Q11
-  const float e = fast_exp(sv - max_all);                     // .cu:130-131
+  const float e = fast_exp_m2(sv, m2);                        // .cu:130-131
   const bool same = (lab == li);
-  const bool selp = (sgn_p * sv <= thr_p);                    // .cu:79-98 as one compare
-  const bool seln = AN_NEG ? (sv >= bound_n) : (sv <= bound_n);   // .cu:100-119 as one compare
-  A += (same && selp) ? e : 0.f;
-  B += (!same && seln) ? e : 0.f;
+  const float key = sv * (same ? sgn_p : sgn_n);              // .cu:79-120 as one compare  +-s <= thr'
+  const float es = (key <= (same ? thr_p : thr_n)) ? e : 0.f;
+  T += es;
+  if (same) A += es;
 }
 
-template <bool AN_NEG>
+// The last block to finish also performs the job of the old finalize kernel (loss, retrieval ratios, asum, error word).
 __global__ void __launch_bounds__(256) lse_rows_kernel(const float* __restrict__ S, long long ldS, int Q, int N,
                                                        const float* __restrict__ lab_rows, const float* __restrict__ lab_cols,
-                                                       int self_offset, MiningParams mp, RowArrays ra) {
+                                                       int self_offset, MiningParams mp, RowArrays ra, BlockScalars* bs,
+                                                       int num_tops, float* __restrict__ tops) {
   const int lane = threadIdx.x & 31;
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (i >= Q) return;
-  const float li = lab_rows[i];
-  const int self_col = i + self_offset;
-  const float max_all = ord2f(ra.st_maxall[i]);
-  const float tp = ra.posi_thr[i] + mp.margin_ident;          // fp32 add as in .cu:81
-  const float tn = ra.nega_thr[i] + mp.margin_diff;           // .cu:102
-  const float sgn_p = ap_sign(mp.ap_method);
-  const float thr_p = ap_thr(tp, mp.ap_method), thr_n = an_thr(tn, mp.an_method);
-  const float bound_n = AN_NEG ? -thr_n : thr_n;              // -s <= t  <=>  s >= -t
-  const int cs = ra.cnt_same[i];
-  const float scut = cs > 0 ? retrieval_cut(ord2f(ra.st_maxw[i]), max_all, lane) : INFINITY;
-  const float* row = S + static_cast<long long>(i) * ldS;
-  float A = 0.f, B = 0.f; int c = 0;
-  for (int base = 0; base < N; base += 512) {
-    float4 v[4], l[4];
+  if (i < Q) {
+    const float li = lab_rows[i];
+    const int self_col = i + self_offset;
+    const float max_all = ord2f(ra.st_maxall[i]);
+    const float m2 = max_all * NPAIR_LOG2E;
+    const float tp = ra.posi_thr[i] + mp.margin_ident;          // fp32 add as in .cu:81
+    const float tn = ra.nega_thr[i] + mp.margin_diff;           // .cu:102
+    const float sgn_p = ap_sign(mp.ap_method), sgn_n = an_sign(mp.an_method);
+    const float thr_p = ap_thr(tp, mp.ap_method), thr_n = an_thr(tn, mp.an_method);
+    const int cs = ra.cnt_same[i];
+    const float scut = cs > 0 ? retrieval_cut(ord2f(ra.st_maxw[i]), max_all, lane) : INFINITY;
+    const float* row = S + static_cast<long long>(i) * ldS;
+    float A = 0.f, T = 0.f; int c = 0;
+    for (int base = 0; base < N; base += 512) {
+      float4 v[4], l[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int j4 = base + u * 128 + lane * 4;
-      if (j4 < N) {
-        v[u] = *reinterpret_cast<const float4*>(row + j4);
-        l[u] = (j4 + 3 < N) ? *reinterpret_cast<const float4*>(lab_cols + j4)
-                            : make_float4(lab_cols[j4], j4 + 1 < N ? lab_cols[j4 + 1] : 0.f, j4 + 2 < N ? lab_cols[j4 + 2] : 0.f, 0.f);
+      for (int u = 0; u < 4; ++u) {
+        const int j4 = base + u * 128 + lane * 4;
+        if (j4 < N) {
+          v[u] = *reinterpret_cast<const float4*>(row + j4);
+          l[u] = (j4 + 3 < N) ? *reinterpret_cast<const float4*>(lab_cols + j4)
+                              : make_float4(lab_cols[j4], j4 + 1 < N ? lab_cols[j4 + 1] : 0.f, j4 + 2 < N ? lab_cols[j4 + 2] : 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j4 = base + u * 128 + lane * 4;
+        if (j4 >= N) continue;
+        const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+        const float ll[4] = {l[u].x, l[u].y, l[u].z, l[u].w};
+        if ((j4 + 3 < N) && (self_col < j4 || self_col > j4 + 3)) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) lse_elem(vv[q], ll[q], li, scut, m2, sgn_p, thr_p, sgn_n, thr_n, A, T, c);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (j4 + q < N && j4 + q != self_col) lse_elem(vv[q], ll[q], li, scut, m2, sgn_p, thr_p, sgn_n, thr_n, A, T, c);
+        }
       }
     }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int j4 = base + u * 128 + lane * 4;
-      if (j4 >= N) continue;
-      const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-      const float ll[4] = {l[u].x, l[u].y, l[u].z, l[u].w};
-      if ((j4 + 3 < N) && (self_col < j4 || self_col > j4 + 3)) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) lse_elem<AN_NEG>(vv[q], ll[q], li, scut, max_all, sgn_p, thr_p, bound_n, A, B, c);
-      } else {
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if (j4 + q < N && j4 + q != self_col) lse_elem<AN_NEG>(vv[q], ll[q], li, scut, max_all, sgn_p, thr_p, bound_n, A, B, c);
-      }
+    A = warp_sum(A); T = warp_sum(T); c = warp_sum_i(c);
+    if (lane == 0) {
+      ra.A[i] = A; ra.T[i] = T;                                 // T = A + B (.cu:380)
+      ra.logv[i] = (A == 0.f || T == 0.f) ? 0.f : logf(A / T);  // .cu:162-169
+      const int lim = N - 2;
+      ra.hits[i] = (cs > 0 && c <= min(1, lim)) ? 1 : 0;
+      ra.hits[Q + i] = (cs > 0 && c <= min(5, lim)) ? 1 : 0;
+      ra.hits[2 * Q + i] = (cs > 0 && c <= min(10, lim)) ? 1 : 0;
+      const float invA = A == 0.f ? 0.f : 1.f / A;              // Get_Query_Diff_Part zero rules (.cu:410-415)
+      const float invT = T == 0.f ? 0.f : 1.f / T;
+      ra.rs_maxall[i] = m2;                                     // max_all * log2(e): the backward uses the same exponential
+      ra.rs_tp[i] = thr_p; ra.rs_tn[i] = thr_n;                 // transformed thresholds (ap_thr / an_thr)
+      ra.rs_cA[i] = invT - invA;                                // same-label weight:  -1/A + 1/T
+      ra.rs_cT[i] = invT;                                       // diff-label weight:   1/T
     }
   }
-  A = warp_sum(A); B = warp_sum(B); c = warp_sum_i(c);
-  if (lane == 0) {
-    const float T = A + B;                                    // .cu:380
-    ra.A[i] = A; ra.T[i] = T;
-    ra.logv[i] = (A == 0.f || T == 0.f) ? 0.f : logf(A / T);  // .cu:162-169
-    const int lim = N - 2;
-    ra.hits[i] = (cs > 0 && c <= min(1, lim)) ? 1 : 0;
-    ra.hits[Q + i] = (cs > 0 && c <= min(5, lim)) ? 1 : 0;
-    ra.hits[2 * Q + i] = (cs > 0 && c <= min(10, lim)) ? 1 : 0;
-    const float invA = A == 0.f ? 0.f : 1.f / A;              // Get_Query_Diff_Part zero rules (.cu:410-415)
-    const float invT = T == 0.f ? 0.f : 1.f / T;
-    ra.rs_maxall[i] = max_all; ra.rs_tp[i] = thr_p; ra.rs_tn[i] = bound_n;  // transformed thresholds (ap_thr / s-domain bound)
-    ra.rs_cA[i] = invT - invA;                                // same-label weight:  -1/A + 1/T
-    ra.rs_cT[i] = invT;                                       // diff-label weight:   1/T
-  }
-}
-void launch_lse_rows(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
-                     int self_offset, MiningParams mp, RowArrays ra, cudaStream_t st) {
-  int wpb = 8;
-  while (wpb > 1 && (Q + wpb - 1) / wpb < 296) wpb >>= 1;     // keep >= 2 blocks per SM when the rank has few rows
-  const int grid = (Q + wpb - 1) / wpb;
-  if (an_sign(mp.an_method) < 0.f) lse_rows_kernel<true><<<grid, wpb * 32, 0, st>>>(S, ldS, Q, N, lab_rows, lab_cols, self_offset, mp, ra);
-  else lse_rows_kernel<false><<<grid, wpb * 32, 0, st>>>(S, ldS, Q, N, lab_rows, lab_cols, self_offset, mp, ra);
-}
-
-// --------------------------------------------------------------------------------------------
-// finalize: loss = -sum(log)/Q (.cu:384-385), retrieval ratios (.cu:205), feature asum / num (.cu:400-401),
-// top layout of .cu:388-401 (last top is always the asum).
-// --------------------------------------------------------------------------------------------
-__global__ void finalize_kernel(RowArrays ra, int Q, int num_tops, const BlockScalars* __restrict__ bs, float* __restrict__ tops) {
-  __shared__ double s_l[32];
-  __shared__ int s_h[3][32];
+  // ---- grid-level completion: the last block reduces the row results (fixed order -> deterministic) ----
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&bs->ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  __shared__ double s_l[8];
+  __shared__ int s_h[3][8];
   double ls = 0.0; int h[3] = {0, 0, 0};
-  for (int i = threadIdx.x; i < Q; i += blockDim.x) {
-    ls += ra.logv[i];
-    h[0] += ra.hits[i]; h[1] += ra.hits[Q + i]; h[2] += ra.hits[2 * Q + i];
+  for (int r = threadIdx.x; r < Q; r += blockDim.x) {
+    ls += __ldcg(&ra.logv[r]);
+    h[0] += __ldcg(&ra.hits[r]); h[1] += __ldcg(&ra.hits[Q + r]); h[2] += __ldcg(&ra.hits[2 * Q + r]);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     ls += __shfl_xor_sync(0xffffffffu, ls, o);
     h[0] += __shfl_xor_sync(0xffffffffu, h[0], o); h[1] += __shfl_xor_sync(0xffffffffu, h[1], o); h[2] += __shfl_xor_sync(0xffffffffu, h[2], o);
   }
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  if (l == 0) { s_l[w] = ls; s_h[0][w] = h[0]; s_h[1][w] = h[1]; s_h[2][w] = h[2]; }
+  const int w = threadIdx.x >> 5;
+  if (lane == 0) { s_l[w] = ls; s_h[0][w] = h[0]; s_h[1][w] = h[1]; s_h[2][w] = h[2]; }
   __syncthreads();
   if (threadIdx.x == 0) {
     ls = 0.0; h[0] = h[1] = h[2] = 0;
     for (int k = 0; k < (blockDim.x >> 5); ++k) { ls += s_l[k]; h[0] += s_h[0][k]; h[1] += s_h[1][k]; h[2] += s_h[2][k]; }
     float out[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-    out[0] = static_cast<float>(ls) / static_cast<float>(-Q);
-    for (int t = 1; t <= num_tops - 2 && t <= 3; ++t) out[t] = static_cast<float>(h[t - 1]) / static_cast<float>(Q);
-    out[num_tops - 1] = bs->asum / static_cast<float>(Q);
+    out[0] = static_cast<float>(ls) / static_cast<float>(-Q);                       // .cu:384-385
+    for (int t = 1; t <= num_tops - 2 && t <= 3; ++t) out[t] = static_cast<float>(h[t - 1]) / static_cast<float>(Q);   // .cu:205
+    out[num_tops - 1] = bs->asum / static_cast<float>(Q);                           // .cu:400-401 (always the LAST top)
     for (int t = 0; t < 5; ++t) tops[t] = out[t];
     reinterpret_cast<int*>(tops)[5] = bs->err;
+    bs->ticket = 0;
     __threadfence_system();
   }
 }
-void launch_finalize(RowArrays ra, int Q, int num_tops, const BlockScalars* bs, float* tops_dev, cudaStream_t st) {
-  finalize_kernel<<<1, 1024, 0, st>>>(ra, Q, num_tops, bs, tops_dev);
+void launch_lse_rows(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
+                     int self_offset, MiningParams mp, RowArrays ra, BlockScalars* bs, int num_tops, float* tops_dev, cudaStream_t st) {
+  int wpb = 8;
+  while (wpb > 1 && (Q + wpb - 1) / wpb < 296) wpb >>= 1;     // keep >= 2 blocks per SM when the rank has few rows
+  const int grid = (Q + wpb - 1) / wpb;
+  lse_rows_kernel<<<grid, wpb * 32, 0, st>>>(S, ldS, Q, N, lab_rows, lab_cols, self_offset, mp, ra, bs, num_tops, tops_dev);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -655,15 +662,13 @@ void launch_finalize(RowArrays ra, int Q, int num_tops, const BlockScalars* bs, 
 //   world  > 1 :  H[j][m]  = g'(j,m)  and  HT[m][j] = g'(j,m)
 //                 local = H . X_total ,  total = HT . X_local , then reduce-scatter and blend (.cu:462-497)
 // --------------------------------------------------------------------------------------------
-struct RowScal { float maxall, tp, tn, cA, cT, lab; };   // tp: ap_thr-transformed; tn: s-domain bound of the diff rule
+struct RowScal { float maxall, tp, tn, cA, cT, lab; };   // maxall: max_all*log2e; tp/tn: ap_thr / an_thr transformed thresholds
 
-template <bool AN_NEG>
-__device__ __forceinline__ float gprime(float sv, bool same, const RowScal& r, float sgn_p) {
-  const float e = fast_exp(sv - r.maxall);
-  const bool selp = (sgn_p * sv <= r.tp);
-  const bool seln = AN_NEG ? (sv >= r.tn) : (sv <= r.tn);
-  const bool sel = same ? selp : seln;
-  return sel ? e * (same ? r.cA : r.cT) : 0.f;
+// r.maxall holds max_all * log2(e) (see lse_rows_kernel)
+__device__ __forceinline__ float gprime(float sv, bool same, const RowScal& r, float sgn_p, float sgn_n) {
+  const float e = fast_exp_m2(sv, r.maxall);
+  const float key = sv * (same ? sgn_p : sgn_n);
+  return (key <= (same ? r.tp : r.tn)) ? e * (same ? r.cA : r.cT) : 0.f;
 }
 
 // four consecutive weights -> NS pieces, one 8-byte store per piece
@@ -701,15 +706,15 @@ __global__ void __launch_bounds__(256) build_weights_kernel(const float* __restr
   __shared__ RowScal sc_a[TS], sc_b[TS];
   const int a0 = ta * TS, b0 = tb * TS;
   const int t = threadIdx.x, tr = t >> 4, tc = t & 15;
-  const float sgn_p = ap_sign(mp.ap_method);
+  const float sgn_p = ap_sign(mp.ap_method), sgn_n = an_sign(mp.an_method);
   if (t < TS) {
     const int j = a0 + t;
-    RowScal r = {0.f, -INFINITY, AN_NEG ? INFINITY : -INFINITY, 0.f, 0.f, 0.f};
+    RowScal r = {0.f, -INFINITY, -INFINITY, 0.f, 0.f, 0.f};
     if (j < Q) { r.maxall = ra.rs_maxall[j]; r.tp = ra.rs_tp[j]; r.tn = ra.rs_tn[j]; r.cA = ra.rs_cA[j]; r.cT = ra.rs_cT[j]; r.lab = lab_rows[j]; }
     sc_a[t] = r;
   } else if (t < 2 * TS) {
     const int mm = t - TS, m = b0 + mm;
-    RowScal r = {0.f, -INFINITY, AN_NEG ? INFINITY : -INFINITY, 0.f, 0.f, 0.f};
+    RowScal r = {0.f, -INFINITY, -INFINITY, 0.f, 0.f, 0.f};
     if (FUSED) {   // world == 1: column m is also a local row
       if (m < Q) { r.maxall = ra.rs_maxall[m]; r.tp = ra.rs_tp[m]; r.tn = ra.rs_tn[m]; r.cA = ra.rs_cA[m]; r.cT = ra.rs_cT[m]; r.lab = lab_rows[m]; }
     } else if (m < N) r.lab = lab_cols[m];
@@ -744,8 +749,8 @@ __global__ void __launch_bounds__(256) build_weights_kernel(const float* __restr
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const bool same = ra4[i].lab == rb4[e].lab;
-        float x = gprime<AN_NEG>(m1[i][e], same, ra4[i], sgn_p);
-        if (FUSED) x += gprime<AN_NEG>(m2[e][i], same, rb4[e], sgn_p);
+        float x = gprime(m1[i][e], same, ra4[i], sgn_p, sgn_n);
+        if (FUSED) x += gprime(m2[e][i], same, rb4[e], sgn_p, sgn_n);
         g[i][e] = x;
       }
   } else {
@@ -757,8 +762,8 @@ __global__ void __launch_bounds__(256) build_weights_kernel(const float* __restr
         float x = 0.f;
         if (j < Q && m < N && m != j + self_offset) {
           const bool same = ra4[i].lab == rb4[e].lab;
-          x = gprime<AN_NEG>(m1[i][e], same, ra4[i], sgn_p);
-          if (FUSED) x += gprime<AN_NEG>(m2[e][i], same, rb4[e], sgn_p);
+          x = gprime(m1[i][e], same, ra4[i], sgn_p, sgn_n);
+          if (FUSED) x += gprime(m2[e][i], same, rb4[e], sgn_p, sgn_n);
         }
         g[i][e] = x;
       }

@@ -22,6 +22,7 @@ struct BlockScalars {
   float gmax_between;                      // max over all diff-label pairs (diff_global.back(), .cu:296)
   float posi_global, nega_global;          // GLOBAL-region thresholds (valid when the region is GLOBAL)
   int err;                                 // DERR_* bits
+  unsigned int ticket;                     // block-completion counter of the row pass (last block finalises)
   // radix-select state, one per side (0 = AP over same pairs, 1 = AN over diff pairs)
   unsigned long long sel_rank[2];          // remaining 0-based rank inside the current prefix bucket
   uint32_t sel_prefix[2];                  // ordered-uint prefix decided so far
@@ -67,8 +68,8 @@ void launch_global_select(const float* S, long long ldS, int Q, int N, const flo
                           int self_offset, int side, float sn, RowArrays ra, unsigned long long* hist /*[2048]*/,
                           BlockScalars* bs, cudaStream_t st);
 void launch_lse_rows(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
-                     int self_offset, MiningParams mp, RowArrays ra, cudaStream_t st);
-void launch_finalize(RowArrays ra, int Q, int num_tops, const BlockScalars* bs, float* tops_dev /*[5]+err*/, cudaStream_t st);
+                     int self_offset, MiningParams mp, RowArrays ra, BlockScalars* bs, int num_tops, float* tops_dev /*[5]+err*/,
+                     cudaStream_t st);
 void launch_build_weights(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
                           int self_offset, int world, MiningParams mp, RowArrays ra, int prec,
                           uint16_t* H, long long ldH /*Np*/, uint16_t* HT, long long ldHT /*Qp*/, cudaStream_t st);
