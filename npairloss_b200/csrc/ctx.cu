@@ -119,7 +119,7 @@ static inline int nsplit_of_prec(int prec) { return prec == PREC_BF16 ? 1 : (pre
 // K-block per (operand format, GEMM role); see GemmCfg
 static inline int bk_of(int prec, int epi) {
   if (prec == PREC_BF16X3) return 32;
-  if (prec == PREC_FP16X2) return epi == EPI_SIM ? 64 : 32;
+  if (prec == PREC_FP16X2) return epi == EPI_OUT ? 32 : 64;
   return 64;
 }
 
@@ -133,16 +133,26 @@ static cudaError_t launch_split_gemm_t(const CUtensorMap& a, const CUtensorMap& 
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  const int tiles = p.tiles_m * p.tiles_n * p.splits;
+  const int tiles = p.tile_list ? p.num_tiles_list : p.tiles_m * p.tiles_n * p.splits;
   const int grid = tiles < sms ? tiles : sms;
   kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a, b, sm, p);
   return cudaGetLastError();
 }
 // `sm`: fp32 tensor map of the similarity matrix for EPI_SIM's TMA stores (ignored by EPI_OUT: pass any valid map)
 static cudaError_t launch_split_gemm(int prec, int epi, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& sm, const GemmParams& p, int sms, cudaStream_t st) {
-  if (prec == PREC_BF16) return epi == EPI_SIM ? launch_split_gemm_t<1, true, EPI_SIM, 64>(a, b, sm, p, sms, st) : launch_split_gemm_t<1, true, EPI_OUT, 64>(a, b, sm, p, sms, st);
-  if (prec == PREC_FP16X2) return epi == EPI_SIM ? launch_split_gemm_t<2, false, EPI_SIM, 64>(a, b, sm, p, sms, st) : launch_split_gemm_t<2, false, EPI_OUT, 32>(a, b, sm, p, sms, st);
-  return epi == EPI_SIM ? launch_split_gemm_t<3, true, EPI_SIM, 32>(a, b, sm, p, sms, st) : launch_split_gemm_t<3, true, EPI_OUT, 32>(a, b, sm, p, sms, st);
+  if (prec == PREC_BF16) {
+    if (epi == EPI_SIM) return launch_split_gemm_t<1, true, EPI_SIM, 64>(a, b, sm, p, sms, st);
+    if (epi == EPI_SIM_SYM) return launch_split_gemm_t<1, true, EPI_SIM_SYM, 64>(a, b, sm, p, sms, st);
+    return launch_split_gemm_t<1, true, EPI_OUT, 64>(a, b, sm, p, sms, st);
+  }
+  if (prec == PREC_FP16X2) {
+    if (epi == EPI_SIM) return launch_split_gemm_t<2, false, EPI_SIM, 64>(a, b, sm, p, sms, st);
+    if (epi == EPI_SIM_SYM) return launch_split_gemm_t<2, false, EPI_SIM_SYM, 64>(a, b, sm, p, sms, st);
+    return launch_split_gemm_t<2, false, EPI_OUT, 32>(a, b, sm, p, sms, st);
+  }
+  if (epi == EPI_SIM) return launch_split_gemm_t<3, true, EPI_SIM, 32>(a, b, sm, p, sms, st);
+  if (epi == EPI_SIM_SYM) return launch_split_gemm_t<3, true, EPI_SIM_SYM, 32>(a, b, sm, p, sms, st);
+  return launch_split_gemm_t<3, true, EPI_OUT, 32>(a, b, sm, p, sms, st);
 }
 
 // SIMT cross-check of the same contraction on the same split operands (tests only; NPAIR_GEMM_SIMT_CHECK).
@@ -263,6 +273,8 @@ struct npair_ctx {
   float* S = nullptr;
   uint16_t *Xs = nullptr, *XsT = nullptr, *XlT = nullptr, *H = nullptr, *HT = nullptr;
   float* OUT2 = nullptr;         // world > 1: N x D transposed-term product before the reduce-scatter
+  int2* sym_tiles = nullptr;     // world == 1: (m_blk, n_blk) of the similarity tiles touching the upper triangle
+  int n_sym_tiles = 0;
   float* part = nullptr;         // split-K partial products of the gradient GEMM
   long long part_floats = 0;
   void* row_block = nullptr;     // backing store of RowArrays
@@ -376,7 +388,7 @@ void npair_destroy(npair_ctx* c) {
   if (c->device >= 0) cudaSetDevice(c->device);
   if (c->comm && c->own_comm) { NcclApi* api = nccl_api(); if (api->CommDestroy) api->CommDestroy(c->comm); }
   cudaFree(c->Xtot_buf); cudaFree(c->labtot_buf); cudaFree(c->S); cudaFree(c->Xs); cudaFree(c->XsT); cudaFree(c->XlT);
-  cudaFree(c->H); cudaFree(c->HT); cudaFree(c->OUT2); cudaFree(c->part); cudaFree(c->row_block); cudaFree(c->bs); cudaFree(c->partial); cudaFree(c->ghist);
+  cudaFree(c->H); cudaFree(c->HT); cudaFree(c->OUT2); cudaFree(c->part); cudaFree(c->sym_tiles); cudaFree(c->row_block); cudaFree(c->bs); cudaFree(c->partial); cudaFree(c->ghist);
   if (c->tops_pinned) cudaFreeHost(c->tops_pinned);
   if (c->ev_made) for (int i = 0; i < NPAIR_PROF_PHASES; ++i) { cudaEventDestroy(c->ev[i][0]); cudaEventDestroy(c->ev[i][1]); }
   delete c;
@@ -485,6 +497,16 @@ static int create_impl(const npair_config* cfg, const void* id128, void* ext_com
     }
     if (!ok) { g_create_err = te; npair_destroy(c); return NPAIR_E_CUDA; }
   }
+  if (c->world == 1 && cfg->gemm_backend == NPAIR_GEMM_TCGEN05) {
+    // S = X X^T is symmetric: only tiles (m_blk, n_blk) whose 256 columns reach the 128-row block's diagonal or beyond
+    std::vector<int2> tl;
+    const int tm = (Q + 127) / 128, tn = (N + 255) / 256;
+    for (int mb = 0; mb < tm; ++mb)
+      for (int nb = mb / 2; nb < tn; ++nb) tl.push_back(make_int2(mb, nb));
+    c->n_sym_tiles = static_cast<int>(tl.size());
+    CREATE_TRY(cudaMalloc(&c->sym_tiles, sizeof(int2) * tl.size()));
+    CREATE_TRY(cudaMemcpy(c->sym_tiles, tl.data(), sizeof(int2) * tl.size(), cudaMemcpyHostToDevice));
+  }
   // ---- NCCL ----
   if (c->world > 1 && (id128 || ext_comm)) {
     NcclApi* api = nccl_api();
@@ -576,7 +598,8 @@ static int forward_impl(npair_ctx* c, const float* d_feat, const float* d_label,
   gp.st_minw = c->ra.st_minw; gp.st_maxw = c->ra.st_maxw; gp.st_maxb = c->ra.st_maxb; gp.st_maxall = c->ra.st_maxall; gp.cnt_same = c->ra.cnt_same;
   if (c->cfg.gemm_backend == NPAIR_GEMM_TCGEN05) {
     PhaseTimer pt(c, 2, st);
-    CUDA_TRY(c, launch_split_gemm(c->prec, EPI_SIM, c->tm_simA, c->tm_simB, c->tm_S, gp, c->sms, st));
+    if (c->sym_tiles) { gp.tile_list = c->sym_tiles; gp.num_tiles_list = c->n_sym_tiles; }
+    CUDA_TRY(c, launch_split_gemm(c->prec, c->sym_tiles ? EPI_SIM_SYM : EPI_SIM, c->tm_simA, c->tm_simB, c->tm_S, gp, c->sms, st));
   } else {
     CUDA_TRY(c, launch_simt_gemm(c->prec, EPI_SIM, c->Xs + static_cast<long long>(self_off) * c->Dp, c->Dp, static_cast<long long>(N) * c->Dp,
                                  c->Xs, c->Dp, static_cast<long long>(N) * c->Dp, D, gp, st));

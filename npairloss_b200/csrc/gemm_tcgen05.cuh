@@ -27,7 +27,13 @@
 
 namespace npair {
 
-enum { EPI_SIM = 0, EPI_OUT = 1 };
+// EPI_SIM     : similarity tile -> S + fused row statistics (any world size)
+// EPI_OUT     : alpha * acc (+ beta * out) gradient tile
+// EPI_SIM_SYM : world == 1 only.  S = X X^T is symmetric, so only tiles that touch the upper triangle are computed
+//               (tile list from the host, ~52 % of the tiles); every strictly-upper 128-column block is also written
+//               MIRRORED (second TMA store) and contributes COLUMN statistics (warp redux) to the rows it mirrors into.
+//               S comes out bitwise symmetric, which the backward weight builder relies on.
+enum { EPI_SIM = 0, EPI_OUT = 1, EPI_SIM_SYM = 2 };
 
 // order-preserving float <-> uint32 map so atomicMin/atomicMax work on floats of either sign
 __host__ __device__ __forceinline__ uint32_t f2ord(float f) {
@@ -51,6 +57,8 @@ struct GemmParams {
   int M, Nn;           // logical output extent
   int num_kblocks;     // K_pad / BK
   int tiles_m, tiles_n;
+  const int2* tile_list;      // optional explicit (m_blk, n_blk) list (EPI_SIM_SYM); tiles_m*tiles_n entries are then ignored
+  int num_tiles_list;
   int splits, kb_per_split;   // split-K (EPI_OUT only): tile = (m_blk*tiles_n + n_blk)*splits + split, k-blocks [split*kb_per_split, ...)
   float* part;                // splits > 1: partial products [split][M][ldo]; a reduce kernel sums them in fixed order
   // ---- EPI_SIM ----
@@ -122,15 +130,15 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   float* s_lab = reinterpret_cast<float*>(aux + 256);                // [256] column labels of the current tile (EPI_SIM)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = p.tiles_m * p.tiles_n * p.splits;
+  const int num_tiles = p.tile_list ? p.num_tiles_list : p.tiles_m * p.tiles_n * p.splits;
   const float inv_scale = p.dev_scale ? *p.dev_scale : 1.f;
-  const float out_scale = (EPI == EPI_SIM) ? inv_scale * inv_scale : 1.f;
+  const float out_scale = (EPI != EPI_OUT) ? inv_scale * inv_scale : 1.f;
   const float alpha = p.alpha * inv_scale;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmapA);
     ptx::prefetch_tmap(&tmapB);
-    if (EPI == EPI_SIM) ptx::prefetch_tmap(&tmapS);
+    if (EPI != EPI_OUT) ptx::prefetch_tmap(&tmapS);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
@@ -152,7 +160,8 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int mn = tile / p.splits, split = tile - mn * p.splits;
-        const int m_blk = mn / p.tiles_n, n_blk = mn % p.tiles_n;
+        int m_blk = mn / p.tiles_n, n_blk = mn % p.tiles_n;
+        if (p.tile_list) { const int2 tl = p.tile_list[tile]; m_blk = tl.x; n_blk = tl.y; }
         const int kb0 = split * p.kb_per_split, kb1 = min(p.num_kblocks, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -210,13 +219,14 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int mn = tile / p.splits, split = tile - mn * p.splits;
-      const int m_blk = mn / p.tiles_n, n_blk = mn % p.tiles_n;
+      int m_blk = mn / p.tiles_n, n_blk = mn % p.tiles_n;
+      if (p.tile_list) { const int2 tl = p.tile_list[tile]; m_blk = tl.x; n_blk = tl.y; }
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int row = m_blk * BM + ew * 32 + lane;
       const int col_base = n_blk * BN;
       float lab_i = 0.f;
-      if (EPI == EPI_SIM) {
+      if (EPI != EPI_OUT) {
         asm volatile("bar.sync 1, 128;" ::: "memory");   // previous tile's readers are done with s_lab
         for (int c = et; c < BN; c += 128) s_lab[c] = (col_base + c < p.Nn) ? p.lab_cols[col_base + c] : 0.f;
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -231,11 +241,13 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       const int self_col = row + p.self_offset;
 #pragma unroll 1
       for (int ch = 0; ch < BN / 32; ++ch) {
+        const int col0 = col_base + ch * 32;
+        const int cb = col0 >> 7;                          // 128-wide column block (EPI_SIM_SYM bookkeeping)
+        if (EPI == EPI_SIM_SYM && cb < m_blk) continue;    // lower-triangle half of a straddling tile: produced by mirroring
         uint32_t r[32];
         ptx::tmem_ld_32x32b_x32(t_row + ch * 32, r);
         ptx::tmem_ld_wait();
-        const int col0 = col_base + ch * 32;
-        if (EPI == EPI_SIM) {
+        if (EPI != EPI_OUT) {
           float v[32];
 #pragma unroll
           for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(r[c]) * out_scale;
@@ -279,6 +291,41 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
             __syncwarp();
             if (lane == 0) { ptx::tma_store_2d(&tmapS, stg, col0, m_blk * BM + ew * 32); ptx::tma_store_commit(); }
           }
+          if (EPI == EPI_SIM_SYM && cb > m_blk && m_blk * BM + ew * 32 < p.M && col0 < p.Nn) {
+            // ---- mirrored statistics: column c of this chunk is ROW gc = col0 + c of the symmetric matrix and its 32
+            //      entries sit in the 32 lanes -> warp redux on order-preserving keys; lane c keeps column c's result ----
+            const float* lab = s_lab + ch * 32;
+            const bool rvalid = row < p.M;
+            uint32_t k_minw = 0xFFFFFFFFu, k_maxw = 0u, k_maxb = 0u;
+            int k_cnt = 0;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const bool same = rvalid && (lab[c] == lab_i);
+              const bool diff = rvalid && (lab[c] != lab_i);
+              const uint32_t key = f2ord(v[c]);
+              const uint32_t mn_ = __reduce_min_sync(0xffffffffu, same ? key : 0xFFFFFFFFu);
+              const uint32_t mx_ = __reduce_max_sync(0xffffffffu, same ? key : 0u);
+              const uint32_t mb_ = __reduce_max_sync(0xffffffffu, diff ? key : 0u);
+              const int cn_ = __popc(__ballot_sync(0xffffffffu, same));
+              if (lane == c) { k_minw = mn_; k_maxw = mx_; k_maxb = mb_; k_cnt = cn_; }
+            }
+            const int gc = col0 + lane;
+            if (gc < p.Nn) {                                 // keys 0 / ~0 are no-ops against the initialised sentinels
+              if (k_cnt) { atomicMin(&p.st_minw[gc], k_minw); atomicMax(&p.st_maxw[gc], k_maxw); atomicAdd(&p.cnt_same[gc], k_cnt); }
+              atomicMax(&p.st_maxb[gc], k_maxb);
+              atomicMax(&p.st_maxall[gc], k_maxw > k_maxb ? k_maxw : k_maxb);
+            }
+            // ---- mirrored store: staging row c holds S[col0 + c][rows of this warp]; box lands at (x = row block, y = col0) ----
+            uint8_t* stg = store_stage + ew * 4096;
+            if (lane == 0) ptx::tma_store_wait_read<0>();
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+              *reinterpret_cast<float*>(stg + c * 128 + ((((lane >> 2) ^ (c & 7))) << 4) + ((lane & 3) << 2)) = v[c];
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) { ptx::tma_store_2d(&tmapS, stg, m_blk * BM + ew * 32, col0); ptx::tma_store_commit(); }
+          }
         } else {
           if (row < p.M) {
             float* obase = p.splits > 1 ? p.part + static_cast<long long>(split) * p.M * p.ldo : p.out;
@@ -311,7 +358,7 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
-      if (EPI == EPI_SIM && row < p.M) {
+      if (EPI != EPI_OUT && row < p.M) {
         maxall = fmaxf(maxw, maxb);                       // every valid column is either same- or diff-label
         if (cnt) {
           atomicMin(&p.st_minw[row], f2ord(minw));
@@ -323,7 +370,7 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       }
     }
   }
-  if (EPI == EPI_SIM && warp >= 4 && lane == 0) ptx::tma_store_wait<0>();   // bulk stores complete before exit
+  if (EPI != EPI_OUT && warp >= 4 && lane == 0) ptx::tma_store_wait<0>();   // bulk stores complete before exit
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 2) {

@@ -566,31 +566,44 @@ __global__ void __launch_bounds__(256) lse_rows_kernel(const float* __restrict__
     const float scut = cs > 0 ? retrieval_cut(ord2f(ra.st_maxw[i]), max_all, lane) : INFINITY;
     const float* row = S + static_cast<long long>(i) * ldS;
     float A = 0.f, T = 0.f; int c = 0;
-    for (int base = 0; base < N; base += 512) {
-      float4 v[4], l[4];
+    // ---- full 512-column blocks: unguarded 128-bit loads (4 in flight per lane for S, 4 for the labels) ----
+    const int n_full = N & ~511;
+    const float4* srow4 = reinterpret_cast<const float4*>(row) + lane;
+    const float4* lab4 = reinterpret_cast<const float4*>(lab_cols) + lane;
+    const bool lab_aligned = (reinterpret_cast<uintptr_t>(lab_cols) & 15) == 0;
+    int base = 0;
+    if (lab_aligned) {
+      for (; base < n_full; base += 512, srow4 += 128, lab4 += 128) {
+        float4 v[4], l[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int j4 = base + u * 128 + lane * 4;
-        if (j4 < N) {
-          v[u] = *reinterpret_cast<const float4*>(row + j4);
-          l[u] = (j4 + 3 < N) ? *reinterpret_cast<const float4*>(lab_cols + j4)
-                              : make_float4(lab_cols[j4], j4 + 1 < N ? lab_cols[j4 + 1] : 0.f, j4 + 2 < N ? lab_cols[j4 + 2] : 0.f, 0.f);
+        for (int u = 0; u < 4; ++u) { v[u] = __ldg(srow4 + 32 * u); l[u] = __ldg(lab4 + 32 * u); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j4 = base + u * 128 + lane * 4;
+          const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+          const float ll[4] = {l[u].x, l[u].y, l[u].z, l[u].w};
+          if (self_col < j4 || self_col > j4 + 3) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) lse_elem(vv[q], ll[q], li, scut, m2, sgn_p, thr_p, sgn_n, thr_n, A, T, c);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (j4 + q != self_col) lse_elem(vv[q], ll[q], li, scut, m2, sgn_p, thr_p, sgn_n, thr_n, A, T, c);
+          }
         }
       }
-#pragma unroll
+    }
+    // ---- ragged tail (and the whole row when the label pointer is not 16-byte aligned) ----
+    for (; base < N; base += 512) {
+#pragma unroll 1
       for (int u = 0; u < 4; ++u) {
         const int j4 = base + u * 128 + lane * 4;
         if (j4 >= N) continue;
-        const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-        const float ll[4] = {l[u].x, l[u].y, l[u].z, l[u].w};
-        if ((j4 + 3 < N) && (self_col < j4 || self_col > j4 + 3)) {
+        const float4 v4 = *reinterpret_cast<const float4*>(row + j4);      // row stride ldS is a multiple of 32: in bounds
+        const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
-          for (int q = 0; q < 4; ++q) lse_elem(vv[q], ll[q], li, scut, m2, sgn_p, thr_p, sgn_n, thr_n, A, T, c);
-        } else {
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (j4 + q < N && j4 + q != self_col) lse_elem(vv[q], ll[q], li, scut, m2, sgn_p, thr_p, sgn_n, thr_n, A, T, c);
-        }
+        for (int q = 0; q < 4; ++q)
+          if (j4 + q < N && j4 + q != self_col) lse_elem(vv[q], lab_cols[j4 + q], li, scut, m2, sgn_p, thr_p, sgn_n, thr_n, A, T, c);
       }
     }
     A = warp_sum(A); T = warp_sum(T); c = warp_sum_i(c);
@@ -689,20 +702,20 @@ __device__ __forceinline__ void store_quad(uint16_t* __restrict__ base, long lon
         make_uint2(static_cast<uint32_t>(p[0][s]) | (static_cast<uint32_t>(p[1][s]) << 16), static_cast<uint32_t>(p[2][s]) | (static_cast<uint32_t>(p[3][s]) << 16));
 }
 
-// 64 x 64 tiles, 256 threads; thread (tr = t/16, tc = t%16) owns the 4 x 4 micro-tile rows 4tr.., columns 4tc.. .
-// FUSED (world == 1): H = G + G^T is symmetric.  A block handles the tile PAIR (a,b), a <= b; each thread loads its
-//   micro-tile of S tile (a,b) AND the mirrored micro-tile of S tile (b,a) (both sector-exact 16-byte row segments),
-//   evaluates g' for each unordered pair once, and stores the 4 x 4 result to H tile (a,b) and, transposed in
-//   registers, to H tile (b,a): no shared-memory transposition, no block barrier after the scalar preload.
-// !FUSED (world > 1): a block handles tile (a = local row block, b = global column block): H rows and HT rows.
-template <int PREC, bool FUSED, bool AN_NEG>
+// 64 x 64 tiles, 256 threads; thread (tr = t/16, tc = t%16) owns the 4 x 4 micro-tile rows 4tr.., columns 4tc.. :
+// one 16-byte load per row of the micro-tile, one 8-byte store per row and operand piece -- every request covers whole
+// sectors, nothing is transposed.
+// SYM (world == 1): the similarity GEMM wrote a bitwise symmetric S (EPI_SIM_SYM), so
+//     H[j][m] = g'(S[j][m]; row j) + g'(S[j][m]; row m)                       (= G + G^T, .cu:448-497 folded)
+//   needs only the row scalars of BOTH indices, which are local when world == 1.
+// !SYM (world > 1): H[j][m] = g'(j,m) and the transposed copy HT[m][j] (micro-tile transposed in registers).
+template <int PREC, bool SYM>
 __global__ void __launch_bounds__(256) build_weights_kernel(const float* __restrict__ S, long long ldS, int Q, int N,
                                                             const float* __restrict__ lab_rows, const float* __restrict__ lab_cols,
                                                             int self_offset, MiningParams mp, RowArrays ra,
                                                             uint16_t* __restrict__ H, long long ldH, uint16_t* __restrict__ HT, long long ldHT) {
   constexpr int TS = 64;
   const int ta = blockIdx.y, tb = blockIdx.x;
-  if (FUSED && ta > tb) return;
   __shared__ RowScal sc_a[TS], sc_b[TS];
   const int a0 = ta * TS, b0 = tb * TS;
   const int t = threadIdx.x, tr = t >> 4, tc = t & 15;
@@ -715,27 +728,19 @@ __global__ void __launch_bounds__(256) build_weights_kernel(const float* __restr
   } else if (t < 2 * TS) {
     const int mm = t - TS, m = b0 + mm;
     RowScal r = {0.f, -INFINITY, -INFINITY, 0.f, 0.f, 0.f};
-    if (FUSED) {   // world == 1: column m is also a local row
+    if (SYM) {   // world == 1: column m is also a local row
       if (m < Q) { r.maxall = ra.rs_maxall[m]; r.tp = ra.rs_tp[m]; r.tn = ra.rs_tn[m]; r.cA = ra.rs_cA[m]; r.cT = ra.rs_cT[m]; r.lab = lab_rows[m]; }
     } else if (m < N) r.lab = lab_cols[m];
     sc_b[mm] = r;
   }
   __syncthreads();
   const int ja0 = a0 + 4 * tr, mb0 = b0 + 4 * tc;       // my rows of block a, my columns of block b
-  float m1[4][4], m2[4][4];
+  float m1[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ja0 + i < Q && mb0 < N) v = *reinterpret_cast<const float4*>(S + static_cast<long long>(ja0 + i) * ldS + mb0);
     m1[i][0] = v.x; m1[i][1] = v.y; m1[i][2] = v.z; m1[i][3] = v.w;
-  }
-  if (FUSED) {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {                        // mirrored micro-tile: rows of block b, columns of block a
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (mb0 + e < Q && ja0 < N) v = *reinterpret_cast<const float4*>(S + static_cast<long long>(mb0 + e) * ldS + ja0);
-      m2[e][0] = v.x; m2[e][1] = v.y; m2[e][2] = v.z; m2[e][3] = v.w;
-    }
   }
   RowScal ra4[4], rb4[4];
 #pragma unroll
@@ -750,7 +755,7 @@ __global__ void __launch_bounds__(256) build_weights_kernel(const float* __restr
       for (int e = 0; e < 4; ++e) {
         const bool same = ra4[i].lab == rb4[e].lab;
         float x = gprime(m1[i][e], same, ra4[i], sgn_p, sgn_n);
-        if (FUSED) x += gprime(m2[e][i], same, rb4[e], sgn_p, sgn_n);
+        if (SYM) x += gprime(m1[i][e], same, rb4[e], sgn_p, sgn_n);
         g[i][e] = x;
       }
   } else {
@@ -763,7 +768,7 @@ __global__ void __launch_bounds__(256) build_weights_kernel(const float* __restr
         if (j < Q && m < N && m != j + self_offset) {
           const bool same = ra4[i].lab == rb4[e].lab;
           x = gprime(m1[i][e], same, ra4[i], sgn_p, sgn_n);
-          if (FUSED) x += gprime(m2[e][i], same, rb4[e], sgn_p, sgn_n);
+          if (SYM) x += gprime(m1[i][e], same, rb4[e], sgn_p, sgn_n);
         }
         g[i][e] = x;
       }
@@ -772,16 +777,7 @@ __global__ void __launch_bounds__(256) build_weights_kernel(const float* __restr
 #pragma unroll
   for (int i = 0; i < 4; ++i)
     if (ja0 + i < Q && mb0 < ldH) store_quad<PREC>(H, psH, static_cast<long long>(ja0 + i) * ldH + mb0, g[i]);
-  if (FUSED) {
-    if (ta != tb) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e)
-        if (mb0 + e < Q && ja0 < ldH) {
-          const float gt[4] = {g[0][e], g[1][e], g[2][e], g[3][e]};
-          store_quad<PREC>(H, psH, static_cast<long long>(mb0 + e) * ldH + ja0, gt);
-        }
-    }
-  } else {
+  if (!SYM) {
     const long long psT = static_cast<long long>(N) * ldHT;
 #pragma unroll
     for (int e = 0; e < 4; ++e)
@@ -795,14 +791,11 @@ void launch_build_weights(const float* S, long long ldS, int Q, int N, const flo
                           int self_offset, int world, MiningParams mp, RowArrays ra, int prec, uint16_t* H, long long ldH,
                           uint16_t* HT, long long ldHT, cudaStream_t st) {
   dim3 grid((N + 63) / 64, (Q + 63) / 64);
-  const bool neg = an_sign(mp.an_method) < 0.f;
 #define NPAIR_BW_ARGS S, ldS, Q, N, lab_rows, lab_cols, self_offset, mp, ra, H, ldH, HT, ldHT
-#define NPAIR_LAUNCH_BW(P)                                                                                         \
-  do {                                                                                                             \
-    if (world == 1) { if (neg) build_weights_kernel<P, true, true><<<grid, 256, 0, st>>>(NPAIR_BW_ARGS);           \
-                      else build_weights_kernel<P, true, false><<<grid, 256, 0, st>>>(NPAIR_BW_ARGS); }            \
-    else            { if (neg) build_weights_kernel<P, false, true><<<grid, 256, 0, st>>>(NPAIR_BW_ARGS);          \
-                      else build_weights_kernel<P, false, false><<<grid, 256, 0, st>>>(NPAIR_BW_ARGS); }           \
+#define NPAIR_LAUNCH_BW(P)                                                                            \
+  do {                                                                                                \
+    if (world == 1) build_weights_kernel<P, true><<<grid, 256, 0, st>>>(NPAIR_BW_ARGS);               \
+    else build_weights_kernel<P, false><<<grid, 256, 0, st>>>(NPAIR_BW_ARGS);                         \
   } while (0)
   if (prec == PREC_BF16) NPAIR_LAUNCH_BW(PREC_BF16);
   else if (prec == PREC_FP16X2) NPAIR_LAUNCH_BW(PREC_FP16X2);
