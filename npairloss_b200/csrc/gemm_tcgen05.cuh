@@ -95,7 +95,7 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = NSPLIT * (A_PIECE + B_PIECE);
   static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;   // fill 192 KB with operand stages
   static constexpr int NPASS = (NSPLIT == 1) ? 1 : (NSPLIT == 2 ? 3 : 6);
-  static constexpr int STORE_STAGE_BYTES = 4 * 4096;          // one 32x32 fp32 TMA-store staging tile per epilogue warp
+  static constexpr int STORE_STAGE_BYTES = 4 * 2 * 4096;      // two 32x32 fp32 TMA-store staging tiles per epilogue warp
   static constexpr int SMEM_AUX = 2048;                       // barriers + tmem ptr + column labels
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STORE_STAGE_BYTES + SMEM_AUX + 1024 /*alignment slack*/;
   static constexpr int THREADS = 256;
@@ -109,6 +109,35 @@ __device__ __forceinline__ void pass_pieces(int nsplit, int p, int& sa, int& sb)
   const int A[6] = {0, 0, 1, 1, 0, 2};
   const int B[6] = {0, 1, 0, 1, 2, 0};
   sa = A[p]; sb = B[p];
+}
+
+// Per-thread statistics of 32 consecutive similarities against 32 labels staged in shared memory.
+// fast: no bounds / self-pair checks, branch-free (predicated).  Otherwise entry c is valid iff idx0 + c < limit and
+// idx0 + c != self_idx.
+__device__ __forceinline__ void stats32(const float (&v)[32], const float* __restrict__ lab, float lab_i, bool fast, int idx0,
+                                        int limit, int self_idx, float& minw, float& maxw, float& maxb, int& cnt) {
+  if (fast) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 l4 = *reinterpret_cast<const float4*>(lab + 4 * q);
+      const float ll[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float x = v[4 * q + e];
+        if (ll[e] == lab_i) { minw = fminf(minw, x); maxw = fmaxf(maxw, x); ++cnt; }
+        else maxb = fmaxf(maxb, x);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      const int idx = idx0 + c;
+      const bool valid = (idx < limit) && (idx != self_idx);
+      const bool same = (lab[c] == lab_i);
+      if (valid && same) { minw = fminf(minw, v[c]); maxw = fmaxf(maxw, v[c]); ++cnt; }
+      if (valid && !same) maxb = fmaxf(maxb, v[c]);
+    }
+  }
 }
 
 template <int NSPLIT, bool BF16, int EPI, int BK_>
@@ -127,7 +156,8 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   uint64_t* tfull_bar = empty_bar + STAGES;                          // [2]
   uint64_t* tempty_bar = tfull_bar + 2;                              // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* s_lab = reinterpret_cast<float*>(aux + 256);                // [256] column labels of the current tile (EPI_SIM)
+  float* s_lab = reinterpret_cast<float*>(aux + 256);                // [256] column labels of the current tile (EPI_SIM*)
+  float* s_labr = reinterpret_cast<float*>(aux + 256 + 1024);        // [128] row labels of the current tile (EPI_SIM_SYM)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = p.tile_list ? p.num_tiles_list : p.tiles_m * p.tiles_n * p.splits;
@@ -216,6 +246,7 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     // ===================================== epilogue =====================================
     const int ew = warp - 4;                     // TMEM lane group = warp % 4
     const int et = threadIdx.x - 128;            // 0..127
+    bool last_was_mirror = false;                // which staging buffer received the most recent TMA store (warp-uniform)
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int mn = tile / p.splits, split = tile - mn * p.splits;
@@ -229,8 +260,9 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       if (EPI != EPI_OUT) {
         asm volatile("bar.sync 1, 128;" ::: "memory");   // previous tile's readers are done with s_lab
         for (int c = et; c < BN; c += 128) s_lab[c] = (col_base + c < p.Nn) ? p.lab_cols[col_base + c] : 0.f;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
         if (row < p.M) lab_i = p.lab_rows[row];
+        if (EPI == EPI_SIM_SYM) s_labr[et] = lab_i;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tc_fence_after();
@@ -251,37 +283,17 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
           float v[32];
 #pragma unroll
           for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(r[c]) * out_scale;
-          if (row < p.M && col0 < p.Nn) {
-            const float* lab = s_lab + ch * 32;
-            if (col0 + 32 <= p.Nn && (self_col < col0 || self_col >= col0 + 32)) {
-              // interior chunk: no bounds / self-pair checks, branch-free (predicated) statistics
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float4 l4 = *reinterpret_cast<const float4*>(lab + 4 * q);
-                const float ll[4] = {l4.x, l4.y, l4.z, l4.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float x = v[4 * q + e];
-                  if (ll[e] == lab_i) { minw = fminf(minw, x); maxw = fmaxf(maxw, x); ++cnt; }
-                  else maxb = fmaxf(maxb, x);
-                }
-              }
-            } else {
-#pragma unroll
-              for (int c = 0; c < 32; ++c) {
-                const int col = col0 + c;
-                const bool valid = (col < p.Nn) && (col != self_col);
-                const bool same = (lab[c] == lab_i);
-                if (valid && same) { minw = fminf(minw, v[c]); maxw = fmaxf(maxw, v[c]); ++cnt; }
-                if (valid && !same) maxb = fmaxf(maxb, v[c]);
-              }
-            }
-          }
+          if (row < p.M && col0 < p.Nn)
+            stats32(v, s_lab + ch * 32, lab_i, col0 + 32 <= p.Nn && (self_col < col0 || self_col >= col0 + 32), col0, p.Nn, self_col,
+                    minw, maxw, maxb, cnt);
           // registers -> 128B-swizzled staging tile -> one TMA store of a 32x32 fp32 box (full 128-byte lines;
           // rows >= M and columns >= Nn are clipped by the tensor map)
           if (m_blk * BM + ew * 32 < p.M && col0 < p.Nn) {          // warp-uniform
-            uint8_t* stg = store_stage + ew * 4096;
-            if (lane == 0) ptx::tma_store_wait_read<0>();             // previous box has been read out of smem
+            uint8_t* stg = store_stage + ew * 8192;
+            if (lane == 0) {                                          // this buffer's previous box has been read out of smem
+              if (last_was_mirror) ptx::tma_store_wait_read<1>(); else ptx::tma_store_wait_read<0>();
+            }
+            last_was_mirror = false;
             __syncwarp();
             uint8_t* srow = stg + lane * 128;
 #pragma unroll
@@ -292,32 +304,10 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
             if (lane == 0) { ptx::tma_store_2d(&tmapS, stg, col0, m_blk * BM + ew * 32); ptx::tma_store_commit(); }
           }
           if (EPI == EPI_SIM_SYM && cb > m_blk && m_blk * BM + ew * 32 < p.M && col0 < p.Nn) {
-            // ---- mirrored statistics: column c of this chunk is ROW gc = col0 + c of the symmetric matrix and its 32
-            //      entries sit in the 32 lanes -> warp redux on order-preserving keys; lane c keeps column c's result ----
-            const float* lab = s_lab + ch * 32;
-            const bool rvalid = row < p.M;
-            uint32_t k_minw = 0xFFFFFFFFu, k_maxw = 0u, k_maxb = 0u;
-            int k_cnt = 0;
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              const bool same = rvalid && (lab[c] == lab_i);
-              const bool diff = rvalid && (lab[c] != lab_i);
-              const uint32_t key = f2ord(v[c]);
-              const uint32_t mn_ = __reduce_min_sync(0xffffffffu, same ? key : 0xFFFFFFFFu);
-              const uint32_t mx_ = __reduce_max_sync(0xffffffffu, same ? key : 0u);
-              const uint32_t mb_ = __reduce_max_sync(0xffffffffu, diff ? key : 0u);
-              const int cn_ = __popc(__ballot_sync(0xffffffffu, same));
-              if (lane == c) { k_minw = mn_; k_maxw = mx_; k_maxb = mb_; k_cnt = cn_; }
-            }
-            const int gc = col0 + lane;
-            if (gc < p.Nn) {                                 // keys 0 / ~0 are no-ops against the initialised sentinels
-              if (k_cnt) { atomicMin(&p.st_minw[gc], k_minw); atomicMax(&p.st_maxw[gc], k_maxw); atomicAdd(&p.cnt_same[gc], k_cnt); }
-              atomicMax(&p.st_maxb[gc], k_maxb);
-              atomicMax(&p.st_maxall[gc], k_maxw > k_maxb ? k_maxw : k_maxb);
-            }
             // ---- mirrored store: staging row c holds S[col0 + c][rows of this warp]; box lands at (x = row block, y = col0) ----
-            uint8_t* stg = store_stage + ew * 4096;
-            if (lane == 0) ptx::tma_store_wait_read<0>();
+            uint8_t* stg = store_stage + ew * 8192 + 4096;
+            if (lane == 0) ptx::tma_store_wait_read<1>();             // pending: this chunk's direct box (may still be read) + older
+            last_was_mirror = true;
             __syncwarp();
 #pragma unroll
             for (int c = 0; c < 32; ++c)
@@ -325,6 +315,28 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
             ptx::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) { ptx::tma_store_2d(&tmapS, stg, m_blk * BM + ew * 32, col0); ptx::tma_store_commit(); }
+            // ---- mirrored statistics: the staging tile is the transposed chunk, so lane L reads back ROW gc = col0 + L of the
+            //      symmetric matrix (32 entries against this warp's 32 row labels) and reuses the per-thread statistics ----
+            const int gc = col0 + lane;
+            float vt[32];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 t4 = *reinterpret_cast<const float4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4));
+              vt[4 * q] = t4.x; vt[4 * q + 1] = t4.y; vt[4 * q + 2] = t4.z; vt[4 * q + 3] = t4.w;
+            }
+            float t_minw = FLT_MAX, t_maxw = -FLT_MAX, t_maxb = -FLT_MAX;
+            int t_cnt = 0;
+            const int r0 = m_blk * BM + ew * 32;
+            if (gc < p.Nn) {
+              stats32(vt, s_labr + ew * 32, s_lab[ch * 32 + lane], r0 + 32 <= p.M, r0, p.M, -1, t_minw, t_maxw, t_maxb, t_cnt);
+              if (t_cnt) {
+                atomicMin(&p.st_minw[gc], f2ord(t_minw));
+                atomicMax(&p.st_maxw[gc], f2ord(t_maxw));
+                atomicAdd(&p.cnt_same[gc], t_cnt);
+              }
+              atomicMax(&p.st_maxb[gc], f2ord(t_maxb));
+              atomicMax(&p.st_maxall[gc], f2ord(fmaxf(t_maxw, t_maxb)));
+            }
           }
         } else {
           if (row < p.M) {
