@@ -95,10 +95,10 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = NSPLIT * (A_PIECE + B_PIECE);
   static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;   // fill 192 KB with operand stages
   static constexpr int NPASS = (NSPLIT == 1) ? 1 : (NSPLIT == 2 ? 3 : 6);
-  static constexpr int STORE_STAGE_BYTES = 4 * 2 * 4096;      // two 32x32 fp32 TMA-store staging tiles per epilogue warp
+  static constexpr int STORE_STAGE_BYTES = 8 * 4096;          // one 32x32 fp32 TMA-store staging tile per epilogue warp
   static constexpr int SMEM_AUX = 2048;                       // barriers + tmem ptr + column labels
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STORE_STAGE_BYTES + SMEM_AUX + 1024 /*alignment slack*/;
-  static constexpr int THREADS = 256;
+  static constexpr int THREADS = 384;                         // 4 control warps + 8 epilogue warps
 };
 
 __device__ __forceinline__ void pass_pieces(int nsplit, int p, int& sa, int& sb) {
@@ -141,7 +141,7 @@ __device__ __forceinline__ void stats32(const float (&v)[32], const float* __res
 }
 
 template <int NSPLIT, bool BF16, int EPI, int BK_>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
                   const __grid_constant__ CUtensorMap tmapS, const GemmParams p) {
   using Cfg = GemmCfg<NSPLIT, BK_>;
@@ -172,7 +172,7 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 4); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 8); }
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
@@ -244,9 +244,11 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     }
   } else if (warp >= 4) {
     // ===================================== epilogue =====================================
-    const int ew = warp - 4;                     // TMEM lane group = warp % 4
-    const int et = threadIdx.x - 128;            // 0..127
-    bool last_was_mirror = false;                // which staging buffer received the most recent TMA store (warp-uniform)
+    // 8 epilogue warps: warp w reads TMEM lanes 32*(w%4) (hardware rule) and the column half (w-4)/4 of the 256-wide tile
+    const int ew = (warp - 4) & 3;
+    const int half = (warp - 4) >> 2;
+    const int et = threadIdx.x - 128;            // 0..255
+    uint8_t* const stg = store_stage + (warp - 4) * 4096;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int mn = tile / p.splits, split = tile - mn * p.splits;
@@ -258,11 +260,11 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       const int col_base = n_blk * BN;
       float lab_i = 0.f;
       if (EPI != EPI_OUT) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // previous tile's readers are done with s_lab
-        for (int c = et; c < BN; c += 128) s_lab[c] = (col_base + c < p.Nn) ? p.lab_cols[col_base + c] : 0.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // previous tile's readers are done with s_lab
+        s_lab[et] = (col_base + et < p.Nn) ? p.lab_cols[col_base + et] : 0.f;
         if (row < p.M) lab_i = p.lab_rows[row];
-        if (EPI == EPI_SIM_SYM) s_labr[et] = lab_i;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (EPI == EPI_SIM_SYM && half == 0) s_labr[ew * 32 + lane] = lab_i;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tc_fence_after();
@@ -272,7 +274,7 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       int cnt = 0;
       const int self_col = row + p.self_offset;
 #pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
+      for (int ch = half * 4; ch < half * 4 + 4; ++ch) {
         const int col0 = col_base + ch * 32;
         const int cb = col0 >> 7;                          // 128-wide column block (EPI_SIM_SYM bookkeeping)
         if (EPI == EPI_SIM_SYM && cb < m_blk) continue;    // lower-triangle half of a straddling tile: produced by mirroring
@@ -289,11 +291,7 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
           // registers -> 128B-swizzled staging tile -> one TMA store of a 32x32 fp32 box (full 128-byte lines;
           // rows >= M and columns >= Nn are clipped by the tensor map)
           if (m_blk * BM + ew * 32 < p.M && col0 < p.Nn) {          // warp-uniform
-            uint8_t* stg = store_stage + ew * 8192;
-            if (lane == 0) {                                          // this buffer's previous box has been read out of smem
-              if (last_was_mirror) ptx::tma_store_wait_read<1>(); else ptx::tma_store_wait_read<0>();
-            }
-            last_was_mirror = false;
+            if (lane == 0) ptx::tma_store_wait_read<0>();             // this warp's previous box has been read out of smem
             __syncwarp();
             uint8_t* srow = stg + lane * 128;
 #pragma unroll
@@ -305,9 +303,7 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
           }
           if (EPI == EPI_SIM_SYM && cb > m_blk && m_blk * BM + ew * 32 < p.M && col0 < p.Nn) {
             // ---- mirrored store: staging row c holds S[col0 + c][rows of this warp]; box lands at (x = row block, y = col0) ----
-            uint8_t* stg = store_stage + ew * 8192 + 4096;
-            if (lane == 0) ptx::tma_store_wait_read<1>();             // pending: this chunk's direct box (may still be read) + older
-            last_was_mirror = true;
+            if (lane == 0) ptx::tma_store_wait_read<0>();
             __syncwarp();
 #pragma unroll
             for (int c = 0; c < 32; ++c)
