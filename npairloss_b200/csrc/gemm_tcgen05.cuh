@@ -285,9 +285,6 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
           float v[32];
 #pragma unroll
           for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(r[c]) * out_scale;
-          if (row < p.M && col0 < p.Nn)
-            stats32(v, s_lab + ch * 32, lab_i, col0 + 32 <= p.Nn && (self_col < col0 || self_col >= col0 + 32), col0, p.Nn, self_col,
-                    minw, maxw, maxb, cnt);
           // registers -> 128B-swizzled staging tile -> one TMA store of a 32x32 fp32 box (full 128-byte lines;
           // rows >= M and columns >= Nn are clipped by the tensor map)
           if (m_blk * BM + ew * 32 < p.M && col0 < p.Nn) {          // warp-uniform
@@ -299,8 +296,14 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
               *reinterpret_cast<float4*>(srow + ((q ^ (lane & 7)) << 4)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
             ptx::fence_proxy_async_smem();
             __syncwarp();
+#ifndef NPAIR_DBG_SKIP_DSTORE
             if (lane == 0) { ptx::tma_store_2d(&tmapS, stg, col0, m_blk * BM + ew * 32); ptx::tma_store_commit(); }
+#endif
           }
+          // statistics AFTER issuing the store: the ~200 ALU instructions hide the bulk store's shared-memory read
+          if (row < p.M && col0 < p.Nn)
+            stats32(v, s_lab + ch * 32, lab_i, col0 + 32 <= p.Nn && (self_col < col0 || self_col >= col0 + 32), col0, p.Nn, self_col,
+                    minw, maxw, maxb, cnt);
           if (EPI == EPI_SIM_SYM && cb > m_blk && m_blk * BM + ew * 32 < p.M && col0 < p.Nn) {
             // ---- mirrored store: staging row c holds S[col0 + c][rows of this warp]; box lands at (x = row block, y = col0) ----
             if (lane == 0) ptx::tma_store_wait_read<0>();
@@ -310,7 +313,9 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
               *reinterpret_cast<float*>(stg + c * 128 + ((((lane >> 2) ^ (c & 7))) << 4) + ((lane & 3) << 2)) = v[c];
             ptx::fence_proxy_async_smem();
             __syncwarp();
+#ifndef NPAIR_DBG_SKIP_MSTORE
             if (lane == 0) { ptx::tma_store_2d(&tmapS, stg, m_blk * BM + ew * 32, col0); ptx::tma_store_commit(); }
+#endif
             // ---- mirrored statistics: the staging tile is the transposed chunk, so lane L reads back ROW gc = col0 + L of the
             //      symmetric matrix (32 entries against this warp's 32 row labels) and reuses the per-thread statistics ----
             const int gc = col0 + lane;
@@ -323,7 +328,11 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
             float t_minw = FLT_MAX, t_maxw = -FLT_MAX, t_maxb = -FLT_MAX;
             int t_cnt = 0;
             const int r0 = m_blk * BM + ew * 32;
+#ifdef NPAIR_DBG_SKIP_MSTATS
+            if (false) {
+#else
             if (gc < p.Nn) {
+#endif
               stats32(vt, s_labr + ew * 32, s_lab[ch * 32 + lane], r0 + 32 <= p.M, r0, p.M, -1, t_minw, t_maxw, t_maxb, t_cnt);
               if (t_cnt) {
                 atomicMin(&p.st_minw[gc], f2ord(t_minw));
