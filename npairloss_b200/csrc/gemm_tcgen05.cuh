@@ -117,6 +117,11 @@ __device__ __forceinline__ void pass_pieces(int nsplit, int p, int& sa, int& sb)
 __device__ __forceinline__ void stats32(const float (&v)[32], const float* __restrict__ lab, float lab_i, bool fast, int idx0,
                                         int limit, int self_idx, float& minw, float& maxw, float& maxb, int& cnt) {
   if (fast) {
+    // four independent accumulator sets (one per element of a float4): an epilogue warp is alone on its scheduler most of the
+    // time, so instruction-level parallelism, not warp-level, has to hide the 4-cycle ALU latency of the min/max chains
+    float mnw[4] = {FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX}, mxw[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+    float mxb[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+    int cn[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const float4 l4 = *reinterpret_cast<const float4*>(lab + 4 * q);
@@ -124,10 +129,14 @@ __device__ __forceinline__ void stats32(const float (&v)[32], const float* __res
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float x = v[4 * q + e];
-        if (ll[e] == lab_i) { minw = fminf(minw, x); maxw = fmaxf(maxw, x); ++cnt; }
-        else maxb = fmaxf(maxb, x);
+        if (ll[e] == lab_i) { mnw[e] = fminf(mnw[e], x); mxw[e] = fmaxf(mxw[e], x); ++cn[e]; }
+        else mxb[e] = fmaxf(mxb[e], x);
       }
     }
+    minw = fminf(minw, fminf(fminf(mnw[0], mnw[1]), fminf(mnw[2], mnw[3])));
+    maxw = fmaxf(maxw, fmaxf(fmaxf(mxw[0], mxw[1]), fmaxf(mxw[2], mxw[3])));
+    maxb = fmaxf(maxb, fmaxf(fmaxf(mxb[0], mxb[1]), fmaxf(mxb[2], mxb[3])));
+    cnt += (cn[0] + cn[1]) + (cn[2] + cn[3]);
   } else {
 #pragma unroll
     for (int c = 0; c < 32; ++c) {
@@ -281,13 +290,17 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         uint32_t r[32];
         ptx::tmem_ld_32x32b_x32(t_row + ch * 32, r);
         ptx::tmem_ld_wait();
+#ifndef NPAIR_DBG_EPI_LEVEL
+#define NPAIR_DBG_EPI_LEVEL 9
+#endif
+        if (EPI != EPI_OUT && NPAIR_DBG_EPI_LEVEL == 0) continue;
         if (EPI != EPI_OUT) {
           float v[32];
 #pragma unroll
           for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(r[c]) * out_scale;
           // registers -> 128B-swizzled staging tile -> one TMA store of a 32x32 fp32 box (full 128-byte lines;
           // rows >= M and columns >= Nn are clipped by the tensor map)
-          if (m_blk * BM + ew * 32 < p.M && col0 < p.Nn) {          // warp-uniform
+          if (NPAIR_DBG_EPI_LEVEL >= 1 && m_blk * BM + ew * 32 < p.M && col0 < p.Nn) {          // warp-uniform
             if (lane == 0) ptx::tma_store_wait_read<0>();             // this warp's previous box has been read out of smem
             __syncwarp();
             uint8_t* srow = stg + lane * 128;
@@ -301,10 +314,10 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
 #endif
           }
           // statistics AFTER issuing the store: the ~200 ALU instructions hide the bulk store's shared-memory read
-          if (row < p.M && col0 < p.Nn)
+          if (NPAIR_DBG_EPI_LEVEL >= 2 && row < p.M && col0 < p.Nn)
             stats32(v, s_lab + ch * 32, lab_i, col0 + 32 <= p.Nn && (self_col < col0 || self_col >= col0 + 32), col0, p.Nn, self_col,
                     minw, maxw, maxb, cnt);
-          if (EPI == EPI_SIM_SYM && cb > m_blk && m_blk * BM + ew * 32 < p.M && col0 < p.Nn) {
+          if (NPAIR_DBG_EPI_LEVEL >= 3 && EPI == EPI_SIM_SYM && cb > m_blk && m_blk * BM + ew * 32 < p.M && col0 < p.Nn) {
             // ---- mirrored store: staging row c holds S[col0 + c][rows of this warp]; box lands at (x = row block, y = col0) ----
             if (lane == 0) ptx::tma_store_wait_read<0>();
             __syncwarp();
@@ -328,11 +341,7 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
             float t_minw = FLT_MAX, t_maxw = -FLT_MAX, t_maxb = -FLT_MAX;
             int t_cnt = 0;
             const int r0 = m_blk * BM + ew * 32;
-#ifdef NPAIR_DBG_SKIP_MSTATS
-            if (false) {
-#else
-            if (gc < p.Nn) {
-#endif
+            if (NPAIR_DBG_EPI_LEVEL >= 4 && gc < p.Nn) {
               stats32(vt, s_labr + ew * 32, s_lab[ch * 32 + lane], r0 + 32 <= p.M, r0, p.M, -1, t_minw, t_maxw, t_maxb, t_cnt);
               if (t_cnt) {
                 atomicMin(&p.st_minw[gc], f2ord(t_minw));

@@ -710,7 +710,7 @@ __device__ __forceinline__ void store_quad(uint16_t* __restrict__ base, long lon
 //   needs only the row scalars of BOTH indices, which are local when world == 1.
 // !SYM (world > 1): H[j][m] = g'(j,m) and the transposed copy HT[m][j] (micro-tile transposed in registers).
 template <int PREC, bool SYM>
-__global__ void __launch_bounds__(256) build_weights_kernel(const float* __restrict__ S, long long ldS, int Q, int N,
+__global__ void __launch_bounds__(256, 4) build_weights_kernel(const float* __restrict__ S, long long ldS, int Q, int N,
                                                             const float* __restrict__ lab_rows, const float* __restrict__ lab_cols,
                                                             int self_offset, MiningParams mp, RowArrays ra,
                                                             uint16_t* __restrict__ H, long long ldH, uint16_t* __restrict__ HT, long long ldHT) {
@@ -735,56 +735,43 @@ __global__ void __launch_bounds__(256) build_weights_kernel(const float* __restr
   }
   __syncthreads();
   const int ja0 = a0 + 4 * tr, mb0 = b0 + 4 * tc;       // my rows of block a, my columns of block b
-  float m1[4][4];
+  RowScal rb4[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (ja0 + i < Q && mb0 < N) v = *reinterpret_cast<const float4*>(S + static_cast<long long>(ja0 + i) * ldS + mb0);
-    m1[i][0] = v.x; m1[i][1] = v.y; m1[i][2] = v.z; m1[i][3] = v.w;
-  }
-  RowScal ra4[4], rb4[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { ra4[i] = sc_a[4 * tr + i]; rb4[i] = sc_b[4 * tc + i]; }
-  float g[4][4];
+  for (int e = 0; e < 4; ++e) rb4[e] = sc_b[4 * tc + e];
   // block-uniform fast path: tile fully inside the matrix and not touching the self-pair diagonal
   const bool interior = (a0 + TS <= Q) && (b0 + TS <= N) && (a0 + self_offset + TS <= b0 || b0 + TS <= a0 + self_offset);
-  if (interior) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const bool same = ra4[i].lab == rb4[e].lab;
-        float x = gprime(m1[i][e], same, ra4[i], sgn_p, sgn_n);
-        if (SYM) x += gprime(m1[i][e], same, rb4[e], sgn_p, sgn_n);
-        g[i][e] = x;
-      }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int j = ja0 + i, m = mb0 + e;
-        float x = 0.f;
-        if (j < Q && m < N && m != j + self_offset) {
-          const bool same = ra4[i].lab == rb4[e].lab;
-          x = gprime(m1[i][e], same, ra4[i], sgn_p, sgn_n);
-          if (SYM) x += gprime(m1[i][e], same, rb4[e], sgn_p, sgn_n);
-        }
-        g[i][e] = x;
-      }
-  }
   const long long psH = static_cast<long long>(Q) * ldH;
+  float gT[4][4];                                        // !SYM: transposed copy for HT
+  float4 v4[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-    if (ja0 + i < Q && mb0 < ldH) store_quad<PREC>(H, psH, static_cast<long long>(ja0 + i) * ldH + mb0, g[i]);
+  for (int i = 0; i < 4; ++i) {                          // all four 16-byte loads in flight before the arithmetic
+    v4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ja0 + i < Q && mb0 < N) v4[i] = *reinterpret_cast<const float4*>(S + static_cast<long long>(ja0 + i) * ldS + mb0);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const RowScal rsa = sc_a[4 * tr + i];
+    const float sv[4] = {v4[i].x, v4[i].y, v4[i].z, v4[i].w};
+    float g[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = ja0 + i, m = mb0 + e;
+      float x = 0.f;
+      if (interior || (j < Q && m < N && m != j + self_offset)) {
+        const bool same = rsa.lab == rb4[e].lab;
+        x = gprime(sv[e], same, rsa, sgn_p, sgn_n);
+        if (SYM) x += gprime(sv[e], same, rb4[e], sgn_p, sgn_n);
+      }
+      g[e] = x;
+      if (!SYM) gT[e][i] = x;
+    }
+    if (ja0 + i < Q && mb0 < ldH) store_quad<PREC>(H, psH, static_cast<long long>(ja0 + i) * ldH + mb0, g);
+  }
   if (!SYM) {
     const long long psT = static_cast<long long>(N) * ldHT;
 #pragma unroll
     for (int e = 0; e < 4; ++e)
-      if (mb0 + e < N && ja0 < ldHT) {
-        const float gt[4] = {g[0][e], g[1][e], g[2][e], g[3][e]};   // rows beyond Q are already zero
-        store_quad<PREC>(HT, psT, static_cast<long long>(mb0 + e) * ldHT + ja0, gt);
-      }
+      if (mb0 + e < N && ja0 < ldHT) store_quad<PREC>(HT, psT, static_cast<long long>(mb0 + e) * ldHT + ja0, gT[e]);   // rows beyond Q are zero
   }
 }
 void launch_build_weights(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
