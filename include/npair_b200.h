@@ -74,7 +74,15 @@ typedef struct {
   int32_t sim_precision; /* NPAIR_PREC_*  */
   int32_t gemm_backend;  /* NPAIR_GEMM_*  */
   int32_t device;        /* CUDA device ordinal; -1 = current device */
+  int32_t bwd_exchange;  /* world > 1 only.  NPAIR_BWD_AUTO: row-scalar exchange when the operand format gives a bitwise
+                            symmetric similarity GEMM (fp16x2, bf16), else reduce-scatter.  NPAIR_BWD_REDUCE_SCATTER forces the
+                            reference's form (all-reduce of the N x D transposed product, .cu:455-497). */
 } npair_config;
+
+enum { NPAIR_BWD_AUTO = 0, NPAIR_BWD_REDUCE_SCATTER = 1 };
+/* what a context actually uses: 0 = single rank (symmetric tiles), 1 = reduce-scatter, 2 = row-scalar exchange */
+enum { NPAIR_BWDMODE_SINGLE = 0, NPAIR_BWDMODE_REDUCE_SCATTER = 1, NPAIR_BWDMODE_ROW_SCALARS = 2 };
+int npair_bwd_exchange_mode(const npair_ctx* ctx);
 
 /* fills proto defaults (caffe.proto:4-7,19-22), world=1, rank=0, num_tops=5, fp32-faithful fp16x2, tcgen05 */
 void npair_config_default(npair_config* cfg, int32_t Q, int32_t D);
@@ -115,6 +123,14 @@ int npair_backward(npair_ctx* ctx, float loss_weight, float* d_feat_diff, void* 
  *     world == 1: d_total_half may be NULL; d_local_half then receives the complete gradient. */
 int npair_forward_gathered(npair_ctx* ctx, const float* d_feat_total, const float* d_label_total, float tops_host[5], void* stream);
 int npair_backward_partial(npair_ctx* ctx, float loss_weight, float* d_local_half, float* d_total_half, void* stream);
+/* Row-scalar exchange form (contexts whose npair_bwd_exchange_mode is NPAIR_BWDMODE_ROW_SCALARS).  Because the similarity
+ * GEMM is bitwise symmetric across ranks, rank r can evaluate the transposed gradient weights G[m][j] of every other rank
+ * from its own S[j][m] and five scalars of row m, so the backward exchange is an all-gather of 5*Q floats per rank instead of
+ * the reference's N x D all-reduce:
+ *   npair_row_scalars       : copies this rank's [5][Q] scalars (after a forward) to d_out_5Q
+ *   npair_backward_gathered : d_rs_total = [world][5][Q] scalars of all ranks; writes the complete bottom.diff (Q x D) */
+int npair_row_scalars(npair_ctx* ctx, float* d_out_5Q, void* stream);
+int npair_backward_gathered(npair_ctx* ctx, float loss_weight, const float* d_rs_total, float* d_feat_diff, void* stream);
 
 const char* npair_last_error(const npair_ctx* ctx);   /* ctx may be NULL: last create() error of this thread */
 const char* npair_version(void);

@@ -21,11 +21,11 @@ class NpairConfig(C.Structure):
     _fields_ = [("Q", C.c_int32), ("D", C.c_int32), ("world", C.c_int32), ("rank", C.c_int32), ("num_tops", C.c_int32),
                 ("margin_ident", C.c_float), ("margin_diff", C.c_float), ("identsn", C.c_float), ("diffsn", C.c_float),
                 ("ap_region", C.c_int32), ("ap_method", C.c_int32), ("an_region", C.c_int32), ("an_method", C.c_int32),
-                ("sim_precision", C.c_int32), ("gemm_backend", C.c_int32), ("device", C.c_int32)]
+                ("sim_precision", C.c_int32), ("gemm_backend", C.c_int32), ("device", C.c_int32), ("bwd_exchange", C.c_int32)]
 
 
 EXPORTS = ["npair_config_default", "npair_workspace_bytes", "npair_nccl_unique_id", "npair_create", "npair_create_with_comm",
-           "npair_destroy", "npair_forward", "npair_backward", "npair_forward_gathered", "npair_backward_partial", "npair_profile_enable", "npair_profile_read", "npair_util_f64_to_f32", "npair_util_f32_to_f64", "npair_last_error", "npair_version", "npair_debug_read",
+           "npair_destroy", "npair_forward", "npair_backward", "npair_forward_gathered", "npair_backward_partial", "npair_bwd_exchange_mode", "npair_row_scalars", "npair_backward_gathered", "npair_profile_enable", "npair_profile_read", "npair_util_f64_to_f32", "npair_util_f32_to_f64", "npair_last_error", "npair_version", "npair_debug_read",
            "npair_debug_gemm"]
 
 _LIB = None
@@ -58,6 +58,9 @@ def lib():
         L.npair_backward.argtypes = [vp, C.c_float, vp, vp]
         L.npair_forward_gathered.argtypes = [vp, vp, vp, fp, vp]
         L.npair_backward_partial.argtypes = [vp, C.c_float, vp, vp, vp]
+        L.npair_bwd_exchange_mode.argtypes = [vp]
+        L.npair_row_scalars.argtypes = [vp, vp, vp]
+        L.npair_backward_gathered.argtypes = [vp, C.c_float, vp, vp, vp]
         L.npair_profile_enable.argtypes = [vp, C.c_int]
         L.npair_profile_read.argtypes = [vp, fp]
         L.npair_last_error.argtypes = [vp]
@@ -71,9 +74,9 @@ def lib():
 
 def make_config(Q, D, world=1, rank=0, num_tops=5, margin_ident=0.0, margin_diff=0.0, identsn=-1.0, diffsn=-1.0,
                 ap_region=LOCAL, ap_method=RAND, an_region=LOCAL, an_method=RAND, sim_precision=PREC_FP32_FP16X2,
-                gemm_backend=GEMM_TCGEN05, device=-1) -> NpairConfig:
+                gemm_backend=GEMM_TCGEN05, device=-1, bwd_exchange=0) -> NpairConfig:
     return NpairConfig(Q, D, world, rank, num_tops, margin_ident, margin_diff, identsn, diffsn, ap_region, ap_method,
-                       an_region, an_method, sim_precision, gemm_backend, device)
+                       an_region, an_method, sim_precision, gemm_backend, device, bwd_exchange)
 
 
 def nccl_unique_id() -> bytes:
@@ -144,6 +147,18 @@ class Context:
         self._check(lib().npair_backward_partial(self._h, C.c_float(loss_weight), local_half.data_ptr(),
                                                  total_half.data_ptr() if total_half is not None else None,
                                                  torch.cuda.current_stream().cuda_stream))
+
+    def bwd_exchange_mode(self):
+        return lib().npair_bwd_exchange_mode(self._h)
+
+    def row_scalars(self, out):
+        import torch
+        self._check(lib().npair_row_scalars(self._h, out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+
+    def backward_gathered(self, loss_weight, rs_total, diff):
+        import torch
+        self._check(lib().npair_backward_gathered(self._h, C.c_float(loss_weight), rs_total.data_ptr(), diff.data_ptr(),
+                                                  torch.cuda.current_stream().cuda_stream))
 
     def profile_enable(self, on=True):
         self._check(lib().npair_profile_enable(self._h, 1 if on else 0))

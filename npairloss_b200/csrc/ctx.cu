@@ -139,7 +139,9 @@ static cudaError_t launch_split_gemm_t(const CUtensorMap& a, const CUtensorMap& 
   return cudaGetLastError();
 }
 // `sm`: fp32 tensor map of the similarity matrix for EPI_SIM's TMA stores (ignored by EPI_OUT: pass any valid map)
-static cudaError_t launch_split_gemm(int prec, int epi, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& sm, const GemmParams& p, int sms, cudaStream_t st) {
+// `cat`: fp16 operands in the K-concatenated [hi | hi/lo interleaved] layout -> one fp16 pass over K = 3*Dp
+static cudaError_t launch_split_gemm(int prec, int epi, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& sm, const GemmParams& p, int sms, cudaStream_t st, bool cat = false) {
+  if (cat) return launch_split_gemm_t<1, false, EPI_SIM, 64>(a, b, sm, p, sms, st);
   if (prec == PREC_BF16) {
     if (epi == EPI_SIM) return launch_split_gemm_t<1, true, EPI_SIM, 64>(a, b, sm, p, sms, st);
     if (epi == EPI_SIM_SYM) return launch_split_gemm_t<1, true, EPI_SIM_SYM, 64>(a, b, sm, p, sms, st);
@@ -273,6 +275,10 @@ struct npair_ctx {
   float* S = nullptr;
   uint16_t *Xs = nullptr, *XsT = nullptr, *XlT = nullptr, *H = nullptr, *HT = nullptr;
   float* OUT2 = nullptr;         // world > 1: N x D transposed-term product before the reduce-scatter
+  int bwd_mode = 0;              // NPAIR_BWDMODE_*
+  uint16_t *XcatA = nullptr, *XcatB = nullptr;   // row-scalar mode, fp16x2: K-concatenated operands [N][3*Dp]
+  float* rs_total = nullptr;     // row-scalar mode: all-gathered [world][5][Q] row scalars
+  CUtensorMap tm_catA, tm_catB;
   int2* sym_tiles = nullptr;     // world == 1: (m_blk, n_blk) of the similarity tiles touching the upper triangle
   int n_sym_tiles = 0;
   float* part = nullptr;         // split-K partial products of the gradient GEMM
@@ -329,6 +335,7 @@ static int validate(const npair_config* c, std::string* err) {
   if (c->ap_method < 0 || c->ap_method > 4 || c->an_method < 0 || c->an_method > 4) { *err = "bad mining method"; return NPAIR_E_ARG; }
   if (c->sim_precision < 0 || c->sim_precision > 2) { *err = "bad sim_precision"; return NPAIR_E_ARG; }
   if (c->gemm_backend < 0 || c->gemm_backend > 1) { *err = "bad gemm_backend"; return NPAIR_E_ARG; }
+  if (c->bwd_exchange < 0 || c->bwd_exchange > 1) { *err = "bad bwd_exchange"; return NPAIR_E_ARG; }
   if (static_cast<long long>(c->Q) * c->world > 0x7fffffffLL) { *err = "N = Q*world exceeds int32"; return NPAIR_E_ARG; }
   return NPAIR_OK;
 }
@@ -361,7 +368,7 @@ void npair_config_default(npair_config* c, int32_t Q, int32_t D) {
   c->Q = Q; c->D = D; c->world = 1; c->rank = 0; c->num_tops = 5;
   c->margin_ident = 0.f; c->margin_diff = 0.f; c->identsn = -1.f; c->diffsn = -1.f;       // caffe.proto:4-7
   c->ap_region = NPAIR_LOCAL; c->ap_method = NPAIR_RAND; c->an_region = NPAIR_LOCAL; c->an_method = NPAIR_RAND;   // :19-22
-  c->sim_precision = NPAIR_PREC_FP32_FP16X2; c->gemm_backend = NPAIR_GEMM_TCGEN05; c->device = -1;
+  c->sim_precision = NPAIR_PREC_FP32_FP16X2; c->gemm_backend = NPAIR_GEMM_TCGEN05; c->device = -1; c->bwd_exchange = NPAIR_BWD_AUTO;
 }
 
 size_t npair_workspace_bytes(const npair_config* cfg) {
@@ -388,7 +395,7 @@ void npair_destroy(npair_ctx* c) {
   if (c->device >= 0) cudaSetDevice(c->device);
   if (c->comm && c->own_comm) { NcclApi* api = nccl_api(); if (api->CommDestroy) api->CommDestroy(c->comm); }
   cudaFree(c->Xtot_buf); cudaFree(c->labtot_buf); cudaFree(c->S); cudaFree(c->Xs); cudaFree(c->XsT); cudaFree(c->XlT);
-  cudaFree(c->H); cudaFree(c->HT); cudaFree(c->OUT2); cudaFree(c->part); cudaFree(c->sym_tiles); cudaFree(c->row_block); cudaFree(c->bs); cudaFree(c->partial); cudaFree(c->ghist);
+  cudaFree(c->H); cudaFree(c->HT); cudaFree(c->OUT2); cudaFree(c->part); cudaFree(c->sym_tiles); cudaFree(c->XcatA); cudaFree(c->XcatB); cudaFree(c->rs_total); cudaFree(c->row_block); cudaFree(c->bs); cudaFree(c->partial); cudaFree(c->ghist);
   if (c->tops_pinned) cudaFreeHost(c->tops_pinned);
   if (c->ev_made) for (int i = 0; i < NPAIR_PROF_PHASES; ++i) { cudaEventDestroy(c->ev[i][0]); cudaEventDestroy(c->ev[i][1]); }
   delete c;
@@ -441,7 +448,18 @@ static int create_impl(const npair_config* cfg, const void* id128, void* ext_com
   CREATE_TRY(cudaMemset(c->XsT, 0, 2ull * ns * D * c->Np));
   CREATE_TRY(cudaMalloc(&c->H, 2ull * ns * Q * c->Np));
   CREATE_TRY(cudaMemset(c->H, 0, 2ull * ns * Q * c->Np));
-  if (c->world > 1) {
+  c->bwd_mode = c->world == 1 ? NPAIR_BWDMODE_SINGLE
+              : ((cfg->bwd_exchange == NPAIR_BWD_AUTO && c->prec != PREC_BF16X3) ? NPAIR_BWDMODE_ROW_SCALARS : NPAIR_BWDMODE_REDUCE_SCATTER);
+  if (c->bwd_mode == NPAIR_BWDMODE_ROW_SCALARS) {
+    CREATE_TRY(cudaMalloc(&c->rs_total, sizeof(float) * 5ull * N));
+    if (c->prec == PREC_FP16X2 && cfg->gemm_backend == NPAIR_GEMM_TCGEN05) {
+      CREATE_TRY(cudaMalloc(&c->XcatA, 2ull * N * 3 * c->Dp));
+      CREATE_TRY(cudaMemset(c->XcatA, 0, 2ull * N * 3 * c->Dp));
+      CREATE_TRY(cudaMalloc(&c->XcatB, 2ull * N * 3 * c->Dp));
+      CREATE_TRY(cudaMemset(c->XcatB, 0, 2ull * N * 3 * c->Dp));
+    }
+  }
+  if (c->bwd_mode == NPAIR_BWDMODE_REDUCE_SCATTER) {
     CREATE_TRY(cudaMalloc(&c->XlT, 2ull * ns * D * c->Qp));
     CREATE_TRY(cudaMemset(c->XlT, 0, 2ull * ns * D * c->Qp));
     CREATE_TRY(cudaMalloc(&c->HT, 2ull * ns * N * c->Qp));
@@ -491,7 +509,11 @@ static int create_impl(const npair_config* cfg, const void* id128, void* ext_com
     // gradient 1: A = H [Q x N], B = XsT [D x N]; K = N
     ok = ok && make_tmap_pieces(&c->tm_b1A, c->H, N, Q, ns, c->Np, static_cast<long long>(Q) * c->Np, bkg, 128, &te);
     ok = ok && make_tmap_pieces(&c->tm_b1B, c->XsT, N, D, ns, c->Np, static_cast<long long>(D) * c->Np, bkg, 256, &te);
-    if (c->world > 1) {   // gradient 2: A = HT [N x Q], B = XlT [D x Q]; K = Q
+    if (c->XcatA) {       // bitwise-symmetric similarity: one fp16 pass over K = 3*Dp
+      ok = ok && make_tmap_pieces(&c->tm_catA, c->XcatA + static_cast<long long>(c->rank) * Q * 3 * c->Dp, static_cast<int>(3 * c->Dp), Q, 1, 3 * c->Dp, static_cast<long long>(N) * 3 * c->Dp, 64, 128, &te);
+      ok = ok && make_tmap_pieces(&c->tm_catB, c->XcatB, static_cast<int>(3 * c->Dp), N, 1, 3 * c->Dp, static_cast<long long>(N) * 3 * c->Dp, 64, 256, &te);
+    }
+    if (c->bwd_mode == NPAIR_BWDMODE_REDUCE_SCATTER) {   // gradient 2: A = HT [N x Q], B = XlT [D x Q]; K = Q
       ok = ok && make_tmap_pieces(&c->tm_b2A, c->HT, Q, N, ns, c->Qp, static_cast<long long>(N) * c->Qp, bkg, 128, &te);
       ok = ok && make_tmap_pieces(&c->tm_b2B, c->XlT, Q, D, ns, c->Qp, static_cast<long long>(D) * c->Qp, bkg, 256, &te);
     }
@@ -586,7 +608,7 @@ static int forward_impl(npair_ctx* c, const float* d_feat, const float* d_label,
     PhaseTimer pt(c, 1, st);
     launch_absmax_asum(d_feat, static_cast<long long>(Q) * D, c->x_total, static_cast<long long>(N) * D, c->partial, c->bs,
                        c->prec == PREC_FP16X2 ? 1 : 0, st);
-    launch_split(c->x_total, N, D, c->prec, c->bs, c->Xs, c->Dp, c->XsT, c->Np, c->XlT, c->Qp, self_off, Q, st);
+    launch_split(c->x_total, N, D, c->prec, c->bs, c->Xs, c->Dp, c->XsT, c->Np, c->XlT, c->Qp, self_off, Q, c->XcatA, c->XcatB, c->Dp, st);
     launch_init_stats(c->ra, Q, c->bs, st);
   }
   // ---- S = X_local . X_total^T (.cu:218) with fused masks + row statistics (.cu:44-66, :225-265) ----
@@ -599,6 +621,10 @@ static int forward_impl(npair_ctx* c, const float* d_feat, const float* d_label,
   if (c->cfg.gemm_backend == NPAIR_GEMM_TCGEN05) {
     PhaseTimer pt(c, 2, st);
     if (c->sym_tiles) { gp.tile_list = c->sym_tiles; gp.num_tiles_list = c->n_sym_tiles; }
+    if (c->XcatA) {
+      gp.num_kblocks = static_cast<int>(3 * c->Dp / 64); gp.kb_per_split = gp.num_kblocks;
+      CUDA_TRY(c, launch_split_gemm(c->prec, EPI_SIM, c->tm_catA, c->tm_catB, c->tm_S, gp, c->sms, st, true));
+    } else
     CUDA_TRY(c, launch_split_gemm(c->prec, c->sym_tiles ? EPI_SIM_SYM : EPI_SIM, c->tm_simA, c->tm_simB, c->tm_S, gp, c->sms, st));
   } else {
     CUDA_TRY(c, launch_simt_gemm(c->prec, EPI_SIM, c->Xs + static_cast<long long>(self_off) * c->Dp, c->Dp, static_cast<long long>(N) * c->Dp,
@@ -633,17 +659,19 @@ static int forward_impl(npair_ctx* c, const float* d_feat, const float* d_label,
   return NPAIR_OK;
 }
 
-static int backward_impl(npair_ctx* c, float loss_weight, float* d_diff, float* d_total_ext, cudaStream_t st);
+static int backward_impl(npair_ctx* c, float loss_weight, float* d_diff, float* d_total_ext, const float* d_rs_ext, cudaStream_t st);
+
+int npair_bwd_exchange_mode(const npair_ctx* c) { return c ? c->bwd_mode : NPAIR_E_ARG; }
 
 int npair_backward(npair_ctx* c, float loss_weight, float* d_diff, void* stream) {
   if (!c) return NPAIR_E_ARG;
   if (!d_diff) { c->err = "null gradient pointer"; return NPAIR_E_ARG; }
   if (!c->fwd_done) { c->err = "npair_backward called without a successful npair_forward"; return NPAIR_E_STATE; }
-  if (c->world > 1 && !c->comm) { c->err = "context was created without a communicator: use npair_backward_partial"; return NPAIR_E_STATE; }
+  if (c->world > 1 && !c->comm) { c->err = "context was created without a communicator: use npair_backward_partial / npair_backward_gathered"; return NPAIR_E_STATE; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CUDA_TRY(c, cudaSetDevice(c->device));
   c->last_stream = st;
-  return backward_impl(c, loss_weight, d_diff, nullptr, st);
+  return backward_impl(c, loss_weight, d_diff, nullptr, nullptr, st);
 }
 
 /* External-collectives variant of Backward_gpu up to the all-reduce (.cu:420-460):
@@ -655,25 +683,61 @@ int npair_backward_partial(npair_ctx* c, float loss_weight, float* d_local_half,
   if (!c) return NPAIR_E_ARG;
   if (!d_local_half || (c->world > 1 && !d_total_half)) { c->err = "null gradient pointer"; return NPAIR_E_ARG; }
   if (!c->fwd_done) { c->err = "npair_backward_partial called without a successful forward"; return NPAIR_E_STATE; }
+  if (c->bwd_mode == NPAIR_BWDMODE_ROW_SCALARS) { c->err = "this context exchanges row scalars: use npair_row_scalars + npair_backward_gathered"; return NPAIR_E_STATE; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CUDA_TRY(c, cudaSetDevice(c->device));
   c->last_stream = st;
-  return backward_impl(c, loss_weight, d_local_half, c->world > 1 ? d_total_half : nullptr, st);
+  return backward_impl(c, loss_weight, d_local_half, c->world > 1 ? d_total_half : nullptr, nullptr, st);
 }
 
-static int backward_impl(npair_ctx* c, float loss_weight, float* d_diff, float* d_total_ext, cudaStream_t st) {
+int npair_row_scalars(npair_ctx* c, float* d_out, void* stream) {
+  if (!c || !d_out) return NPAIR_E_ARG;
+  if (!c->fwd_done) { c->err = "npair_row_scalars called without a successful forward"; return NPAIR_E_STATE; }
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  // rs_maxall, rs_tp, rs_tn, rs_cA, rs_cT are five consecutive Q-float arrays of the row block
+  CUDA_TRY(c, cudaMemcpyAsync(d_out, c->ra.rs_maxall, sizeof(float) * 5ull * c->Q, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  return NPAIR_OK;
+}
+
+int npair_backward_gathered(npair_ctx* c, float loss_weight, const float* d_rs_total, float* d_diff, void* stream) {
+  if (!c) return NPAIR_E_ARG;
+  if (!d_rs_total || !d_diff) { c->err = "null pointer argument"; return NPAIR_E_ARG; }
+  if (!c->fwd_done) { c->err = "npair_backward_gathered called without a successful forward"; return NPAIR_E_STATE; }
+  if (c->bwd_mode != NPAIR_BWDMODE_ROW_SCALARS) { c->err = "this context does not exchange row scalars (see npair_bwd_exchange_mode)"; return NPAIR_E_STATE; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  c->last_stream = st;
+  return backward_impl(c, loss_weight, d_diff, nullptr, d_rs_total, st);
+}
+
+static int backward_impl(npair_ctx* c, float loss_weight, float* d_diff, float* d_total_ext, const float* d_rs_ext, cudaStream_t st) {
   const int Q = c->Q, N = c->N, D = c->D;
   const MiningParams mp = mining_of(c->cfg);
   const int self_off = c->rank * Q;
   const float lw_over_q = loss_weight / static_cast<float>(Q);     // loss_weight / dot_normalizer (.cu:427,448)
+  const bool tc = c->cfg.gemm_backend == NPAIR_GEMM_TCGEN05;
+  const float* rs_total = nullptr;
+  int bw_mode = BW_SYM;
+  if (c->bwd_mode == NPAIR_BWDMODE_ROW_SCALARS) {
+    bw_mode = BW_ROWSCAL;
+    if (d_rs_ext) rs_total = d_rs_ext;
+    else {
+      // the only backward exchange: 5*Q floats per rank (replaces the N x D MPI_Allreduce of .cu:462-489)
+      PhaseTimer pt(c, 0, st);
+      NcclApi* api = nccl_api();
+      int r = api->AllGather(c->ra.rs_maxall, c->rs_total, 5ull * Q, NCCL_FLOAT32, c->comm, st);
+      if (r != 0) { c->err = fmt("ncclAllGather(row scalars): %s", api->GetErrorString(r)); return NPAIR_E_NCCL; }
+      rs_total = c->rs_total;
+    }
+  } else if (c->bwd_mode == NPAIR_BWDMODE_REDUCE_SCATTER) bw_mode = BW_SPLIT;
   {
     PhaseTimer pt(c, 5, st);
-    launch_build_weights(c->S, c->ldS, Q, N, c->cur_label, c->lab_total, self_off, c->world, mp, c->ra, c->prec, c->H, c->Np, c->HT, c->Qp, st);
+    launch_build_weights(c->S, c->ldS, Q, N, c->cur_label, c->lab_total, self_off, c->world, bw_mode, rs_total, mp, c->ra, c->prec, c->H, c->Np, c->HT, c->Qp, st);
   }
   GemmParams gp; memset(&gp, 0, sizeof(gp));
   gp.dev_scale = &c->bs->x_inv_scale;
-  const bool tc = c->cfg.gemm_backend == NPAIR_GEMM_TCGEN05;
-  if (c->world > 1) {
+  const bool rs_path = c->bwd_mode == NPAIR_BWDMODE_REDUCE_SCATTER;
+  if (rs_path) {
     // total = (1/2)(1/k)(lw/Q) * G^T . X_local  (N x D)  -> reduce-scatter (== all-reduce + own slice, .cu:462-497)
     gp.M = N; gp.Nn = D; gp.num_kblocks = static_cast<int>((Q + c->bk_grad - 1) / c->bk_grad);
     gp.tiles_m = (N + 127) / 128; gp.tiles_n = (D + 255) / 256; gp.splits = 1; gp.kb_per_split = gp.num_kblocks;
@@ -690,10 +754,10 @@ static int backward_impl(npair_ctx* c, float loss_weight, float* d_diff, float* 
       if (r != 0) { c->err = fmt("ncclReduceScatter: %s", api->GetErrorString(r)); return NPAIR_E_NCCL; }
     }
   }
-  // local = (1/2)(lw/Q) * G . X_total, accumulated onto the scattered transposed term when world > 1
+  // d_diff = (1/2)(lw/Q) * H . X_total  (H = G + G^T/world in the symmetric modes; accumulated onto the scattered term otherwise)
   gp.M = Q; gp.Nn = D; gp.num_kblocks = static_cast<int>((N + c->bk_grad - 1) / c->bk_grad);
   gp.tiles_m = (Q + 127) / 128; gp.tiles_n = (D + 255) / 256;
-  gp.out = d_diff; gp.ldo = D; gp.alpha = 0.5f * lw_over_q; gp.beta = (c->world > 1 && !d_total_ext) ? 1.f : 0.f;
+  gp.out = d_diff; gp.ldo = D; gp.alpha = 0.5f * lw_over_q; gp.beta = (rs_path && !d_total_ext) ? 1.f : 0.f;
   gp.splits = 1; gp.kb_per_split = gp.num_kblocks; gp.part = c->part;
   if (tc && c->part) plan_splits(&gp, c->sms, c->part_floats);
   {
@@ -849,8 +913,8 @@ int npair_debug_gemm(int precision, int backend, int M, int Nn, int K, const flo
       float sc[2] = {1.f, 1.f};
       DG_TRY(cudaMemcpy(&bs->x_scale, sc, 8, cudaMemcpyHostToDevice));
     }
-    launch_split(dA, M, K, precision, bs, As, Kp, dummyT, tmax, nullptr, 0, 0, 0, st);
-    launch_split(dB, Nn, K, precision, bs, Bs, Kp, dummyT, tmax, nullptr, 0, 0, 0, st);
+    launch_split(dA, M, K, precision, bs, As, Kp, dummyT, tmax, nullptr, 0, 0, 0, nullptr, nullptr, 0, st);
+    launch_split(dB, Nn, K, precision, bs, Bs, Kp, dummyT, tmax, nullptr, 0, 0, 0, nullptr, nullptr, 0, st);
     GemmParams gp; memset(&gp, 0, sizeof(gp));
     gp.M = M; gp.Nn = Nn; gp.num_kblocks = (K + bk - 1) / bk; gp.tiles_m = (M + 127) / 128; gp.tiles_n = (Nn + 255) / 256;
     gp.out = dC; gp.ldo = Nn; gp.alpha = 1.f; gp.beta = 0.f; gp.splits = 1; gp.kb_per_split = gp.num_kblocks;

@@ -193,7 +193,8 @@ void launch_absmax_asum(const float* x_local, long long n_local, const float* x_
 template <int PREC>
 __global__ void split_kernel(const float* __restrict__ x, int N, int D, const BlockScalars* __restrict__ bs,
                              uint16_t* __restrict__ Xs, long long ldXs, uint16_t* __restrict__ XsT, long long ldXsT,
-                             uint16_t* __restrict__ XlT, long long ldXlT, int row0, int Q) {
+                             uint16_t* __restrict__ XlT, long long ldXlT, int row0, int Q,
+                             uint16_t* __restrict__ XcatA, uint16_t* __restrict__ XcatB, long long Dp) {
   constexpr int NS = (PREC == PREC_BF16) ? 1 : (PREC == PREC_FP16X2 ? 2 : 3);
   __shared__ uint16_t tile[NS][32][34];
   const float sc = (PREC == PREC_FP16X2) ? bs->x_scale : 1.f;
@@ -209,6 +210,17 @@ __global__ void split_kernel(const float* __restrict__ x, int N, int D, const Bl
     for (int s = 0; s < NS; ++s) {
       tile[s][ty + 8 * r][tx] = p[s];
       if (n < N && d < D) Xs[s * ps + static_cast<long long>(n) * ldXs + d] = p[s];
+    }
+    // K-concatenated layout of the two-piece format (world > 1, bitwise-symmetric similarity GEMM):
+    //   A row = [ hi(0..Dp) | hi(8) lo(8) hi(8) lo(8) ... ]      B row = [ hi(0..Dp) | lo(8) hi(8) lo(8) hi(8) ... ]
+    // so that ONE K=16 MMA sums 8 products hi_j*lo_m and 8 products lo_j*hi_m: swapping the operand roles only permutes
+    // the products inside an instruction, whose sum is order-invariant (measured: tests/diag_mma_symmetry.py).
+    if (PREC == PREC_FP16X2 && XcatA && n < N && d < D) {
+      const long long rowo = static_cast<long long>(n) * (3 * Dp);
+      const long long c = Dp + 16ll * (d >> 3) + (d & 7);
+      XcatA[rowo + d] = p[0]; XcatB[rowo + d] = p[0];
+      XcatA[rowo + c] = p[0]; XcatA[rowo + c + 8] = p[1];
+      XcatB[rowo + c] = p[1]; XcatB[rowo + c + 8] = p[0];
     }
   }
   __syncthreads();
@@ -228,11 +240,12 @@ __global__ void split_kernel(const float* __restrict__ x, int N, int D, const Bl
   }
 }
 void launch_split(const float* x_total, int N, int D, int prec, const BlockScalars* bs, uint16_t* Xs, long long ldXs,
-                  uint16_t* XsT, long long ldXsT, uint16_t* XlT, long long ldXlT, int row0_local, int Q, cudaStream_t st) {
+                  uint16_t* XsT, long long ldXsT, uint16_t* XlT, long long ldXlT, int row0_local, int Q,
+                  uint16_t* XcatA, uint16_t* XcatB, long long Dp, cudaStream_t st) {
   dim3 grid((D + 31) / 32, (N + 31) / 32), block(32, 8);
-  if (prec == PREC_BF16) split_kernel<PREC_BF16><<<grid, block, 0, st>>>(x_total, N, D, bs, Xs, ldXs, XsT, ldXsT, XlT, ldXlT, row0_local, Q);
-  else if (prec == PREC_FP16X2) split_kernel<PREC_FP16X2><<<grid, block, 0, st>>>(x_total, N, D, bs, Xs, ldXs, XsT, ldXsT, XlT, ldXlT, row0_local, Q);
-  else split_kernel<PREC_BF16X3><<<grid, block, 0, st>>>(x_total, N, D, bs, Xs, ldXs, XsT, ldXsT, XlT, ldXlT, row0_local, Q);
+  if (prec == PREC_BF16) split_kernel<PREC_BF16><<<grid, block, 0, st>>>(x_total, N, D, bs, Xs, ldXs, XsT, ldXsT, XlT, ldXlT, row0_local, Q, XcatA, XcatB, Dp);
+  else if (prec == PREC_FP16X2) split_kernel<PREC_FP16X2><<<grid, block, 0, st>>>(x_total, N, D, bs, Xs, ldXs, XsT, ldXsT, XlT, ldXlT, row0_local, Q, XcatA, XcatB, Dp);
+  else split_kernel<PREC_BF16X3><<<grid, block, 0, st>>>(x_total, N, D, bs, Xs, ldXs, XsT, ldXsT, XlT, ldXlT, row0_local, Q, XcatA, XcatB, Dp);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -709,11 +722,16 @@ __device__ __forceinline__ void store_quad(uint16_t* __restrict__ base, long lon
 //     H[j][m] = g'(S[j][m]; row j) + g'(S[j][m]; row m)                       (= G + G^T, .cu:448-497 folded)
 //   needs only the row scalars of BOTH indices, which are local when world == 1.
 // !SYM (world > 1): H[j][m] = g'(j,m) and the transposed copy HT[m][j] (micro-tile transposed in registers).
-template <int PREC, bool SYM>
+// MODE BW_ROWSCAL (world > 1): the similarity GEMM is bitwise symmetric ACROSS ranks (K-concatenated operands), so the
+//   transposed term G[m][j] of row m on another rank is evaluated here from S[j][m] and row m's all-gathered scalars:
+//     H[j][m] = g'(S[j][m]; row j) + (1/world) g'(S[j][m]; row m)          -- no N x D reduce-scatter (.cu:455-497)
+template <int PREC, int MODE>
 __global__ void __launch_bounds__(256, 4) build_weights_kernel(const float* __restrict__ S, long long ldS, int Q, int N,
                                                             const float* __restrict__ lab_rows, const float* __restrict__ lab_cols,
-                                                            int self_offset, MiningParams mp, RowArrays ra,
+                                                            int self_offset, float inv_world, const float* __restrict__ rs_total,
+                                                            MiningParams mp, RowArrays ra,
                                                             uint16_t* __restrict__ H, long long ldH, uint16_t* __restrict__ HT, long long ldHT) {
+  constexpr bool SYM = (MODE != BW_SPLIT);      // both symmetric modes add the row-m term
   constexpr int TS = 64;
   const int ta = blockIdx.y, tb = blockIdx.x;
   __shared__ RowScal sc_a[TS], sc_b[TS];
@@ -728,8 +746,13 @@ __global__ void __launch_bounds__(256, 4) build_weights_kernel(const float* __re
   } else if (t < 2 * TS) {
     const int mm = t - TS, m = b0 + mm;
     RowScal r = {0.f, -INFINITY, -INFINITY, 0.f, 0.f, 0.f};
-    if (SYM) {   // world == 1: column m is also a local row
+    if (MODE == BW_SYM) {   // world == 1: column m is also a local row
       if (m < Q) { r.maxall = ra.rs_maxall[m]; r.tp = ra.rs_tp[m]; r.tn = ra.rs_tn[m]; r.cA = ra.rs_cA[m]; r.cT = ra.rs_cT[m]; r.lab = lab_rows[m]; }
+    } else if (MODE == BW_ROWSCAL) {   // all-gathered [rank][5][Q] row scalars; the 1/world of .cu:474 folded into the weights
+      if (m < N) {
+        const float* b = rs_total + static_cast<long long>(m / Q) * 5 * Q + (m % Q);
+        r.maxall = b[0]; r.tp = b[Q]; r.tn = b[2 * Q]; r.cA = b[3 * Q] * inv_world; r.cT = b[4 * Q] * inv_world; r.lab = lab_cols[m];
+      }
     } else if (m < N) r.lab = lab_cols[m];
     sc_b[mm] = r;
   }
@@ -741,7 +764,7 @@ __global__ void __launch_bounds__(256, 4) build_weights_kernel(const float* __re
   // block-uniform fast path: tile fully inside the matrix and not touching the self-pair diagonal
   const bool interior = (a0 + TS <= Q) && (b0 + TS <= N) && (a0 + self_offset + TS <= b0 || b0 + TS <= a0 + self_offset);
   const long long psH = static_cast<long long>(Q) * ldH;
-  float gT[4][4];                                        // !SYM: transposed copy for HT
+  float gT[4][4];                                        // BW_SPLIT: transposed copy for HT
   float4 v4[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {                          // all four 16-byte loads in flight before the arithmetic
@@ -775,14 +798,16 @@ __global__ void __launch_bounds__(256, 4) build_weights_kernel(const float* __re
   }
 }
 void launch_build_weights(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
-                          int self_offset, int world, MiningParams mp, RowArrays ra, int prec, uint16_t* H, long long ldH,
-                          uint16_t* HT, long long ldHT, cudaStream_t st) {
+                          int self_offset, int world, int mode, const float* rs_total, MiningParams mp, RowArrays ra, int prec,
+                          uint16_t* H, long long ldH, uint16_t* HT, long long ldHT, cudaStream_t st) {
   dim3 grid((N + 63) / 64, (Q + 63) / 64);
-#define NPAIR_BW_ARGS S, ldS, Q, N, lab_rows, lab_cols, self_offset, mp, ra, H, ldH, HT, ldHT
+  const float inv_world = 1.f / static_cast<float>(world);
+#define NPAIR_BW_ARGS S, ldS, Q, N, lab_rows, lab_cols, self_offset, inv_world, rs_total, mp, ra, H, ldH, HT, ldHT
 #define NPAIR_LAUNCH_BW(P)                                                                            \
   do {                                                                                                \
-    if (world == 1) build_weights_kernel<P, true><<<grid, 256, 0, st>>>(NPAIR_BW_ARGS);               \
-    else build_weights_kernel<P, false><<<grid, 256, 0, st>>>(NPAIR_BW_ARGS);                         \
+    if (mode == BW_SYM) build_weights_kernel<P, BW_SYM><<<grid, 256, 0, st>>>(NPAIR_BW_ARGS);         \
+    else if (mode == BW_ROWSCAL) build_weights_kernel<P, BW_ROWSCAL><<<grid, 256, 0, st>>>(NPAIR_BW_ARGS); \
+    else build_weights_kernel<P, BW_SPLIT><<<grid, 256, 0, st>>>(NPAIR_BW_ARGS);                      \
   } while (0)
   if (prec == PREC_BF16) NPAIR_LAUNCH_BW(PREC_BF16);
   else if (prec == PREC_FP16X2) NPAIR_LAUNCH_BW(PREC_FP16X2);

@@ -56,7 +56,8 @@ void launch_absmax_asum(const float* x_local, long long n_local, const float* x_
                         float* partial /*[2*1024]*/, BlockScalars* bs, int want_scale, cudaStream_t st);
 void launch_split(const float* x_total, int N, int D, int prec, const BlockScalars* bs,
                   uint16_t* Xs, long long ldXs /*Dp*/, uint16_t* XsT, long long ldXsT /*Np*/,
-                  uint16_t* XlT, long long ldXlT /*Qp, or 0*/, int row0_local, int Q, cudaStream_t st);
+                  uint16_t* XlT, long long ldXlT /*Qp, or 0*/, int row0_local, int Q,
+                  uint16_t* XcatA /*or NULL*/, uint16_t* XcatB, long long Dp, cudaStream_t st);
 void launch_init_stats(RowArrays ra, int Q, BlockScalars* bs, cudaStream_t st);
 void launch_row_stats_ref(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
                           int self_offset, RowArrays ra, cudaStream_t st);
@@ -70,8 +71,11 @@ void launch_global_select(const float* S, long long ldS, int Q, int N, const flo
 void launch_lse_rows(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
                      int self_offset, MiningParams mp, RowArrays ra, BlockScalars* bs, int num_tops, float* tops_dev /*[5]+err*/,
                      cudaStream_t st);
+// mode: BW_SPLIT (world > 1, reduce-scatter form: H and HT), BW_SYM (world == 1), BW_ROWSCAL (world > 1, row-scalar
+// exchange: rs_total = all-gathered [world][5][Q] row scalars)
+enum { BW_SPLIT = 0, BW_SYM = 1, BW_ROWSCAL = 2 };
 void launch_build_weights(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
-                          int self_offset, int world, MiningParams mp, RowArrays ra, int prec,
+                          int self_offset, int world, int mode, const float* rs_total, MiningParams mp, RowArrays ra, int prec,
                           uint16_t* H, long long ldH /*Np*/, uint16_t* HT, long long ldHT /*Qp*/, cudaStream_t st);
 void launch_axpy_rows(float* dst, const float* src, long long n, float a, cudaStream_t st);
 

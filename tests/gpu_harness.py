@@ -18,9 +18,9 @@ S_REL = {capi.PREC_FP32_BF16X3: 3e-5, capi.PREC_FP32_FP16X2: 1.5e-5, capi.PREC_B
 G_TOL = {capi.PREC_FP32_BF16X3: 1e-5, capi.PREC_FP32_FP16X2: 1e-5, capi.PREC_BF16: 2e-2}
 
 
-def gpu_step_world(x, lab, Q, world, mining, prec, backend, loss_weight=1.0, num_tops=5, want_grad=True):
-    """Emulates every rank on one GPU through the external-collectives API.
-    Returns dict(tops[world,5], dx[N,D], S[N,N], posi[N], nega[N])."""
+def gpu_step_world(x, lab, Q, world, mining, prec, backend, loss_weight=1.0, num_tops=5, want_grad=True, bwd_exchange=0):
+    """Emulates every rank on one GPU through the external-collectives API (the test plays NCCL's role).
+    Returns dict(tops[world,5], dx[N,D], S[N,N], posi[N], nega[N], mode)."""
     N, D = x.shape
     dev = torch.device("cuda:0")
     xt = torch.from_numpy(x).to(dev).contiguous()
@@ -31,33 +31,51 @@ def gpu_step_world(x, lab, Q, world, mining, prec, backend, loss_weight=1.0, num
     nega = np.zeros(N, dtype=np.float32)
     local = torch.zeros((N, D), dtype=torch.float32, device=dev)
     total = torch.zeros((N, D), dtype=torch.float32, device=dev)
-    for r in range(world):
-        cfg = capi.make_config(Q, D, world=world, rank=r, num_tops=num_tops, sim_precision=prec, gemm_backend=backend, **mining)
-        ctx = capi.Context(cfg)
-        try:
+    ctxs = []
+    try:
+        for r in range(world):
+            cfg = capi.make_config(Q, D, world=world, rank=r, num_tops=num_tops, sim_precision=prec, gemm_backend=backend,
+                                   bwd_exchange=bwd_exchange, **mining)
+            ctx = capi.Context(cfg)
+            ctxs.append(ctx)
             tops[r] = ctx.forward_gathered(xt, lt)
             S[r * Q:(r + 1) * Q] = ctx.debug_read(0, Q * N).reshape(Q, N)
             posi[r * Q:(r + 1) * Q] = ctx.debug_read(1, Q)
             nega[r * Q:(r + 1) * Q] = ctx.debug_read(2, Q)
-            if want_grad:
-                lh = torch.full((Q, D), float("nan"), dtype=torch.float32, device=dev)
-                if world > 1:
-                    th = torch.full((N, D), float("nan"), dtype=torch.float32, device=dev)
-                    ctx.backward_partial(loss_weight, lh, th)
-                    total += th
-                else:
-                    ctx.backward_partial(loss_weight, lh, None)
-                local[r * Q:(r + 1) * Q] = lh
-        finally:
-            ctx.close()
+        mode = ctxs[0].bwd_exchange_mode()
+        if want_grad:
+            if mode == 2:       # row-scalar exchange: "all-gather" the 5*Q scalars of every rank
+                rs = torch.empty((world, 5, Q), dtype=torch.float32, device=dev)
+                for r in range(world):
+                    ctxs[r].row_scalars(rs[r])
+                for r in range(world):
+                    g = torch.full((Q, D), float("nan"), dtype=torch.float32, device=dev)
+                    ctxs[r].backward_gathered(loss_weight, rs, g)
+                    local[r * Q:(r + 1) * Q] = g
+            else:
+                for r in range(world):
+                    lh = torch.full((Q, D), float("nan"), dtype=torch.float32, device=dev)
+                    if world > 1:
+                        th = torch.full((N, D), float("nan"), dtype=torch.float32, device=dev)
+                        ctxs[r].backward_partial(loss_weight, lh, th)
+                        total += th
+                    else:
+                        ctxs[r].backward_partial(loss_weight, lh, None)
+                    local[r * Q:(r + 1) * Q] = lh
+    finally:
+        for c in ctxs:
+            c.close()
     torch.cuda.synchronize()
     dx = (local + total).cpu().numpy() if want_grad else None
-    return dict(tops=tops, dx=dx, S=S, posi=posi, nega=nega)
+    return dict(tops=tops, dx=dx, S=S, posi=posi, nega=nega, mode=mode)
 
 
-def check_parity(oracle, x, lab, Q, world, mining, prec, backend, loss_weight=1.0, num_tops=5, tag=""):
+def check_parity(oracle, x, lab, Q, world, mining, prec, backend, loss_weight=1.0, num_tops=5, tag="", bwd_exchange=0):
     N, D = x.shape
-    g = gpu_step_world(x, lab, Q, world, mining, prec, backend, loss_weight, num_tops)
+    g = gpu_step_world(x, lab, Q, world, mining, prec, backend, loss_weight, num_tops, bwd_exchange=bwd_exchange)
+    if g["mode"] != 1:
+        # single-rank symmetric tiles / row-scalar exchange both rely on a bitwise symmetric similarity matrix
+        assert np.array_equal(g["S"], g["S"].T), f"{tag} S is not bitwise symmetric (mode {g['mode']})"
     cfg = oracle.make_config(Q, D, world=world, num_tops=num_tops, faithful_sorts=0, **mining)
     # ---- level 1: similarities ----
     S_ref = (x.astype(np.float64) @ x.astype(np.float64).T).astype(np.float32)

@@ -64,9 +64,10 @@ def test_kat_survey_9_3(cuda, oracle, backend):
 
 
 @pytest.mark.parametrize("backend", [capi.GEMM_SIMT_CHECK, capi.GEMM_TCGEN05])
-@pytest.mark.parametrize("world", [1, 2])
-def test_all_mining_modes_small(cuda, oracle, world, backend):
-    """Every (region, method) combination, both GEMM engines, emulated ranks."""
+@pytest.mark.parametrize("world,bwd_exchange", [(1, 0), (2, 0), (2, 1), (3, 0)])
+def test_all_mining_modes_small(cuda, oracle, world, bwd_exchange, backend):
+    """Every (region, method) combination, both GEMM engines, emulated ranks, both backward exchange forms
+    (bwd_exchange 0 = row-scalar exchange over the bitwise-symmetric GEMM, 1 = the reference's reduce-scatter form)."""
     from gpu_harness import check_parity
     Q, D = 48, 40
     x, lab = synth.make_inputs(Q * world, D, seed=100 + world, imgs_per_class=3, noise=0.7)
@@ -74,7 +75,19 @@ def test_all_mining_modes_small(cuda, oracle, world, backend):
         mining = dict(margin_ident=0.02, margin_diff=-0.03, identsn=-0.4, diffsn=-0.3,
                       ap_region=apR, ap_method=apM, an_region=anR, an_method=anM)
         check_parity(oracle, x, lab, Q, world, mining, capi.PREC_FP32_FP16X2, backend, loss_weight=0.7,
-                     tag=f"w{world} b{backend} {apR}{apM}{anR}{anM}")
+                     tag=f"w{world} x{bwd_exchange} b{backend} {apR}{apM}{anR}{anM}", bwd_exchange=bwd_exchange)
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("bwd_exchange", [0, 1])
+def test_multirank_precisions_and_exchange_forms(cuda, oracle, prec, bwd_exchange):
+    """world = 4 at a size with several tiles per rank; bf16x3 always takes the reduce-scatter form."""
+    from gpu_harness import check_parity
+    Q, world, D = 160, 4, 200
+    x, lab = synth.make_inputs(Q * world, D, seed=77, imgs_per_class=2, noise=2.5)
+    r = check_parity(oracle, x, lab, Q, world, synth.USAGE_MINING, prec, capi.GEMM_TCGEN05, tag=f"w4 {PREC_NAME[prec]} x{bwd_exchange}",
+                     bwd_exchange=bwd_exchange)
+    print(PREC_NAME[prec], bwd_exchange, r)
 
 
 @pytest.mark.parametrize("prec", PRECS)
