@@ -118,10 +118,10 @@ static bool make_tmap_f32_store(CUtensorMap* m, const void* base, int cols, int 
 static inline int nsplit_of_prec(int prec) { return prec == PREC_BF16 ? 1 : (prec == PREC_FP16X2 ? 2 : 3); }
 // K-block per (operand format, GEMM role); see GemmCfg
 static inline int bk_of(int prec, int epi) {
-  if (prec == PREC_BF16X3) return 32;
-  if (prec == PREC_FP16X2) return epi == EPI_OUT ? 32 : 64;
-  return 64;
+  if (epi != EPI_OUT) return 64;                 // similarity GEMM: single pass, 64-element K blocks
+  return prec == PREC_BF16 ? 64 : 32;
 }
+static inline int kcat_mult(int prec) { return prec == PREC_FP16X2 ? 3 : (prec == PREC_BF16X3 ? 6 : 1); }
 
 template <int NSPLIT, bool BF16, int EPI, int BK>
 static cudaError_t launch_split_gemm_t(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& sm, const GemmParams& p, int sms, cudaStream_t st) {
@@ -139,21 +139,16 @@ static cudaError_t launch_split_gemm_t(const CUtensorMap& a, const CUtensorMap& 
   return cudaGetLastError();
 }
 // `sm`: fp32 tensor map of the similarity matrix for EPI_SIM's TMA stores (ignored by EPI_OUT: pass any valid map)
-// `cat`: fp16 operands in the K-concatenated [hi | hi/lo interleaved] layout -> one fp16 pass over K = 3*Dp
-static cudaError_t launch_split_gemm(int prec, int epi, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& sm, const GemmParams& p, int sms, cudaStream_t st, bool cat = false) {
-  if (cat) return launch_split_gemm_t<1, false, EPI_SIM, 64>(a, b, sm, p, sms, st);
-  if (prec == PREC_BF16) {
-    if (epi == EPI_SIM) return launch_split_gemm_t<1, true, EPI_SIM, 64>(a, b, sm, p, sms, st);
-    if (epi == EPI_SIM_SYM) return launch_split_gemm_t<1, true, EPI_SIM_SYM, 64>(a, b, sm, p, sms, st);
-    return launch_split_gemm_t<1, true, EPI_OUT, 64>(a, b, sm, p, sms, st);
-  }
-  if (prec == PREC_FP16X2) {
-    if (epi == EPI_SIM) return launch_split_gemm_t<2, false, EPI_SIM, 64>(a, b, sm, p, sms, st);
-    if (epi == EPI_SIM_SYM) return launch_split_gemm_t<2, false, EPI_SIM_SYM, 64>(a, b, sm, p, sms, st);
-    return launch_split_gemm_t<2, false, EPI_OUT, 32>(a, b, sm, p, sms, st);
-  }
-  if (epi == EPI_SIM) return launch_split_gemm_t<3, true, EPI_SIM, 32>(a, b, sm, p, sms, st);
-  if (epi == EPI_SIM_SYM) return launch_split_gemm_t<3, true, EPI_SIM_SYM, 32>(a, b, sm, p, sms, st);
+// Similarity GEMM: always ONE MMA pass over K-concatenated operands (see split_kernel), fp16 or bf16 elements.
+static cudaError_t launch_sim_gemm(int prec, bool sym_tiles, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& sm, const GemmParams& p, int sms, cudaStream_t st) {
+  if (prec == PREC_FP16X2) return sym_tiles ? launch_split_gemm_t<1, false, EPI_SIM_SYM, 64>(a, b, sm, p, sms, st) : launch_split_gemm_t<1, false, EPI_SIM, 64>(a, b, sm, p, sms, st);
+  return sym_tiles ? launch_split_gemm_t<1, true, EPI_SIM_SYM, 64>(a, b, sm, p, sms, st) : launch_split_gemm_t<1, true, EPI_SIM, 64>(a, b, sm, p, sms, st);
+}
+// Gradient GEMM: A = split gradient weights, B = split transposed features (EPI_OUT)
+static cudaError_t launch_split_gemm(int prec, int epi, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& sm, const GemmParams& p, int sms, cudaStream_t st) {
+  (void)epi;
+  if (prec == PREC_BF16) return launch_split_gemm_t<1, true, EPI_OUT, 64>(a, b, sm, p, sms, st);
+  if (prec == PREC_FP16X2) return launch_split_gemm_t<2, false, EPI_OUT, 32>(a, b, sm, p, sms, st);
   return launch_split_gemm_t<3, true, EPI_OUT, 32>(a, b, sm, p, sms, st);
 }
 
@@ -449,15 +444,14 @@ static int create_impl(const npair_config* cfg, const void* id128, void* ext_com
   CREATE_TRY(cudaMalloc(&c->H, 2ull * ns * Q * c->Np));
   CREATE_TRY(cudaMemset(c->H, 0, 2ull * ns * Q * c->Np));
   c->bwd_mode = c->world == 1 ? NPAIR_BWDMODE_SINGLE
-              : ((cfg->bwd_exchange == NPAIR_BWD_AUTO && c->prec != PREC_BF16X3) ? NPAIR_BWDMODE_ROW_SCALARS : NPAIR_BWDMODE_REDUCE_SCATTER);
-  if (c->bwd_mode == NPAIR_BWDMODE_ROW_SCALARS) {
-    CREATE_TRY(cudaMalloc(&c->rs_total, sizeof(float) * 5ull * N));
-    if (c->prec == PREC_FP16X2 && cfg->gemm_backend == NPAIR_GEMM_TCGEN05) {
-      CREATE_TRY(cudaMalloc(&c->XcatA, 2ull * N * 3 * c->Dp));
-      CREATE_TRY(cudaMemset(c->XcatA, 0, 2ull * N * 3 * c->Dp));
-      CREATE_TRY(cudaMalloc(&c->XcatB, 2ull * N * 3 * c->Dp));
-      CREATE_TRY(cudaMemset(c->XcatB, 0, 2ull * N * 3 * c->Dp));
-    }
+              : (cfg->bwd_exchange == NPAIR_BWD_AUTO ? NPAIR_BWDMODE_ROW_SCALARS : NPAIR_BWDMODE_REDUCE_SCATTER);
+  if (c->bwd_mode == NPAIR_BWDMODE_ROW_SCALARS) CREATE_TRY(cudaMalloc(&c->rs_total, sizeof(float) * 5ull * N));
+  if (c->prec != PREC_BF16 && cfg->gemm_backend == NPAIR_GEMM_TCGEN05) {
+    const size_t cat_bytes = 2ull * N * kcat_mult(c->prec) * c->Dp;
+    CREATE_TRY(cudaMalloc(&c->XcatA, cat_bytes));
+    CREATE_TRY(cudaMemset(c->XcatA, 0, cat_bytes));
+    CREATE_TRY(cudaMalloc(&c->XcatB, cat_bytes));
+    CREATE_TRY(cudaMemset(c->XcatB, 0, cat_bytes));
   }
   if (c->bwd_mode == NPAIR_BWDMODE_REDUCE_SCATTER) {
     CREATE_TRY(cudaMalloc(&c->XlT, 2ull * ns * D * c->Qp));
@@ -509,9 +503,10 @@ static int create_impl(const npair_config* cfg, const void* id128, void* ext_com
     // gradient 1: A = H [Q x N], B = XsT [D x N]; K = N
     ok = ok && make_tmap_pieces(&c->tm_b1A, c->H, N, Q, ns, c->Np, static_cast<long long>(Q) * c->Np, bkg, 128, &te);
     ok = ok && make_tmap_pieces(&c->tm_b1B, c->XsT, N, D, ns, c->Np, static_cast<long long>(D) * c->Np, bkg, 256, &te);
-    if (c->XcatA) {       // bitwise-symmetric similarity: one fp16 pass over K = 3*Dp
-      ok = ok && make_tmap_pieces(&c->tm_catA, c->XcatA + static_cast<long long>(c->rank) * Q * 3 * c->Dp, static_cast<int>(3 * c->Dp), Q, 1, 3 * c->Dp, static_cast<long long>(N) * 3 * c->Dp, 64, 128, &te);
-      ok = ok && make_tmap_pieces(&c->tm_catB, c->XcatB, static_cast<int>(3 * c->Dp), N, 1, 3 * c->Dp, static_cast<long long>(N) * 3 * c->Dp, 64, 256, &te);
+    if (c->XcatA) {       // bitwise-symmetric similarity: one pass over K_cat = 3*Dp (fp16x2) / 6*Dp (bf16x3)
+      const long long kc = kcat_mult(c->prec) * c->Dp;
+      ok = ok && make_tmap_pieces(&c->tm_catA, c->XcatA + static_cast<long long>(c->rank) * Q * kc, static_cast<int>(kc), Q, 1, kc, static_cast<long long>(N) * kc, 64, 128, &te);
+      ok = ok && make_tmap_pieces(&c->tm_catB, c->XcatB, static_cast<int>(kc), N, 1, kc, static_cast<long long>(N) * kc, 64, 256, &te);
     }
     if (c->bwd_mode == NPAIR_BWDMODE_REDUCE_SCATTER) {   // gradient 2: A = HT [N x Q], B = XlT [D x Q]; K = Q
       ok = ok && make_tmap_pieces(&c->tm_b2A, c->HT, Q, N, ns, c->Qp, static_cast<long long>(N) * c->Qp, bkg, 128, &te);
@@ -622,10 +617,10 @@ static int forward_impl(npair_ctx* c, const float* d_feat, const float* d_label,
     PhaseTimer pt(c, 2, st);
     if (c->sym_tiles) { gp.tile_list = c->sym_tiles; gp.num_tiles_list = c->n_sym_tiles; }
     if (c->XcatA) {
-      gp.num_kblocks = static_cast<int>(3 * c->Dp / 64); gp.kb_per_split = gp.num_kblocks;
-      CUDA_TRY(c, launch_split_gemm(c->prec, EPI_SIM, c->tm_catA, c->tm_catB, c->tm_S, gp, c->sms, st, true));
+      gp.num_kblocks = static_cast<int>(kcat_mult(c->prec) * c->Dp / 64); gp.kb_per_split = gp.num_kblocks;
+      CUDA_TRY(c, launch_sim_gemm(c->prec, c->sym_tiles != nullptr, c->tm_catA, c->tm_catB, c->tm_S, gp, c->sms, st));
     } else
-    CUDA_TRY(c, launch_split_gemm(c->prec, c->sym_tiles ? EPI_SIM_SYM : EPI_SIM, c->tm_simA, c->tm_simB, c->tm_S, gp, c->sms, st));
+      CUDA_TRY(c, launch_sim_gemm(c->prec, c->sym_tiles != nullptr, c->tm_simA, c->tm_simB, c->tm_S, gp, c->sms, st));
   } else {
     CUDA_TRY(c, launch_simt_gemm(c->prec, EPI_SIM, c->Xs + static_cast<long long>(self_off) * c->Dp, c->Dp, static_cast<long long>(N) * c->Dp,
                                  c->Xs, c->Dp, static_cast<long long>(N) * c->Dp, D, gp, st));

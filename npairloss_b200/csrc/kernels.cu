@@ -211,16 +211,27 @@ __global__ void split_kernel(const float* __restrict__ x, int N, int D, const Bl
       tile[s][ty + 8 * r][tx] = p[s];
       if (n < N && d < D) Xs[s * ps + static_cast<long long>(n) * ldXs + d] = p[s];
     }
-    // K-concatenated layout of the two-piece format (world > 1, bitwise-symmetric similarity GEMM):
-    //   A row = [ hi(0..Dp) | hi(8) lo(8) hi(8) lo(8) ... ]      B row = [ hi(0..Dp) | lo(8) hi(8) lo(8) hi(8) ... ]
-    // so that ONE K=16 MMA sums 8 products hi_j*lo_m and 8 products lo_j*hi_m: swapping the operand roles only permutes
-    // the products inside an instruction, whose sum is order-invariant (measured: tests/diag_mma_symmetry.py).
-    if (PREC == PREC_FP16X2 && XcatA && n < N && d < D) {
-      const long long rowo = static_cast<long long>(n) * (3 * Dp);
-      const long long c = Dp + 16ll * (d >> 3) + (d & 7);
+    // K-concatenated operands of the bitwise-symmetric similarity GEMM (one MMA pass over K_cat):
+    //   fp16x2 : A row = [ hi | hi(8) lo(8) ... ]                         B row = [ hi | lo(8) hi(8) ... ]                  K_cat = 3*Dp
+    //   bf16x3 : A row = [ hi | mid | hi(8) mid(8) ... | hi(8) lo(8) ... ]   B row = [ hi | mid | mid(8) hi(8) ... | lo(8) hi(8) ... ]   K_cat = 6*Dp
+    // ONE K=16 MMA then sums 8 products p_j*q_m and the 8 mirrored products q_j*p_m: swapping the operand roles only
+    // permutes the products inside an instruction, whose sum is order-invariant (measured: tests/diag_mma_symmetry.py),
+    // so S[j][m] == S[m][j] bit for bit, on one rank and across ranks.
+    if (PREC != PREC_BF16 && XcatA && n < N && d < D) {
+      const long long kcat = (PREC == PREC_FP16X2 ? 3 : 6) * Dp;
+      const long long rowo = static_cast<long long>(n) * kcat;
+      const long long x = 16ll * (d >> 3) + (d & 7);
       XcatA[rowo + d] = p[0]; XcatB[rowo + d] = p[0];
-      XcatA[rowo + c] = p[0]; XcatA[rowo + c + 8] = p[1];
-      XcatB[rowo + c] = p[1]; XcatB[rowo + c + 8] = p[0];
+      if (PREC == PREC_FP16X2) {
+        XcatA[rowo + Dp + x] = p[0]; XcatA[rowo + Dp + x + 8] = p[1];
+        XcatB[rowo + Dp + x] = p[1]; XcatB[rowo + Dp + x + 8] = p[0];
+      } else {
+        XcatA[rowo + Dp + d] = p[1]; XcatB[rowo + Dp + d] = p[1];
+        XcatA[rowo + 2 * Dp + x] = p[0]; XcatA[rowo + 2 * Dp + x + 8] = p[1];
+        XcatB[rowo + 2 * Dp + x] = p[1]; XcatB[rowo + 2 * Dp + x + 8] = p[0];
+        XcatA[rowo + 4 * Dp + x] = p[0]; XcatA[rowo + 4 * Dp + x + 8] = p[2];
+        XcatB[rowo + 4 * Dp + x] = p[2]; XcatB[rowo + 4 * Dp + x + 8] = p[0];
+      }
     }
   }
   __syncthreads();
