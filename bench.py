@@ -299,7 +299,7 @@ def main():
 
     # ---------------- profiled pass: per-phase CUDA events (roofline of the dominant kernel) ----------------
     ctx.profile_enable(True)
-    phases = np.zeros(8)
+    phases = np.zeros(9)
     nprof = min(args.steps, 10)
     for _ in range(nprof):
         step_device()
@@ -318,7 +318,8 @@ def main():
                 "duration_ms": sim_ms, "traffic": None,
                 "note": "achieved = algorithmic 2*Q*N*D flops / live CUDA-event duration; the fp32-faithful modes issue mma_passes "
                         "bf16-rate MMA passes per algorithmic flop, frac_of_issued_mma counts them"}
-    phase_names = ["collectives", "operand_prep", "sim_gemm", "thresholds_select", "row_pass_finalize", "weight_build", "grad_gemm", "grad_gemm_T"]
+    phase_names = ["fwd_allgather", "operand_prep", "sim_gemm", "thresholds_select", "row_pass_finalize", "weight_build", "grad_gemm",
+                   "grad_gemm_T", "bwd_exchange"]
     phase_ms = {n: float(v) for n, v in zip(phase_names, phases)}
     # memory-bound kernels: algorithmic bytes = one fp32 pass over the Q x N block
     sbytes = 4.0 * Q * N
@@ -328,8 +329,8 @@ def main():
 
     # kernels launched per step by OUR library (counted from the launch sequence in ctx.cu)
     launches = 2 + 1 + 1 + 1 + 1 + 1 + 1 + 1               # absmax x2, split, init, sim gemm, thresholds, row pass (+finalize), build, grad gemm
-    if world > 1:
-        launches += 1                                       # transposed gradient GEMM
+    if world > 1 and Q * 1 < 128 * 148:
+        launches += 1                                       # split-K reduce of the gradient GEMM when Q = B/world leaves few tiles
     gpu_launches = launches * args.steps
 
     # ---------------- CPU baseline (rank 0, bounded sample) ----------------

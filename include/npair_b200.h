@@ -136,10 +136,11 @@ const char* npair_last_error(const npair_ctx* ctx);   /* ctx may be NULL: last c
 const char* npair_version(void);
 
 /* Per-phase CUDA-event timing on the caller's stream (used by bench.py for the roofline of the dominant kernel).
- * ms_out[8]: 0 collectives  1 operand prep  2 similarity GEMM (+fused statistics)  3 thresholds / radix selects
- *            4 forward row pass + finalize  5 backward weight builder  6 gradient GEMM  7 transposed gradient GEMM */
+ * ms_out[9]: 0 forward all-gather  1 operand prep  2 similarity GEMM (+fused statistics)  3 thresholds / radix selects
+ *            4 forward row pass + finalize  5 backward weight builder  6 gradient GEMM  7 transposed gradient GEMM
+ *            8 backward exchange (row-scalar all-gather or reduce-scatter) */
 int npair_profile_enable(npair_ctx* ctx, int on);
-int npair_profile_read(npair_ctx* ctx, float ms_out[8]);
+int npair_profile_read(npair_ctx* ctx, float ms_out[9]);
 
 /* Device-side dtype bridges for the Dtype=double instantiation of the Caffe layer (INSTANTIATE_CLASS, reference
  * npair_multi_class_loss.cpp:190); the reference's arithmetic is fp32 there too (expf/logf/FLT_MAX). */

@@ -164,9 +164,9 @@ class Context:
         self._check(lib().npair_profile_enable(self._h, 1 if on else 0))
 
     def profile_read(self):
-        ms = (C.c_float * 8)()
+        ms = (C.c_float * 9)()
         self._check(lib().npair_profile_read(self._h, ms))
-        return [ms[i] for i in range(8)]
+        return [ms[i] for i in range(9)]
 
     def debug_read(self, which: int, n: int):
         import numpy as np

@@ -257,7 +257,7 @@ static inline long long round_up(long long v, long long m) { return (v + m - 1) 
 
 using namespace npair;
 
-#define NPAIR_PROF_PHASES 8
+#define NPAIR_PROF_PHASES 9
 
 // ------------------------------------------------------------------------------------------------ context
 struct npair_ctx {
@@ -718,7 +718,7 @@ static int backward_impl(npair_ctx* c, float loss_weight, float* d_diff, float* 
     if (d_rs_ext) rs_total = d_rs_ext;
     else {
       // the only backward exchange: 5*Q floats per rank (replaces the N x D MPI_Allreduce of .cu:462-489)
-      PhaseTimer pt(c, 0, st);
+      PhaseTimer pt(c, 8, st);
       NcclApi* api = nccl_api();
       int r = api->AllGather(c->ra.rs_maxall, c->rs_total, 5ull * Q, NCCL_FLOAT32, c->comm, st);
       if (r != 0) { c->err = fmt("ncclAllGather(row scalars): %s", api->GetErrorString(r)); return NPAIR_E_NCCL; }
@@ -743,7 +743,7 @@ static int backward_impl(npair_ctx* c, float loss_weight, float* d_diff, float* 
       else CUDA_TRY(c, launch_simt_gemm(c->prec, EPI_OUT, c->HT, c->Qp, static_cast<long long>(N) * c->Qp, c->XlT, c->Qp, static_cast<long long>(D) * c->Qp, Q, gp, st));
     }
     if (!d_total_ext) {
-      PhaseTimer pt(c, 0, st);
+      PhaseTimer pt(c, 8, st);
       NcclApi* api = nccl_api();
       int r = api->ReduceScatter(c->OUT2, d_diff, static_cast<size_t>(Q) * D, NCCL_FLOAT32, NCCL_SUM, c->comm, st);
       if (r != 0) { c->err = fmt("ncclReduceScatter: %s", api->GetErrorString(r)); return NPAIR_E_NCCL; }
@@ -770,7 +770,7 @@ static int backward_impl(npair_ctx* c, float loss_weight, float* d_diff, float* 
 }
 
 /* Per-phase CUDA-event timing on the caller's stream (bench.py's roofline leg).  Phases:
- * 0 collectives (all-gather, reduce-scatter; the backward one overwrites the forward one)  1 operand prep (asum/absmax, split, stat init)
+ * 0 forward all-gather   8 backward exchange (row-scalar all-gather or reduce-scatter)   1 operand prep (asum/absmax, split, stat init)
  * 2 similarity GEMM + fused statistics   3 thresholds + radix selects   4 forward row pass + finalize
  * 5 backward weight builder   6 gradient GEMM (G . X_total)   7 transposed gradient GEMM (G^T . X_local, world > 1) */
 int npair_profile_enable(npair_ctx* c, int on) {
@@ -784,7 +784,7 @@ int npair_profile_enable(npair_ctx* c, int on) {
   for (int i = 0; i < NPAIR_PROF_PHASES; ++i) c->ev_used[i] = false;
   return NPAIR_OK;
 }
-/* milliseconds of each phase of the most recent forward+backward; synchronises the stream.  ms_out[8]. */
+/* milliseconds of each phase of the most recent forward+backward; synchronises the stream.  ms_out[9]. */
 int npair_profile_read(npair_ctx* c, float* ms_out) {
   if (!c || !ms_out) return NPAIR_E_ARG;
   CUDA_TRY(c, cudaSetDevice(c->device));
@@ -908,8 +908,8 @@ int npair_debug_gemm(int precision, int backend, int M, int Nn, int K, const flo
       float sc[2] = {1.f, 1.f};
       DG_TRY(cudaMemcpy(&bs->x_scale, sc, 8, cudaMemcpyHostToDevice));
     }
-    launch_split(dA, M, K, precision, bs, As, Kp, dummyT, tmax, nullptr, 0, 0, 0, nullptr, nullptr, 0, st);
-    launch_split(dB, Nn, K, precision, bs, Bs, Kp, dummyT, tmax, nullptr, 0, 0, 0, nullptr, nullptr, 0, st);
+    launch_split(dA, M, K, precision, bs, As, Kp, dummyT, tmax, nullptr, 0, 0, 0, nullptr, nullptr, Kp, st);
+    launch_split(dB, Nn, K, precision, bs, Bs, Kp, dummyT, tmax, nullptr, 0, 0, 0, nullptr, nullptr, Kp, st);
     GemmParams gp; memset(&gp, 0, sizeof(gp));
     gp.M = M; gp.Nn = Nn; gp.num_kblocks = (K + bk - 1) / bk; gp.tiles_m = (M + 127) / 128; gp.tiles_n = (Nn + 255) / 256;
     gp.out = dC; gp.ldo = Nn; gp.alpha = 1.f; gp.beta = 0.f; gp.splits = 1; gp.kb_per_split = gp.num_kblocks;

@@ -190,62 +190,94 @@ void launch_absmax_asum(const float* x_local, long long n_local, const float* x_
 // operand split: x_total fp32 [N x D] -> Xs[s][N][ldXs] (K-major for the similarity GEMM) and the transposed
 // XsT[s][D][ldXsT] (K-major for the gradient GEMM whose K is the sample index); XlT = local columns only.
 // --------------------------------------------------------------------------------------------
+// Block = 256 threads, tile = 32 rows (n) x 64 features (d).  Thread (nl = t/8, dg = t%8) converts 8 consecutive features of
+// one row: two 16-byte loads, one 16-byte store per piece / section; the transposed pieces go through a shared tile so
+// that they, too, are written as 16-byte row segments.
 template <int PREC>
-__global__ void split_kernel(const float* __restrict__ x, int N, int D, const BlockScalars* __restrict__ bs,
-                             uint16_t* __restrict__ Xs, long long ldXs, uint16_t* __restrict__ XsT, long long ldXsT,
-                             uint16_t* __restrict__ XlT, long long ldXlT, int row0, int Q,
-                             uint16_t* __restrict__ XcatA, uint16_t* __restrict__ XcatB, long long Dp) {
+__global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ x, int N, int D, const BlockScalars* __restrict__ bs,
+                                                    uint16_t* __restrict__ Xs, long long ldXs, uint16_t* __restrict__ XsT, long long ldXsT,
+                                                    uint16_t* __restrict__ XlT, long long ldXlT, int row0, int Q,
+                                                    uint16_t* __restrict__ XcatA, uint16_t* __restrict__ XcatB, long long Dp) {
   constexpr int NS = (PREC == PREC_BF16) ? 1 : (PREC == PREC_FP16X2 ? 2 : 3);
-  __shared__ uint16_t tile[NS][32][34];
+  __shared__ __align__(16) uint16_t tile[NS][64][40];      // [piece][d][n], row padded to 80 bytes (16-byte aligned, spreads banks)
   const float sc = (PREC == PREC_FP16X2) ? bs->x_scale : 1.f;
-  const int n0 = blockIdx.y * 32, d0 = blockIdx.x * 32;
-  const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
-  const long long ps = static_cast<long long>(N) * ldXs;
+  const int n0 = blockIdx.y * 32, d0 = blockIdx.x * 64;
+  const int t = threadIdx.x, nl = t >> 3, dg = t & 7;
+  const int n = n0 + nl, d = d0 + 8 * dg;
+  uint16_t p[8][3];
+  float v[8];
+  const bool rowok = n < N;
+  if (rowok && d + 7 < D && (D & 3) == 0) {
+    const float4 a = *reinterpret_cast<const float4*>(x + static_cast<long long>(n) * D + d);
+    const float4 b4 = *reinterpret_cast<const float4*>(x + static_cast<long long>(n) * D + d + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b4.x; v[5] = b4.y; v[6] = b4.z; v[7] = b4.w;
+  } else {
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int n = n0 + ty + 8 * r, d = d0 + tx;
-    uint16_t p[3] = {0, 0, 0};
-    if (n < N && d < D) split3<PREC>(x[static_cast<long long>(n) * D + d] * sc, p[0], p[1], p[2]);
+    for (int e = 0; e < 8; ++e) v[e] = (rowok && d + e < D) ? x[static_cast<long long>(n) * D + d + e] : 0.f;
+  }
 #pragma unroll
-    for (int s = 0; s < NS; ++s) {
-      tile[s][ty + 8 * r][tx] = p[s];
-      if (n < N && d < D) Xs[s * ps + static_cast<long long>(n) * ldXs + d] = p[s];
-    }
+  for (int e = 0; e < 8; ++e) split3<PREC>(v[e] * sc, p[e][0], p[e][1], p[e][2]);
+  uint4 pk[3];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    pk[s] = make_uint4(p[0][s] | (static_cast<uint32_t>(p[1][s]) << 16), p[2][s] | (static_cast<uint32_t>(p[3][s]) << 16),
+                       p[4][s] | (static_cast<uint32_t>(p[5][s]) << 16), p[6][s] | (static_cast<uint32_t>(p[7][s]) << 16));
+#pragma unroll
+    for (int e = 0; e < 8; ++e) tile[s][8 * dg + e][nl] = p[e][s];
+  }
+  // every destination row is padded to a multiple of 64 elements (Dp), so whole 16-byte groups can be stored even when
+  // D is ragged: the excess elements are zeros (v = 0 above) and lie beyond the TMA extent anyway
+  if (rowok && d < Dp) {
+    const long long ps = static_cast<long long>(N) * ldXs;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) *reinterpret_cast<uint4*>(Xs + s * ps + static_cast<long long>(n) * ldXs + d) = pk[s];
     // K-concatenated operands of the bitwise-symmetric similarity GEMM (one MMA pass over K_cat):
     //   fp16x2 : A row = [ hi | hi(8) lo(8) ... ]                         B row = [ hi | lo(8) hi(8) ... ]                  K_cat = 3*Dp
     //   bf16x3 : A row = [ hi | mid | hi(8) mid(8) ... | hi(8) lo(8) ... ]   B row = [ hi | mid | mid(8) hi(8) ... | lo(8) hi(8) ... ]   K_cat = 6*Dp
     // ONE K=16 MMA then sums 8 products p_j*q_m and the 8 mirrored products q_j*p_m: swapping the operand roles only
     // permutes the products inside an instruction, whose sum is order-invariant (measured: tests/diag_mma_symmetry.py),
     // so S[j][m] == S[m][j] bit for bit, on one rank and across ranks.
-    if (PREC != PREC_BF16 && XcatA && n < N && d < D) {
+    if (PREC != PREC_BF16 && XcatA) {
       const long long kcat = (PREC == PREC_FP16X2 ? 3 : 6) * Dp;
-      const long long rowo = static_cast<long long>(n) * kcat;
-      const long long x = 16ll * (d >> 3) + (d & 7);
-      XcatA[rowo + d] = p[0]; XcatB[rowo + d] = p[0];
+      uint16_t* ra = XcatA + static_cast<long long>(n) * kcat;
+      uint16_t* rb = XcatB + static_cast<long long>(n) * kcat;
+      const bool local = (n >= row0 && n < row0 + Q);        // only the rank's own rows are ever an A operand
+      *reinterpret_cast<uint4*>(rb + d) = pk[0];
+      if (local) *reinterpret_cast<uint4*>(ra + d) = pk[0];
       if (PREC == PREC_FP16X2) {
-        XcatA[rowo + Dp + x] = p[0]; XcatA[rowo + Dp + x + 8] = p[1];
-        XcatB[rowo + Dp + x] = p[1]; XcatB[rowo + Dp + x + 8] = p[0];
+        *reinterpret_cast<uint4*>(rb + Dp + 2 * d) = pk[1]; *reinterpret_cast<uint4*>(rb + Dp + 2 * d + 8) = pk[0];
+        if (local) { *reinterpret_cast<uint4*>(ra + Dp + 2 * d) = pk[0]; *reinterpret_cast<uint4*>(ra + Dp + 2 * d + 8) = pk[1]; }
       } else {
-        XcatA[rowo + Dp + d] = p[1]; XcatB[rowo + Dp + d] = p[1];
-        XcatA[rowo + 2 * Dp + x] = p[0]; XcatA[rowo + 2 * Dp + x + 8] = p[1];
-        XcatB[rowo + 2 * Dp + x] = p[1]; XcatB[rowo + 2 * Dp + x + 8] = p[0];
-        XcatA[rowo + 4 * Dp + x] = p[0]; XcatA[rowo + 4 * Dp + x + 8] = p[2];
-        XcatB[rowo + 4 * Dp + x] = p[2]; XcatB[rowo + 4 * Dp + x + 8] = p[0];
+        *reinterpret_cast<uint4*>(rb + Dp + d) = pk[1];
+        *reinterpret_cast<uint4*>(rb + 2 * Dp + 2 * d) = pk[1]; *reinterpret_cast<uint4*>(rb + 2 * Dp + 2 * d + 8) = pk[0];
+        *reinterpret_cast<uint4*>(rb + 4 * Dp + 2 * d) = pk[2]; *reinterpret_cast<uint4*>(rb + 4 * Dp + 2 * d + 8) = pk[0];
+        if (local) {
+          *reinterpret_cast<uint4*>(ra + Dp + d) = pk[1];
+          *reinterpret_cast<uint4*>(ra + 2 * Dp + 2 * d) = pk[0]; *reinterpret_cast<uint4*>(ra + 2 * Dp + 2 * d + 8) = pk[1];
+          *reinterpret_cast<uint4*>(ra + 4 * Dp + 2 * d) = pk[0]; *reinterpret_cast<uint4*>(ra + 4 * Dp + 2 * d + 8) = pk[2];
+        }
       }
     }
   }
   __syncthreads();
-  const long long pt = static_cast<long long>(D) * ldXsT;
-  const long long pl = static_cast<long long>(D) * ldXlT;
+  // transposed pieces: thread (dl = t/4, nc = t%4) stores 8 consecutive rows n of feature d0 + dl
+  const int dl = t >> 2, nc = t & 3;
+  const int dd = d0 + dl, nn = n0 + 8 * nc;
+  if (dd < D && nn < N) {
+    const long long pt = static_cast<long long>(D) * ldXsT;
+    const long long pl = static_cast<long long>(D) * ldXlT;
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int d = d0 + ty + 8 * r, n = n0 + tx;
-    if (d < D && n < N) {
-#pragma unroll
-      for (int s = 0; s < NS; ++s) {
-        const uint16_t v = tile[s][tx][ty + 8 * r];
-        XsT[s * pt + static_cast<long long>(d) * ldXsT + n] = v;
-        if (XlT && n >= row0 && n < row0 + Q) XlT[s * pl + static_cast<long long>(d) * ldXlT + (n - row0)] = v;
+    for (int s = 0; s < NS; ++s) {
+      const uint4 q = *reinterpret_cast<const uint4*>(&tile[s][dl][8 * nc]);
+      *reinterpret_cast<uint4*>(XsT + s * pt + static_cast<long long>(dd) * ldXsT + nn) = q;     // ldXsT, nn multiples of 8
+      if (XlT && nn >= row0 && nn < row0 + Q) {
+        if (((nn - row0) & 7) == 0 && nn + 8 <= row0 + Q) *reinterpret_cast<uint4*>(XlT + s * pl + static_cast<long long>(dd) * ldXlT + (nn - row0)) = q;
+        else
+          for (int e = 0; e < 8; ++e)
+            if (nn + e < row0 + Q && nn + e < N) XlT[s * pl + static_cast<long long>(dd) * ldXlT + (nn + e - row0)] = tile[s][dl][8 * nc + e];
+      } else if (XlT && nn < row0 && nn + 8 > row0) {
+        for (int e = 0; e < 8; ++e)
+          if (nn + e >= row0 && nn + e < row0 + Q && nn + e < N) XlT[s * pl + static_cast<long long>(dd) * ldXlT + (nn + e - row0)] = tile[s][dl][8 * nc + e];
       }
     }
   }
@@ -253,10 +285,10 @@ __global__ void split_kernel(const float* __restrict__ x, int N, int D, const Bl
 void launch_split(const float* x_total, int N, int D, int prec, const BlockScalars* bs, uint16_t* Xs, long long ldXs,
                   uint16_t* XsT, long long ldXsT, uint16_t* XlT, long long ldXlT, int row0_local, int Q,
                   uint16_t* XcatA, uint16_t* XcatB, long long Dp, cudaStream_t st) {
-  dim3 grid((D + 31) / 32, (N + 31) / 32), block(32, 8);
-  if (prec == PREC_BF16) split_kernel<PREC_BF16><<<grid, block, 0, st>>>(x_total, N, D, bs, Xs, ldXs, XsT, ldXsT, XlT, ldXlT, row0_local, Q, XcatA, XcatB, Dp);
-  else if (prec == PREC_FP16X2) split_kernel<PREC_FP16X2><<<grid, block, 0, st>>>(x_total, N, D, bs, Xs, ldXs, XsT, ldXsT, XlT, ldXlT, row0_local, Q, XcatA, XcatB, Dp);
-  else split_kernel<PREC_BF16X3><<<grid, block, 0, st>>>(x_total, N, D, bs, Xs, ldXs, XsT, ldXsT, XlT, ldXlT, row0_local, Q, XcatA, XcatB, Dp);
+  dim3 grid((D + 63) / 64, (N + 31) / 32);
+  if (prec == PREC_BF16) split_kernel<PREC_BF16><<<grid, 256, 0, st>>>(x_total, N, D, bs, Xs, ldXs, XsT, ldXsT, XlT, ldXlT, row0_local, Q, XcatA, XcatB, Dp);
+  else if (prec == PREC_FP16X2) split_kernel<PREC_FP16X2><<<grid, 256, 0, st>>>(x_total, N, D, bs, Xs, ldXs, XsT, ldXsT, XlT, ldXlT, row0_local, Q, XcatA, XcatB, Dp);
+  else split_kernel<PREC_BF16X3><<<grid, 256, 0, st>>>(x_total, N, D, bs, Xs, ldXs, XsT, ldXsT, XlT, ldXlT, row0_local, Q, XcatA, XcatB, Dp);
 }
 
 // --------------------------------------------------------------------------------------------

@@ -14,9 +14,9 @@ dg = torch.empty_like(dx)
 for _ in range(5):
     ctx.forward(dx, dl); ctx.backward(1.0, dg)
 ctx.profile_enable(True)
-acc = np.zeros(8); n = 20
+acc = np.zeros(9); n = 20
 for _ in range(n):
     ctx.forward(dx, dl); ctx.backward(1.0, dg); acc += np.array(ctx.profile_read())
 acc /= n
-names = ["coll", "prep", "sim", "thr", "row", "build", "grad", "gradT"]
+names = ["allg", "prep", "sim", "thr", "row", "build", "grad", "gradT", "bwdx"]
 print(os.environ.get("NPAIR_LIB", "default"), sys.argv[1:], " ".join(f"{k}={v*1e3:.1f}us" for k, v in zip(names, acc)), f"sum={acc.sum()*1e3:.1f}us")
