@@ -328,7 +328,7 @@ def main():
            "hbm_peak_GBs": peaks["hbm_gbs"]}
 
     # kernels launched per step by OUR library (counted from the launch sequence in ctx.cu)
-    launches = 2 + 1 + 1 + 1 + 1 + 1 + 1 + 1               # absmax x2, split, init, sim gemm, thresholds, row pass (+finalize), build, grad gemm
+    launches = 1 + 1 + 1 + 1 + 1 + 1 + 1                   # prep-reduce, split, sim gemm, thresholds, row pass (+finalize), build, grad gemm
     if world > 1 and Q * 1 < 128 * 148:
         launches += 1                                       # split-K reduce of the gradient GEMM when Q = B/world leaves few tiles
     gpu_launches = launches * args.steps

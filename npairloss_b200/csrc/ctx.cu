@@ -601,10 +601,9 @@ static int forward_impl(npair_ctx* c, const float* d_feat, const float* d_label,
   // ---- operand preparation: |x| sum (top asum, .cu:400), power-of-two pre-scale, split to tensor-core pieces ----
   {
     PhaseTimer pt(c, 1, st);
-    launch_absmax_asum(d_feat, static_cast<long long>(Q) * D, c->x_total, static_cast<long long>(N) * D, c->partial, c->bs,
-                       c->prec == PREC_FP16X2 ? 1 : 0, st);
+    launch_prep_reduce(d_feat, static_cast<long long>(Q) * D, c->x_total, static_cast<long long>(N) * D, c->partial,
+                       c->prec == PREC_FP16X2 ? 1 : 0, c->ra, Q, c->bs, st);
     launch_split(c->x_total, N, D, c->prec, c->bs, c->Xs, c->Dp, c->XsT, c->Np, c->XlT, c->Qp, self_off, Q, c->XcatA, c->XcatB, c->Dp, st);
-    launch_init_stats(c->ra, Q, c->bs, st);
   }
   // ---- S = X_local . X_total^T (.cu:218) with fused masks + row statistics (.cu:44-66, :225-265) ----
   GemmParams gp; memset(&gp, 0, sizeof(gp));
@@ -629,7 +628,7 @@ static int forward_impl(npair_ctx* c, const float* d_feat, const float* d_label,
   // ---- thresholds (.cu:275-337) ----
   {
   PhaseTimer pt(c, 3, st);
-  launch_thresholds(c->ra, Q, N, mp, c->bs, st);
+  launch_thresholds(c->ra, Q, N, mp, c->bs, c->partial, st);
   if (is_rel_m(mp.ap_method) && !sn_max(mp.identsn)) {
     if (mp.ap_region == NPAIR_LOCAL) launch_local_select(c->S, c->ldS, Q, N, d_label, c->lab_total, self_off, 0, mp.identsn, c->ra, c->bs, st);
     else launch_global_select(c->S, c->ldS, Q, N, d_label, c->lab_total, self_off, 0, mp.identsn, c->ra, c->ghist, c->bs, st);

@@ -135,6 +135,67 @@ __device__ __forceinline__ bool sel_an(float s, float tn, int m) {   // .cu:100-
 // --------------------------------------------------------------------------------------------
 // absmax / asum  (caffe_gpu_asum .cu:400; operand pre-scale for PREC_FP16X2)
 // --------------------------------------------------------------------------------------------
+// One kernel: per-block partial |x| sums (local rows) and max|x| (all rows), the reset of the per-row statistics, and --
+// in the last block to finish (ticket) -- the final asum, the power-of-two operand scale and the reset of the step state.
+__global__ void __launch_bounds__(256) prep_reduce_kernel(const float* __restrict__ xl, long long nl, const float* __restrict__ xt, long long ntot,
+                                                          float* __restrict__ partial, int want_scale, RowArrays ra, int Q, BlockScalars* bs) {
+  __shared__ float s_sum[8], s_max[8];
+  __shared__ int s_last;
+  float sum = 0.f, mx = 0.f;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long t0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (long long i = t0; i < nl; i += stride) sum += fabsf(xl[i]);
+  if (want_scale)
+    for (long long i = t0; i < ntot; i += stride) mx = fmaxf(mx, fabsf(xt[i]));
+  for (long long i = t0; i < Q; i += stride) {                  // caffe_set of the stat blobs, .cu:230-236
+    ra.st_minw[i] = f2ord(FLT_MAX); ra.st_maxw[i] = f2ord(-FLT_MAX);
+    ra.st_maxb[i] = f2ord(-FLT_MAX); ra.st_maxall[i] = f2ord(-FLT_MAX);
+    ra.cnt_same[i] = 0;
+  }
+  sum = warp_sum(sum); mx = warp_max(mx);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { s_sum[w] = sum; s_max[w] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    sum = 0.f; mx = 0.f;
+    for (int k = 0; k < (blockDim.x >> 5); ++k) { sum += s_sum[k]; mx = fmaxf(mx, s_max[k]); }
+    partial[blockIdx.x] = sum; partial[1024 + blockIdx.x] = mx;
+    __threadfence();
+    s_last = (atomicAdd(&bs->ticket0, 1u) == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  __shared__ double s_dsum[8];
+  double dsum = 0.0; mx = 0.f;
+  for (int b = threadIdx.x; b < static_cast<int>(gridDim.x); b += blockDim.x) { dsum += __ldcg(&partial[b]); mx = fmaxf(mx, __ldcg(&partial[1024 + b])); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { dsum += __shfl_xor_sync(0xffffffffu, dsum, o); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+  if (l == 0) { s_dsum[w] = dsum; s_max[w] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    dsum = 0.0; mx = 0.f;
+    for (int k = 0; k < (blockDim.x >> 5); ++k) { dsum += s_dsum[k]; mx = fmaxf(mx, s_max[k]); }
+    bs->asum = static_cast<float>(dsum);
+    bs->x_absmax = mx;
+    float sc = 1.f, inv = 1.f;
+    if (want_scale && mx > 0.f && isfinite(mx)) {
+      int e; frexpf(mx, &e);                 // mx = m * 2^e, m in [0.5,1)
+      sc = ldexpf(1.f, -e); inv = ldexpf(1.f, e);
+    }
+    bs->x_scale = sc; bs->x_inv_scale = inv;
+    bs->err = 0; bs->ticket = 0; bs->ticket2 = 0; bs->ticket0 = 0; bs->sel_active[0] = 0; bs->sel_active[1] = 0;
+    bs->n_same = 0; bs->n_diff = 0;
+  }
+}
+void launch_prep_reduce(const float* x_local, long long n_local, const float* x_total, long long n_total, float* partial,
+                        int want_scale, RowArrays ra, int Q, BlockScalars* bs, cudaStream_t st) {
+  long long nmax = n_local > n_total ? n_local : n_total;
+  int nb = static_cast<int>((nmax + 256 * 16 - 1) / (256 * 16));
+  if (nb < 1) nb = 1; if (nb > 592) nb = 592;
+  prep_reduce_kernel<<<nb, 256, 0, st>>>(x_local, n_local, x_total, n_total, partial, want_scale, ra, Q, bs);
+}
+
 __global__ void absmax_asum_partial_kernel(const float* __restrict__ xl, long long nl, const float* __restrict__ xt, long long ntot,
                                            float* __restrict__ partial, int want_scale) {
   __shared__ float s_sum[32], s_max[32];
@@ -302,7 +363,7 @@ __global__ void init_stats_kernel(RowArrays ra, int Q, BlockScalars* bs) {
     ra.cnt_same[i] = 0;
   }
   if (i == 0) {
-    bs->err = 0; bs->ticket = 0; bs->sel_active[0] = 0; bs->sel_active[1] = 0;
+    bs->err = 0; bs->ticket = 0; bs->ticket2 = 0; bs->sel_active[0] = 0; bs->sel_active[1] = 0;
     bs->n_same = 0; bs->n_diff = 0;
   }
 }
@@ -344,15 +405,30 @@ void launch_row_stats_ref(const float* S, long long ldS, int Q, int N, const flo
 __device__ __forceinline__ bool is_rel(int m) { return m == M_RELATIVE_HARD || m == M_RELATIVE_EASY; }
 __host__ __device__ inline bool sn_is_max(float sn) { return sn >= 0.f && static_cast<int>(sn) == 0; }   // pos = size-1
 
-__global__ void thresholds_kernel(RowArrays ra, int Q, int N, MiningParams mp, BlockScalars* bs) {
-  __shared__ unsigned long long s_ns[32];
-  __shared__ float s_mn[32], s_mxw[32], s_mxb[32];
-  __shared__ int s_err;
+// Multi-block: every block reduces its slice of the row statistics and writes the LOCAL-region thresholds of its rows
+// (they need no global value); the last block to finish (ticket) combines the per-block partials into the block-wide
+// sizes / extrema, the GLOBAL-region thresholds (read directly by the row pass) and the radix-select arming.
+struct ThrPartial { unsigned long long ns; float mn, mxw, mxb; int err; };
+__global__ void __launch_bounds__(256) thresholds_kernel(RowArrays ra, int Q, int N, MiningParams mp, BlockScalars* bs, ThrPartial* part) {
+  __shared__ unsigned long long s_ns[8];
+  __shared__ float s_mn[8], s_mxw[8], s_mxb[8];
+  __shared__ int s_err, s_last;
   if (threadIdx.x == 0) s_err = 0;
+  __syncthreads();
   unsigned long long ns = 0; float mn = FLT_MAX, mxw = -FLT_MAX, mxb = -FLT_MAX;
-  for (int i = threadIdx.x; i < Q; i += blockDim.x) {
-    ns += static_cast<unsigned long long>(ra.cnt_same[i]);
-    mn = fminf(mn, ord2f(ra.st_minw[i])); mxw = fmaxf(mxw, ord2f(ra.st_maxw[i])); mxb = fmaxf(mxb, ord2f(ra.st_maxb[i]));
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Q; i += gridDim.x * blockDim.x) {
+    const int cs = ra.cnt_same[i];
+    const float r_mn = ord2f(ra.st_minw[i]), r_mxw = ord2f(ra.st_maxw[i]), r_mxb = ord2f(ra.st_maxb[i]);
+    ns += static_cast<unsigned long long>(cs);
+    mn = fminf(mn, r_mn); mxw = fmaxf(mxw, r_mxw); mxb = fmaxf(mxb, r_mxb);
+    if (mp.ap_region == REGION_LOCAL) {
+      if (!is_rel(mp.ap_method)) ra.posi_thr[i] = r_mxb;                                                   // .cu:279
+      else if (sn_is_max(mp.identsn)) { if (cs == 0) atomicOr(&s_err, DERR_EMPTY_LIST); ra.posi_thr[i] = clamp_thr(r_mxw); }
+    }
+    if (mp.an_region == REGION_LOCAL) {
+      if (!is_rel(mp.an_method)) ra.nega_thr[i] = r_mn;                                                    // .cu:310
+      else if (sn_is_max(mp.diffsn)) { if (N - 1 - cs == 0) atomicOr(&s_err, DERR_EMPTY_LIST); ra.nega_thr[i] = clamp_thr(r_mxb); }
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) ns += __shfl_xor_sync(0xffffffffu, ns, o);
@@ -360,67 +436,54 @@ __global__ void thresholds_kernel(RowArrays ra, int Q, int N, MiningParams mp, B
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   if (l == 0) { s_ns[w] = ns; s_mn[w] = mn; s_mxw[w] = mxw; s_mxb[w] = mxb; }
   __syncthreads();
-  if (w == 0) {
-    const int nw = blockDim.x >> 5;
-    ns = l < nw ? s_ns[l] : 0ull; mn = l < nw ? s_mn[l] : FLT_MAX; mxw = l < nw ? s_mxw[l] : -FLT_MAX; mxb = l < nw ? s_mxb[l] : -FLT_MAX;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ns += __shfl_xor_sync(0xffffffffu, ns, o);
-    mn = warp_min(mn); mxw = warp_max(mxw); mxb = warp_max(mxb);
-    if (l == 0) { s_ns[0] = ns; s_mn[0] = mn; s_mxw[0] = mxw; s_mxb[0] = mxb; }
+  if (threadIdx.x == 0) {
+    ThrPartial t; t.ns = 0; t.mn = FLT_MAX; t.mxw = -FLT_MAX; t.mxb = -FLT_MAX; t.err = s_err;
+    for (int k = 0; k < (blockDim.x >> 5); ++k) { t.ns += s_ns[k]; t.mn = fminf(t.mn, s_mn[k]); t.mxw = fmaxf(t.mxw, s_mxw[k]); t.mxb = fmaxf(t.mxb, s_mxb[k]); }
+    part[blockIdx.x] = t;
+    __threadfence();
+    s_last = (atomicAdd(&bs->ticket2, 1u) == gridDim.x - 1) ? 1 : 0;
   }
   __syncthreads();
-  const unsigned long long n_same = s_ns[0];
+  if (!s_last || threadIdx.x != 0) return;
+  __threadfence();
+  unsigned long long n_same = 0; float gmin_w = FLT_MAX, gmax_w = -FLT_MAX, gmax_b = -FLT_MAX; int err = 0;
+  for (int g = 0; g < static_cast<int>(gridDim.x); ++g) {
+    const ThrPartial t = part[g];
+    n_same += t.ns; gmin_w = fminf(gmin_w, t.mn); gmax_w = fmaxf(gmax_w, t.mxw); gmax_b = fmaxf(gmax_b, t.mxb); err |= t.err;
+  }
   const unsigned long long n_diff = static_cast<unsigned long long>(Q) * static_cast<unsigned long long>(N - 1) - n_same;
-  const float gmin_w = s_mn[0], gmax_w = s_mxw[0], gmax_b = s_mxb[0];
-  int err = 0;
   float posi_g = 0.f, nega_g = 0.f;
   bool arm_ap = false, arm_an = false;
-  // ---- AP side ----
   if (mp.ap_region == REGION_GLOBAL) {
     if (!is_rel(mp.ap_method)) { if (n_diff == 0) err |= DERR_EMPTY_LIST; posi_g = gmax_b; }              // .cu:296
     else if (sn_is_max(mp.identsn)) { if (n_same == 0) err |= DERR_EMPTY_LIST; posi_g = clamp_thr(gmax_w); }   // pos = size-1
     else arm_ap = true;                                                                                    // .cu:300-304
   }
-  // ---- AN side ----
   if (mp.an_region == REGION_GLOBAL) {
     if (!is_rel(mp.an_method)) { if (n_same == 0) err |= DERR_EMPTY_LIST; nega_g = gmin_w; }               // .cu:327
     else if (sn_is_max(mp.diffsn)) { if (n_diff == 0) err |= DERR_EMPTY_LIST; nega_g = clamp_thr(gmax_b); }
     else arm_an = true;                                                                                    // .cu:331-335
   }
-  for (int i = threadIdx.x; i < Q; i += blockDim.x) {
-    const int cs = ra.cnt_same[i];
-    const int cd = N - 1 - cs;
-    if (mp.ap_region == REGION_LOCAL) {
-      if (!is_rel(mp.ap_method)) ra.posi_thr[i] = ord2f(ra.st_maxb[i]);                                    // .cu:279
-      else if (sn_is_max(mp.identsn)) { if (cs == 0) atomicOr(&s_err, DERR_EMPTY_LIST); ra.posi_thr[i] = clamp_thr(ord2f(ra.st_maxw[i])); }
-    } else if (!arm_ap) ra.posi_thr[i] = posi_g;
-    if (mp.an_region == REGION_LOCAL) {
-      if (!is_rel(mp.an_method)) ra.nega_thr[i] = ord2f(ra.st_minw[i]);                                    // .cu:310
-      else if (sn_is_max(mp.diffsn)) { if (cd == 0) atomicOr(&s_err, DERR_EMPTY_LIST); ra.nega_thr[i] = clamp_thr(ord2f(ra.st_maxb[i])); }
-    } else if (!arm_an) ra.nega_thr[i] = nega_g;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    err |= s_err;
-    bs->n_same = n_same; bs->n_diff = n_diff;
-    bs->gmin_within = gmin_w; bs->gmax_within = gmax_w; bs->gmax_between = gmax_b;
-    bs->posi_global = posi_g; bs->nega_global = nega_g;
-    for (int side = 0; side < 2; ++side) {
-      const bool arm = side == 0 ? arm_ap : arm_an;
-      bs->sel_active[side] = 0;
-      if (arm) {
-        unsigned long long pos = 0;
-        const unsigned long long size = side == 0 ? n_same : n_diff;
-        if (size == 0) err |= DERR_EMPTY_LIST;
-        else if (!pos_index(side == 0 ? mp.identsn : mp.diffsn, size, pos)) err |= DERR_POS_RANGE;
-        else { bs->sel_active[side] = 1; bs->sel_rank[side] = pos; bs->sel_prefix[side] = 0; bs->sel_mask[side] = 0; }
-      }
+  bs->n_same = n_same; bs->n_diff = n_diff;
+  bs->gmin_within = gmin_w; bs->gmax_within = gmax_w; bs->gmax_between = gmax_b;
+  bs->posi_global = posi_g; bs->nega_global = nega_g;
+  for (int side = 0; side < 2; ++side) {
+    const bool arm = side == 0 ? arm_ap : arm_an;
+    bs->sel_active[side] = 0;
+    if (arm) {
+      unsigned long long pos = 0;
+      const unsigned long long size = side == 0 ? n_same : n_diff;
+      if (size == 0) err |= DERR_EMPTY_LIST;
+      else if (!pos_index(side == 0 ? mp.identsn : mp.diffsn, size, pos)) err |= DERR_POS_RANGE;
+      else { bs->sel_active[side] = 1; bs->sel_rank[side] = pos; bs->sel_prefix[side] = 0; bs->sel_mask[side] = 0; }
     }
-    bs->err |= err;
   }
+  bs->err |= err;
+  bs->ticket2 = 0;
 }
-void launch_thresholds(RowArrays ra, int Q, int N, MiningParams mp, BlockScalars* bs, cudaStream_t st) {
-  thresholds_kernel<<<1, 1024, 0, st>>>(ra, Q, N, mp, bs);
+void launch_thresholds(RowArrays ra, int Q, int N, MiningParams mp, BlockScalars* bs, float* scratch, cudaStream_t st) {
+  int grid = (Q + 255) / 256; if (grid > 64) grid = 64; if (grid < 1) grid = 1;
+  thresholds_kernel<<<grid, 256, 0, st>>>(ra, Q, N, mp, bs, reinterpret_cast<ThrPartial*>(scratch));
 }
 
 // --------------------------------------------------------------------------------------------
@@ -614,8 +677,12 @@ __global__ void __launch_bounds__(256) lse_rows_kernel(const float* __restrict__
     const int self_col = i + self_offset;
     const float max_all = ord2f(ra.st_maxall[i]);
     const float m2 = max_all * NPAIR_LOG2E;
-    const float tp = ra.posi_thr[i] + mp.margin_ident;          // fp32 add as in .cu:81
-    const float tn = ra.nega_thr[i] + mp.margin_diff;           // .cu:102
+    // GLOBAL-region thresholds are block-wide scalars (thresholds_kernel / global_pick_kernel); LOCAL ones are per row
+    const float posi = mp.ap_region == REGION_GLOBAL ? bs->posi_global : ra.posi_thr[i];
+    const float nega = mp.an_region == REGION_GLOBAL ? bs->nega_global : ra.nega_thr[i];
+    if (lane == 0) { ra.posi_thr[i] = posi; ra.nega_thr[i] = nega; }   // kept per row for inspection (npair_debug_read)
+    const float tp = posi + mp.margin_ident;                    // fp32 add as in .cu:81
+    const float tn = nega + mp.margin_diff;                     // .cu:102
     const float sgn_p = ap_sign(mp.ap_method), sgn_n = an_sign(mp.an_method);
     const float thr_p = ap_thr(tp, mp.ap_method), thr_n = an_thr(tn, mp.an_method);
     const int cs = ra.cnt_same[i];

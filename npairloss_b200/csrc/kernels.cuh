@@ -23,6 +23,8 @@ struct BlockScalars {
   float posi_global, nega_global;          // GLOBAL-region thresholds (valid when the region is GLOBAL)
   int err;                                 // DERR_* bits
   unsigned int ticket;                     // block-completion counter of the row pass (last block finalises)
+  unsigned int ticket2;                    // block-completion counter of the thresholds kernel
+  unsigned int ticket0;                    // block-completion counter of the prep kernel
   // radix-select state, one per side (0 = AP over same pairs, 1 = AN over diff pairs)
   unsigned long long sel_rank[2];          // remaining 0-based rank inside the current prefix bucket
   uint32_t sel_prefix[2];                  // ordered-uint prefix decided so far
@@ -54,6 +56,8 @@ struct RowArrays {
 // launchers (kernels.cu)
 void launch_absmax_asum(const float* x_local, long long n_local, const float* x_total, long long n_total,
                         float* partial /*[2*1024]*/, BlockScalars* bs, int want_scale, cudaStream_t st);
+void launch_prep_reduce(const float* x_local, long long n_local, const float* x_total, long long n_total, float* partial /*[2*1024]*/,
+                        int want_scale, RowArrays ra, int Q, BlockScalars* bs, cudaStream_t st);
 void launch_split(const float* x_total, int N, int D, int prec, const BlockScalars* bs,
                   uint16_t* Xs, long long ldXs /*Dp*/, uint16_t* XsT, long long ldXsT /*Np*/,
                   uint16_t* XlT, long long ldXlT /*Qp, or 0*/, int row0_local, int Q,
@@ -61,7 +65,7 @@ void launch_split(const float* x_total, int N, int D, int prec, const BlockScala
 void launch_init_stats(RowArrays ra, int Q, BlockScalars* bs, cudaStream_t st);
 void launch_row_stats_ref(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
                           int self_offset, RowArrays ra, cudaStream_t st);
-void launch_thresholds(RowArrays ra, int Q, int N, MiningParams mp, BlockScalars* bs, cudaStream_t st);
+void launch_thresholds(RowArrays ra, int Q, int N, MiningParams mp, BlockScalars* bs, float* scratch /*>= 2 KB*/, cudaStream_t st);
 void launch_local_select(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
                          int self_offset, int side /*0 AP same, 1 AN diff*/, float sn, RowArrays ra, BlockScalars* bs,
                          cudaStream_t st);
