@@ -125,11 +125,11 @@ int npair_forward_gathered(npair_ctx* ctx, const float* d_feat_total, const floa
 int npair_backward_partial(npair_ctx* ctx, float loss_weight, float* d_local_half, float* d_total_half, void* stream);
 /* Row-scalar exchange form (contexts whose npair_bwd_exchange_mode is NPAIR_BWDMODE_ROW_SCALARS).  Because the similarity
  * GEMM is bitwise symmetric across ranks, rank r can evaluate the transposed gradient weights G[m][j] of every other rank
- * from its own S[j][m] and five scalars of row m, so the backward exchange is an all-gather of 5*Q floats per rank instead of
- * the reference's N x D all-reduce:
- *   npair_row_scalars       : copies this rank's [5][Q] scalars (after a forward) to d_out_5Q
- *   npair_backward_gathered : d_rs_total = [world][5][Q] scalars of all ranks; writes the complete bottom.diff (Q x D) */
-int npair_row_scalars(npair_ctx* ctx, float* d_out_5Q, void* stream);
+ * from its own S[j][m] and a 32-byte record of row m, so the backward exchange is an all-gather of 8*Q floats per rank instead
+ * of the reference's N x D all-reduce:
+ *   npair_row_scalars       : copies this rank's [Q][8] records (after a forward) to d_out_8Q
+ *   npair_backward_gathered : d_rs_total = [N][8] records of all ranks in global row order; writes the complete bottom.diff */
+int npair_row_scalars(npair_ctx* ctx, float* d_out_8Q, void* stream);
 int npair_backward_gathered(npair_ctx* ctx, float loss_weight, const float* d_rs_total, float* d_feat_diff, void* stream);
 
 const char* npair_last_error(const npair_ctx* ctx);   /* ctx may be NULL: last create() error of this thread */

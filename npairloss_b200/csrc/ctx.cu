@@ -18,6 +18,7 @@
 
 #include "../../include/npair_b200.h"
 #include "gemm_tcgen05.cuh"
+#include "grad_fused.cuh"
 #include "kernels.cuh"
 
 namespace npair {
@@ -101,12 +102,12 @@ static bool make_tmap_pieces(CUtensorMap* m, const void* base, int cols, int row
 }
 
 // 2-D fp32 map over the similarity matrix [rows x ld], inner extent `cols`, box {32, 32}, 128B swizzle (TMA stores)
-static bool make_tmap_f32_store(CUtensorMap* m, const void* base, int cols, int rows, long long ld_elems, std::string* err) {
+static bool make_tmap_f32_store(CUtensorMap* m, const void* base, int cols, int rows, long long ld_elems, std::string* err, int box_rows = 32) {
   auto fn = tmap_encode_fn();
   if (!fn) { *err = "cuTensorMapEncodeTiled entry point not available"; return false; }
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld_elems) * 4ull};
-  cuuint32_t box[2] = {32u, 32u};
+  cuuint32_t box[2] = {32u, static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -150,6 +151,26 @@ static cudaError_t launch_split_gemm(int prec, int epi, const CUtensorMap& a, co
   if (prec == PREC_BF16) return launch_split_gemm_t<1, true, EPI_OUT, 64>(a, b, sm, p, sms, st);
   if (prec == PREC_FP16X2) return launch_split_gemm_t<2, false, EPI_OUT, 32>(a, b, sm, p, sms, st);
   return launch_split_gemm_t<3, true, EPI_OUT, 32>(a, b, sm, p, sms, st);
+}
+
+template <int NSPLIT, bool BF16>
+static cudaError_t launch_fused_grad_t(const CUtensorMap& b, const CUtensorMap& sm, const FusedGradParams& p, int sms, cudaStream_t st) {
+  using Cfg = FusedCfg<NSPLIT>;
+  auto kern = fused_grad_kernel<NSPLIT, BF16>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int tiles = p.tiles_m * p.tiles_n * p.splits;
+  kern<<<tiles < sms ? tiles : sms, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(b, sm, p);
+  return cudaGetLastError();
+}
+static cudaError_t launch_fused_grad(int prec, const CUtensorMap& b, const CUtensorMap& sm, const FusedGradParams& p, int sms, cudaStream_t st) {
+  if (prec == PREC_BF16) return launch_fused_grad_t<1, true>(b, sm, p, sms, st);
+  if (prec == PREC_FP16X2) return launch_fused_grad_t<2, false>(b, sm, p, sms, st);
+  return launch_fused_grad_t<3, true>(b, sm, p, sms, st);
 }
 
 // SIMT cross-check of the same contraction on the same split operands (tests only; NPAIR_GEMM_SIMT_CHECK).
@@ -272,8 +293,10 @@ struct npair_ctx {
   float* OUT2 = nullptr;         // world > 1: N x D transposed-term product before the reduce-scatter
   int bwd_mode = 0;              // NPAIR_BWDMODE_*
   uint16_t *XcatA = nullptr, *XcatB = nullptr;   // row-scalar mode, fp16x2: K-concatenated operands [N][3*Dp]
-  float* rs_total = nullptr;     // row-scalar mode: all-gathered [world][5][Q] row scalars
+  float* rs_total = nullptr;     // row-scalar mode: all-gathered [N][8] row records
   CUtensorMap tm_catA, tm_catB;
+  CUtensorMap tm_fB, tm_fS;      // fused gradient kernel: X^T pieces with 32-wide K boxes, 128-row fp32 boxes of S
+  bool fused_grad = false;
   int2* sym_tiles = nullptr;     // world == 1: (m_blk, n_blk) of the similarity tiles touching the upper triangle
   int n_sym_tiles = 0;
   float* part = nullptr;         // split-K partial products of the gradient GEMM
@@ -445,7 +468,7 @@ static int create_impl(const npair_config* cfg, const void* id128, void* ext_com
   CREATE_TRY(cudaMemset(c->H, 0, 2ull * ns * Q * c->Np));
   c->bwd_mode = c->world == 1 ? NPAIR_BWDMODE_SINGLE
               : (cfg->bwd_exchange == NPAIR_BWD_AUTO ? NPAIR_BWDMODE_ROW_SCALARS : NPAIR_BWDMODE_REDUCE_SCATTER);
-  if (c->bwd_mode == NPAIR_BWDMODE_ROW_SCALARS) CREATE_TRY(cudaMalloc(&c->rs_total, sizeof(float) * 5ull * N));
+  if (c->bwd_mode == NPAIR_BWDMODE_ROW_SCALARS) CREATE_TRY(cudaMalloc(&c->rs_total, sizeof(float) * 8ull * N));
   if (c->prec != PREC_BF16 && cfg->gemm_backend == NPAIR_GEMM_TCGEN05) {
     const size_t cat_bytes = 2ull * N * kcat_mult(c->prec) * c->Dp;
     CREATE_TRY(cudaMalloc(&c->XcatA, cat_bytes));
@@ -469,9 +492,9 @@ static int create_impl(const npair_config* cfg, const void* id128, void* ext_com
       CREATE_TRY(cudaMalloc(&c->part, sizeof(float) * c->part_floats));
     }
   }
-  // row arrays: 5 uint32/int stats, 2 thr, 3 fwd, 3 hits, 5 row scalars = 18 arrays of Q 4-byte words
-  CREATE_TRY(cudaMalloc(&c->row_block, 4ull * 18 * Q));
-  CREATE_TRY(cudaMemset(c->row_block, 0, 4ull * 18 * Q));
+  // row arrays: 5 uint32/int stats, 2 thr, 3 fwd, 3 hits = 13 arrays of Q 4-byte words + the [Q][8] row records
+  CREATE_TRY(cudaMalloc(&c->row_block, 4ull * 21 * Q + 64));
+  CREATE_TRY(cudaMemset(c->row_block, 0, 4ull * 21 * Q + 64));
   {
     uint32_t* w = static_cast<uint32_t*>(c->row_block);
     RowArrays& ra = c->ra;
@@ -480,8 +503,8 @@ static int create_impl(const npair_config* cfg, const void* id128, void* ext_com
     ra.posi_thr = reinterpret_cast<float*>(w); w += Q; ra.nega_thr = reinterpret_cast<float*>(w); w += Q;
     ra.A = reinterpret_cast<float*>(w); w += Q; ra.T = reinterpret_cast<float*>(w); w += Q; ra.logv = reinterpret_cast<float*>(w); w += Q;
     ra.hits = reinterpret_cast<int*>(w); w += 3 * Q;
-    ra.rs_maxall = reinterpret_cast<float*>(w); w += Q; ra.rs_tp = reinterpret_cast<float*>(w); w += Q; ra.rs_tn = reinterpret_cast<float*>(w); w += Q;
-    ra.rs_cA = reinterpret_cast<float*>(w); w += Q; ra.rs_cT = reinterpret_cast<float*>(w); w += Q;
+    w = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(w) + 31) & ~static_cast<uintptr_t>(31));
+    ra.rowscal = reinterpret_cast<float*>(w); w += 8ll * Q;
   }
   CREATE_TRY(cudaMalloc(&c->bs, sizeof(BlockScalars)));
   CREATE_TRY(cudaMemset(c->bs, 0, sizeof(BlockScalars)));
@@ -503,6 +526,11 @@ static int create_impl(const npair_config* cfg, const void* id128, void* ext_com
     // gradient 1: A = H [Q x N], B = XsT [D x N]; K = N
     ok = ok && make_tmap_pieces(&c->tm_b1A, c->H, N, Q, ns, c->Np, static_cast<long long>(Q) * c->Np, bkg, 128, &te);
     ok = ok && make_tmap_pieces(&c->tm_b1B, c->XsT, N, D, ns, c->Np, static_cast<long long>(D) * c->Np, bkg, 256, &te);
+    c->fused_grad = (c->bwd_mode != NPAIR_BWDMODE_REDUCE_SCATTER) && !getenv("NPAIR_NO_FUSED_GRAD");
+    if (c->fused_grad) {
+      ok = ok && make_tmap_pieces(&c->tm_fB, c->XsT, N, D, ns, c->Np, static_cast<long long>(D) * c->Np, 32, 256, &te);
+      ok = ok && make_tmap_f32_store(&c->tm_fS, c->S, N, Q, c->ldS, &te, 128);
+    }
     if (c->XcatA) {       // bitwise-symmetric similarity: one pass over K_cat = 3*Dp (fp16x2) / 6*Dp (bf16x3)
       const long long kc = kcat_mult(c->prec) * c->Dp;
       ok = ok && make_tmap_pieces(&c->tm_catA, c->XcatA + static_cast<long long>(c->rank) * Q * kc, static_cast<int>(kc), Q, 1, kc, static_cast<long long>(N) * kc, 64, 128, &te);
@@ -688,8 +716,7 @@ int npair_row_scalars(npair_ctx* c, float* d_out, void* stream) {
   if (!c || !d_out) return NPAIR_E_ARG;
   if (!c->fwd_done) { c->err = "npair_row_scalars called without a successful forward"; return NPAIR_E_STATE; }
   CUDA_TRY(c, cudaSetDevice(c->device));
-  // rs_maxall, rs_tp, rs_tn, rs_cA, rs_cT are five consecutive Q-float arrays of the row block
-  CUDA_TRY(c, cudaMemcpyAsync(d_out, c->ra.rs_maxall, sizeof(float) * 5ull * c->Q, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  CUDA_TRY(c, cudaMemcpyAsync(d_out, c->ra.rowscal, sizeof(float) * 8ull * c->Q, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
   return NPAIR_OK;
 }
 
@@ -716,14 +743,47 @@ static int backward_impl(npair_ctx* c, float loss_weight, float* d_diff, float* 
     bw_mode = BW_ROWSCAL;
     if (d_rs_ext) rs_total = d_rs_ext;
     else {
-      // the only backward exchange: 5*Q floats per rank (replaces the N x D MPI_Allreduce of .cu:462-489)
+      // the only backward exchange: 8*Q floats per rank (replaces the N x D MPI_Allreduce of .cu:462-489)
       PhaseTimer pt(c, 8, st);
       NcclApi* api = nccl_api();
-      int r = api->AllGather(c->ra.rs_maxall, c->rs_total, 5ull * Q, NCCL_FLOAT32, c->comm, st);
+      int r = api->AllGather(c->ra.rowscal, c->rs_total, 8ull * Q, NCCL_FLOAT32, c->comm, st);
       if (r != 0) { c->err = fmt("ncclAllGather(row scalars): %s", api->GetErrorString(r)); return NPAIR_E_NCCL; }
       rs_total = c->rs_total;
     }
   } else if (c->bwd_mode == NPAIR_BWDMODE_REDUCE_SCATTER) bw_mode = BW_SPLIT;
+  if (tc && c->fused_grad) {
+    // weights are produced inside the gradient GEMM: no H in HBM
+    FusedGradParams fp; memset(&fp, 0, sizeof(fp));
+    fp.Q = Q; fp.N = N; fp.D = D; fp.num_kblocks = (N + 31) / 32;
+    fp.tiles_m = (Q + 127) / 128; fp.tiles_n = (D + 255) / 256;
+    fp.rowrec = c->ra.rowscal; fp.colrec = rs_total ? rs_total : c->ra.rowscal;
+    fp.self_offset = self_off; fp.inv_world = 1.f / static_cast<float>(c->world);
+    fp.sgn_p = (mp.ap_method == M_EASY || mp.ap_method == M_RELATIVE_EASY) ? -1.f : 1.f;
+    fp.sgn_n = (mp.an_method == M_HARD || mp.an_method == M_RELATIVE_HARD) ? -1.f : 1.f;
+    fp.out = d_diff; fp.ldo = D; fp.alpha = 0.5f * lw_over_q; fp.beta = 0.f; fp.dev_scale = &c->bs->x_inv_scale;
+    fp.part = c->part; fp.splits = 1; fp.kb_per_split = fp.num_kblocks;
+    if (c->part) {
+      const int tiles = fp.tiles_m * fp.tiles_n;
+      int splits = c->sms / (tiles > 0 ? tiles : 1);
+      if (splits > 16) splits = 16;
+      if (splits > fp.num_kblocks / 8) splits = fp.num_kblocks / 8;        // keep >= 8 K blocks (256 columns) per split
+      while (splits > 1 && static_cast<long long>(splits) * Q * D > c->part_floats) --splits;
+      if (splits < 1) splits = 1;
+      const int kpb = (fp.num_kblocks + splits - 1) / splits;
+      fp.splits = (fp.num_kblocks + kpb - 1) / kpb; fp.kb_per_split = kpb;
+    }
+    {
+      PhaseTimer pt(c, 6, st);
+      CUDA_TRY(c, launch_fused_grad(c->prec, c->tm_fB, c->tm_fS, fp, c->sms, st));
+      if (fp.splits > 1) {
+        const long long n = static_cast<long long>(Q) * D;
+        int nb = static_cast<int>((n / 4 + 255) / 256); if (nb > c->sms * 8) nb = c->sms * 8; if (nb < 1) nb = 1;
+        splitk_reduce_kernel<<<nb, 256, 0, st>>>(c->part, fp.splits, n, d_diff, 0.f);
+      }
+    }
+    CUDA_TRY(c, cudaGetLastError());
+    return NPAIR_OK;
+  }
   {
     PhaseTimer pt(c, 5, st);
     launch_build_weights(c->S, c->ldS, Q, N, c->cur_label, c->lab_total, self_off, c->world, bw_mode, rs_total, mp, c->ra, c->prec, c->H, c->Np, c->HT, c->Qp, st);

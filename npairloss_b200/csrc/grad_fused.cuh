@@ -1,0 +1,305 @@
+// grad_fused.cuh -- gradient GEMM with the weight builder fused in as its A-operand producer (sm_100a).
+//
+//   dX[j][:] = alpha * sum_m H[j][m] * X_total[m][:]        H[j][m] = g'(S[j][m]; row j) + (1/world) g'(S[j][m]; row m)
+//
+// Replaces Get_Query_Diff_Part x3 + six cublasSgemm + the N x D all-reduce of the reference (npair_multi_class_loss.cu:438-497).
+// H (Q x N) is never written to HBM: per 32-column K block the 8 producer warps read a 128 x 32 fp32 tile of S (TMA,
+// 128B-swizzled) and the 32 column records (bulk copy), evaluate the weights in registers (row record in registers,
+// thread = row), split them into the 2-byte operand pieces and store those straight into the 64B-swizzled K-major
+// shared-memory tiles that tcgen05.mma consumes.  Requires a bitwise symmetric S (EPI_SIM_SYM tiles at world == 1,
+// K-concatenated operands across ranks) -- see gemm_tcgen05.cuh / kernels.cu.
+//
+// CTA = 384 threads: warp 0 TMA producer (B pieces of X^T, S tile, column records), warp 1 MMA issuer, warp 2 TMEM
+// allocator, warps 4-11 weight producers, which also run the epilogue (TMEM -> alpha*acc -> out / split-K partial).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gemm_tcgen05.cuh"
+#include "ptx.cuh"
+
+namespace npair {
+
+#define NPAIR_LOG2E_F 1.4426950408889634f
+
+struct FusedGradParams {
+  int Q, N, D;
+  int num_kblocks;              // ceil(N / 32)
+  int tiles_m, tiles_n;         // 128-row blocks, 256-column tiles of D
+  int splits, kb_per_split;     // split-K over the sample index (few row blocks when Q = B / world is small)
+  float* part;                  // split-K partials [split][Q][ldo]
+  const float* S;               // only for address checks; tiles come through the tensor map
+  const float* rowrec;          // [Q][8]  this rank's row records {m2, thr_p, thr_n, cA, cT, label, 0, 0}
+  const float* colrec;          // [N][8]  records of every column's row (== rowrec when world == 1)
+  int self_offset;              // global column of local row 0
+  float inv_world;
+  float sgn_p, sgn_n;           // +-1: direction of the same-/diff-label selection compare
+  float* out; long long ldo;
+  float alpha, beta;
+  const float* dev_scale;       // inverse operand pre-scale (power of two) or NULL
+};
+
+template <int NSPLIT>
+struct FusedCfg {
+  static constexpr int BM = 128, BN = 256, BK = 32;
+  static constexpr int A_PIECE = BM * 64;                 // 64-byte rows (32 x 2-byte), SWIZZLE_64B
+  static constexpr int B_PIECE = BN * 64;
+  static constexpr int S_TILE = BM * 128;                 // 128-byte rows (32 x fp32), SWIZZLE_128B
+  static constexpr int CREC = BK * 32;                    // 32 column records of 32 bytes
+  static constexpr int STAGE_BYTES = NSPLIT * (A_PIECE + B_PIECE) + S_TILE + CREC;
+  static constexpr int STAGES = (NSPLIT == 1) ? 4 : (NSPLIT == 2 ? 3 : 2);
+  static constexpr int NPASS = (NSPLIT == 1) ? 1 : (NSPLIT == 2 ? 3 : 6);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*barriers*/ + 1024 /*alignment*/;
+  static constexpr int THREADS = 384;
+};
+
+// two fp32 weights -> packed 2-byte pieces (lo 16 bits = first value)
+template <int NSPLIT, bool BF16>
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t (&out)[3]) {
+  if (NSPLIT == 1) {
+    out[0] = static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16_rn(a))) | (static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16_rn(b))) << 16);
+  } else if (NSPLIT == 2) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    out[0] = *reinterpret_cast<const uint32_t*>(&h);
+    out[1] = *reinterpret_cast<const uint32_t*>(&l);
+  } else {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    const float2 hf = __bfloat1622float2(h);
+    const float r1a = a - hf.x, r1b = b - hf.y;
+    const __nv_bfloat162 m = __floats2bfloat162_rn(r1a, r1b);
+    const float2 mf = __bfloat1622float2(m);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(r1a - mf.x, r1b - mf.y);
+    out[0] = *reinterpret_cast<const uint32_t*>(&h);
+    out[1] = *reinterpret_cast<const uint32_t*>(&m);
+    out[2] = *reinterpret_cast<const uint32_t*>(&l);
+  }
+}
+
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(ptx::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(ptx::smem_u32(bar))
+               : "memory");
+}
+
+template <int NSPLIT, bool BF16>
+__global__ void __launch_bounds__(384, 1)
+fused_grad_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ CUtensorMap tmapS, const FusedGradParams p) {
+  using Cfg = FusedCfg<NSPLIT>;
+  constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* aux = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);            // [STAGES] TMA bytes landed (B, S tile, column records)
+  uint64_t* aready_bar = full_bar + STAGES;                          // [STAGES] producers wrote the A pieces
+  uint64_t* empty_bar = aready_bar + STAGES;                         // [STAGES] MMAs of the stage retired
+  uint64_t* tfull_bar = empty_bar + STAGES;                          // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;                              // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = p.tiles_m * p.tiles_n * p.splits;
+  const float inv_scale = p.dev_scale ? *p.dev_scale : 1.f;
+  const float alpha = p.alpha * inv_scale;
+
+  if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tmapB); ptx::prefetch_tmap(&tmapS); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&aready_bar[s], 8); ptx::mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 8); }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) { ptx::tmem_alloc<512>(tmem_ptr); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int mn = tile / p.splits, split = tile - mn * p.splits;
+        const int m_blk = mn / p.tiles_n, n_blk = mn % p.tiles_n;
+        const int kb0 = split * p.kb_per_split, kb1 = min(p.num_kblocks, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          const int m0 = kb * BK;
+          const uint32_t crec_bytes = static_cast<uint32_t>(min(BK, p.N - m0)) * 32u;
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], NSPLIT * Cfg::B_PIECE + Cfg::S_TILE + crec_bytes);
+          uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
+#pragma unroll
+          for (int s = 0; s < NSPLIT; ++s)
+            ptx::tma_load_3d(st + NSPLIT * Cfg::A_PIECE + s * Cfg::B_PIECE, &tmapB, &full_bar[stage], m0, n_blk * BN, s);
+          ptx::tma_load_2d(st + NSPLIT * (Cfg::A_PIECE + Cfg::B_PIECE), &tmapS, &full_bar[stage], m0, m_blk * BM);
+          bulk_copy_g2s(st + NSPLIT * (Cfg::A_PIECE + Cfg::B_PIECE) + Cfg::S_TILE, p.colrec + 8ll * m0, crec_bytes, &full_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =====================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_f16(BF16, BM, BN);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        const int split = tile % p.splits;
+        const int kb0 = split * p.kb_per_split, kb1 = min(p.num_kblocks, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::mbar_wait(&aready_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t a0 = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t b0 = a0 + NSPLIT * Cfg::A_PIECE;
+#pragma unroll
+          for (int ps = 0; ps < Cfg::NPASS; ++ps) {
+            int sa, sb;
+            pass_pieces(NSPLIT, ps, sa, sb);
+#pragma unroll
+            for (int k2 = 0; k2 < BK / 16; ++k2) {
+              const uint64_t ad = ptx::make_kmajor_desc(a0 + sa * Cfg::A_PIECE + k2 * 32, 512u, 4u);   // SWIZZLE_64B, 8 rows = 512 B
+              const uint64_t bd = ptx::make_kmajor_desc(b0 + sb * Cfg::B_PIECE + k2 * 32, 512u, 4u);
+              ptx::mma_f16_ss(d_tmem, ad, bd, idesc, ((kb - kb0) | ps | k2) != 0 ? 1u : 0u);
+            }
+          }
+          ptx::mma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        ptx::mma_commit(&tfull_bar[acc]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================== weight producers + epilogue =====================================
+    const int ew = (warp - 4) & 3;               // TMEM lane group / 32-row group
+    const int half = (warp - 4) >> 2;            // K half inside a 32-column block while producing, D half in the epilogue
+    int stage = 0; uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int mn = tile / p.splits, split = tile - mn * p.splits;
+      const int m_blk = mn / p.tiles_n, n_blk = mn % p.tiles_n;
+      const int kb0 = split * p.kb_per_split, kb1 = min(p.num_kblocks, kb0 + p.kb_per_split);
+      const int rl = ew * 32 + lane;             // row inside the tile
+      const int row = m_blk * BM + rl;
+      // row record (neutral when the row does not exist: thresholds -inf -> nothing selected)
+      float r_m2 = 0.f, r_tp = -INFINITY, r_tn = -INFINITY, r_cA = 0.f, r_cT = 0.f, r_lab = 0.f;
+      if (row < p.Q) {
+        const float4 a = *reinterpret_cast<const float4*>(p.rowrec + 8ll * row);
+        const float4 b = *reinterpret_cast<const float4*>(p.rowrec + 8ll * row + 4);
+        r_m2 = a.x; r_tp = a.y; r_tn = a.z; r_cA = a.w; r_cT = b.x; r_lab = b.y;
+      }
+      const int self_col = row + p.self_offset;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
+        const uint8_t* s_tile = st + NSPLIT * (Cfg::A_PIECE + Cfg::B_PIECE);
+        const float4* crec = reinterpret_cast<const float4*>(s_tile + Cfg::S_TILE) + 2 * (16 * half);
+        // my 16 similarities: chunks 4*half .. 4*half+3 of row rl (128B swizzle: chunk ^ (row & 7))
+        float sv[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 t4 = *reinterpret_cast<const float4*>(s_tile + rl * 128 + (((4 * half + q) ^ (rl & 7)) << 4));
+          sv[4 * q] = t4.x; sv[4 * q + 1] = t4.y; sv[4 * q + 2] = t4.z; sv[4 * q + 3] = t4.w;
+        }
+        const int m0 = kb * BK + 16 * half;      // global column of sv[0]
+        float g[16];
+#pragma unroll
+        for (int cc = 0; cc < 16; ++cc) {
+          const float4 ca = crec[2 * cc], cb = crec[2 * cc + 1];   // {m2, thr_p, thr_n, cA} {cT, label, -, -}
+          const float s = sv[cc];
+          const bool same = (cb.y == r_lab);
+          float e1, e2;                                            // same formula as the forward row pass (fast_exp_m2)
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(s, NPAIR_LOG2E_F, -r_m2)));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(fmaf(s, NPAIR_LOG2E_F, -ca.x)));
+          const float key = s * (same ? p.sgn_p : p.sgn_n);
+          const float w1 = (key <= (same ? r_tp : r_tn)) ? e1 * (same ? r_cA : r_cT) : 0.f;
+          const float w2 = (key <= (same ? ca.y : ca.z)) ? e2 * (same ? ca.w : cb.x) : 0.f;
+          g[cc] = fmaf(w2, p.inv_world, w1);
+        }
+        // rare fix-ups: self pair inside this block, columns beyond N in the last block
+        if ((self_col >= m0 && self_col < m0 + 16) || m0 + 16 > p.N) {
+#pragma unroll
+          for (int cc = 0; cc < 16; ++cc)
+            if (m0 + cc == self_col || m0 + cc >= p.N) g[cc] = 0.f;
+        }
+        // pieces -> K-major 64B-swizzled A tiles: row rl, 16-byte chunks 2*half, 2*half+1 (physical chunk ^ ((row >> 1) & 3))
+        uint32_t pk[NSPLIT][8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          uint32_t o[3];
+          split_pair<NSPLIT, BF16>(g[2 * q], g[2 * q + 1], o);
+#pragma unroll
+          for (int s = 0; s < NSPLIT; ++s) pk[s][q] = o[s];
+        }
+#pragma unroll
+        for (int s = 0; s < NSPLIT; ++s) {
+          uint8_t* arow = st + s * Cfg::A_PIECE + rl * 64;
+          *reinterpret_cast<uint4*>(arow + (((2 * half) ^ ((rl >> 1) & 3)) << 4)) = make_uint4(pk[s][0], pk[s][1], pk[s][2], pk[s][3]);
+          *reinterpret_cast<uint4*>(arow + (((2 * half + 1) ^ ((rl >> 1) & 3)) << 4)) = make_uint4(pk[s][4], pk[s][5], pk[s][6], pk[s][7]);
+        }
+        ptx::fence_proxy_async_smem();           // generic-proxy writes -> visible to the tensor core's async proxy
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&aready_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      // ---- epilogue of this tile: TMEM -> alpha * acc (+ beta * out) ----
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
+      float* obase = p.splits > 1 ? p.part + static_cast<long long>(split) * p.Q * p.ldo : p.out;
+      const float beta = p.splits > 1 ? 0.f : p.beta;
+#pragma unroll 1
+      for (int ch = half * 4; ch < half * 4 + 4; ++ch) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(t_row + ch * 32, r);
+        ptx::tmem_ld_wait();
+        const int col0 = n_blk * BN + ch * 32;
+        if (row < p.Q) {
+          float* dst = obase + static_cast<long long>(row) * p.ldo + col0;
+          if (col0 + 32 <= p.D && (p.ldo & 3) == 0) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float4 o = make_float4(alpha * __uint_as_float(r[4 * q]), alpha * __uint_as_float(r[4 * q + 1]),
+                                     alpha * __uint_as_float(r[4 * q + 2]), alpha * __uint_as_float(r[4 * q + 3]));
+              if (beta != 0.f) {
+                const float4 old = reinterpret_cast<float4*>(dst)[q];
+                o.x += beta * old.x; o.y += beta * old.y; o.z += beta * old.z; o.w += beta * old.w;
+              }
+              reinterpret_cast<float4*>(dst)[q] = o;
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+              if (col0 + c < p.D) {
+                float o = alpha * __uint_as_float(r[c]);
+                if (beta != 0.f) o += beta * dst[c];
+                dst[c] = o;
+              }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace npair

@@ -44,8 +44,8 @@ def gpu_step_world(x, lab, Q, world, mining, prec, backend, loss_weight=1.0, num
             nega[r * Q:(r + 1) * Q] = ctx.debug_read(2, Q)
         mode = ctxs[0].bwd_exchange_mode()
         if want_grad:
-            if mode == 2:       # row-scalar exchange: "all-gather" the 5*Q scalars of every rank
-                rs = torch.empty((world, 5, Q), dtype=torch.float32, device=dev)
+            if mode == 2:       # row-scalar exchange: "all-gather" the [Q][8] records of every rank
+                rs = torch.empty((world, Q, 8), dtype=torch.float32, device=dev)
                 for r in range(world):
                     ctxs[r].row_scalars(rs[r])
                 for r in range(world):
