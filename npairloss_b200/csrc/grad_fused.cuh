@@ -32,7 +32,7 @@ struct FusedGradParams {
   int splits, kb_per_split;     // split-K over the sample index (few row blocks when Q = B / world is small)
   float* part;                  // split-K partials [split][Q][ldo]
   const float* S;               // only for address checks; tiles come through the tensor map
-  const float* rowrec;          // [Q][8]  this rank's row records {m2, thr_p, thr_n, cA, cT, label, 0, 0}
+  const float* rowrec;          // [Q][8]  this rank's row records {m2, thr_n, cT, label | thr_p, cA, 0, 0}
   const float* colrec;          // [N][8]  records of every column's row (== rowrec when world == 1)
   int self_offset;              // global column of local row 0
   float inv_world;
@@ -53,7 +53,7 @@ struct FusedCfg {
   static constexpr int STAGES = (NSPLIT == 1) ? 4 : (NSPLIT == 2 ? 3 : 2);
   static constexpr int NPASS = (NSPLIT == 1) ? 1 : (NSPLIT == 2 ? 3 : 6);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*barriers*/ + 1024 /*alignment*/;
-  static constexpr int THREADS = 384;
+  static constexpr int THREADS = 640;                         // 4 control warps + 16 producer / epilogue warps
 };
 
 // two fp32 weights -> packed 2-byte pieces (lo 16 bits = first value)
@@ -87,7 +87,7 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, 
 }
 
 template <int NSPLIT, bool BF16>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(640, 1)
 fused_grad_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ CUtensorMap tmapS, const FusedGradParams p) {
   using Cfg = FusedCfg<NSPLIT>;
   constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES;
@@ -108,8 +108,8 @@ fused_grad_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_consta
 
   if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tmapB); ptx::prefetch_tmap(&tmapS); }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&aready_bar[s], 8); ptx::mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 8); }
+    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&aready_bar[s], 16); ptx::mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 16); }
     ptx::fence_mbar_init();
   }
   if (warp == 2) { ptx::tmem_alloc<512>(tmem_ptr); ptx::tmem_relinquish(); }
@@ -181,7 +181,7 @@ fused_grad_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_consta
   } else if (warp >= 4) {
     // ===================================== weight producers + epilogue =====================================
     const int ew = (warp - 4) & 3;               // TMEM lane group / 32-row group
-    const int half = (warp - 4) >> 2;            // K half inside a 32-column block while producing, D half in the epilogue
+    const int qt = (warp - 4) >> 2;              // quarter: 8 of the 32 K columns while producing, 64 of the 256 D columns in the epilogue
     int stage = 0; uint32_t phase = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -195,57 +195,67 @@ fused_grad_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_consta
       if (row < p.Q) {
         const float4 a = *reinterpret_cast<const float4*>(p.rowrec + 8ll * row);
         const float4 b = *reinterpret_cast<const float4*>(p.rowrec + 8ll * row + 4);
-        r_m2 = a.x; r_tp = a.y; r_tn = a.z; r_cA = a.w; r_cT = b.x; r_lab = b.y;
+        r_m2 = a.x; r_tn = a.y; r_cT = a.z; r_lab = a.w; r_tp = b.x; r_cA = b.y;
       }
       const int self_col = row + p.self_offset;
       for (int kb = kb0; kb < kb1; ++kb) {
         ptx::mbar_wait(&full_bar[stage], phase);
         uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
         const uint8_t* s_tile = st + NSPLIT * (Cfg::A_PIECE + Cfg::B_PIECE);
-        const float4* crec = reinterpret_cast<const float4*>(s_tile + Cfg::S_TILE) + 2 * (16 * half);
-        // my 16 similarities: chunks 4*half .. 4*half+3 of row rl (128B swizzle: chunk ^ (row & 7))
-        float sv[16];
+        const float4* crec = reinterpret_cast<const float4*>(s_tile + Cfg::S_TILE) + 2 * (8 * qt);
+        // my 8 similarities: chunks 2*qt, 2*qt+1 of row rl (128B swizzle: chunk ^ (row & 7))
+        float sv[8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 t4 = *reinterpret_cast<const float4*>(s_tile + rl * 128 + (((4 * half + q) ^ (rl & 7)) << 4));
+        for (int q = 0; q < 2; ++q) {
+          const float4 t4 = *reinterpret_cast<const float4*>(s_tile + rl * 128 + (((2 * qt + q) ^ (rl & 7)) << 4));
           sv[4 * q] = t4.x; sv[4 * q + 1] = t4.y; sv[4 * q + 2] = t4.z; sv[4 * q + 3] = t4.w;
         }
-        const int m0 = kb * BK + 16 * half;      // global column of sv[0]
-        float g[16];
+        const int m0 = kb * BK + 8 * qt;         // global column of sv[0]
+        float g[8];
+        bool any_same = false;
 #pragma unroll
-        for (int cc = 0; cc < 16; ++cc) {
-          const float4 ca = crec[2 * cc], cb = crec[2 * cc + 1];   // {m2, thr_p, thr_n, cA} {cT, label, -, -}
+        for (int cc = 0; cc < 8; ++cc) {
+          const float4 ca = crec[2 * cc];        // {m2, thr_n, cT, label}: everything a diff-label pair needs
           const float s = sv[cc];
-          const bool same = (cb.y == r_lab);
-          float e1, e2;                                            // same formula as the forward row pass (fast_exp_m2)
+          float e1, e2;                          // same formula as the forward row pass (fast_exp_m2)
           asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(s, NPAIR_LOG2E_F, -r_m2)));
           asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(fmaf(s, NPAIR_LOG2E_F, -ca.x)));
-          const float key = s * (same ? p.sgn_p : p.sgn_n);
-          const float w1 = (key <= (same ? r_tp : r_tn)) ? e1 * (same ? r_cA : r_cT) : 0.f;
-          const float w2 = (key <= (same ? ca.y : ca.z)) ? e2 * (same ? ca.w : cb.x) : 0.f;
+          const float key = s * p.sgn_n;
+          const float w1 = (key <= r_tn) ? e1 * r_cT : 0.f;
+          const float w2 = (key <= ca.y) ? e2 * ca.z : 0.f;
           g[cc] = fmaf(w2, p.inv_world, w1);
+          any_same |= (ca.w == r_lab);
         }
-        // rare fix-ups: self pair inside this block, columns beyond N in the last block
-        if ((self_col >= m0 && self_col < m0 + 16) || m0 + 16 > p.N) {
+        // rare fix-ups: same-label pairs (the other selection rule and weight), the self pair, columns beyond N
+        if (any_same || (self_col >= m0 && self_col < m0 + 8) || m0 + 8 > p.N) {
 #pragma unroll
-          for (int cc = 0; cc < 16; ++cc)
+          for (int cc = 0; cc < 8; ++cc) {
+            const float4 ca = crec[2 * cc], cb = crec[2 * cc + 1];   // cb = {thr_p, cA, -, -}
+            if (ca.w == r_lab) {
+              const float s = sv[cc];
+              float e1, e2;
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(s, NPAIR_LOG2E_F, -r_m2)));
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(fmaf(s, NPAIR_LOG2E_F, -ca.x)));
+              const float key = s * p.sgn_p;
+              const float w1 = (key <= r_tp) ? e1 * r_cA : 0.f;
+              const float w2 = (key <= cb.x) ? e2 * cb.y : 0.f;
+              g[cc] = fmaf(w2, p.inv_world, w1);
+            }
             if (m0 + cc == self_col || m0 + cc >= p.N) g[cc] = 0.f;
+          }
         }
-        // pieces -> K-major 64B-swizzled A tiles: row rl, 16-byte chunks 2*half, 2*half+1 (physical chunk ^ ((row >> 1) & 3))
-        uint32_t pk[NSPLIT][8];
+        // pieces -> K-major 64B-swizzled A tiles: row rl, 16-byte chunk qt (physical chunk ^ ((row >> 1) & 3))
+        uint32_t pk[NSPLIT][4];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < 4; ++q) {
           uint32_t o[3];
           split_pair<NSPLIT, BF16>(g[2 * q], g[2 * q + 1], o);
 #pragma unroll
           for (int s = 0; s < NSPLIT; ++s) pk[s][q] = o[s];
         }
 #pragma unroll
-        for (int s = 0; s < NSPLIT; ++s) {
-          uint8_t* arow = st + s * Cfg::A_PIECE + rl * 64;
-          *reinterpret_cast<uint4*>(arow + (((2 * half) ^ ((rl >> 1) & 3)) << 4)) = make_uint4(pk[s][0], pk[s][1], pk[s][2], pk[s][3]);
-          *reinterpret_cast<uint4*>(arow + (((2 * half + 1) ^ ((rl >> 1) & 3)) << 4)) = make_uint4(pk[s][4], pk[s][5], pk[s][6], pk[s][7]);
-        }
+        for (int s = 0; s < NSPLIT; ++s)
+          *reinterpret_cast<uint4*>(st + s * Cfg::A_PIECE + rl * 64 + ((qt ^ ((rl >> 1) & 3)) << 4)) = make_uint4(pk[s][0], pk[s][1], pk[s][2], pk[s][3]);
         ptx::fence_proxy_async_smem();           // generic-proxy writes -> visible to the tensor core's async proxy
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&aready_bar[stage]);
@@ -260,7 +270,7 @@ fused_grad_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_consta
       float* obase = p.splits > 1 ? p.part + static_cast<long long>(split) * p.Q * p.ldo : p.out;
       const float beta = p.splits > 1 ? 0.f : p.beta;
 #pragma unroll 1
-      for (int ch = half * 4; ch < half * 4 + 4; ++ch) {
+      for (int ch = qt * 2; ch < qt * 2 + 2; ++ch) {
         uint32_t r[32];
         ptx::tmem_ld_32x32b_x32(t_row + ch * 32, r);
         ptx::tmem_ld_wait();

@@ -739,11 +739,11 @@ __global__ void __launch_bounds__(256) lse_rows_kernel(const float* __restrict__
       ra.hits[2 * Q + i] = (cs > 0 && c <= min(10, lim)) ? 1 : 0;
       const float invA = A == 0.f ? 0.f : 1.f / A;              // Get_Query_Diff_Part zero rules (.cu:410-415)
       const float invT = T == 0.f ? 0.f : 1.f / T;
-      // {max_all*log2(e) (the backward uses the same exponential), transformed thresholds (ap_thr / an_thr),
-      //  same-label weight -1/A + 1/T, diff-label weight 1/T, label}
+      // first 16 bytes = all a diff-label pair needs: {max_all*log2(e) (the backward uses the same exponential), an_thr-transformed
+      // threshold, diff-label weight 1/T, label}; second 16 bytes = the same-label rule: {ap_thr threshold, weight -1/A + 1/T}
       float4* rec = reinterpret_cast<float4*>(ra.rowscal + 8ll * i);
-      rec[0] = make_float4(m2, thr_p, thr_n, invT - invA);
-      rec[1] = make_float4(invT, li, 0.f, 0.f);
+      rec[0] = make_float4(m2, thr_n, invT, li);
+      rec[1] = make_float4(thr_p, invT - invA, 0.f, 0.f);
     }
   }
   // ---- grid-level completion: the last block reduces the row results (fixed order -> deterministic) ----
@@ -852,17 +852,17 @@ __global__ void __launch_bounds__(256, 4) build_weights_kernel(const float* __re
   if (t < TS) {
     const int j = a0 + t;
     RowScal r = {0.f, -INFINITY, -INFINITY, 0.f, 0.f, 0.f};
-    if (j < Q) { const float* b = ra.rowscal + 8ll * j; r.maxall = b[0]; r.tp = b[1]; r.tn = b[2]; r.cA = b[3]; r.cT = b[4]; r.lab = b[5]; }
+    if (j < Q) { const float* b = ra.rowscal + 8ll * j; r.maxall = b[0]; r.tn = b[1]; r.cT = b[2]; r.lab = b[3]; r.tp = b[4]; r.cA = b[5]; }
     sc_a[t] = r;
   } else if (t < 2 * TS) {
     const int mm = t - TS, m = b0 + mm;
     RowScal r = {0.f, -INFINITY, -INFINITY, 0.f, 0.f, 0.f};
     if (MODE == BW_SYM) {   // world == 1: column m is also a local row
-      if (m < Q) { const float* b = ra.rowscal + 8ll * m; r.maxall = b[0]; r.tp = b[1]; r.tn = b[2]; r.cA = b[3]; r.cT = b[4]; r.lab = b[5]; }
+      if (m < Q) { const float* b = ra.rowscal + 8ll * m; r.maxall = b[0]; r.tn = b[1]; r.cT = b[2]; r.lab = b[3]; r.tp = b[4]; r.cA = b[5]; }
     } else if (MODE == BW_ROWSCAL) {   // all-gathered [N][8] row records; the 1/world of .cu:474 folded into the weights
       if (m < N) {
         const float* b = rs_total + 8ll * m;
-        r.maxall = b[0]; r.tp = b[1]; r.tn = b[2]; r.cA = b[3] * inv_world; r.cT = b[4] * inv_world; r.lab = b[5];
+        r.maxall = b[0]; r.tn = b[1]; r.cT = b[2] * inv_world; r.lab = b[3]; r.tp = b[4]; r.cA = b[5] * inv_world;
       }
     } else if (m < N) r.lab = lab_cols[m];
     sc_b[mm] = r;

@@ -49,7 +49,7 @@ struct RowArrays {
   // forward row results
   float *A, *T, *logv;
   int* hits;                 // [3][Q] retrieval hit flags for k=1,5,10
-  // row scalars consumed by the backward: [Q][8] floats {max_all*log2e, thr_p', thr_n', cA, cT, label, 0, 0}
+  // row scalars consumed by the backward: [Q][8] floats {max_all*log2e, thr_n', cT, label | thr_p', cA, 0, 0}
   // (one 32-byte record per row: all-gathered as is when world > 1, bulk-copied per K block by the fused gradient kernel)
   float* rowscal;
 };
