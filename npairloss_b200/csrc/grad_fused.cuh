@@ -5,9 +5,10 @@
 // Replaces Get_Query_Diff_Part x3 + six cublasSgemm + the N x D all-reduce of the reference (npair_multi_class_loss.cu:438-497).
 // H (Q x N) is never written to HBM: per 32-column K block the 8 producer warps read a 128 x 32 fp32 tile of S (TMA,
 // 128B-swizzled) and the 32 column records (bulk copy), evaluate the weights in registers (row record in registers,
-// thread = row), split them into the 2-byte operand pieces and store those straight into the 64B-swizzled K-major
-// shared-memory tiles that tcgen05.mma consumes.  Requires a bitwise symmetric S (EPI_SIM_SYM tiles at world == 1,
-// K-concatenated operands across ranks) -- see gemm_tcgen05.cuh / kernels.cu.
+// thread = row), split them into the 2-byte operand pieces and store those with tcgen05.st straight into TENSOR MEMORY,
+// from where tcgen05.mma takes its A operand (the multi-pass GEMM is shared-memory-bandwidth bound in 1-CTA mode: every
+// pass re-reads its operands from smem, so keeping A out of smem removes a third of that traffic).  Requires a bitwise
+// symmetric S (EPI_SIM_SYM tiles at world == 1, K-concatenated operands across ranks) -- see gemm_tcgen05.cuh / kernels.cu.
 //
 // CTA = 384 threads: warp 0 TMA producer (B pieces of X^T, S tile, column records), warp 1 MMA issuer, warp 2 TMEM
 // allocator, warps 4-11 weight producers, which also run the epilogue (TMEM -> alpha*acc -> out / split-K partial).
@@ -45,12 +46,15 @@ struct FusedGradParams {
 template <int NSPLIT>
 struct FusedCfg {
   static constexpr int BM = 128, BN = 256, BK = 32;
-  static constexpr int A_PIECE = BM * 64;                 // 64-byte rows (32 x 2-byte), SWIZZLE_64B
-  static constexpr int B_PIECE = BN * 64;
+  static constexpr int B_PIECE = BN * 64;                 // 64-byte rows (32 x 2-byte), SWIZZLE_64B
   static constexpr int S_TILE = BM * 128;                 // 128-byte rows (32 x fp32), SWIZZLE_128B
   static constexpr int CREC = BK * 32;                    // 32 column records of 32 bytes
-  static constexpr int STAGE_BYTES = NSPLIT * (A_PIECE + B_PIECE) + S_TILE + CREC;
-  static constexpr int STAGES = (NSPLIT == 1) ? 4 : (NSPLIT == 2 ? 3 : 2);
+  static constexpr int STAGE_BYTES = NSPLIT * B_PIECE + S_TILE + CREC;
+  static constexpr int STAGES = (NSPLIT == 1) ? 6 : (NSPLIT == 2 ? 4 : 3);
+  // tensor memory: columns [0,256) = the 128 x 256 fp32 accumulator; A operand pieces behind it,
+  // 16 packed columns (32 two-byte K elements) per piece and stage
+  static constexpr int TMEM_A0 = 256;
+  static constexpr int A_COLS = BK / 2;
   static constexpr int NPASS = (NSPLIT == 1) ? 1 : (NSPLIT == 2 ? 3 : 6);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*barriers*/ + 1024 /*alignment*/;
   static constexpr int THREADS = 640;                         // 4 control warps + 16 producer / epilogue warps
@@ -134,9 +138,9 @@ fused_grad_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_consta
           uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
 #pragma unroll
           for (int s = 0; s < NSPLIT; ++s)
-            ptx::tma_load_3d(st + NSPLIT * Cfg::A_PIECE + s * Cfg::B_PIECE, &tmapB, &full_bar[stage], m0, n_blk * BN, s);
-          ptx::tma_load_2d(st + NSPLIT * (Cfg::A_PIECE + Cfg::B_PIECE), &tmapS, &full_bar[stage], m0, m_blk * BM);
-          bulk_copy_g2s(st + NSPLIT * (Cfg::A_PIECE + Cfg::B_PIECE) + Cfg::S_TILE, p.colrec + 8ll * m0, crec_bytes, &full_bar[stage]);
+            ptx::tma_load_3d(st + s * Cfg::B_PIECE, &tmapB, &full_bar[stage], m0, n_blk * BN, s);
+          ptx::tma_load_2d(st + NSPLIT * Cfg::B_PIECE, &tmapS, &full_bar[stage], m0, m_blk * BM);
+          bulk_copy_g2s(st + NSPLIT * Cfg::B_PIECE + Cfg::S_TILE, p.colrec + 8ll * m0, crec_bytes, &full_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -148,28 +152,27 @@ fused_grad_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_consta
       int stage = 0; uint32_t phase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
+        const int acc = 0;                       // one accumulator: the producers run the epilogue themselves
+        const uint32_t acc_phase = it & 1;
         ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_base;
         const int split = tile % p.splits;
         const int kb0 = split * p.kb_per_split, kb1 = min(p.num_kblocks, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::mbar_wait(&aready_bar[stage], phase);
           ptx::tc_fence_after();
-          const uint32_t a0 = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint32_t b0 = a0 + NSPLIT * Cfg::A_PIECE;
+          const uint32_t b0 = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t a_t = tmem_base + Cfg::TMEM_A0 + stage * NSPLIT * Cfg::A_COLS;
 #pragma unroll
           for (int ps = 0; ps < Cfg::NPASS; ++ps) {
             int sa, sb;
             pass_pieces(NSPLIT, ps, sa, sb);
 #pragma unroll
             for (int k2 = 0; k2 < BK / 16; ++k2) {
-              const uint64_t ad = ptx::make_kmajor_desc(a0 + sa * Cfg::A_PIECE + k2 * 32, 512u, 4u);   // SWIZZLE_64B, 8 rows = 512 B
-              const uint64_t bd = ptx::make_kmajor_desc(b0 + sb * Cfg::B_PIECE + k2 * 32, 512u, 4u);
-              ptx::mma_f16_ss(d_tmem, ad, bd, idesc, ((kb - kb0) | ps | k2) != 0 ? 1u : 0u);
+              const uint64_t bd = ptx::make_kmajor_desc(b0 + sb * Cfg::B_PIECE + k2 * 32, 512u, 4u);   // SWIZZLE_64B, 8 rows = 512 B
+              ptx::mma_f16_ts(d_tmem, a_t + sa * Cfg::A_COLS + k2 * 8, bd, idesc, ((kb - kb0) | ps | k2) != 0 ? 1u : 0u);
             }
           }
           ptx::mma_commit(&empty_bar[stage]);
@@ -201,7 +204,7 @@ fused_grad_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_consta
       for (int kb = kb0; kb < kb1; ++kb) {
         ptx::mbar_wait(&full_bar[stage], phase);
         uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
-        const uint8_t* s_tile = st + NSPLIT * (Cfg::A_PIECE + Cfg::B_PIECE);
+        const uint8_t* s_tile = st + NSPLIT * Cfg::B_PIECE;
         const float4* crec = reinterpret_cast<const float4*>(s_tile + Cfg::S_TILE) + 2 * (8 * qt);
         // my 8 similarities: chunks 2*qt, 2*qt+1 of row rl (128B swizzle: chunk ^ (row & 7))
         float sv[8];
@@ -244,7 +247,7 @@ fused_grad_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_consta
             if (m0 + cc == self_col || m0 + cc >= p.N) g[cc] = 0.f;
           }
         }
-        // pieces -> K-major 64B-swizzled A tiles: row rl, 16-byte chunk qt (physical chunk ^ ((row >> 1) & 3))
+        // pieces -> tensor memory: lane = row, 4 packed columns (8 K elements) at column offset 4*qt of each piece
         uint32_t pk[NSPLIT][4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -253,20 +256,21 @@ fused_grad_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_consta
 #pragma unroll
           for (int s = 0; s < NSPLIT; ++s) pk[s][q] = o[s];
         }
+        const uint32_t a_t = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + Cfg::TMEM_A0 + stage * NSPLIT * Cfg::A_COLS + 4 * qt;
 #pragma unroll
-        for (int s = 0; s < NSPLIT; ++s)
-          *reinterpret_cast<uint4*>(st + s * Cfg::A_PIECE + rl * 64 + ((qt ^ ((rl >> 1) & 3)) << 4)) = make_uint4(pk[s][0], pk[s][1], pk[s][2], pk[s][3]);
-        ptx::fence_proxy_async_smem();           // generic-proxy writes -> visible to the tensor core's async proxy
+        for (int s = 0; s < NSPLIT; ++s) ptx::tmem_st_32x32b_x4(a_t + s * Cfg::A_COLS, pk[s][0], pk[s][1], pk[s][2], pk[s][3]);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();                   // order the tcgen05.st before the arrive that releases the MMA issuer
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&aready_bar[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       // ---- epilogue of this tile: TMEM -> alpha * acc (+ beta * out) ----
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
+      const int acc = 0;
+      const uint32_t acc_phase = it & 1;
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
       float* obase = p.splits > 1 ? p.part + static_cast<long long>(split) * p.Q * p.ldo : p.out;
       const float beta = p.splits > 1 ? 0.f : p.beta;
 #pragma unroll 1
