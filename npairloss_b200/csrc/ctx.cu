@@ -297,6 +297,7 @@ struct npair_ctx {
   CUtensorMap tm_catA, tm_catB;
   CUtensorMap tm_fB, tm_fS;      // fused gradient kernel: X^T pieces with 32-wide K boxes, 128-row fp32 boxes of S
   bool fused_grad = false;
+  bool rs_gathered = false;
   int2* sym_tiles = nullptr;     // world == 1: (m_blk, n_blk) of the similarity tiles touching the upper triangle
   int n_sym_tiles = 0;
   float* part = nullptr;         // split-K partial products of the gradient GEMM
@@ -671,6 +672,16 @@ static int forward_impl(npair_ctx* c, const float* d_feat, const float* d_label,
     PhaseTimer pt(c, 4, st);
     launch_lse_rows(c->S, c->ldS, Q, N, d_label, c->lab_total, self_off, mp, c->ra, c->bs, c->cfg.num_tops, c->tops_dev, st);
   }
+  c->rs_gathered = false;
+  if (c->bwd_mode == NPAIR_BWDMODE_ROW_SCALARS && c->comm) {
+    // The only backward exchange (8*Q floats per rank, replaces the N x D MPI_Allreduce of .cu:462-489) does not depend on
+    // the loss weight, so it is enqueued here: it runs while the host wakes up from the synchronisation below.
+    PhaseTimer pt(c, 8, st);
+    NcclApi* api = nccl_api();
+    int r = api->AllGather(c->ra.rowscal, c->rs_total, 8ull * Q, NCCL_FLOAT32, c->comm, st);
+    if (r != 0) { c->err = fmt("ncclAllGather(row records): %s", api->GetErrorString(r)); return NPAIR_E_NCCL; }
+    c->rs_gathered = true;
+  }
   CUDA_TRY(c, cudaGetLastError());
   CUDA_TRY(c, cudaStreamSynchronize(st));          // the reference also blocks here (host reads of loss/asum, .cu:384,400)
   const int derr = reinterpret_cast<int*>(c->tops_pinned)[5];
@@ -743,12 +754,8 @@ static int backward_impl(npair_ctx* c, float loss_weight, float* d_diff, float* 
     bw_mode = BW_ROWSCAL;
     if (d_rs_ext) rs_total = d_rs_ext;
     else {
-      // the only backward exchange: 8*Q floats per rank (replaces the N x D MPI_Allreduce of .cu:462-489)
-      PhaseTimer pt(c, 8, st);
-      NcclApi* api = nccl_api();
-      int r = api->AllGather(c->ra.rowscal, c->rs_total, 8ull * Q, NCCL_FLOAT32, c->comm, st);
-      if (r != 0) { c->err = fmt("ncclAllGather(row scalars): %s", api->GetErrorString(r)); return NPAIR_E_NCCL; }
-      rs_total = c->rs_total;
+      if (!c->rs_gathered) { c->err = "row records were not gathered by the forward pass"; return NPAIR_E_STATE; }
+      rs_total = c->rs_total;                  // all-gathered at the end of npair_forward
     }
   } else if (c->bwd_mode == NPAIR_BWDMODE_REDUCE_SCATTER) bw_mode = BW_SPLIT;
   if (tc && c->fused_grad) {

@@ -355,22 +355,6 @@ void launch_split(const float* x_total, int N, int D, int prec, const BlockScala
 // --------------------------------------------------------------------------------------------
 // statistics init / reference row statistics (caffe_set of the three stat blobs, .cu:230-236)
 // --------------------------------------------------------------------------------------------
-__global__ void init_stats_kernel(RowArrays ra, int Q, BlockScalars* bs) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < Q) {
-    ra.st_minw[i] = f2ord(FLT_MAX); ra.st_maxw[i] = f2ord(-FLT_MAX);
-    ra.st_maxb[i] = f2ord(-FLT_MAX); ra.st_maxall[i] = f2ord(-FLT_MAX);
-    ra.cnt_same[i] = 0;
-  }
-  if (i == 0) {
-    bs->err = 0; bs->ticket = 0; bs->ticket2 = 0; bs->sel_active[0] = 0; bs->sel_active[1] = 0;
-    bs->n_same = 0; bs->n_diff = 0;
-  }
-}
-void launch_init_stats(RowArrays ra, int Q, BlockScalars* bs, cudaStream_t st) {
-  init_stats_kernel<<<(Q + 255) / 256, 256, 0, st>>>(ra, Q, bs);
-}
-
 // One block per row; same outputs as the sim-GEMM epilogue.  Used by the SIMT cross-check backend and by tests.
 __global__ void row_stats_ref_kernel(const float* __restrict__ S, long long ldS, int Q, int N, const float* __restrict__ lab_rows,
                                      const float* __restrict__ lab_cols, int self_offset, RowArrays ra) {

@@ -63,7 +63,6 @@ void launch_split(const float* x_total, int N, int D, int prec, const BlockScala
                   uint16_t* Xs, long long ldXs /*Dp*/, uint16_t* XsT, long long ldXsT /*Np*/,
                   uint16_t* XlT, long long ldXlT /*Qp, or 0*/, int row0_local, int Q,
                   uint16_t* XcatA /*or NULL*/, uint16_t* XcatB, long long Dp, cudaStream_t st);
-void launch_init_stats(RowArrays ra, int Q, BlockScalars* bs, cudaStream_t st);
 void launch_row_stats_ref(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
                           int self_offset, RowArrays ra, cudaStream_t st);
 void launch_thresholds(RowArrays ra, int Q, int N, MiningParams mp, BlockScalars* bs, float* scratch /*>= 2 KB*/, cudaStream_t st);
