@@ -94,6 +94,13 @@ class ClockSampler:
         return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
 
 
+def host_threads():
+    """Threads for the CPU oracle: one per physical core (the sort-heavy oracle loses 4x with SMT oversubscription:
+    683 vs 2690 samples/s on the 128-thread gpurun box).  torchrun exports OMP_NUM_THREADS=1, so never rely on the default."""
+    n = os.cpu_count() or 1
+    return max(1, n // 2) if n >= 32 else n
+
+
 def run_reference(args, B, D, mining, noise):
     """CPU baseline arm: the oracle with the reference's unconditional sorts on all host threads.  Each step is the
     rank-0 block of the 8-way anchor sharding (1024 anchors x 8192 database), a bounded sample of the same workload."""
@@ -103,8 +110,8 @@ def run_reference(args, B, D, mining, noise):
     x, lab = synth.make_inputs(B, D, 20171225 + 5, noise=noise)
     world_s = 8
     Qs = B // world_s
-    cores = os.cpu_count() or 1
-    cfg = o.make_config(Qs, D, world=world_s, rank=0, accum_double=0, faithful_sorts=1, num_threads=0, **mining)
+    cores = host_threads()
+    cfg = o.make_config(Qs, D, world=world_s, rank=0, accum_double=0, faithful_sorts=1, num_threads=cores, **mining)
     L = o.lib()
     buf = np.zeros(L.npo_state_floats(C.byref(cfg)), dtype=np.float32)
     st = o.NpoState()
@@ -340,7 +347,7 @@ def main():
         o.build()
         world_s = 8
         Qs = B // world_s
-        ocfg = o.make_config(Qs, D, world=world_s, rank=0, accum_double=0, faithful_sorts=1, num_threads=0, **mining)
+        ocfg = o.make_config(Qs, D, world=world_s, rank=0, accum_double=0, faithful_sorts=1, num_threads=host_threads(), **mining)
         L = o.lib()
         buf = np.zeros(L.npo_state_floats(C.byref(ocfg)), dtype=np.float32)
         st = o.NpoState()
@@ -354,9 +361,9 @@ def main():
             assert L.npo_backward_partial(C.byref(ocfg), o._fp(x), C.byref(st), C.c_float(1.0), o._fp(ld), o._fp(td)) == 0
             reps += 1
         dt = (time.perf_counter() - t0) / reps
-        cpu = {"value": Qs / dt, "unit": "samples/s", "cores": os.cpu_count() or 1, "kind": "port",
+        cpu = {"value": Qs / dt, "unit": "samples/s", "cores": host_threads(), "kind": "port",
                "sample": f"rank-0 block of the 8-way anchor sharding: {Qs} anchors x {B} database x D={D}, {reps} reps, "
-                         "faithful unconditional sorts, fp32 accumulate, OpenMP on all cores"}
+                         "faithful unconditional sorts, fp32 accumulate, OpenMP, one thread per physical core"}
 
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

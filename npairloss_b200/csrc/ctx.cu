@@ -365,14 +365,18 @@ static Sizes sizes_of(const npair_config* c) {
   s.N = static_cast<long long>(c->Q) * c->world;
   s.Dp = round_up(c->D, 64); s.Np = round_up(s.N, 64); s.Qp = round_up(c->Q, 64); s.ldS = round_up(s.N, 32);
   s.ns = nsplit_of_prec(c->sim_precision);
+  const bool tc = c->gemm_backend == NPAIR_GEMM_TCGEN05;
+  const bool rs = c->world > 1 && c->bwd_exchange != NPAIR_BWD_AUTO;
+  const bool fused = tc && !rs;
   size_t t = 0;
-  if (c->world > 1) t += sizeof(float) * (s.N * c->D + s.N);
-  t += sizeof(float) * c->Q * s.ldS;                       // S
-  t += 2ull * s.ns * s.N * s.Dp;                            // Xs
-  t += 2ull * s.ns * c->D * s.Np;                           // XsT
-  t += 2ull * s.ns * c->Q * s.Np;                           // H
-  if (c->world > 1) { t += 2ull * s.ns * c->D * s.Qp; t += 2ull * s.ns * s.N * s.Qp; t += sizeof(float) * s.N * c->D; }
-  t += 64ull * c->Q + 65536;                                // row arrays + scalars
+  if (c->world > 1) t += sizeof(float) * (s.N * c->D + s.N);                       // all-gather targets
+  t += sizeof(float) * c->Q * s.ldS;                                                // S
+  t += 2ull * s.ns * s.N * s.Dp + 2ull * s.ns * c->D * s.Np;                        // operand pieces, transposed pieces
+  if (tc && c->sim_precision != NPAIR_PREC_BF16) t += 2ull * 2 * s.N * kcat_mult(c->sim_precision) * s.Dp;   // K-concatenated operands
+  if (!fused) t += 2ull * s.ns * c->Q * s.Np;                                       // materialised gradient weights
+  if (rs) { t += 2ull * s.ns * c->D * s.Qp + 2ull * s.ns * s.N * s.Qp + sizeof(float) * s.N * c->D; }
+  if (c->world > 1 && !rs) t += sizeof(float) * 8ull * s.N;                         // gathered row records
+  t += 4ull * 21 * c->Q + 65536;                                                    // row arrays, records, scalars
   s.total = t;
   return s;
 }
@@ -465,8 +469,16 @@ static int create_impl(const npair_config* cfg, const void* id128, void* ext_com
   CREATE_TRY(cudaMemset(c->Xs, 0, 2ull * ns * N * c->Dp));
   CREATE_TRY(cudaMalloc(&c->XsT, 2ull * ns * D * c->Np));
   CREATE_TRY(cudaMemset(c->XsT, 0, 2ull * ns * D * c->Np));
-  CREATE_TRY(cudaMalloc(&c->H, 2ull * ns * Q * c->Np));
-  CREATE_TRY(cudaMemset(c->H, 0, 2ull * ns * Q * c->Np));
+  // gradient weights are only materialised when the fused tensor-memory kernel is not used
+  // (reduce-scatter exchange, SIMT cross-check backend, NPAIR_NO_FUSED_GRAD)
+  {
+    const bool multi_rs = c->world > 1 && cfg->bwd_exchange != NPAIR_BWD_AUTO;
+    c->fused_grad = cfg->gemm_backend == NPAIR_GEMM_TCGEN05 && !multi_rs && !getenv("NPAIR_NO_FUSED_GRAD");
+  }
+  if (!c->fused_grad) {
+    CREATE_TRY(cudaMalloc(&c->H, 2ull * ns * Q * c->Np));
+    CREATE_TRY(cudaMemset(c->H, 0, 2ull * ns * Q * c->Np));
+  }
   c->bwd_mode = c->world == 1 ? NPAIR_BWDMODE_SINGLE
               : (cfg->bwd_exchange == NPAIR_BWD_AUTO ? NPAIR_BWDMODE_ROW_SCALARS : NPAIR_BWDMODE_REDUCE_SCATTER);
   if (c->bwd_mode == NPAIR_BWDMODE_ROW_SCALARS) CREATE_TRY(cudaMalloc(&c->rs_total, sizeof(float) * 8ull * N));
@@ -525,9 +537,8 @@ static int create_impl(const npair_config* cfg, const void* id128, void* ext_com
     ok = ok && make_tmap_pieces(&c->tm_simB, c->Xs, D, N, ns, c->Dp, static_cast<long long>(N) * c->Dp, bks, 256, &te);
     ok = ok && make_tmap_f32_store(&c->tm_S, c->S, N, Q, c->ldS, &te);
     // gradient 1: A = H [Q x N], B = XsT [D x N]; K = N
-    ok = ok && make_tmap_pieces(&c->tm_b1A, c->H, N, Q, ns, c->Np, static_cast<long long>(Q) * c->Np, bkg, 128, &te);
+    if (c->H) ok = ok && make_tmap_pieces(&c->tm_b1A, c->H, N, Q, ns, c->Np, static_cast<long long>(Q) * c->Np, bkg, 128, &te);
     ok = ok && make_tmap_pieces(&c->tm_b1B, c->XsT, N, D, ns, c->Np, static_cast<long long>(D) * c->Np, bkg, 256, &te);
-    c->fused_grad = (c->bwd_mode != NPAIR_BWDMODE_REDUCE_SCATTER) && !getenv("NPAIR_NO_FUSED_GRAD");
     if (c->fused_grad) {
       ok = ok && make_tmap_pieces(&c->tm_fB, c->XsT, N, D, ns, c->Np, static_cast<long long>(D) * c->Np, 32, 256, &te);
       ok = ok && make_tmap_f32_store(&c->tm_fS, c->S, N, Q, c->ldS, &te, 128);

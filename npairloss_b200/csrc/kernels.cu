@@ -650,7 +650,13 @@ __device__ __forceinline__ void lse_elem(float sv, float lab, float li, float sc
 }
 
 // The last block to finish also performs the job of the old finalize kernel (loss, retrieval ratios, asum, error word).
-__global__ void __launch_bounds__(256) lse_rows_kernel(const float* __restrict__ S, long long ldS, int Q, int N,
+#ifndef NPAIR_LSE_U
+#define NPAIR_LSE_U 4            // 16-byte loads in flight per lane and array (S, labels)
+#endif
+#ifndef NPAIR_LSE_MINB
+#define NPAIR_LSE_MINB 4
+#endif
+__global__ void __launch_bounds__(256, NPAIR_LSE_MINB) lse_rows_kernel(const float* __restrict__ S, long long ldS, int Q, int N,
                                                        const float* __restrict__ lab_rows, const float* __restrict__ lab_cols,
                                                        int self_offset, MiningParams mp, RowArrays ra, BlockScalars* bs,
                                                        int num_tops, float* __restrict__ tops) {
@@ -674,18 +680,19 @@ __global__ void __launch_bounds__(256) lse_rows_kernel(const float* __restrict__
     const float* row = S + static_cast<long long>(i) * ldS;
     float A = 0.f, T = 0.f; int c = 0;
     // ---- full 512-column blocks: unguarded 128-bit loads (4 in flight per lane for S, 4 for the labels) ----
-    const int n_full = N & ~511;
+    constexpr int U = NPAIR_LSE_U;
+    const int n_full = N - N % (128 * U);
     const float4* srow4 = reinterpret_cast<const float4*>(row) + lane;
     const float4* lab4 = reinterpret_cast<const float4*>(lab_cols) + lane;
     const bool lab_aligned = (reinterpret_cast<uintptr_t>(lab_cols) & 15) == 0;
     int base = 0;
     if (lab_aligned) {
-      for (; base < n_full; base += 512, srow4 += 128, lab4 += 128) {
-        float4 v[4], l[4];
+      for (; base < n_full; base += 128 * U, srow4 += 32 * U, lab4 += 32 * U) {
+        float4 v[U], l[U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { v[u] = __ldg(srow4 + 32 * u); l[u] = __ldg(lab4 + 32 * u); }
+        for (int u = 0; u < U; ++u) { v[u] = __ldg(srow4 + 32 * u); l[u] = __ldg(lab4 + 32 * u); }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
           const int j4 = base + u * 128 + lane * 4;
           const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
           const float ll[4] = {l[u].x, l[u].y, l[u].z, l[u].w};
