@@ -139,6 +139,34 @@ static cudaError_t launch_split_gemm_t(const CUtensorMap& a, const CUtensorMap& 
   kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a, b, sm, p);
   return cudaGetLastError();
 }
+// CTA-pair launch (cluster dimension 2, tcgen05 cta_group::2); p counts 256-row pair blocks (tiles_m / tile list)
+template <bool BF16, int EPI>
+static cudaError_t launch_pair_gemm_t(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& sm, const GemmParams& p, int sms, cudaStream_t st) {
+  using Cfg = GemmCfg<1, 64, 2>;
+  auto kern = split_gemm_kernel<1, BF16, EPI, 64, 2>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int tiles = p.tile_list ? p.num_tiles_list : p.tiles_m * p.tiles_n * p.splits;
+  const int pairs = sms / 2;
+  cudaLaunchConfig_t lc; memset(&lc, 0, sizeof(lc));
+  lc.gridDim = dim3(2 * (tiles < pairs ? tiles : pairs));
+  lc.blockDim = dim3(Cfg::THREADS);
+  lc.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  lc.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  lc.attrs = at; lc.numAttrs = 1;
+  return cudaLaunchKernelEx(&lc, kern, a, b, sm, p);
+}
+static cudaError_t launch_sim_gemm_pair(int prec, bool sym_tiles, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& sm, const GemmParams& p, int sms, cudaStream_t st) {
+  if (prec == PREC_FP16X2) return sym_tiles ? launch_pair_gemm_t<false, EPI_SIM_SYM>(a, b, sm, p, sms, st) : launch_pair_gemm_t<false, EPI_SIM>(a, b, sm, p, sms, st);
+  return sym_tiles ? launch_pair_gemm_t<true, EPI_SIM_SYM>(a, b, sm, p, sms, st) : launch_pair_gemm_t<true, EPI_SIM>(a, b, sm, p, sms, st);
+}
 // `sm`: fp32 tensor map of the similarity matrix for EPI_SIM's TMA stores (ignored by EPI_OUT: pass any valid map)
 // Similarity GEMM: always ONE MMA pass over K-concatenated operands (see split_kernel), fp16 or bf16 elements.
 static cudaError_t launch_sim_gemm(int prec, bool sym_tiles, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& sm, const GemmParams& p, int sms, cudaStream_t st) {
@@ -295,6 +323,10 @@ struct npair_ctx {
   uint16_t *XcatA = nullptr, *XcatB = nullptr;   // row-scalar mode, fp16x2: K-concatenated operands [N][3*Dp]
   float* rs_total = nullptr;     // row-scalar mode: all-gathered [N][8] row records
   CUtensorMap tm_catA, tm_catB;
+  CUtensorMap tm_simB2, tm_catB2;   // 128-row B boxes for the CTA-pair similarity GEMM
+  bool sim_pair = false;            // similarity GEMM runs in CTA-pair mode (cta_group::2)
+  int2* sym_tiles2 = nullptr;       // world == 1: (pair_m, n_blk) list of the pair kernel
+  int n_sym_tiles2 = 0;
   CUtensorMap tm_fB, tm_fS;      // fused gradient kernel: X^T pieces with 32-wide K boxes, 128-row fp32 boxes of S
   bool fused_grad = false;
   bool rs_gathered = false;
@@ -418,7 +450,7 @@ void npair_destroy(npair_ctx* c) {
   if (c->device >= 0) cudaSetDevice(c->device);
   if (c->comm && c->own_comm) { NcclApi* api = nccl_api(); if (api->CommDestroy) api->CommDestroy(c->comm); }
   cudaFree(c->Xtot_buf); cudaFree(c->labtot_buf); cudaFree(c->S); cudaFree(c->Xs); cudaFree(c->XsT); cudaFree(c->XlT);
-  cudaFree(c->H); cudaFree(c->HT); cudaFree(c->OUT2); cudaFree(c->part); cudaFree(c->sym_tiles); cudaFree(c->XcatA); cudaFree(c->XcatB); cudaFree(c->rs_total); cudaFree(c->row_block); cudaFree(c->bs); cudaFree(c->partial); cudaFree(c->ghist);
+  cudaFree(c->H); cudaFree(c->HT); cudaFree(c->OUT2); cudaFree(c->part); cudaFree(c->sym_tiles); cudaFree(c->sym_tiles2); cudaFree(c->XcatA); cudaFree(c->XcatB); cudaFree(c->rs_total); cudaFree(c->row_block); cudaFree(c->bs); cudaFree(c->partial); cudaFree(c->ghist);
   if (c->tops_pinned) cudaFreeHost(c->tops_pinned);
   if (c->ev_made) for (int i = 0; i < NPAIR_PROF_PHASES; ++i) { cudaEventDestroy(c->ev[i][0]); cudaEventDestroy(c->ev[i][1]); }
   delete c;
@@ -535,6 +567,7 @@ static int create_impl(const npair_config* cfg, const void* id128, void* ext_com
     // similarity: A = local rows of Xs, B = all rows of Xs; K = D
     ok = ok && make_tmap_pieces(&c->tm_simA, c->Xs + static_cast<long long>(c->rank) * Q * c->Dp, D, Q, ns, c->Dp, static_cast<long long>(N) * c->Dp, bks, 128, &te);
     ok = ok && make_tmap_pieces(&c->tm_simB, c->Xs, D, N, ns, c->Dp, static_cast<long long>(N) * c->Dp, bks, 256, &te);
+    ok = ok && make_tmap_pieces(&c->tm_simB2, c->Xs, D, N, ns, c->Dp, static_cast<long long>(N) * c->Dp, bks, 128, &te);
     ok = ok && make_tmap_f32_store(&c->tm_S, c->S, N, Q, c->ldS, &te);
     // gradient 1: A = H [Q x N], B = XsT [D x N]; K = N
     if (c->H) ok = ok && make_tmap_pieces(&c->tm_b1A, c->H, N, Q, ns, c->Np, static_cast<long long>(Q) * c->Np, bkg, 128, &te);
@@ -547,6 +580,7 @@ static int create_impl(const npair_config* cfg, const void* id128, void* ext_com
       const long long kc = kcat_mult(c->prec) * c->Dp;
       ok = ok && make_tmap_pieces(&c->tm_catA, c->XcatA + static_cast<long long>(c->rank) * Q * kc, static_cast<int>(kc), Q, 1, kc, static_cast<long long>(N) * kc, 64, 128, &te);
       ok = ok && make_tmap_pieces(&c->tm_catB, c->XcatB, static_cast<int>(kc), N, 1, kc, static_cast<long long>(N) * kc, 64, 256, &te);
+      ok = ok && make_tmap_pieces(&c->tm_catB2, c->XcatB, static_cast<int>(kc), N, 1, kc, static_cast<long long>(N) * kc, 64, 128, &te);
     }
     if (c->bwd_mode == NPAIR_BWDMODE_REDUCE_SCATTER) {   // gradient 2: A = HT [N x Q], B = XlT [D x Q]; K = Q
       ok = ok && make_tmap_pieces(&c->tm_b2A, c->HT, Q, N, ns, c->Qp, static_cast<long long>(N) * c->Qp, bkg, 128, &te);
@@ -563,6 +597,18 @@ static int create_impl(const npair_config* cfg, const void* id128, void* ext_com
     c->n_sym_tiles = static_cast<int>(tl.size());
     CREATE_TRY(cudaMalloc(&c->sym_tiles, sizeof(int2) * tl.size()));
     CREATE_TRY(cudaMemcpy(c->sym_tiles, tl.data(), sizeof(int2) * tl.size(), cudaMemcpyHostToDevice));
+    // pair kernel: 256-row block pm covers m_blk 2pm, 2pm+1 -> the same set of 128 x 256 tiles (n_blk >= pm)
+    std::vector<int2> tl2;
+    for (int pm = 0; pm < (tm + 1) / 2; ++pm)
+      for (int nb = pm; nb < tn; ++nb) tl2.push_back(make_int2(pm, nb));
+    c->n_sym_tiles2 = static_cast<int>(tl2.size());
+    CREATE_TRY(cudaMalloc(&c->sym_tiles2, sizeof(int2) * tl2.size()));
+    CREATE_TRY(cudaMemcpy(c->sym_tiles2, tl2.data(), sizeof(int2) * tl2.size(), cudaMemcpyHostToDevice));
+  }
+  {
+    // CTA-pair similarity GEMM whenever there are at least two 128-row blocks (NPAIR_SIM_1CTA=1 keeps the single-CTA kernel)
+    const char* e1 = getenv("NPAIR_SIM_1CTA");
+    c->sim_pair = cfg->gemm_backend == NPAIR_GEMM_TCGEN05 && Q > 128 && !(e1 && e1[0] == '1');
   }
   // ---- NCCL ----
   if (c->world > 1 && (id128 || ext_comm)) {
@@ -655,8 +701,13 @@ static int forward_impl(npair_ctx* c, const float* d_feat, const float* d_label,
   if (c->cfg.gemm_backend == NPAIR_GEMM_TCGEN05) {
     PhaseTimer pt(c, 2, st);
     if (c->sym_tiles) { gp.tile_list = c->sym_tiles; gp.num_tiles_list = c->n_sym_tiles; }
-    if (c->XcatA) {
-      gp.num_kblocks = static_cast<int>(kcat_mult(c->prec) * c->Dp / 64); gp.kb_per_split = gp.num_kblocks;
+    if (c->XcatA) { gp.num_kblocks = static_cast<int>(kcat_mult(c->prec) * c->Dp / 64); gp.kb_per_split = gp.num_kblocks; }
+    if (c->sim_pair) {
+      gp.tiles_m = (gp.tiles_m + 1) / 2;
+      if (c->sym_tiles2) { gp.tile_list = c->sym_tiles2; gp.num_tiles_list = c->n_sym_tiles2; }
+      CUDA_TRY(c, launch_sim_gemm_pair(c->prec, c->sym_tiles != nullptr, c->XcatA ? c->tm_catA : c->tm_simA, c->XcatA ? c->tm_catB2 : c->tm_simB2,
+                                       c->tm_S, gp, c->sms, st));
+    } else if (c->XcatA) {
       CUDA_TRY(c, launch_sim_gemm(c->prec, c->sym_tiles != nullptr, c->tm_catA, c->tm_catB, c->tm_S, gp, c->sms, st));
     } else
       CUDA_TRY(c, launch_sim_gemm(c->prec, c->sym_tiles != nullptr, c->tm_simA, c->tm_simB, c->tm_S, gp, c->sms, st));

@@ -83,15 +83,20 @@ struct GemmParams {
 // BK_ = K-block in elements = one swizzle span per smem row (64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B).  Measured on B200
 // (gpurun_out/tune1.log): the short-K similarity GEMM (K = D) prefers 64, the long-K gradient GEMM (K = N) with two
 // fp16 pieces prefers 32 (four 48 KB stages hide the TMA latency better than two 96 KB ones: 164 -> 141 us).
-template <int NSPLIT, int BK_>
+// NCTA = 2: CTA-pair mode (tcgen05.mma.cta_group::2).  A cluster of two CTAs on one TPC computes a 256 x 256 block: each CTA
+// stages its own 128 rows of A and 128 of the 256 B rows, the leader issues one M = 256 MMA that reads both CTAs' shared
+// memory, and each CTA's tensor memory receives its 128 x 256 half.  Per SM the operand traffic through shared memory drops
+// from 12 KB to 8 KB per K = 16 step, which is what bounds these kernels.
+template <int NSPLIT, int BK_, int NCTA = 1>
 struct GemmCfg {
   static constexpr int BM = 128, BN = 256;
+  static constexpr int B_ROWS = BN / NCTA;                    // B rows staged by one CTA
   static constexpr int BK = BK_;
   static constexpr int ROW_BYTES = BK * 2;                    // 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
   static constexpr uint32_t LAYOUT = (ROW_BYTES == 128) ? 2u : 4u;
   static constexpr uint32_t SBO = 8 * ROW_BYTES;              // byte distance between 8-row groups
   static constexpr int A_PIECE = BM * ROW_BYTES;
-  static constexpr int B_PIECE = BN * ROW_BYTES;
+  static constexpr int B_PIECE = B_ROWS * ROW_BYTES;
   static constexpr int STAGE_BYTES = NSPLIT * (A_PIECE + B_PIECE);
   static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;   // fill 192 KB with operand stages
   static constexpr int NPASS = (NSPLIT == 1) ? 1 : (NSPLIT == 2 ? 3 : 6);
@@ -149,11 +154,15 @@ __device__ __forceinline__ void stats32(const float (&v)[32], const float* __res
   }
 }
 
-template <int NSPLIT, bool BF16, int EPI, int BK_>
+// NCTA = 2: launched with cluster dimension 2; p.tiles_m and the tile list count 256-row PAIR blocks, tmapB has 128-row boxes.
+template <int NSPLIT, bool BF16, int EPI, int BK_, int NCTA = 1>
 __global__ void __launch_bounds__(384, 1)
 split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
                   const __grid_constant__ CUtensorMap tmapS, const GemmParams p) {
-  using Cfg = GemmCfg<NSPLIT, BK_>;
+  using Cfg = GemmCfg<NSPLIT, BK_, NCTA>;
+  static_assert(NCTA == 1 || (NCTA == 2 && EPI != EPI_OUT), "pair mode is implemented for the similarity epilogues");
+  const int cta_rank = (NCTA == 2) ? static_cast<int>(blockIdx.x & 1u) : 0;      // cluster = blocks {2c, 2c+1}
+  const int worker = static_cast<int>(blockIdx.x) / NCTA, num_workers = static_cast<int>(gridDim.x) / NCTA;
   constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   // keep the pointer in the shared address space (offset arithmetic, no integer round trip): LDS/STS, not generic LD/ST
@@ -181,7 +190,7 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 8); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 8 * NCTA); }
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
@@ -190,6 +199,7 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (NCTA == 2) ptx::cluster_sync_all();      // the peer's barriers are initialised before anything signals them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -197,19 +207,33 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     // ===================================== TMA producer =====================================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < num_tiles; tile += num_workers) {
         const int mn = tile / p.splits, split = tile - mn * p.splits;
         int m_blk = mn / p.tiles_n, n_blk = mn % p.tiles_n;
         if (p.tile_list) { const int2 tl = p.tile_list[tile]; m_blk = tl.x; n_blk = tl.y; }
+        m_blk = m_blk * NCTA + cta_rank;
         const int kb0 = split * p.kb_per_split, kb1 = min(p.num_kblocks, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
+          if (NCTA == 1) {
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
 #pragma unroll
-          for (int s = 0; s < NSPLIT; ++s) {
-            ptx::tma_load_3d(st + s * Cfg::A_PIECE, &tmapA, &full_bar[stage], kb * BK, m_blk * BM, s);
-            ptx::tma_load_3d(st + NSPLIT * Cfg::A_PIECE + s * Cfg::B_PIECE, &tmapB, &full_bar[stage], kb * BK, n_blk * BN, s);
+            for (int s = 0; s < NSPLIT; ++s) {
+              ptx::tma_load_3d(st + s * Cfg::A_PIECE, &tmapA, &full_bar[stage], kb * BK, m_blk * BM, s);
+              ptx::tma_load_3d(st + NSPLIT * Cfg::A_PIECE + s * Cfg::B_PIECE, &tmapB, &full_bar[stage], kb * BK, n_blk * BN, s);
+            }
+          } else {
+            // both CTAs' boxes complete on the LEADER's barrier, which expects the bytes of the whole pair stage (the peer's
+            // bytes may land before the leader's expect_tx: the transaction count may go negative inside a phase)
+            if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES * NCTA);
+            const uint32_t lead_full = ptx::mapa_u32(ptx::smem_u32(&full_bar[stage]), 0);
+#pragma unroll
+            for (int s = 0; s < NSPLIT; ++s) {
+              ptx::tma_load_3d_pair(st + s * Cfg::A_PIECE, &tmapA, lead_full, kb * BK, m_blk * BM, s);
+              ptx::tma_load_3d_pair(st + NSPLIT * Cfg::A_PIECE + s * Cfg::B_PIECE, &tmapB, lead_full, kb * BK,
+                                    n_blk * BN + cta_rank * Cfg::B_ROWS, s);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -217,11 +241,11 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =====================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_f16(BF16, BM, BN);
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_f16(BF16, BM * NCTA, BN);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = worker; tile < num_tiles; tile += num_workers, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -242,13 +266,16 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
             for (int k4 = 0; k4 < BK / 16; ++k4) {
               const uint64_t ad = ptx::make_kmajor_desc(a0 + sa * Cfg::A_PIECE + k4 * 32, Cfg::SBO, Cfg::LAYOUT);
               const uint64_t bd = ptx::make_kmajor_desc(b0 + sb * Cfg::B_PIECE + k4 * 32, Cfg::SBO, Cfg::LAYOUT);
-              ptx::mma_f16_ss(d_tmem, ad, bd, idesc, ((kb - kb0) | ps | k4) != 0 ? 1u : 0u);
+              if (NCTA == 1) ptx::mma_f16_ss(d_tmem, ad, bd, idesc, ((kb - kb0) | ps | k4) != 0 ? 1u : 0u);
+              else ptx::mma_f16_ss_pair(d_tmem, ad, bd, idesc, ((kb - kb0) | ps | k4) != 0 ? 1u : 0u);
             }
           }
-          ptx::mma_commit(&empty_bar[stage]);   // smem slot reusable once these MMAs retire
+          // smem slot reusable once these MMAs retire (pair mode: in both CTAs)
+          if (NCTA == 1) ptx::mma_commit(&empty_bar[stage]); else ptx::mma_commit_pair(&empty_bar[stage], 3);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        ptx::mma_commit(&tfull_bar[acc]);        // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (pair mode: each CTA drains its own 128 rows)
+        if (NCTA == 1) ptx::mma_commit(&tfull_bar[acc]); else ptx::mma_commit_pair(&tfull_bar[acc], 3);
       }
     }
   } else if (warp >= 4) {
@@ -259,10 +286,12 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     const int et = threadIdx.x - 128;            // 0..255
     uint8_t* const stg = store_stage + (warp - 4) * 4096;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    const uint32_t lead_tempty = (NCTA == 2) ? ptx::mapa_u32(ptx::smem_u32(&tempty_bar[0]), 0) : 0u;
+    for (int tile = worker; tile < num_tiles; tile += num_workers, ++it) {
       const int mn = tile / p.splits, split = tile - mn * p.splits;
       int m_blk = mn / p.tiles_n, n_blk = mn % p.tiles_n;
       if (p.tile_list) { const int2 tl = p.tile_list[tile]; m_blk = tl.x; n_blk = tl.y; }
+      m_blk = m_blk * NCTA + cta_rank;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int row = m_blk * BM + ew * 32 + lane;
@@ -383,7 +412,7 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       // accumulator drained -> MMA warp may overwrite it
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) { if (NCTA == 1) ptx::mbar_arrive(&tempty_bar[acc]); else ptx::mbar_arrive_cluster(lead_tempty + 8u * acc); }
       if (EPI != EPI_OUT && row < p.M) {
         maxall = fmaxf(maxw, maxb);                       // every valid column is either same- or diff-label
         if (cnt) {
@@ -399,6 +428,7 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   if (EPI != EPI_OUT && warp >= 4 && lane == 0) ptx::tma_store_wait<0>();   // bulk stores complete before exit
   ptx::tc_fence_before();
   __syncthreads();
+  if (NCTA == 2) ptx::cluster_sync_all();      // no CTA of the pair exits while the other may still signal or read it
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<512>(tmem_base);
