@@ -195,6 +195,35 @@ static cudaError_t launch_fused_grad_t(const CUtensorMap& b, const CUtensorMap& 
   kern<<<tiles < sms ? tiles : sms, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(b, sm, p);
   return cudaGetLastError();
 }
+// CTA-pair launch of the fused gradient kernel (cluster dimension 2); p.tiles_m counts 256-row pair blocks, `b` has 128-row boxes
+template <int NSPLIT, bool BF16>
+static cudaError_t launch_fused_grad_pair_t(const CUtensorMap& b, const CUtensorMap& sm, const FusedGradParams& p, int sms, cudaStream_t st) {
+  using Cfg = FusedCfg<NSPLIT, 2>;
+  auto kern = fused_grad_kernel<NSPLIT, BF16, 2>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int tiles = p.tiles_m * p.tiles_n * p.splits;
+  const int pairs = sms / 2;
+  cudaLaunchConfig_t lc; memset(&lc, 0, sizeof(lc));
+  lc.gridDim = dim3(2 * (tiles < pairs ? tiles : pairs));
+  lc.blockDim = dim3(Cfg::THREADS);
+  lc.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  lc.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  lc.attrs = at; lc.numAttrs = 1;
+  return cudaLaunchKernelEx(&lc, kern, b, sm, p);
+}
+static cudaError_t launch_fused_grad_pair(int prec, const CUtensorMap& b, const CUtensorMap& sm, const FusedGradParams& p, int sms, cudaStream_t st) {
+  if (prec == PREC_BF16) return launch_fused_grad_pair_t<1, true>(b, sm, p, sms, st);
+  if (prec == PREC_FP16X2) return launch_fused_grad_pair_t<2, false>(b, sm, p, sms, st);
+  return launch_fused_grad_pair_t<3, true>(b, sm, p, sms, st);
+}
 static cudaError_t launch_fused_grad(int prec, const CUtensorMap& b, const CUtensorMap& sm, const FusedGradParams& p, int sms, cudaStream_t st) {
   if (prec == PREC_BF16) return launch_fused_grad_t<1, true>(b, sm, p, sms, st);
   if (prec == PREC_FP16X2) return launch_fused_grad_t<2, false>(b, sm, p, sms, st);
@@ -327,6 +356,8 @@ struct npair_ctx {
   bool sim_pair = false;            // similarity GEMM runs in CTA-pair mode (cta_group::2)
   int2* sym_tiles2 = nullptr;       // world == 1: (pair_m, n_blk) list of the pair kernel
   int n_sym_tiles2 = 0;
+  CUtensorMap tm_fB2;            // 128-row boxes of X^T for the CTA-pair gradient kernel
+  bool grad_pair = false;        // fused gradient kernel runs in CTA-pair mode
   CUtensorMap tm_fB, tm_fS;      // fused gradient kernel: X^T pieces with 32-wide K boxes, 128-row fp32 boxes of S
   bool fused_grad = false;
   bool rs_gathered = false;
@@ -574,6 +605,7 @@ static int create_impl(const npair_config* cfg, const void* id128, void* ext_com
     ok = ok && make_tmap_pieces(&c->tm_b1B, c->XsT, N, D, ns, c->Np, static_cast<long long>(D) * c->Np, bkg, 256, &te);
     if (c->fused_grad) {
       ok = ok && make_tmap_pieces(&c->tm_fB, c->XsT, N, D, ns, c->Np, static_cast<long long>(D) * c->Np, 32, 256, &te);
+      ok = ok && make_tmap_pieces(&c->tm_fB2, c->XsT, N, D, ns, c->Np, static_cast<long long>(D) * c->Np, 32, 128, &te);
       ok = ok && make_tmap_f32_store(&c->tm_fS, c->S, N, Q, c->ldS, &te, 128);
     }
     if (c->XcatA) {       // bitwise-symmetric similarity: one pass over K_cat = 3*Dp (fp16x2) / 6*Dp (bf16x3)
@@ -609,6 +641,8 @@ static int create_impl(const npair_config* cfg, const void* id128, void* ext_com
     // CTA-pair similarity GEMM whenever there are at least two 128-row blocks (NPAIR_SIM_1CTA=1 keeps the single-CTA kernel)
     const char* e1 = getenv("NPAIR_SIM_1CTA");
     c->sim_pair = cfg->gemm_backend == NPAIR_GEMM_TCGEN05 && Q > 128 && !(e1 && e1[0] == '1');
+    const char* e2 = getenv("NPAIR_GRAD_1CTA");
+    c->grad_pair = c->fused_grad && Q > 128 && !(e2 && e2[0] == '1');
   }
   // ---- NCCL ----
   if (c->world > 1 && (id128 || ext_comm)) {
@@ -831,9 +865,10 @@ static int backward_impl(npair_ctx* c, float loss_weight, float* d_diff, float* 
     fp.sgn_n = (mp.an_method == M_HARD || mp.an_method == M_RELATIVE_HARD) ? -1.f : 1.f;
     fp.out = d_diff; fp.ldo = D; fp.alpha = 0.5f * lw_over_q; fp.beta = 0.f; fp.dev_scale = &c->bs->x_inv_scale;
     fp.part = c->part; fp.splits = 1; fp.kb_per_split = fp.num_kblocks;
+    if (c->grad_pair) fp.tiles_m = (fp.tiles_m + 1) / 2;       // 256-row pair blocks, one cluster of two CTAs each
     if (c->part) {
       const int tiles = fp.tiles_m * fp.tiles_n;
-      int splits = c->sms / (tiles > 0 ? tiles : 1);
+      int splits = (c->grad_pair ? c->sms / 2 : c->sms) / (tiles > 0 ? tiles : 1);
       if (splits > 16) splits = 16;
       if (splits > fp.num_kblocks / 8) splits = fp.num_kblocks / 8;        // keep >= 8 K blocks (256 columns) per split
       while (splits > 1 && static_cast<long long>(splits) * Q * D > c->part_floats) --splits;
@@ -843,7 +878,8 @@ static int backward_impl(npair_ctx* c, float loss_weight, float* d_diff, float* 
     }
     {
       PhaseTimer pt(c, 6, st);
-      CUDA_TRY(c, launch_fused_grad(c->prec, c->tm_fB, c->tm_fS, fp, c->sms, st));
+      if (c->grad_pair) CUDA_TRY(c, launch_fused_grad_pair(c->prec, c->tm_fB2, c->tm_fS, fp, c->sms, st));
+      else CUDA_TRY(c, launch_fused_grad(c->prec, c->tm_fB, c->tm_fS, fp, c->sms, st));
       if (fp.splits > 1) {
         const long long n = static_cast<long long>(Q) * D;
         int nb = static_cast<int>((n / 4 + 255) / 256); if (nb > c->sms * 8) nb = c->sms * 8; if (nb < 1) nb = 1;

@@ -98,9 +98,11 @@ struct GemmCfg {
   static constexpr int A_PIECE = BM * ROW_BYTES;
   static constexpr int B_PIECE = B_ROWS * ROW_BYTES;
   static constexpr int STAGE_BYTES = NSPLIT * (A_PIECE + B_PIECE);
-  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;   // fill 192 KB with operand stages
+  // pair mode: two TMA-store staging tiles per epilogue warp (direct + mirrored box in flight together), 160 KB of stages
+  static constexpr int STORE_BUFS = (NCTA == 2) ? 2 : 1;
+  static constexpr int STAGES = ((NCTA == 2 ? 160 : 192) * 1024) / STAGE_BYTES;   // fill 192 / 160 KB with operand stages
   static constexpr int NPASS = (NSPLIT == 1) ? 1 : (NSPLIT == 2 ? 3 : 6);
-  static constexpr int STORE_STAGE_BYTES = 8 * 4096;          // one 32x32 fp32 TMA-store staging tile per epilogue warp
+  static constexpr int STORE_STAGE_BYTES = 8 * 4096 * STORE_BUFS;   // 32x32 fp32 TMA-store staging tiles, per epilogue warp
   static constexpr int SMEM_AUX = 2048;                       // barriers + tmem ptr + column labels
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STORE_STAGE_BYTES + SMEM_AUX + 1024 /*alignment slack*/;
   static constexpr int THREADS = 384;                         // 4 control warps + 8 epilogue warps
@@ -155,6 +157,24 @@ __device__ __forceinline__ void stats32(const float (&v)[32], const float* __res
 }
 
 // NCTA = 2: launched with cluster dimension 2; p.tiles_m and the tile list count 256-row PAIR blocks, tmapB has 128-row boxes.
+// 256-bit global store (sm_100: STG.E.256): one full 32-byte sector per lane
+__device__ __forceinline__ void st_global_v8(float* dst, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+// How the similarity epilogue writes S (measured at B = 8192, D = 512, pair kernel; MMA-only floor 74 us):
+//   NPAIR_EPI_STG = 1 (default): DIRECT chunks leave the registers with 256-bit stores (lane = row, 128 contiguous bytes per
+//     lane, no staging / proxy fence / bulk-store wait): 86 us with direct stores only, against 93 us for TMA-stored boxes.
+//   NPAIR_EPI_MSTG = 0 (default): MIRRORED chunks are transposed through a 128B-swizzled per-warp staging tile and leave as one
+//     32x32 fp32 TMA-store box; = 1 reads the transposed rows back and uses the 256-bit store (measured slower: 129 vs 110 us
+//     with both on TMA).
+#ifndef NPAIR_EPI_STG
+#define NPAIR_EPI_STG 1
+#endif
+#ifndef NPAIR_EPI_MSTG
+#define NPAIR_EPI_MSTG 0
+#endif
+
 template <int NSPLIT, bool BF16, int EPI, int BK_, int NCTA = 1>
 __global__ void __launch_bounds__(384, 1)
 split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
@@ -284,7 +304,9 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     const int ew = (warp - 4) & 3;
     const int half = (warp - 4) >> 2;
     const int et = threadIdx.x - 128;            // 0..255
-    uint8_t* const stg = store_stage + (warp - 4) * 4096;
+    constexpr int SB = Cfg::STORE_BUFS;
+    uint8_t* const stg0 = store_stage + (warp - 4) * 4096 * SB;
+    uint32_t sgrp = 0;                            // bulk-store groups issued by this warp (SB == 2: alternate the two tiles)
     int it = 0;
     const uint32_t lead_tempty = (NCTA == 2) ? ptx::mapa_u32(ptx::smem_u32(&tempty_bar[0]), 0) : 0u;
     for (int tile = worker; tile < num_tiles; tile += num_workers, ++it) {
@@ -329,9 +351,19 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
           for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(r[c]) * out_scale;
           // registers -> 128B-swizzled staging tile -> one TMA store of a 32x32 fp32 box (full 128-byte lines;
           // rows >= M and columns >= Nn are clipped by the tensor map)
-          if (NPAIR_DBG_EPI_LEVEL >= 1 && m_blk * BM + ew * 32 < p.M && col0 < p.Nn) {          // warp-uniform
-            if (lane == 0) ptx::tma_store_wait_read<0>();             // this warp's previous box has been read out of smem
+          if (NPAIR_EPI_STG) {
+            // ldS is a multiple of 32, so a partial last chunk stores zeros (zero-filled operand rows) into the row padding
+            if (NPAIR_DBG_EPI_LEVEL >= 1 && row < p.M && col0 < p.Nn) {
+              float* dst = p.S + static_cast<long long>(row) * p.ldS + col0;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) st_global_v8(dst + 8 * q, v + 8 * q);
+            }
+          } else if (NPAIR_DBG_EPI_LEVEL >= 1 && m_blk * BM + ew * 32 < p.M && col0 < p.Nn) {          // warp-uniform
+            // this warp's previous box (SB == 2: the one before it, which used the same tile) has been read out of smem
+            if (lane == 0) { if (SB == 2) ptx::tma_store_wait_read<1>(); else ptx::tma_store_wait_read<0>(); }
             __syncwarp();
+            uint8_t* const stg = stg0 + (SB == 2 ? (sgrp & 1u) * 4096u : 0u);
+            ++sgrp;
             uint8_t* srow = stg + lane * 128;
 #pragma unroll
             for (int q = 0; q < 8; ++q)
@@ -348,15 +380,17 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
                     minw, maxw, maxb, cnt);
           if (NPAIR_DBG_EPI_LEVEL >= 3 && EPI == EPI_SIM_SYM && cb > m_blk && m_blk * BM + ew * 32 < p.M && col0 < p.Nn) {
             // ---- mirrored store: staging row c holds S[col0 + c][rows of this warp]; box lands at (x = row block, y = col0) ----
-            if (lane == 0) ptx::tma_store_wait_read<0>();
-            __syncwarp();
+            if (!NPAIR_EPI_MSTG && lane == 0) { if (SB == 2) ptx::tma_store_wait_read<1>(); else ptx::tma_store_wait_read<0>(); }
+            __syncwarp();                                  // (register-store variant: the previous read-back is complete)
+            uint8_t* const stg = stg0 + ((!NPAIR_EPI_MSTG && SB == 2) ? (sgrp & 1u) * 4096u : 0u);
+            ++sgrp;
 #pragma unroll
             for (int c = 0; c < 32; ++c)
               *reinterpret_cast<float*>(stg + c * 128 + ((((lane >> 2) ^ (c & 7))) << 4) + ((lane & 3) << 2)) = v[c];
-            ptx::fence_proxy_async_smem();
+            if (!NPAIR_EPI_MSTG) ptx::fence_proxy_async_smem();
             __syncwarp();
 #ifndef NPAIR_DBG_SKIP_MSTORE
-            if (lane == 0) { ptx::tma_store_2d(&tmapS, stg, m_blk * BM + ew * 32, col0); ptx::tma_store_commit(); }
+            if (!NPAIR_EPI_MSTG && lane == 0) { ptx::tma_store_2d(&tmapS, stg, m_blk * BM + ew * 32, col0); ptx::tma_store_commit(); }
 #endif
             // ---- mirrored statistics: the staging tile is the transposed chunk, so lane L reads back ROW gc = col0 + L of the
             //      symmetric matrix (32 entries against this warp's 32 row labels) and reuses the per-thread statistics ----
@@ -370,6 +404,11 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
             float t_minw = FLT_MAX, t_maxw = -FLT_MAX, t_maxb = -FLT_MAX;
             int t_cnt = 0;
             const int r0 = m_blk * BM + ew * 32;
+            if (NPAIR_EPI_MSTG && gc < p.Nn) {             // row gc of the symmetric matrix, columns r0 .. r0 + 31
+              float* dst = p.S + static_cast<long long>(gc) * p.ldS + r0;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) st_global_v8(dst + 8 * q, vt + 8 * q);
+            }
             if (NPAIR_DBG_EPI_LEVEL >= 4 && gc < p.Nn) {
               stats32(vt, s_labr + ew * 32, s_lab[ch * 32 + lane], r0 + 32 <= p.M, r0, p.M, -1, t_minw, t_maxw, t_maxb, t_cnt);
               if (t_cnt) {

@@ -43,14 +43,18 @@ struct FusedGradParams {
   const float* dev_scale;       // inverse operand pre-scale (power of two) or NULL
 };
 
-template <int NSPLIT>
+// NCTA = 2: CTA-pair mode (cluster of 2, tcgen05.mma.cta_group::2, M = 256).  Each CTA produces the weights of its own 128 rows
+// into its own tensor memory and stages 128 of the 256 rows of the B tile; the leader's MMA reads both halves.  Halves the
+// B traffic through each SM's shared memory (the bound of this kernel); p.tiles_m then counts 256-row pair blocks.
+template <int NSPLIT, int NCTA = 1>
 struct FusedCfg {
   static constexpr int BM = 128, BN = 256, BK = 32;
-  static constexpr int B_PIECE = BN * 64;                 // 64-byte rows (32 x 2-byte), SWIZZLE_64B
+  static constexpr int B_ROWS = BN / NCTA;
+  static constexpr int B_PIECE = B_ROWS * 64;             // 64-byte rows (32 x 2-byte), SWIZZLE_64B
   static constexpr int S_TILE = BM * 128;                 // 128-byte rows (32 x fp32), SWIZZLE_128B
   static constexpr int CREC = BK * 32;                    // 32 column records of 32 bytes
   static constexpr int STAGE_BYTES = NSPLIT * B_PIECE + S_TILE + CREC;
-  static constexpr int STAGES = (NSPLIT == 1) ? 6 : (NSPLIT == 2 ? 4 : 3);
+  static constexpr int STAGES = (NCTA == 1) ? ((NSPLIT == 1) ? 6 : (NSPLIT == 2 ? 4 : 3)) : ((NSPLIT == 1) ? 8 : (NSPLIT == 2 ? 6 : 5));
   // tensor memory: columns [0,256) = the 128 x 256 fp32 accumulator; A operand pieces behind it,
   // 16 packed columns (32 two-byte K elements) per piece and stage
   static constexpr int TMEM_A0 = 256;
@@ -90,16 +94,20 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, 
                : "memory");
 }
 
-template <int NSPLIT, bool BF16>
+template <int NSPLIT, bool BF16, int NCTA = 1>
 __global__ void __launch_bounds__(640, 1)
 fused_grad_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ CUtensorMap tmapS, const FusedGradParams p) {
-  using Cfg = FusedCfg<NSPLIT>;
+  using Cfg = FusedCfg<NSPLIT, NCTA>;
+  static_assert(Cfg::TMEM_A0 + Cfg::STAGES * NSPLIT * Cfg::A_COLS <= 512, "A pieces do not fit behind the accumulator");
+  const int cta_rank = (NCTA == 2) ? static_cast<int>(blockIdx.x & 1u) : 0;      // cluster = blocks {2c, 2c+1}
+  const int worker = static_cast<int>(blockIdx.x) / NCTA, num_workers = static_cast<int>(gridDim.x) / NCTA;
   constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* aux = smem + STAGES * Cfg::STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);            // [STAGES] TMA bytes landed (B, S tile, column records)
-  uint64_t* aready_bar = full_bar + STAGES;                          // [STAGES] producers wrote the A pieces
+  uint64_t* bfull_bar = full_bar + STAGES;                           // [STAGES] pair mode: both CTAs' B halves landed (leader's copy is used)
+  uint64_t* aready_bar = bfull_bar + STAGES;                         // [STAGES] producers wrote the A pieces (pair mode: of both CTAs, leader's copy)
   uint64_t* empty_bar = aready_bar + STAGES;                         // [STAGES] MMAs of the stage retired
   uint64_t* tfull_bar = empty_bar + STAGES;                          // [2]
   uint64_t* tempty_bar = tfull_bar + 2;                              // [2]
@@ -112,13 +120,16 @@ fused_grad_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_consta
 
   if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tmapB); ptx::prefetch_tmap(&tmapS); }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&aready_bar[s], 16); ptx::mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 16); }
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&bfull_bar[s], 1); ptx::mbar_init(&aready_bar[s], 16 * NCTA); ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 16 * NCTA); }
     ptx::fence_mbar_init();
   }
   if (warp == 2) { ptx::tmem_alloc<512>(tmem_ptr); ptx::tmem_relinquish(); }
   ptx::tc_fence_before();
   __syncthreads();
+  if (NCTA == 2) ptx::cluster_sync_all();      // the peer's barriers are initialised before anything signals them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -126,19 +137,30 @@ fused_grad_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_consta
     // ===================================== TMA producer =====================================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < num_tiles; tile += num_workers) {
         const int mn = tile / p.splits, split = tile - mn * p.splits;
-        const int m_blk = mn / p.tiles_n, n_blk = mn % p.tiles_n;
+        const int m_blk = (mn / p.tiles_n) * NCTA + cta_rank, n_blk = mn % p.tiles_n;
         const int kb0 = split * p.kb_per_split, kb1 = min(p.num_kblocks, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           const int m0 = kb * BK;
           const uint32_t crec_bytes = static_cast<uint32_t>(min(BK, p.N - m0)) * 32u;
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], NSPLIT * Cfg::B_PIECE + Cfg::S_TILE + crec_bytes);
           uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
+          if (NCTA == 1) {
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], NSPLIT * Cfg::B_PIECE + Cfg::S_TILE + crec_bytes);
 #pragma unroll
-          for (int s = 0; s < NSPLIT; ++s)
-            ptx::tma_load_3d(st + s * Cfg::B_PIECE, &tmapB, &full_bar[stage], m0, n_blk * BN, s);
+            for (int s = 0; s < NSPLIT; ++s)
+              ptx::tma_load_3d(st + s * Cfg::B_PIECE, &tmapB, &full_bar[stage], m0, n_blk * BN, s);
+          } else {
+            // own S tile + column records on the local barrier (the local producers wait for them); the B halves of both CTAs
+            // complete on the leader's bfull barrier (the MMA issuer waits for it)
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::S_TILE + crec_bytes);
+            if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&bfull_bar[stage], NSPLIT * Cfg::B_PIECE * NCTA);
+            const uint32_t lead_bfull = ptx::mapa_u32(ptx::smem_u32(&bfull_bar[stage]), 0);
+#pragma unroll
+            for (int s = 0; s < NSPLIT; ++s)
+              ptx::tma_load_3d_pair(st + s * Cfg::B_PIECE, &tmapB, lead_bfull, m0, n_blk * BN + cta_rank * Cfg::B_ROWS, s);
+          }
           ptx::tma_load_2d(st + NSPLIT * Cfg::B_PIECE, &tmapS, &full_bar[stage], m0, m_blk * BM);
           bulk_copy_g2s(st + NSPLIT * Cfg::B_PIECE + Cfg::S_TILE, p.colrec + 8ll * m0, crec_bytes, &full_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -147,11 +169,11 @@ fused_grad_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_consta
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =====================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_f16(BF16, BM, BN);
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_f16(BF16, BM * NCTA, BN);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = worker; tile < num_tiles; tile += num_workers, ++it) {
         const int acc = 0;                       // one accumulator: the producers run the epilogue themselves
         const uint32_t acc_phase = it & 1;
         ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -160,7 +182,7 @@ fused_grad_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_consta
         const int split = tile % p.splits;
         const int kb0 = split * p.kb_per_split, kb1 = min(p.num_kblocks, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
-          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::mbar_wait(NCTA == 1 ? &full_bar[stage] : &bfull_bar[stage], phase);
           ptx::mbar_wait(&aready_bar[stage], phase);
           ptx::tc_fence_after();
           const uint32_t b0 = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -172,13 +194,14 @@ fused_grad_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_consta
 #pragma unroll
             for (int k2 = 0; k2 < BK / 16; ++k2) {
               const uint64_t bd = ptx::make_kmajor_desc(b0 + sb * Cfg::B_PIECE + k2 * 32, 512u, 4u);   // SWIZZLE_64B, 8 rows = 512 B
-              ptx::mma_f16_ts(d_tmem, a_t + sa * Cfg::A_COLS + k2 * 8, bd, idesc, ((kb - kb0) | ps | k2) != 0 ? 1u : 0u);
+              if (NCTA == 1) ptx::mma_f16_ts(d_tmem, a_t + sa * Cfg::A_COLS + k2 * 8, bd, idesc, ((kb - kb0) | ps | k2) != 0 ? 1u : 0u);
+              else ptx::mma_f16_ts_pair(d_tmem, a_t + sa * Cfg::A_COLS + k2 * 8, bd, idesc, ((kb - kb0) | ps | k2) != 0 ? 1u : 0u);
             }
           }
-          ptx::mma_commit(&empty_bar[stage]);
+          if (NCTA == 1) ptx::mma_commit(&empty_bar[stage]); else ptx::mma_commit_pair(&empty_bar[stage], 3);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        ptx::mma_commit(&tfull_bar[acc]);
+        if (NCTA == 1) ptx::mma_commit(&tfull_bar[acc]); else ptx::mma_commit_pair(&tfull_bar[acc], 3);
       }
     }
   } else if (warp >= 4) {
@@ -187,9 +210,11 @@ fused_grad_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_consta
     const int qt = (warp - 4) >> 2;              // quarter: 8 of the 32 K columns while producing, 64 of the 256 D columns in the epilogue
     int stage = 0; uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    const uint32_t lead_aready = (NCTA == 2) ? ptx::mapa_u32(ptx::smem_u32(&aready_bar[0]), 0) : 0u;
+    const uint32_t lead_tempty = (NCTA == 2) ? ptx::mapa_u32(ptx::smem_u32(&tempty_bar[0]), 0) : 0u;
+    for (int tile = worker; tile < num_tiles; tile += num_workers, ++it) {
       const int mn = tile / p.splits, split = tile - mn * p.splits;
-      const int m_blk = mn / p.tiles_n, n_blk = mn % p.tiles_n;
+      const int m_blk = (mn / p.tiles_n) * NCTA + cta_rank, n_blk = mn % p.tiles_n;
       const int kb0 = split * p.kb_per_split, kb1 = min(p.num_kblocks, kb0 + p.kb_per_split);
       const int rl = ew * 32 + lane;             // row inside the tile
       const int row = m_blk * BM + rl;
@@ -262,7 +287,7 @@ fused_grad_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_consta
         ptx::tmem_st_wait();
         ptx::tc_fence_before();                   // order the tcgen05.st before the arrive that releases the MMA issuer
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&aready_bar[stage]);
+        if (lane == 0) { if (NCTA == 1) ptx::mbar_arrive(&aready_bar[stage]); else ptx::mbar_arrive_cluster(lead_aready + 8u * stage); }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       // ---- epilogue of this tile: TMEM -> alpha * acc (+ beta * out) ----
@@ -305,11 +330,12 @@ fused_grad_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_consta
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) { if (NCTA == 1) ptx::mbar_arrive(&tempty_bar[acc]); else ptx::mbar_arrive_cluster(lead_tempty + 8u * acc); }
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (NCTA == 2) ptx::cluster_sync_all();      // no CTA of the pair exits while the other may still signal or read it
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<512>(tmem_base);

@@ -155,8 +155,11 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
   return r;
 }
+// Remote arrive with the default (CTA-scope release) semantics.  `.release.cluster` would compile to MEMBAR.ALL.GPU + ERRBAR in
+// front of the arrive (measured: the pair-mode gradient kernel went from 182 to 332 us with it on the per-K-block path);
+// what the waiting MMA issuer consumes is tensor memory, ordered by tcgen05.wait::st / tcgen05.fence::before_thread_sync.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
 }
 // TMA load issued by either CTA of a pair: data lands in THIS CTA's smem, the transaction bytes complete on an mbarrier that
 // may live in the peer (`cluster_bar_addr` from mapa_u32)
@@ -174,6 +177,15 @@ __device__ __forceinline__ void mma_f16_ss_pair(uint32_t d_tmem, uint64_t a_desc
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// pair MMA with the A operand in tensor memory: each CTA's TMEM holds its 128 rows of A at `a_tmem`
+__device__ __forceinline__ void mma_f16_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // arrive on the mbarrier at the same smem offset in every CTA of `cta_mask` once the previously issued pair MMAs retire

@@ -1,5 +1,6 @@
-"""Diagnostic (not a test): CTA-pair (cta_group::2) similarity GEMM against the single-CTA kernel -- S and the fused row
-   statistics must agree bitwise.  python tests/diag_pair.py [B] [D] [precision]; run twice internally via NPAIR_SIM_1CTA."""
+"""Diagnostic (not a test): CTA-pair (cta_group::2) kernels against the single-CTA ones -- S, the fused row statistics and the
+   gradient must agree bitwise.  python tests/diag_pair.py [B] [D] [precision] [sim|grad]; runs the configuration twice,
+   toggling NPAIR_SIM_1CTA (or NPAIR_GRAD_1CTA)."""
 import os, sys, subprocess
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -19,7 +20,8 @@ def child(B, D, prec, out):
     acc = np.zeros(9); n = 10
     for _ in range(n):
         ctx.forward(dx, dl); ctx.backward(1.0, dg); acc += np.array(ctx.profile_read())
-    print("1cta" if os.environ.get("NPAIR_SIM_1CTA") == "1" else "pair", B, D, prec, "sim=%.1fus" % (acc[2] / n * 1e3), "tops", tops, flush=True)
+    print("sim", "1cta" if os.environ.get("NPAIR_SIM_1CTA") == "1" else "pair", "grad", "1cta" if os.environ.get("NPAIR_GRAD_1CTA") == "1" else "pair",
+          B, D, prec, "sim=%.1fus grad=%.1fus" % (acc[2] / n * 1e3, acc[6] / n * 1e3), "loss", tops[0], flush=True)
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "child":
@@ -27,9 +29,10 @@ if __name__ == "__main__":
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
     D = int(sys.argv[2]) if len(sys.argv) > 2 else 512
     prec = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+    var = "NPAIR_GRAD_1CTA" if (len(sys.argv) > 4 and sys.argv[4] == "grad") else "NPAIR_SIM_1CTA"
     outs = []
     for one in ("1", "0"):
-        env = dict(os.environ, NPAIR_SIM_1CTA=one)
+        env = dict(os.environ, **{var: one})
         out = f"/tmp/diag_pair_{one}.npz"
         r = subprocess.run([sys.executable, __file__, "child", str(B), str(D), str(prec), out], env=env, timeout=120)
         if r.returncode != 0: print("child failed", one, r.returncode); sys.exit(1)
