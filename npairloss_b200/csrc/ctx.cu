@@ -723,7 +723,9 @@ static int forward_impl(npair_ctx* c, const float* d_feat, const float* d_label,
     PhaseTimer pt(c, 1, st);
     launch_prep_reduce(d_feat, static_cast<long long>(Q) * D, c->x_total, static_cast<long long>(N) * D, c->partial,
                        c->prec == PREC_FP16X2 ? 1 : 0, c->ra, Q, c->bs, st);
-    launch_split(c->x_total, N, D, c->prec, c->bs, c->Xs, c->Dp, c->XsT, c->Np, c->XlT, c->Qp, self_off, Q, c->XcatA, c->XcatB, c->Dp, st);
+    // Xs (the un-concatenated K-major pieces) is only read by the single-pass bf16 similarity GEMM and the SIMT backend
+    uint16_t* xs_dst = (c->XcatA && c->cfg.gemm_backend == NPAIR_GEMM_TCGEN05) ? nullptr : c->Xs;
+    launch_split(c->x_total, N, D, c->prec, c->bs, xs_dst, c->Dp, c->XsT, c->Np, c->XlT, c->Qp, self_off, Q, c->XcatA, c->XcatB, c->Dp, st);
   }
   // ---- S = X_local . X_total^T (.cu:218) with fused masks + row statistics (.cu:44-66, :225-265) ----
   GemmParams gp; memset(&gp, 0, sizeof(gp));

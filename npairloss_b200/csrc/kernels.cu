@@ -144,9 +144,37 @@ __global__ void __launch_bounds__(256) prep_reduce_kernel(const float* __restric
   float sum = 0.f, mx = 0.f;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   const long long t0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  for (long long i = t0; i < nl; i += stride) sum += fabsf(xl[i]);
-  if (want_scale)
-    for (long long i = t0; i < ntot; i += stride) mx = fmaxf(mx, fabsf(xt[i]));
+  // 16-byte loads, four in flight per thread (cudaMalloc'd / framework blobs are 16-byte aligned; otherwise the scalar loop)
+  if ((reinterpret_cast<uintptr_t>(xl) & 15) == 0) {
+    const float4* x4 = reinterpret_cast<const float4*>(xl);
+    const long long n4 = nl >> 2;
+    long long i = t0;
+    for (; i + 3 * stride < n4; i += 4 * stride) {
+      const float4 a = __ldg(x4 + i), b = __ldg(x4 + i + stride), c = __ldg(x4 + i + 2 * stride), d = __ldg(x4 + i + 3 * stride);
+      sum += (fabsf(a.x) + fabsf(a.y)) + (fabsf(a.z) + fabsf(a.w)) + (fabsf(b.x) + fabsf(b.y)) + (fabsf(b.z) + fabsf(b.w)) +
+             (fabsf(c.x) + fabsf(c.y)) + (fabsf(c.z) + fabsf(c.w)) + (fabsf(d.x) + fabsf(d.y)) + (fabsf(d.z) + fabsf(d.w));
+    }
+    for (; i < n4; i += stride) { const float4 a = __ldg(x4 + i); sum += (fabsf(a.x) + fabsf(a.y)) + (fabsf(a.z) + fabsf(a.w)); }
+    for (long long j = (n4 << 2) + t0; j < nl; j += stride) sum += fabsf(xl[j]);
+  } else {
+    for (long long i = t0; i < nl; i += stride) sum += fabsf(xl[i]);
+  }
+  if (want_scale) {
+    if ((reinterpret_cast<uintptr_t>(xt) & 15) == 0) {
+      const float4* x4 = reinterpret_cast<const float4*>(xt);
+      const long long n4 = ntot >> 2;
+      long long i = t0;
+      for (; i + 3 * stride < n4; i += 4 * stride) {
+        const float4 a = __ldg(x4 + i), b = __ldg(x4 + i + stride), c = __ldg(x4 + i + 2 * stride), d = __ldg(x4 + i + 3 * stride);
+        mx = fmaxf(mx, fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))), fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w)))));
+        mx = fmaxf(mx, fmaxf(fmaxf(fmaxf(fabsf(c.x), fabsf(c.y)), fmaxf(fabsf(c.z), fabsf(c.w))), fmaxf(fmaxf(fabsf(d.x), fabsf(d.y)), fmaxf(fabsf(d.z), fabsf(d.w)))));
+      }
+      for (; i < n4; i += stride) { const float4 a = __ldg(x4 + i); mx = fmaxf(mx, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w)))); }
+      for (long long j = (n4 << 2) + t0; j < ntot; j += stride) mx = fmaxf(mx, fabsf(xt[j]));
+    } else {
+      for (long long i = t0; i < ntot; i += stride) mx = fmaxf(mx, fabsf(xt[i]));
+    }
+  }
   for (long long i = t0; i < Q; i += stride) {                  // caffe_set of the stat blobs, .cu:230-236
     ra.st_minw[i] = f2ord(FLT_MAX); ra.st_maxw[i] = f2ord(-FLT_MAX);
     ra.st_maxb[i] = f2ord(-FLT_MAX); ra.st_maxall[i] = f2ord(-FLT_MAX);
@@ -291,7 +319,8 @@ __global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ x,
   if (rowok && d < Dp) {
     const long long ps = static_cast<long long>(N) * ldXs;
 #pragma unroll
-    for (int s = 0; s < NS; ++s) *reinterpret_cast<uint4*>(Xs + s * ps + static_cast<long long>(n) * ldXs + d) = pk[s];
+    if (Xs)      // NULL when the similarity GEMM reads the K-concatenated operands below
+      for (int s = 0; s < NS; ++s) *reinterpret_cast<uint4*>(Xs + s * ps + static_cast<long long>(n) * ldXs + d) = pk[s];
     // K-concatenated operands of the bitwise-symmetric similarity GEMM (one MMA pass over K_cat):
     //   fp16x2 : A row = [ hi | hi(8) lo(8) ... ]                         B row = [ hi | lo(8) hi(8) ... ]                  K_cat = 3*Dp
     //   bf16x3 : A row = [ hi | mid | hi(8) mid(8) ... | hi(8) lo(8) ... ]   B row = [ hi | mid | mid(8) hi(8) ... | lo(8) hi(8) ... ]   K_cat = 6*Dp
@@ -661,7 +690,13 @@ __global__ void __launch_bounds__(256, NPAIR_LSE_MINB) lse_rows_kernel(const flo
                                                        int self_offset, MiningParams mp, RowArrays ra, BlockScalars* bs,
                                                        int num_tops, float* __restrict__ tops) {
   const int lane = threadIdx.x & 31;
-  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  // NPAIR_LSE_REV: walk the rows from the last to the first.  The similarity GEMM produced the high row blocks last, so
+  // their tiles are the ones still resident in the 126 MB L2 when this kernel starts.
+#ifndef NPAIR_LSE_REV
+#define NPAIR_LSE_REV 1
+#endif
+  const int blk = NPAIR_LSE_REV ? static_cast<int>(gridDim.x - 1 - blockIdx.x) : static_cast<int>(blockIdx.x);
+  const int i = blk * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i < Q) {
     const float li = lab_rows[i];
     const int self_col = i + self_offset;
