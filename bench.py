@@ -240,8 +240,10 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
+    launches0 = capi.kernel_launches()
     for _ in range(args.steps):
         tops = step_device()
+    launches_timed = capi.kernel_launches() - launches0
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -334,11 +336,8 @@ def main():
            "weight_build_GBs": sbytes / (phases[5] * 1e-3) / 1e9 if phases[5] > 0 else None,
            "hbm_peak_GBs": peaks["hbm_gbs"]}
 
-    # kernels launched per step by OUR library (counted from the launch sequence in ctx.cu)
-    launches = 1 + 1 + 1 + 1 + 1 + 1 + 1                   # prep-reduce, split, sim gemm, thresholds, row pass (+finalize), build, grad gemm
-    if world > 1 and Q * 1 < 128 * 148:
-        launches += 1                                       # split-K reduce of the gradient GEMM when Q = B/world leaves few tiles
-    gpu_launches = launches * args.steps
+    # kernels launched inside the timed region by OUR library: counted by the library itself (npair_kernel_launches)
+    gpu_launches = launches_timed
 
     # ---------------- CPU baseline (rank 0, bounded sample) ----------------
     cpu = None

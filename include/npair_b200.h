@@ -141,6 +141,9 @@ const char* npair_version(void);
  *            8 backward exchange (row-scalar all-gather or reduce-scatter) */
 int npair_profile_enable(npair_ctx* ctx, int on);
 int npair_profile_read(npair_ctx* ctx, float ms_out[9]);
+/* Cumulative number of CUDA kernels this library has launched in the calling process (all contexts).  bench.py reports
+ * the difference across its timed region as "gpu_launches". */
+unsigned long long npair_kernel_launches(void);
 
 /* Device-side dtype bridges for the Dtype=double instantiation of the Caffe layer (INSTANTIATE_CLASS, reference
  * npair_multi_class_loss.cpp:190); the reference's arithmetic is fp32 there too (expf/logf/FLT_MAX). */

@@ -25,10 +25,17 @@ class NpairConfig(C.Structure):
 
 
 EXPORTS = ["npair_config_default", "npair_workspace_bytes", "npair_nccl_unique_id", "npair_create", "npair_create_with_comm",
-           "npair_destroy", "npair_forward", "npair_backward", "npair_forward_gathered", "npair_backward_partial", "npair_bwd_exchange_mode", "npair_row_scalars", "npair_backward_gathered", "npair_profile_enable", "npair_profile_read", "npair_util_f64_to_f32", "npair_util_f32_to_f64", "npair_last_error", "npair_version", "npair_debug_read",
+           "npair_destroy", "npair_forward", "npair_backward", "npair_forward_gathered", "npair_backward_partial", "npair_bwd_exchange_mode", "npair_row_scalars", "npair_backward_gathered", "npair_profile_enable", "npair_profile_read", "npair_kernel_launches", "npair_util_f64_to_f32", "npair_util_f32_to_f64", "npair_last_error", "npair_version", "npair_debug_read",
            "npair_debug_gemm"]
 
 _LIB = None
+
+
+def kernel_launches() -> int:
+    """Cumulative number of CUDA kernels libnpair_b200 has launched in this process (include/npair_b200.h)."""
+    f = lib().npair_kernel_launches
+    f.restype = C.c_ulonglong
+    return int(f())
 
 
 class NpairError(RuntimeError):

@@ -137,6 +137,7 @@ static cudaError_t launch_split_gemm_t(const CUtensorMap& a, const CUtensorMap& 
   const int tiles = p.tile_list ? p.num_tiles_list : p.tiles_m * p.tiles_n * p.splits;
   const int grid = tiles < sms ? tiles : sms;
   kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a, b, sm, p);
+  count_launch();
   return cudaGetLastError();
 }
 // CTA-pair launch (cluster dimension 2, tcgen05 cta_group::2); p counts 256-row pair blocks (tiles_m / tile list)
@@ -161,6 +162,7 @@ static cudaError_t launch_pair_gemm_t(const CUtensorMap& a, const CUtensorMap& b
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   lc.attrs = at; lc.numAttrs = 1;
+  count_launch();
   return cudaLaunchKernelEx(&lc, kern, a, b, sm, p);
 }
 static cudaError_t launch_sim_gemm_pair(int prec, bool sym_tiles, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& sm, const GemmParams& p, int sms, cudaStream_t st) {
@@ -193,6 +195,7 @@ static cudaError_t launch_fused_grad_t(const CUtensorMap& b, const CUtensorMap& 
   }
   const int tiles = p.tiles_m * p.tiles_n * p.splits;
   kern<<<tiles < sms ? tiles : sms, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(b, sm, p);
+  count_launch();
   return cudaGetLastError();
 }
 // CTA-pair launch of the fused gradient kernel (cluster dimension 2); p.tiles_m counts 256-row pair blocks, `b` has 128-row boxes
@@ -217,6 +220,7 @@ static cudaError_t launch_fused_grad_pair_t(const CUtensorMap& b, const CUtensor
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   lc.attrs = at; lc.numAttrs = 1;
+  count_launch();
   return cudaLaunchKernelEx(&lc, kern, b, sm, p);
 }
 static cudaError_t launch_fused_grad_pair(int prec, const CUtensorMap& b, const CUtensorMap& sm, const FusedGradParams& p, int sms, cudaStream_t st) {
@@ -293,6 +297,7 @@ static cudaError_t launch_simt_gemm(int prec, int epi, const uint16_t* A, long l
   if (prec == PREC_BF16) NPAIR_SIMT(PREC_BF16);
   else if (prec == PREC_FP16X2) NPAIR_SIMT(PREC_FP16X2);
   else NPAIR_SIMT(PREC_BF16X3);
+  count_launch();
 #undef NPAIR_SIMT
   return cudaGetLastError();
 }
@@ -886,6 +891,7 @@ static int backward_impl(npair_ctx* c, float loss_weight, float* d_diff, float* 
         const long long n = static_cast<long long>(Q) * D;
         int nb = static_cast<int>((n / 4 + 255) / 256); if (nb > c->sms * 8) nb = c->sms * 8; if (nb < 1) nb = 1;
         splitk_reduce_kernel<<<nb, 256, 0, st>>>(c->part, fp.splits, n, d_diff, 0.f);
+        count_launch();
       }
     }
     CUDA_TRY(c, cudaGetLastError());
@@ -929,6 +935,7 @@ static int backward_impl(npair_ctx* c, float loss_weight, float* d_diff, float* 
       const long long n = static_cast<long long>(Q) * D;
       int nb = static_cast<int>((n / 4 + 255) / 256); if (nb > c->sms * 8) nb = c->sms * 8; if (nb < 1) nb = 1;
       splitk_reduce_kernel<<<nb, 256, 0, st>>>(c->part, gp.splits, n, d_diff, gp.beta);
+      count_launch();
     }
   }
   CUDA_TRY(c, cudaGetLastError());
@@ -951,6 +958,8 @@ int npair_profile_enable(npair_ctx* c, int on) {
   return NPAIR_OK;
 }
 /* milliseconds of each phase of the most recent forward+backward; synchronises the stream.  ms_out[9]. */
+unsigned long long npair_kernel_launches(void) { return npair::g_kernel_launches; }
+
 int npair_profile_read(npair_ctx* c, float* ms_out) {
   if (!c || !ms_out) return NPAIR_E_ARG;
   CUDA_TRY(c, cudaSetDevice(c->device));
@@ -1027,6 +1036,7 @@ int npair_util_f64_to_f32(const double* d_src, float* d_dst, size_t n, void* str
   if (n == 0) return NPAIR_OK;
   int nb = static_cast<int>((n + 255) / 256); if (nb > 148 * 16) nb = 148 * 16;
   cvt_d2f_kernel<<<nb, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_src, d_dst, n);
+  count_launch();
   return cudaGetLastError() == cudaSuccess ? NPAIR_OK : NPAIR_E_CUDA;
 }
 int npair_util_f32_to_f64(const float* d_src, double* d_dst, size_t n, void* stream) {
@@ -1034,6 +1044,7 @@ int npair_util_f32_to_f64(const float* d_src, double* d_dst, size_t n, void* str
   if (n == 0) return NPAIR_OK;
   int nb = static_cast<int>((n + 255) / 256); if (nb > 148 * 16) nb = 148 * 16;
   cvt_f2d_kernel<<<nb, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_src, d_dst, n);
+  count_launch();
   return cudaGetLastError() == cudaSuccess ? NPAIR_OK : NPAIR_E_CUDA;
 }
 

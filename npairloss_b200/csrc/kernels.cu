@@ -1,5 +1,6 @@
 // kernels.cu -- HBM-bound kernels of the N-pair hot path (everything except the two tensor-core contractions).
 // Each kernel cites the reference code it replaces (paths relative to /root/reference).
+#include <cstdlib>
 #include "kernels.cuh"
 
 #include <cuda_bf16.h>
@@ -9,6 +10,8 @@
 #include "gemm_tcgen05.cuh"   // f2ord / ord2f
 
 namespace npair {
+unsigned long long g_kernel_launches = 0;
+
 
 // --------------------------------------------------------------------------------------------
 // small helpers
@@ -222,6 +225,7 @@ void launch_prep_reduce(const float* x_local, long long n_local, const float* x_
   int nb = static_cast<int>((nmax + 256 * 16 - 1) / (256 * 16));
   if (nb < 1) nb = 1; if (nb > 592) nb = 592;
   prep_reduce_kernel<<<nb, 256, 0, st>>>(x_local, n_local, x_total, n_total, partial, want_scale, ra, Q, bs);
+  count_launch();
 }
 
 __global__ void absmax_asum_partial_kernel(const float* __restrict__ xl, long long nl, const float* __restrict__ xt, long long ntot,
@@ -272,7 +276,9 @@ void launch_absmax_asum(const float* x_local, long long n_local, const float* x_
   int nb = static_cast<int>((nmax + 256 * 8 - 1) / (256 * 8));
   if (nb < 1) nb = 1; if (nb > 1024) nb = 1024;
   absmax_asum_partial_kernel<<<nb, 256, 0, st>>>(x_local, n_local, x_total, n_total, partial, want_scale);
+  count_launch();
   absmax_asum_final_kernel<<<1, 256, 0, st>>>(partial, nb, bs, want_scale);
+  count_launch();
 }
 
 // --------------------------------------------------------------------------------------------
@@ -379,6 +385,7 @@ void launch_split(const float* x_total, int N, int D, int prec, const BlockScala
   if (prec == PREC_BF16) split_kernel<PREC_BF16><<<grid, 256, 0, st>>>(x_total, N, D, bs, Xs, ldXs, XsT, ldXsT, XlT, ldXlT, row0_local, Q, XcatA, XcatB, Dp);
   else if (prec == PREC_FP16X2) split_kernel<PREC_FP16X2><<<grid, 256, 0, st>>>(x_total, N, D, bs, Xs, ldXs, XsT, ldXsT, XlT, ldXlT, row0_local, Q, XcatA, XcatB, Dp);
   else split_kernel<PREC_BF16X3><<<grid, 256, 0, st>>>(x_total, N, D, bs, Xs, ldXs, XsT, ldXsT, XlT, ldXlT, row0_local, Q, XcatA, XcatB, Dp);
+  count_launch();
 }
 
 // --------------------------------------------------------------------------------------------
@@ -409,6 +416,7 @@ __global__ void row_stats_ref_kernel(const float* __restrict__ S, long long ldS,
 void launch_row_stats_ref(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
                           int self_offset, RowArrays ra, cudaStream_t st) {
   row_stats_ref_kernel<<<Q, 256, 0, st>>>(S, ldS, Q, N, lab_rows, lab_cols, self_offset, ra);
+  count_launch();
 }
 
 // --------------------------------------------------------------------------------------------
@@ -497,6 +505,7 @@ __global__ void __launch_bounds__(256) thresholds_kernel(RowArrays ra, int Q, in
 void launch_thresholds(RowArrays ra, int Q, int N, MiningParams mp, BlockScalars* bs, float* scratch, cudaStream_t st) {
   int grid = (Q + 255) / 256; if (grid > 64) grid = 64; if (grid < 1) grid = 1;
   thresholds_kernel<<<grid, 256, 0, st>>>(ra, Q, N, mp, bs, reinterpret_cast<ThrPartial*>(scratch));
+  count_launch();
 }
 
 // --------------------------------------------------------------------------------------------
@@ -551,6 +560,7 @@ __global__ void local_select_kernel(const float* __restrict__ S, long long ldS, 
 void launch_local_select(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
                          int self_offset, int side, float sn, RowArrays ra, BlockScalars* bs, cudaStream_t st) {
   local_select_kernel<<<Q, 256, 0, st>>>(S, ldS, Q, N, lab_rows, lab_cols, self_offset, side, sn, ra, bs);
+  count_launch();
 }
 
 // --------------------------------------------------------------------------------------------
@@ -628,7 +638,9 @@ void launch_global_select(const float* S, long long ldS, int Q, int N, const flo
   const int shifts[3] = {21, 10, 0}, bits[3] = {11, 11, 10};
   for (int p = 0; p < 3; ++p) {
     global_hist_kernel<<<grid, 512, 0, st>>>(S, ldS, Q, N, lab_rows, lab_cols, self_offset, side, shifts[p], bits[p], hist, bs);
+    count_launch();
     global_pick_kernel<<<1, 1024, 0, st>>>(hist, side, shifts[p], bits[p], p == 2, ra, Q, bs);
+    count_launch();
   }
 }
 
@@ -731,7 +743,16 @@ __global__ void __launch_bounds__(256, NPAIR_LSE_MINB) lse_rows_kernel(const flo
           const int j4 = base + u * 128 + lane * 4;
           const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
           const float ll[4] = {l[u].x, l[u].y, l[u].z, l[u].w};
-          if (self_col < j4 || self_col > j4 + 3) {
+          const bool no_self = (self_col < j4 || self_col > j4 + 3);
+          if (no_self && ll[0] != li && ll[1] != li && ll[2] != li && ll[3] != li) {
+            // four diff-label pairs (all but ~cnt_same/4 groups of a row): no label-dependent selects, 8 instructions per pair
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              c += (vv[q] >= scut) ? 1 : 0;
+              const float e = fast_exp_m2(vv[q], m2);
+              if (vv[q] * sgn_n <= thr_n) T += e;
+            }
+          } else if (no_self) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) lse_elem(vv[q], ll[q], li, scut, m2, sgn_p, thr_p, sgn_n, thr_n, A, T, c);
           } else {
@@ -810,10 +831,14 @@ __global__ void __launch_bounds__(256, NPAIR_LSE_MINB) lse_rows_kernel(const flo
 }
 void launch_lse_rows(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
                      int self_offset, MiningParams mp, RowArrays ra, BlockScalars* bs, int num_tops, float* tops_dev, cudaStream_t st) {
+  // 8 warps per block, 4 blocks per SM.  Measured at Q = 8192 (1.73 waves): 7 warps (1.98 waves, less idle tail) is SLOWER
+  // (81.3 vs 78.7 us; 6: 83.7, 5: 87.6) -- the pass is latency-bound, more resident warps win.  NPAIR_LSE_WPB overrides.
   int wpb = 8;
+  if (const char* e = getenv("NPAIR_LSE_WPB")) { const int w = atoi(e); if (w >= 1 && w <= 8) wpb = w; }
   while (wpb > 1 && (Q + wpb - 1) / wpb < 296) wpb >>= 1;     // keep >= 2 blocks per SM when the rank has few rows
   const int grid = (Q + wpb - 1) / wpb;
   lse_rows_kernel<<<grid, wpb * 32, 0, st>>>(S, ldS, Q, N, lab_rows, lab_cols, self_offset, mp, ra, bs, num_tops, tops_dev);
+  count_launch();
 }
 
 // --------------------------------------------------------------------------------------------
@@ -949,6 +974,7 @@ void launch_build_weights(const float* S, long long ldS, int Q, int N, const flo
   if (prec == PREC_BF16) NPAIR_LAUNCH_BW(PREC_BF16);
   else if (prec == PREC_FP16X2) NPAIR_LAUNCH_BW(PREC_FP16X2);
   else NPAIR_LAUNCH_BW(PREC_BF16X3);
+  count_launch();
 #undef NPAIR_LAUNCH_BW
 #undef NPAIR_BW_ARGS
 }
@@ -960,6 +986,7 @@ __global__ void axpy_kernel(float* __restrict__ dst, const float* __restrict__ s
 void launch_axpy_rows(float* dst, const float* src, long long n, float a, cudaStream_t st) {
   int nb = static_cast<int>((n + 255) / 256); if (nb > 148 * 8) nb = 148 * 8; if (nb < 1) nb = 1;
   axpy_kernel<<<nb, 256, 0, st>>>(dst, src, n, a);
+  count_launch();
 }
 
 }  // namespace npair

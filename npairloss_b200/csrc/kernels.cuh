@@ -54,6 +54,11 @@ struct RowArrays {
   float* rowscal;
 };
 
+// Number of kernels this library has launched in this process (every launch site bumps it; read through
+// npair_kernel_launches(): bench.py reports the per-step delta as gpu_launches).
+extern unsigned long long g_kernel_launches;
+inline void count_launch(int n = 1) { g_kernel_launches += static_cast<unsigned long long>(n); }
+
 // launchers (kernels.cu)
 void launch_absmax_asum(const float* x_local, long long n_local, const float* x_total, long long n_total,
                         float* partial /*[2*1024]*/, BlockScalars* bs, int want_scale, cudaStream_t st);
