@@ -316,17 +316,41 @@ def main():
     phases /= nprof
     ctx.profile_enable(False)
     N = B
-    sim_ms = float(phases[2])
-    flops_alg = 2.0 * Q * N * D                                   # one similarity contraction per launch
-    achieved_tf = flops_alg / (sim_ms * 1e-3) / 1e12 if sim_ms > 0 else 0.0
+    sim_ms, grad_ms = float(phases[2]), float(phases[6])
+    flops_alg = 2.0 * Q * N * D                                   # one Q x N x D contraction per launch, both GEMMs
     peak_tf = peaks["tf_sustained"]
-    roofline = {"kernel": "split_gemm_kernel<EPI_SIM> (tcgen05 similarity GEMM + fused row statistics)", "bound": "tensor",
-                "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                "mma_passes": MMA_PASSES[args.precision], "frac_of_issued_mma": achieved_tf * MMA_PASSES[args.precision] / peak_tf,
+    passes = MMA_PASSES[args.precision]
+    # tiles the similarity kernel really issues: world == 1 computes only the 128 x 256 tiles that touch the upper triangle
+    tm, tn = (Q + 127) // 128, (N + 255) // 256
+    sym_frac = (sum(tn - mb // 2 for mb in range(tm)) / float(tm * tn)) if world == 1 else 1.0
+
+    def tensor_roofline(kernel, ms, issued_factor, extra):
+        ach = flops_alg / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+        return {"kernel": kernel, "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                "mma_passes": passes, "issued_tflops": ach * issued_factor, "frac_of_issued_mma": ach * issued_factor / peak_tf,
                 "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
-                "duration_ms": sim_ms, "traffic": None,
-                "note": "achieved = algorithmic 2*Q*N*D flops / live CUDA-event duration; the fp32-faithful modes issue mma_passes "
-                        "bf16-rate MMA passes per algorithmic flop, frac_of_issued_mma counts them"}
+                "duration_ms": ms, "traffic": None,
+                "note": "achieved = algorithmic 2*Q*N*D flops / live CUDA-event duration of the phase; the fp32-faithful modes issue "
+                        "mma_passes bf16-rate MMA passes per algorithmic flop; issued_tflops / frac_of_issued_mma count the MMA work "
+                        "the kernel really issues (" + extra + ")"}
+
+    r_sim = tensor_roofline("split_gemm_kernel<EPI_SIM*> CTA-pair tcgen05 similarity GEMM + fused row statistics", sim_ms, passes * sym_frac,
+                            f"passes x {sym_frac:.3f} of the tiles: symmetric tile list" if world == 1 else "passes x all tiles")
+    r_grad = tensor_roofline("fused_grad_kernel CTA-pair tcgen05 gradient GEMM, weights produced into tensor memory", grad_ms, passes,
+                             "passes x all tiles; includes the split-K reduce when Q = B/world leaves few tiles")
+    # DRAM bytes per launch from the committed ncu --set full capture (profiles/r01_traffic.json), when it is this workload
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")) as f:
+            tr = json.load(f)
+        w = tr["workload"]
+        if (w["B"], w["D"], w["precision"], w["world"]) == (B, D, args.precision, world):
+            r_sim["traffic"] = tr["kernels"]["sim_gemm"]["dram_bytes"]
+            r_grad["traffic"] = tr["kernels"]["grad_gemm"]["dram_bytes"]
+            r_sim["traffic_source"] = r_grad["traffic_source"] = "profiles/r01_traffic.json (ncu --set full, bytes per launch)"
+    except Exception:
+        pass
+    roofline = r_grad if grad_ms >= sim_ms else r_sim              # the dominant kernel of the step
+    roofline_other = [r_sim if grad_ms >= sim_ms else r_grad]
     phase_names = ["fwd_allgather", "operand_prep", "sim_gemm", "thresholds_select", "row_pass_finalize", "weight_build", "grad_gemm",
                    "grad_gemm_T", "bwd_exchange"]
     phase_ms = {n: float(v) for n, v in zip(phase_names, phases)}
@@ -374,7 +398,7 @@ def main():
                                       "AN LOCAL HARD margin_diff -0.05), loss_weight 1", "global_batch": B, "feature_dim": D,
                           "rows_per_rank": Q, "sharding": f"anchor-sharded x{world}", "precision": args.precision, "noise": noise,
                           "l2": f"not flushed: per-step working set (S {4 * Q * N / 1e6:.0f} MB fp32 + split weights) exceeds the 126 MB L2"},
-               "clocks": clocks, "roofline": roofline, "phase_ms": phase_ms, "hbm_kernels": hbm,
+               "clocks": clocks, "roofline": roofline, "roofline_other": roofline_other, "phase_ms": phase_ms, "hbm_kernels": hbm,
                "cpu_baseline": cpu,
                "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": e2e_api,
                        "gradient_matches_device_path": e2e_consistent},
