@@ -776,7 +776,11 @@ static int forward_impl(npair_ctx* c, const float* d_feat, const float* d_label,
     launch_lse_rows(c->S, c->ldS, Q, N, d_label, c->lab_total, self_off, mp, c->ra, c->bs, c->cfg.num_tops, c->tops_dev, st);
   }
   c->rs_gathered = false;
-  if (c->bwd_mode == NPAIR_BWDMODE_ROW_SCALARS && c->comm) {
+  // NPAIR_RS_GATHER_FWD=1 enqueues the row-record exchange here instead of at the start of npair_backward.  Measured on
+  // 8 x B200 (profiles/r01_bench_v6_n8.json): with the collective in front of the forward's host synchronisation the step is
+  // SLOWER (0.293 ms against 0.218 ms with it in the backward, where its rendezvous overlaps the host's return), so it is opt-in.
+  static const bool gather_in_fwd = [] { const char* e = getenv("NPAIR_RS_GATHER_FWD"); return e && e[0] == '1'; }();
+  if (gather_in_fwd && c->bwd_mode == NPAIR_BWDMODE_ROW_SCALARS && c->comm) {
     // The only backward exchange (8*Q floats per rank, replaces the N x D MPI_Allreduce of .cu:462-489) does not depend on
     // the loss weight, so it is enqueued here: it runs while the host wakes up from the synchronisation below.
     PhaseTimer pt(c, 8, st);
@@ -857,8 +861,16 @@ static int backward_impl(npair_ctx* c, float loss_weight, float* d_diff, float* 
     bw_mode = BW_ROWSCAL;
     if (d_rs_ext) rs_total = d_rs_ext;
     else {
-      if (!c->rs_gathered) { c->err = "row records were not gathered by the forward pass"; return NPAIR_E_STATE; }
-      rs_total = c->rs_total;                  // all-gathered at the end of npair_forward
+      if (!c->rs_gathered) {
+        // the only backward exchange: 8*Q floats per rank (replaces the N x D MPI_Allreduce of .cu:462-489)
+        if (!c->comm) { c->err = "no communicator: use npair_backward_gathered with externally gathered row records"; return NPAIR_E_STATE; }
+        PhaseTimer pt(c, 8, st);
+        NcclApi* api = nccl_api();
+        int r = api->AllGather(c->ra.rowscal, c->rs_total, 8ull * Q, NCCL_FLOAT32, c->comm, st);
+        if (r != 0) { c->err = fmt("ncclAllGather(row records): %s", api->GetErrorString(r)); return NPAIR_E_NCCL; }
+        c->rs_gathered = true;
+      }
+      rs_total = c->rs_total;
     }
   } else if (c->bwd_mode == NPAIR_BWDMODE_REDUCE_SCATTER) bw_mode = BW_SPLIT;
   if (tc && c->fused_grad) {
