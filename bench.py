@@ -136,7 +136,7 @@ def run_reference(args, B, D, mining, noise):
     out = {"metric": METRIC, "impl": "reference", "value": val, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"HL: B={B}, D={D}, {B // 2} classes x 2, usage-block mining (AP GLOBAL RELATIVE_HARD, AN LOCAL HARD -0.05)",
+           "config": {"workload": f"HL: B={B}, D={D}, {B // 2} classes x 2, {args.mining_desc}, loss_weight 1",
                       "global_batch": B, "feature_dim": D, "noise": noise},
            "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -168,19 +168,32 @@ def main():
     ap.add_argument("--batch", type=int, default=8192)
     ap.add_argument("--dim", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    # the headline is the reference's own usage block; "rand" (RAND/RAND, cheapest: no selects) and "relative"
+    # (LOCAL RELATIVE_HARD both sides, diffsn -0.3: a radix select per row and side, costliest) are the two other settings it
+    # asks to be reported.  Only "usage" is the BASELINE.json metric.
+    ap.add_argument("--mining", default="usage", choices=["usage", "rand", "relative"])
     args = ap.parse_args()
 
     from npairloss_b200 import synth
     B, D = args.batch, args.dim
-    mining = dict(synth.USAGE_MINING)
     noise = synth.CONFIGS["HL"]["noise"]
+    if args.mining == "usage":
+        mining = dict(synth.USAGE_MINING)
+        mining_desc = "usage-block mining (AP GLOBAL RELATIVE_HARD identsn -0.0, AN LOCAL HARD margin_diff -0.05)"
+    elif args.mining == "rand":
+        mining = dict(synth.DEFAULT_MINING)
+        mining_desc = "RAND/RAND mining (proto defaults: every pair selected)"
+    else:
+        mining = dict(synth.USAGE_MINING, ap_region=synth.LOCAL, ap_method=synth.RELATIVE_HARD, an_region=synth.LOCAL,
+                      an_method=synth.RELATIVE_HARD, identsn=-0.3, diffsn=-0.3, margin_diff=0.0)
+        mining_desc = "LOCAL RELATIVE_HARD / RELATIVE_HARD mining, identsn = diffsn = -0.3 (per-row radix selects on both sides)"
+    args.mining_desc = mining_desc
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        if args.steps == 50 and args.warmup == 10:      # defaults are sized for the GPU arm; keep the CPU arm to minutes
-            args.steps, args.warmup = 3, 1
+        # every step is the bounded rank-0 sample (~0.5 s on the 128-thread gpurun host): K + W = 60 steps end within a minute
         if rank == 0:
             run_reference(args, B, D, mining, noise)
         return
@@ -412,8 +425,8 @@ def main():
                "dtype": {"fp16x2": "f32 (3-pass fp16-split tcgen05, f32 accumulate)", "bf16x3": "f32 (6-pass bf16-split tcgen05, f32 accumulate)",
                          "bf16": "bf16 (f32 accumulate)"}[args.precision],
                "data": "synthetic",
-               "config": {"workload": f"HL: B={B}, D={D}, {B // 2} classes x 2, usage-block mining (AP GLOBAL RELATIVE_HARD identsn -0.0, "
-                                      "AN LOCAL HARD margin_diff -0.05), loss_weight 1", "global_batch": B, "feature_dim": D,
+               "config": {"workload": f"HL: B={B}, D={D}, {B // 2} classes x 2, {args.mining_desc}, loss_weight 1",
+                          "global_batch": B, "feature_dim": D,
                           "rows_per_rank": Q, "sharding": f"anchor-sharded x{world}", "precision": args.precision, "noise": noise,
                           "l2": (f"flushed: a {2 * L2_BYTES >> 20} MB device buffer is rewritten before every timed step (per-rank S = "
                                  f"{4 * Q * N / 1e6:.0f} MB fp32 would otherwise stay in the 126 MB L2); steps timed one by one, flush excluded"
