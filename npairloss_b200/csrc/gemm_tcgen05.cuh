@@ -8,12 +8,15 @@
 //   NSPLIT=3 bf16 hi+mid+lo  6 passes (hh,hm,mh,mm,hl,lh) ~2^-24 relative     -- fp32-faithful, any dynamic range
 // All passes accumulate into the same fp32 TMEM accumulator, so the tensor pipe sees one long K loop.
 //
-// Structure (one CTA per SM, 256 threads):
-//   warp 0   TMA producer: cp.async.bulk.tensor 3-D boxes {BK, rows, 1 piece} -> 128B/64B-swizzled smem ring
-//   warp 1   MMA issuer  : one thread issues tcgen05.mma.cta_group::1.kind::f16 (128 x 256 x 16), fp32 accum in TMEM
-//   warp 2   TMEM allocator (512 columns = two 128x256 fp32 accumulators, double buffered)
-//   warps 4-7 epilogue   : tcgen05.ld 32x32b -> registers -> fused epilogue (similarity store + row statistics,
-//                          or scaled store of a gradient tile), overlapped with the next tile's MMAs
+// Structure (persistent, one CTA per SM, 384 threads):
+//   warp 0    TMA producer: cp.async.bulk.tensor 3-D boxes {BK, rows, 1 piece} -> 128B/64B-swizzled smem ring
+//   warp 1    MMA issuer  : one thread issues tcgen05.mma.kind::f16 (128 x 256 x 16; pair mode 256 x 256 x 16), fp32 accum in TMEM
+//   warp 2    TMEM allocator (512 columns = two 128x256 fp32 accumulators, double buffered)
+//   warps 4-11 epilogue   : tcgen05.ld 32x32b -> registers -> fused epilogue (similarity store + row statistics,
+//                           or scaled store of a gradient tile), overlapped with the next tile's MMAs; warp w drains TMEM
+//                           lanes 32*(w%4) and the column half (w-4)/4 of the tile
+// NCTA = 2 (pair mode, similarity epilogues): a cluster of two CTAs computes a 256 x 256 block with
+// tcgen05.mma.cta_group::2 -- see GemmCfg.
 // Replaces the reference's cublasSgemm calls: sim GEMM npair_multi_class_loss.cu:218 and the six backward
 // GEMMs .cu:448-460; the EPI_SIM epilogue also replaces GetLabelDiffMtx (.cu:44-66) and the host statistics loop
 // (.cu:225-265: min_within / max_between / max_all) -- they are computed while the tile is in registers.

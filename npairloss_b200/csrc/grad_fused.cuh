@@ -3,15 +3,16 @@
 //   dX[j][:] = alpha * sum_m H[j][m] * X_total[m][:]        H[j][m] = g'(S[j][m]; row j) + (1/world) g'(S[j][m]; row m)
 //
 // Replaces Get_Query_Diff_Part x3 + six cublasSgemm + the N x D all-reduce of the reference (npair_multi_class_loss.cu:438-497).
-// H (Q x N) is never written to HBM: per 32-column K block the 8 producer warps read a 128 x 32 fp32 tile of S (TMA,
+// H (Q x N) is never written to HBM: per 32-column K block the 16 producer warps read a 128 x 32 fp32 tile of S (TMA,
 // 128B-swizzled) and the 32 column records (bulk copy), evaluate the weights in registers (row record in registers,
 // thread = row), split them into the 2-byte operand pieces and store those with tcgen05.st straight into TENSOR MEMORY,
 // from where tcgen05.mma takes its A operand (the multi-pass GEMM is shared-memory-bandwidth bound in 1-CTA mode: every
 // pass re-reads its operands from smem, so keeping A out of smem removes a third of that traffic).  Requires a bitwise
 // symmetric S (EPI_SIM_SYM tiles at world == 1, K-concatenated operands across ranks) -- see gemm_tcgen05.cuh / kernels.cu.
 //
-// CTA = 384 threads: warp 0 TMA producer (B pieces of X^T, S tile, column records), warp 1 MMA issuer, warp 2 TMEM
-// allocator, warps 4-11 weight producers, which also run the epilogue (TMEM -> alpha*acc -> out / split-K partial).
+// CTA = 640 threads: warp 0 TMA producer (B pieces of X^T, S tile, column records), warp 1 MMA issuer, warp 2 TMEM
+// allocator, warps 4-19 weight producers (warp w: TMEM lanes 32*(w%4), 8 of the 32 K columns), which also run the
+// epilogue (TMEM -> alpha*acc -> out / split-K partial).  NCTA = 2: CTA-pair mode, see FusedCfg.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
