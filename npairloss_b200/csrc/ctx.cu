@@ -361,6 +361,11 @@ struct npair_ctx {
   bool sim_pair = false;            // similarity GEMM runs in CTA-pair mode (cta_group::2)
   int2* sym_tiles2 = nullptr;       // world == 1: (pair_m, n_blk) list of the pair kernel
   int n_sym_tiles2 = 0;
+  // tile row pass (world == 1, NPAIR_LSE_TILES=1): upper-triangular 128 x 128 tile list, per-row prologue records, partials
+  bool lse_tiles = false;
+  int2* lse_tile_list = nullptr; int n_lse_tiles = 0;
+  float* lse_prep = nullptr; float4* lse_part = nullptr; int* lse_cnt = nullptr; int lse_qpad = 0;
+  CUtensorMap tm_lseS;
   CUtensorMap tm_fB2;            // 128-row boxes of X^T for the CTA-pair gradient kernel
   bool grad_pair = false;        // fused gradient kernel runs in CTA-pair mode
   CUtensorMap tm_fB, tm_fS;      // fused gradient kernel: X^T pieces with 32-wide K boxes, 128-row fp32 boxes of S
@@ -486,7 +491,7 @@ void npair_destroy(npair_ctx* c) {
   if (c->device >= 0) cudaSetDevice(c->device);
   if (c->comm && c->own_comm) { NcclApi* api = nccl_api(); if (api->CommDestroy) api->CommDestroy(c->comm); }
   cudaFree(c->Xtot_buf); cudaFree(c->labtot_buf); cudaFree(c->S); cudaFree(c->Xs); cudaFree(c->XsT); cudaFree(c->XlT);
-  cudaFree(c->H); cudaFree(c->HT); cudaFree(c->OUT2); cudaFree(c->part); cudaFree(c->sym_tiles); cudaFree(c->sym_tiles2); cudaFree(c->XcatA); cudaFree(c->XcatB); cudaFree(c->rs_total); cudaFree(c->row_block); cudaFree(c->bs); cudaFree(c->partial); cudaFree(c->ghist);
+  cudaFree(c->H); cudaFree(c->HT); cudaFree(c->OUT2); cudaFree(c->part); cudaFree(c->sym_tiles); cudaFree(c->sym_tiles2); cudaFree(c->lse_tile_list); cudaFree(c->lse_prep); cudaFree(c->lse_part); cudaFree(c->lse_cnt); cudaFree(c->XcatA); cudaFree(c->XcatB); cudaFree(c->rs_total); cudaFree(c->row_block); cudaFree(c->bs); cudaFree(c->partial); cudaFree(c->ghist);
   if (c->tops_pinned) cudaFreeHost(c->tops_pinned);
   if (c->ev_made) for (int i = 0; i < NPAIR_PROF_PHASES; ++i) { cudaEventDestroy(c->ev[i][0]); cudaEventDestroy(c->ev[i][1]); }
   delete c;
@@ -642,6 +647,27 @@ static int create_impl(const npair_config* cfg, const void* id128, void* ext_com
     CREATE_TRY(cudaMalloc(&c->sym_tiles2, sizeof(int2) * tl2.size()));
     CREATE_TRY(cudaMemcpy(c->sym_tiles2, tl2.data(), sizeof(int2) * tl2.size(), cudaMemcpyHostToDevice));
   }
+  if (c->world == 1 && cfg->gemm_backend == NPAIR_GEMM_TCGEN05) {
+    const char* et = getenv("NPAIR_LSE_TILES");
+    if (et && et[0] == '1') {
+      // tile row pass: reads only the upper triangle of the symmetric S (see kernels.cu); last row blocks first (still in L2)
+      const int tb = (N + 127) / 128;
+      std::vector<int2> tl;
+      for (int I = tb - 1; I >= 0; --I)
+        for (int J = I; J < tb; ++J) tl.push_back(make_int2(I, J));
+      c->n_lse_tiles = static_cast<int>(tl.size());
+      c->lse_qpad = tb * 128;
+      CREATE_TRY(cudaMalloc(&c->lse_tile_list, sizeof(int2) * tl.size()));
+      CREATE_TRY(cudaMemcpy(c->lse_tile_list, tl.data(), sizeof(int2) * tl.size(), cudaMemcpyHostToDevice));
+      CREATE_TRY(cudaMalloc(&c->lse_prep, sizeof(float) * 8ull * Q));
+      CREATE_TRY(cudaMalloc(&c->lse_part, sizeof(float4) * static_cast<size_t>(tb) * c->lse_qpad));
+      CREATE_TRY(cudaMalloc(&c->lse_cnt, sizeof(int) * tb));
+      CREATE_TRY(cudaMemset(c->lse_cnt, 0, sizeof(int) * tb));
+      std::string te;
+      if (!make_tmap_f32_store(&c->tm_lseS, c->S, N, Q, c->ldS, &te, 128)) { g_create_err = te; npair_destroy(c); return NPAIR_E_CUDA; }
+      c->lse_tiles = true;
+    }
+  }
   {
     // CTA-pair similarity GEMM whenever there are at least two 128-row blocks (NPAIR_SIM_1CTA=1 keeps the single-CTA kernel)
     const char* e1 = getenv("NPAIR_SIM_1CTA");
@@ -773,7 +799,11 @@ static int forward_impl(npair_ctx* c, const float* d_feat, const float* d_label,
   // ---- selection + counts + exp + masked sums + log + retrieval in one pass (.cu:343-398) ----
   {
     PhaseTimer pt(c, 4, st);
-    launch_lse_rows(c->S, c->ldS, Q, N, d_label, c->lab_total, self_off, mp, c->ra, c->bs, c->cfg.num_tops, c->tops_dev, st);
+    if (c->lse_tiles)
+      launch_lse_tiles(c->tm_lseS, c->lse_tile_list, c->n_lse_tiles, Q, N, c->lab_total, mp, c->ra, c->bs, c->lse_prep, c->lse_part, c->lse_qpad,
+                       c->lse_cnt, c->cfg.num_tops, c->tops_dev, st);
+    else
+      launch_lse_rows(c->S, c->ldS, Q, N, d_label, c->lab_total, self_off, mp, c->ra, c->bs, c->cfg.num_tops, c->tops_dev, st);
   }
   c->rs_gathered = false;
   // NPAIR_RS_GATHER_FWD=1 enqueues the row-record exchange here instead of at the start of npair_backward.  Measured on

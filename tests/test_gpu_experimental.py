@@ -1,0 +1,45 @@
+"""Opt-in GPU checks of kernels that are compiled in but not on the default path yet (NPAIR_RUN_EXPERIMENTAL=1).
+They compare the opt-in path with the default path of the same build on the same inputs."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("NPAIR_RUN_EXPERIMENTAL") != "1",
+                                                  reason="experimental kernels: set NPAIR_RUN_EXPERIMENTAL=1")]
+
+
+def _run(B, D, mining, env):
+    import torch
+    from npairloss_b200 import capi, synth
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        x, lab = synth.make_inputs(B, D, 1234 + B, noise=2.5)
+        ctx = capi.Context(capi.make_config(B, D, **mining))       # the switches are read at npair_create
+        dx, dl = torch.from_numpy(x).cuda(), torch.from_numpy(lab).cuda()
+        dg = torch.empty_like(dx)
+        tops = ctx.forward(dx, dl)
+        ctx.backward(1.0, dg)
+        A, T = ctx.debug_read(6, B), ctx.debug_read(7, B)
+        tops2 = ctx.forward(dx, dl)                                 # second step: counters were reset
+        return np.array(tops), np.array(tops2), A, T, dg.cpu().numpy()
+    finally:
+        for k, v in old.items():
+            if v is None: os.environ.pop(k, None)
+            else: os.environ[k] = v
+
+
+@pytest.mark.parametrize("B,D", [(256, 64), (1000, 200), (2048, 128), (8192, 512)])
+@pytest.mark.parametrize("mining", ["usage", "default", "hard"])
+def test_tile_row_pass_matches_row_pass(B, D, mining):
+    from npairloss_b200 import synth
+    m = {"usage": synth.USAGE_MINING, "default": synth.DEFAULT_MINING,
+         "hard": dict(synth.DEFAULT_MINING, ap_method=synth.HARD, an_method=synth.HARD)}[mining]
+    t0, t0b, A0, T0, g0 = _run(B, D, m, {"NPAIR_LSE_TILES": "0"})
+    t1, t1b, A1, T1, g1 = _run(B, D, m, {"NPAIR_LSE_TILES": "1"})
+    np.testing.assert_allclose(t1, t0, rtol=2e-6, atol=1e-7)        # other summation order of T only
+    np.testing.assert_allclose(t1b, t1, rtol=0, atol=0)             # deterministic, state reset between steps
+    np.testing.assert_allclose(A1, A0, rtol=2e-6, atol=1e-30)
+    np.testing.assert_allclose(T1, T0, rtol=2e-6, atol=1e-30)
+    assert np.linalg.norm(g1 - g0) <= 2e-6 * max(np.linalg.norm(g0), 1e-30)
