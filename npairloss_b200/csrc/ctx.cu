@@ -199,10 +199,10 @@ static cudaError_t launch_fused_grad_t(const CUtensorMap& b, const CUtensorMap& 
   return cudaGetLastError();
 }
 // CTA-pair launch of the fused gradient kernel (cluster dimension 2); p.tiles_m counts 256-row pair blocks, `b` has 128-row boxes
-template <int NSPLIT, bool BF16>
+template <int NSPLIT, bool BF16, bool ONE_EX2 = false>
 static cudaError_t launch_fused_grad_pair_t(const CUtensorMap& b, const CUtensorMap& sm, const FusedGradParams& p, int sms, cudaStream_t st) {
   using Cfg = FusedCfg<NSPLIT, 2>;
-  auto kern = fused_grad_kernel<NSPLIT, BF16, 2>;
+  auto kern = fused_grad_kernel<NSPLIT, BF16, 2, ONE_EX2>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -224,6 +224,12 @@ static cudaError_t launch_fused_grad_pair_t(const CUtensorMap& b, const CUtensor
   return cudaLaunchKernelEx(&lc, kern, b, sm, p);
 }
 static cudaError_t launch_fused_grad_pair(int prec, const CUtensorMap& b, const CUtensorMap& sm, const FusedGradParams& p, int sms, cudaStream_t st) {
+  static const bool one_ex2 = [] { const char* e = getenv("NPAIR_GRAD_ONE_EX2"); return e && e[0] == '1'; }();
+  if (one_ex2) {       // opt-in producer variant, see grad_fused.cuh
+    if (prec == PREC_BF16) return launch_fused_grad_pair_t<1, true, true>(b, sm, p, sms, st);
+    if (prec == PREC_FP16X2) return launch_fused_grad_pair_t<2, false, true>(b, sm, p, sms, st);
+    return launch_fused_grad_pair_t<3, true, true>(b, sm, p, sms, st);
+  }
   if (prec == PREC_BF16) return launch_fused_grad_pair_t<1, true>(b, sm, p, sms, st);
   if (prec == PREC_FP16X2) return launch_fused_grad_pair_t<2, false>(b, sm, p, sms, st);
   return launch_fused_grad_pair_t<3, true>(b, sm, p, sms, st);

@@ -22,5 +22,10 @@ if __name__ == "__main__":
     new = funcs(sys.argv[2] if len(sys.argv) > 2 else os.path.join(here, "npairloss_b200", "lib", "libnpair_b200.so"))
     print(f"{len(old)} kernels before, {len(new)} after")
     print("changed:", [k for k in old if k in new and old[k] != new[k]])
-    print("new    :", [k for k in new if k not in old])
-    print("removed:", [k for k in old if k not in new])
+    # a renamed kernel (e.g. an added defaulted template parameter) shows up as removed + new with the same body
+    new_only = {k: v for k, v in new.items() if k not in old}
+    removed = {k: v for k, v in old.items() if k not in new}
+    renamed = [(k, k2) for k, v in removed.items() for k2, v2 in new_only.items() if v == v2]
+    print("renamed, identical body:", len(renamed))
+    print("removed without an identical successor:", [k for k in removed if k not in [a for a, _ in renamed]])
+    print("new    :", [k for k in new_only if k not in [b for _, b in renamed]])

@@ -43,3 +43,34 @@ def test_tile_row_pass_matches_row_pass(B, D, mining):
     np.testing.assert_allclose(A1, A0, rtol=2e-6, atol=1e-30)
     np.testing.assert_allclose(T1, T0, rtol=2e-6, atol=1e-30)
     assert np.linalg.norm(g1 - g0) <= 2e-6 * max(np.linalg.norm(g0), 1e-30)
+
+
+@pytest.mark.parametrize("B,D,prec", [(1000, 200, 2), (2048, 512, 0), (8192, 512, 2), (8192, 512, 1)])
+def test_single_exponential_producer_matches(B, D, prec):
+    """NPAIR_GRAD_ONE_EX2=1: e2 formed from e1 and per-row / per-column constants (grad_fused.cuh).  NOTE the switch is read once
+    per process: run this test in its own pytest process, once with the variable set and once without, or rely on the two
+    sub-processes below."""
+    import subprocess, sys, json, tempfile
+    from npairloss_b200 import synth
+    code = r'''
+import sys, json, numpy as np, torch
+sys.path.insert(0, %r)
+from npairloss_b200 import capi, synth
+B, D, prec = %d, %d, %d
+x, lab = synth.make_inputs(B, D, 99, noise=2.5)
+ctx = capi.Context(capi.make_config(B, D, sim_precision=prec, **synth.USAGE_MINING))
+dx, dl = torch.from_numpy(x).cuda(), torch.from_numpy(lab).cuda()
+dg = torch.empty_like(dx)
+ctx.forward(dx, dl); ctx.backward(1.0, dg)
+np.save(sys.argv[1], dg.cpu().numpy())
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), B, D, prec)
+    outs = []
+    for flag in ("0", "1"):
+        with tempfile.NamedTemporaryFile(suffix=".npy", delete=False) as f:
+            path = f.name
+        env = dict(os.environ, NPAIR_GRAD_ONE_EX2=flag)
+        subprocess.run([sys.executable, "-c", code, path], env=env, check=True, timeout=300)
+        outs.append(np.load(path)); os.unlink(path)
+    g0, g1 = outs
+    tol = 5e-6 if prec != 1 else 2e-3
+    assert np.linalg.norm(g1 - g0) <= tol * max(np.linalg.norm(g0), 1e-30)
