@@ -19,6 +19,7 @@
 #include "../../include/npair_b200.h"
 #include "gemm_tcgen05.cuh"
 #include "grad_fused.cuh"
+#include "grad_streamk.cuh"
 #include "kernels.cuh"
 
 namespace npair {
@@ -234,6 +235,41 @@ static cudaError_t launch_fused_grad_pair(int prec, const CUtensorMap& b, const 
   if (prec == PREC_FP16X2) return launch_fused_grad_pair_t<2, false>(b, sm, p, sms, st);
   return launch_fused_grad_pair_t<3, true>(b, sm, p, sms, st);
 }
+// Stream-K launch of the CTA-pair gradient kernel (opt-in, grad_streamk.cuh).  `clusters` must all be co-resident.
+template <int NSPLIT, bool BF16, bool ONE_EX2>
+static cudaError_t launch_fused_grad_sk_t(const CUtensorMap& b, const CUtensorMap& sm, const FusedGradParams& p, const StreamKParams& sk,
+                                          int clusters, cudaStream_t st) {
+  using Cfg = FusedCfg<NSPLIT, 2>;
+  auto kern = fused_grad_sk_kernel<NSPLIT, BF16, ONE_EX2>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  cudaLaunchConfig_t lc; memset(&lc, 0, sizeof(lc));
+  lc.gridDim = dim3(2 * clusters);
+  lc.blockDim = dim3(Cfg::THREADS);
+  lc.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  lc.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  lc.attrs = at; lc.numAttrs = 1;
+  count_launch();
+  return cudaLaunchKernelEx(&lc, kern, b, sm, p, sk);
+}
+static cudaError_t launch_fused_grad_sk(int prec, bool one_ex2, const CUtensorMap& b, const CUtensorMap& sm, const FusedGradParams& p,
+                                        const StreamKParams& sk, int clusters, cudaStream_t st) {
+  if (one_ex2) {
+    if (prec == PREC_BF16) return launch_fused_grad_sk_t<1, true, true>(b, sm, p, sk, clusters, st);
+    if (prec == PREC_FP16X2) return launch_fused_grad_sk_t<2, false, true>(b, sm, p, sk, clusters, st);
+    return launch_fused_grad_sk_t<3, true, true>(b, sm, p, sk, clusters, st);
+  }
+  if (prec == PREC_BF16) return launch_fused_grad_sk_t<1, true, false>(b, sm, p, sk, clusters, st);
+  if (prec == PREC_FP16X2) return launch_fused_grad_sk_t<2, false, false>(b, sm, p, sk, clusters, st);
+  return launch_fused_grad_sk_t<3, true, false>(b, sm, p, sk, clusters, st);
+}
 static cudaError_t launch_fused_grad(int prec, const CUtensorMap& b, const CUtensorMap& sm, const FusedGradParams& p, int sms, cudaStream_t st) {
   if (prec == PREC_BF16) return launch_fused_grad_t<1, true>(b, sm, p, sms, st);
   if (prec == PREC_FP16X2) return launch_fused_grad_t<2, false>(b, sm, p, sms, st);
@@ -372,6 +408,10 @@ struct npair_ctx {
   int2* lse_tile_list = nullptr; int n_lse_tiles = 0;
   float* lse_prep = nullptr; float4* lse_part = nullptr; int* lse_cnt = nullptr; int lse_qpad = 0;
   CUtensorMap tm_lseS;
+  // stream-K gradient kernel (opt-in NPAIR_GRAD_STREAMK=1): equal runs of (block, K block) units per cluster
+  bool grad_sk = false, grad_one_ex2 = false;
+  int sk_clusters = 0, sk_upc = 0, sk_max_slots = 0;
+  float* sk_ws = nullptr; uint32_t* sk_flags = nullptr; uint32_t sk_epoch = 0;
   CUtensorMap tm_fB2;            // 128-row boxes of X^T for the CTA-pair gradient kernel
   bool grad_pair = false;        // fused gradient kernel runs in CTA-pair mode
   CUtensorMap tm_fB, tm_fS;      // fused gradient kernel: X^T pieces with 32-wide K boxes, 128-row fp32 boxes of S
@@ -497,7 +537,7 @@ void npair_destroy(npair_ctx* c) {
   if (c->device >= 0) cudaSetDevice(c->device);
   if (c->comm && c->own_comm) { NcclApi* api = nccl_api(); if (api->CommDestroy) api->CommDestroy(c->comm); }
   cudaFree(c->Xtot_buf); cudaFree(c->labtot_buf); cudaFree(c->S); cudaFree(c->Xs); cudaFree(c->XsT); cudaFree(c->XlT);
-  cudaFree(c->H); cudaFree(c->HT); cudaFree(c->OUT2); cudaFree(c->part); cudaFree(c->sym_tiles); cudaFree(c->sym_tiles2); cudaFree(c->lse_tile_list); cudaFree(c->lse_prep); cudaFree(c->lse_part); cudaFree(c->lse_cnt); cudaFree(c->XcatA); cudaFree(c->XcatB); cudaFree(c->rs_total); cudaFree(c->row_block); cudaFree(c->bs); cudaFree(c->partial); cudaFree(c->ghist);
+  cudaFree(c->H); cudaFree(c->HT); cudaFree(c->OUT2); cudaFree(c->part); cudaFree(c->sym_tiles); cudaFree(c->sym_tiles2); cudaFree(c->sk_ws); cudaFree(c->sk_flags); cudaFree(c->lse_tile_list); cudaFree(c->lse_prep); cudaFree(c->lse_part); cudaFree(c->lse_cnt); cudaFree(c->XcatA); cudaFree(c->XcatB); cudaFree(c->rs_total); cudaFree(c->row_block); cudaFree(c->bs); cudaFree(c->partial); cudaFree(c->ghist);
   if (c->tops_pinned) cudaFreeHost(c->tops_pinned);
   if (c->ev_made) for (int i = 0; i < NPAIR_PROF_PHASES; ++i) { cudaEventDestroy(c->ev[i][0]); cudaEventDestroy(c->ev[i][1]); }
   delete c;
@@ -680,6 +720,24 @@ static int create_impl(const npair_config* cfg, const void* id128, void* ext_com
     c->sim_pair = cfg->gemm_backend == NPAIR_GEMM_TCGEN05 && Q > 128 && !(e1 && e1[0] == '1');
     const char* e2 = getenv("NPAIR_GRAD_1CTA");
     c->grad_pair = c->fused_grad && Q > 128 && !(e2 && e2[0] == '1');
+    const char* e3 = getenv("NPAIR_GRAD_STREAMK");
+    const char* e4 = getenv("NPAIR_GRAD_ONE_EX2");
+    c->grad_one_ex2 = e4 && e4[0] == '1';
+    if (c->grad_pair && e3 && e3[0] == '1') {
+      const long long blocks = static_cast<long long>((Q + 255) / 256) * ((D + 255) / 256);
+      const int nkb = (N + 31) / 32;
+      const long long total = blocks * nkb;
+      long long clusters = c->sms / 2;                          // one cluster per TPC: all co-resident on an otherwise idle GPU
+      if (clusters > total) clusters = total;
+      const long long upc = (total + clusters - 1) / clusters;
+      c->sk_upc = static_cast<int>(upc);
+      c->sk_clusters = static_cast<int>((total + upc - 1) / upc);
+      c->sk_max_slots = static_cast<int>((nkb + upc - 1) / upc) + 1;
+      CREATE_TRY(cudaMalloc(&c->sk_ws, sizeof(float) * static_cast<size_t>(blocks) * c->sk_max_slots * 2 * 128 * 256));
+      CREATE_TRY(cudaMalloc(&c->sk_flags, sizeof(uint32_t) * static_cast<size_t>(blocks) * c->sk_max_slots * 32));
+      CREATE_TRY(cudaMemset(c->sk_flags, 0, sizeof(uint32_t) * static_cast<size_t>(blocks) * c->sk_max_slots * 32));
+      c->grad_sk = true;
+    }
   }
   // ---- NCCL ----
   if (c->world > 1 && (id128 || ext_comm)) {
@@ -933,7 +991,11 @@ static int backward_impl(npair_ctx* c, float loss_weight, float* d_diff, float* 
     }
     {
       PhaseTimer pt(c, 6, st);
-      if (c->grad_pair) CUDA_TRY(c, launch_fused_grad_pair(c->prec, c->tm_fB2, c->tm_fS, fp, c->sms, st));
+      if (c->grad_sk) {
+        StreamKParams sk; sk.ws = c->sk_ws; sk.flags = c->sk_flags; sk.epoch = ++c->sk_epoch; sk.upc = c->sk_upc; sk.max_slots = c->sk_max_slots;
+        fp.splits = 1; fp.kb_per_split = fp.num_kblocks;        // stream-K replaces split-K and its reduce kernel
+        CUDA_TRY(c, launch_fused_grad_sk(c->prec, c->grad_one_ex2, c->tm_fB2, c->tm_fS, fp, sk, c->sk_clusters, st));
+      } else if (c->grad_pair) CUDA_TRY(c, launch_fused_grad_pair(c->prec, c->tm_fB2, c->tm_fS, fp, c->sms, st));
       else CUDA_TRY(c, launch_fused_grad(c->prec, c->tm_fB, c->tm_fS, fp, c->sms, st));
       if (fp.splits > 1) {
         const long long n = static_cast<long long>(Q) * D;

@@ -45,6 +45,39 @@ def test_tile_row_pass_matches_row_pass(B, D, mining):
     assert np.linalg.norm(g1 - g0) <= 2e-6 * max(np.linalg.norm(g0), 1e-30)
 
 
+def _grad_in_subprocess(B, D, prec, env):
+    """Gradient of one forward+backward in a fresh process (the experimental switches are read once per process / context)."""
+    import subprocess, sys, tempfile
+    code = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+from npairloss_b200 import capi, synth
+B, D, prec = %d, %d, %d
+x, lab = synth.make_inputs(B, D, 99, noise=2.5)
+ctx = capi.Context(capi.make_config(B, D, sim_precision=prec, **synth.USAGE_MINING))
+dx, dl = torch.from_numpy(x).cuda(), torch.from_numpy(lab).cuda()
+dg = torch.empty_like(dx)
+for _ in range(3):                       # several launches: epochs / counters must carry over correctly
+    ctx.forward(dx, dl); ctx.backward(1.0, dg)
+np.save(sys.argv[1], dg.cpu().numpy())
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), B, D, prec)
+    with tempfile.NamedTemporaryFile(suffix=".npy", delete=False) as f:
+        path = f.name
+    subprocess.run([sys.executable, "-c", code, path], env=dict(os.environ, **env), check=True, timeout=300)
+    g = np.load(path); os.unlink(path)
+    return g
+
+
+@pytest.mark.parametrize("B,D,prec", [(512, 64, 2), (1000, 200, 2), (2048, 1024, 0), (8192, 512, 2), (8192, 512, 1)])
+@pytest.mark.parametrize("one_ex2", ["0", "1"])
+def test_stream_k_gradient_matches(B, D, prec, one_ex2):
+    """NPAIR_GRAD_STREAMK=1 (grad_streamk.cuh) against the default CTA-pair kernel; only the split of the K sum differs."""
+    g0 = _grad_in_subprocess(B, D, prec, {"NPAIR_GRAD_STREAMK": "0", "NPAIR_GRAD_ONE_EX2": "0"})
+    g1 = _grad_in_subprocess(B, D, prec, {"NPAIR_GRAD_STREAMK": "1", "NPAIR_GRAD_ONE_EX2": one_ex2})
+    tol = (2e-6 if one_ex2 == "0" else 5e-6) if prec != 1 else 2e-3
+    assert np.linalg.norm(g1 - g0) <= tol * max(np.linalg.norm(g0), 1e-30)
+
+
 @pytest.mark.parametrize("B,D,prec", [(1000, 200, 2), (2048, 512, 0), (8192, 512, 2), (8192, 512, 1)])
 def test_single_exponential_producer_matches(B, D, prec):
     """NPAIR_GRAD_ONE_EX2=1: e2 formed from e1 and per-row / per-column constants (grad_fused.cuh).  NOTE the switch is read once
