@@ -107,3 +107,21 @@ np.save(sys.argv[1], dg.cpu().numpy())
     g0, g1 = outs
     tol = 5e-6 if prec != 1 else 2e-3
     assert np.linalg.norm(g1 - g0) <= tol * max(np.linalg.norm(g0), 1e-30)
+
+
+def test_torch_api_matches_capi():
+    """npairloss_b200.torch_api (autograd surface) against direct C-ABI calls."""
+    import torch
+    from npairloss_b200 import capi, synth, torch_api
+    B, D = 512, 128
+    x, lab = synth.make_inputs(B, D, 7, noise=2.5)
+    ctx = capi.Context(capi.make_config(B, D, **synth.USAGE_MINING))
+    dx, dl = torch.from_numpy(x).cuda(), torch.from_numpy(lab).cuda()
+    dg = torch.empty_like(dx)
+    tops = ctx.forward(dx, dl); ctx.backward(0.5, dg)
+    m = torch_api.NPairLoss(**synth.USAGE_MINING)
+    xr = dx.clone().requires_grad_(True)
+    loss, t = m(xr, dl)
+    (0.5 * loss).backward()
+    np.testing.assert_allclose(t.cpu().numpy(), np.array(tops, np.float32), rtol=0, atol=0)
+    np.testing.assert_allclose(xr.grad.cpu().numpy(), dg.cpu().numpy(), rtol=0, atol=0)
