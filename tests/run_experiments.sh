@@ -1,0 +1,17 @@
+#!/bin/bash
+# One gpurun call that measures and checks the opt-in kernels against the default path (round-2 opener):
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tests/run_experiments.sh > gpurun_out/experiments.log 2>&1; tail -60 gpurun_out/experiments.log'
+# Every step runs under its own timeout: the stream-K kernel spins on flags, a bug there must not hang the box.
+cd "$(dirname "$0")/.."
+echo "== per-phase timings (HL: B=8192, D=512, fp16x2) =="
+for v in "NPAIR_NONE=1" "NPAIR_LSE_TILES=1" "NPAIR_GRAD_ONE_EX2=1" "NPAIR_GRAD_STREAMK=1" "NPAIR_GRAD_STREAMK=1 NPAIR_GRAD_ONE_EX2=1" \
+         "NPAIR_LSE_TILES=1 NPAIR_GRAD_STREAMK=1 NPAIR_GRAD_ONE_EX2=1"; do
+  echo "--- $v"
+  env $v timeout 120 python tests/tune_phases.py || echo "FAILED/timeout: $v"
+done
+echo "== bf16 mode =="
+for v in "NPAIR_NONE=1" "NPAIR_GRAD_STREAMK=1 NPAIR_GRAD_ONE_EX2=1"; do
+  echo "--- $v"; env $v timeout 120 python tests/tune_phases.py 8192 512 bf16 || echo "FAILED/timeout: $v"
+done
+echo "== correctness against the default path =="
+NPAIR_RUN_EXPERIMENTAL=1 timeout 1200 python -m pytest tests/test_gpu_experimental.py -q 2>&1 | tail -15
