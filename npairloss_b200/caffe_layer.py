@@ -142,10 +142,13 @@ class Layer:
         if lib().npc_forward_cpu_mode(self._h):
             raise LayerError(lib().npc_last_error().decode())
 
-    def step_host(self):
-        """One training-style step on HOST blobs: new batch in the bottoms (H2D), Forward, Backward, gradient back on the host."""
+    def step_host(self, read_gradient=True):
+        """One training-style step on HOST blobs: new batch in the bottoms (H2D), Forward (tops on the host), Backward.
+        read_gradient=True also brings bottom[0]'s diff back to the host (cpu_diff); False leaves it in the device diff, where
+        the upstream layer's Backward_gpu consumes it in a net."""
         self.touch_bottoms()
         tops, _ = self.forward()
         self.backward()
-        self.bottom_diff()
+        if read_gradient:
+            self.bottom_diff()
         return tops
