@@ -41,6 +41,13 @@ def lib():
         L.npc_bottom_cpu_diff.argtypes = [vp]
         L.npc_bottom_cpu_diff.restype = fp
         L.npc_forward_cpu_mode.argtypes = [vp]
+        L.npc_prefetch_enable.argtypes = [vp]
+        L.npc_set_mutable_cpu_data.argtypes = [vp, C.c_int, C.c_int]
+        L.npc_set_mutable_cpu_data.restype = fp
+        L.npc_prefetch.argtypes = [vp, C.c_int]
+        L.npc_step_set.argtypes = [vp, C.c_int, fp]
+        L.npc_set_cpu_diff.argtypes = [vp, C.c_int]
+        L.npc_set_cpu_diff.restype = fp
         L.npc_parse_only.argtypes = [C.c_char_p, fp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p, C.c_int]
         _LIB = L
     return _LIB
@@ -131,6 +138,39 @@ class Layer:
     def backward(self):
         if lib().npc_backward(self._h):
             raise LayerError(lib().npc_last_error().decode())
+
+    # ---- double-buffered bottoms with an asynchronous H2D prefetch (the role of Caffe's BasePrefetchingDataLayer) ----
+    def prefetch_enable(self):
+        if lib().npc_prefetch_enable(self._h):
+            raise LayerError(lib().npc_last_error().decode())
+
+    def set_data(self, s, i):
+        """numpy view of bottom[i] of set s (0/1); marks it CPU-dirty."""
+        p = lib().npc_set_mutable_cpu_data(self._h, s, i)
+        if not p:
+            raise LayerError(lib().npc_last_error().decode())
+        n = self.num * self.dim if i == 0 else self.num
+        return np.ctypeslib.as_array(p, shape=(n,))
+
+    def prefetch(self, s):
+        """New batch in set s (touch) and start its H2D copy on the copy stream."""
+        lib().npc_set_mutable_cpu_data(self._h, s, 0)
+        lib().npc_set_mutable_cpu_data(self._h, s, 1)
+        if lib().npc_prefetch(self._h, s):
+            raise LayerError(lib().npc_last_error().decode())
+
+    def step_set(self, s):
+        """Forward (tops on the host) + Backward on set s, ordered after the set's prefetch."""
+        tops = (C.c_float * 5)()
+        if lib().npc_step_set(self._h, s, tops):
+            raise LayerError(lib().npc_last_error().decode())
+        return [tops[i] for i in range(5)]
+
+    def set_diff(self, s):
+        p = lib().npc_set_cpu_diff(self._h, s)
+        if not p:
+            raise LayerError(lib().npc_last_error().decode())
+        return np.ctypeslib.as_array(p, shape=(self.num, self.dim))
 
     def bottom_diff(self):
         p = lib().npc_bottom_cpu_diff(self._h)

@@ -18,6 +18,8 @@ class SyncedMemory {
   const void* gpu_data();
   void* mutable_cpu_data();
   void* mutable_gpu_data();
+  // caffe/syncedmem.hpp: host -> device copy of a CPU-dirty blob on `stream`; the caller synchronises before use
+  void async_gpu_push(const cudaStream_t& stream);
   SyncedHead head() const { return head_; }
   size_t size() const { return size_; }
  private:
@@ -65,6 +67,7 @@ class Blob {
   Dtype* mutable_gpu_data() { CHECK(data_); return static_cast<Dtype*>(data_->mutable_gpu_data()); }
   Dtype* mutable_cpu_diff() { CHECK(diff_); return static_cast<Dtype*>(diff_->mutable_cpu_data()); }
   Dtype* mutable_gpu_diff() { CHECK(diff_); return static_cast<Dtype*>(diff_->mutable_gpu_data()); }
+  const shared_ptr<SyncedMemory>& data() const { CHECK(data_); return data_; }
  private:
   shared_ptr<SyncedMemory> data_, diff_;
   vector<int> shape_;

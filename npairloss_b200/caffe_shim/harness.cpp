@@ -19,6 +19,13 @@ struct Net {
   std::vector<Blob<float> > top_store;
   LayerParameter param;
   std::string err;
+  // optional second bottom set + copy stream: the role of Caffe's BasePrefetchingDataLayer (next batch goes to the device on
+  // its own stream while the net computes on the current one)
+  Blob<float> feat2, label2;
+  std::vector<Blob<float>*> bottom2;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ready[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr};
+  std::vector<Blob<float>*>& set(int s) { return s ? bottom2 : bottom; }
 };
 thread_local std::string g_err;
 void set_err(char* buf, int len, const std::string& m) {
@@ -59,7 +66,15 @@ void* npc_net_create(const char* prototxt, int num, int channels, int height, in
   } catch (const std::exception& e) { set_err(errbuf, errlen, e.what()); return nullptr; }
 }
 
-void npc_net_destroy(void* h) { delete static_cast<Net*>(h); }
+void npc_net_destroy(void* h) {
+  Net* n = static_cast<Net*>(h);
+  if (n && n->copy_stream) {
+    cudaStreamSynchronize(n->copy_stream);
+    for (int s = 0; s < 2; ++s) { cudaEventDestroy(n->ready[s]); cudaEventDestroy(n->done[s]); }
+    cudaStreamDestroy(n->copy_stream);
+  }
+  delete n;
+}
 const char* npc_last_error(void) { return g_err.c_str(); }
 
 int npc_num_tops(void* h) { return static_cast<int>(static_cast<Net*>(h)->top.size()); }
@@ -101,6 +116,54 @@ int npc_backward(void* h) {
 const float* npc_bottom_cpu_diff(void* h) {
   try { return static_cast<Net*>(h)->bottom[0]->cpu_diff(); } catch (const std::exception& e) { g_err = e.what(); return nullptr; }
 }
+// ---- prefetching (double-buffered bottoms) ----
+int npc_prefetch_enable(void* h) {
+  Net* n = static_cast<Net*>(h);
+  try {
+    if (n->copy_stream) return 0;
+    n->feat2.Reshape(n->feat.shape()); n->label2.Reshape(n->label.shape());
+    n->bottom2.clear(); n->bottom2.push_back(&n->feat2); n->bottom2.push_back(&n->label2);
+    CUDA_CHECK(cudaStreamCreateWithFlags(&n->copy_stream, cudaStreamNonBlocking));     // must not serialise with the legacy stream
+    for (int s = 0; s < 2; ++s) {
+      CUDA_CHECK(cudaEventCreateWithFlags(&n->ready[s], cudaEventDisableTiming));
+      CUDA_CHECK(cudaEventCreateWithFlags(&n->done[s], cudaEventDisableTiming));
+      CUDA_CHECK(cudaEventRecord(n->done[s], 0));
+    }
+    return 0;
+  } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+// host storage of bottom i of set s (marks it CPU-dirty)
+float* npc_set_mutable_cpu_data(void* h, int s, int i) {
+  try { return static_cast<Net*>(h)->set(s)[i]->mutable_cpu_data(); } catch (const std::exception& e) { g_err = e.what(); return nullptr; }
+}
+// start the H2D copy of set s on the copy stream, after the last step that used this set has finished on the device
+int npc_prefetch(void* h, int s) {
+  Net* n = static_cast<Net*>(h);
+  try {
+    CUDA_CHECK(cudaStreamWaitEvent(n->copy_stream, n->done[s], 0));
+    n->set(s)[0]->data()->async_gpu_push(n->copy_stream);
+    n->set(s)[1]->data()->async_gpu_push(n->copy_stream);
+    CUDA_CHECK(cudaEventRecord(n->ready[s], n->copy_stream));
+    return 0;
+  } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+// Forward + Backward on set s: the layer's stream (legacy default) waits for the set's copy
+int npc_step_set(void* h, int s, float* tops5) {
+  Net* n = static_cast<Net*>(h);
+  try {
+    CUDA_CHECK(cudaStreamWaitEvent(0, n->ready[s], 0));
+    n->layer->Forward(n->set(s), n->top);
+    for (size_t t = 0; t < n->top.size() && t < 5; ++t) tops5[t] = n->top[t]->cpu_data()[0];
+    std::vector<bool> pd(2, false); pd[0] = true;
+    n->layer->Backward(n->top, pd, n->set(s));
+    CUDA_CHECK(cudaEventRecord(n->done[s], 0));
+    return 0;
+  } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+const float* npc_set_cpu_diff(void* h, int s) {
+  try { return static_cast<Net*>(h)->set(s)[0]->cpu_diff(); } catch (const std::exception& e) { g_err = e.what(); return nullptr; }
+}
+
 // Forward through the CPU entry point (fails loudly: no CPU path)
 int npc_forward_cpu_mode(void* h) {
   Net* n = static_cast<Net*>(h);

@@ -56,6 +56,12 @@ void SyncedMemory::to_gpu() {
     default: break;
   }
 }
+void SyncedMemory::async_gpu_push(const cudaStream_t& stream) {
+  CHECK(head_ == HEAD_AT_CPU) << "async_gpu_push needs a CPU-dirty blob";
+  if (!gpu_ptr_) CUDA_CHECK(cudaMalloc(&gpu_ptr_, size_ ? size_ : 1));
+  CUDA_CHECK(cudaMemcpyAsync(gpu_ptr_, cpu_ptr_, size_, cudaMemcpyHostToDevice, stream));
+  head_ = SYNCED;                                  // the caller orders its consumers after `stream` (event / synchronize)
+}
 const void* SyncedMemory::cpu_data() { to_cpu(); return cpu_ptr_; }
 const void* SyncedMemory::gpu_data() { to_gpu(); return gpu_ptr_; }
 void* SyncedMemory::mutable_cpu_data() { to_cpu(); head_ = HEAD_AT_CPU; return cpu_ptr_; }
