@@ -345,6 +345,39 @@ static cudaError_t launch_simt_gemm(int prec, int epi, const uint16_t* A, long l
 }
 
 // out = sum_s part[s] + beta*out, fixed summation order (deterministic split-K)
+// ---- opt-in peer-memory exchange of the row records (NPAIR_P2P_RECORDS=1; written after round 1's GPU budget, not run yet) ----
+// Every rank PUSHES its [Q][8] records into all ranks' buffers with plain stores over NVLink (cudaIpc-mapped peer memory), then
+// raises one flag per peer; the backward waits for the world's flags.  Replaces the ~20 us NCCL all-gather of 256 KB.
+// Buffers and flags are double-buffered by the parity of the step counter; flags carry the step number, never reset.
+__global__ void p2p_push_records_kernel(const float4* __restrict__ rec, float* const* __restrict__ peer_buf, uint32_t* const* __restrict__ peer_flags,
+                                        int world, int rank, int Q, long long N, int parity, uint32_t epoch, unsigned int* ticket) {
+  const long long n4 = 2ll * Q;                                  // float4s of this rank's records
+  const long long off = 2ll * (static_cast<long long>(parity) * N + static_cast<long long>(rank) * Q);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 v = rec[i];
+    for (int r = 0; r < world; ++r) reinterpret_cast<float4*>(peer_buf[r])[off + i] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ int s_last;
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence_system();
+  if (static_cast<int>(threadIdx.x) < world) {
+    uint32_t* f = peer_flags[threadIdx.x] + parity * world + rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
+  }
+  if (threadIdx.x == 0) *ticket = 0;
+}
+__global__ void p2p_wait_records_kernel(const uint32_t* __restrict__ flags, int world, int parity, uint32_t epoch) {
+  if (static_cast<int>(threadIdx.x) < world) {
+    const uint32_t* f = flags + parity * world + threadIdx.x;
+    uint32_t v;
+    do { asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory"); } while (v != epoch);
+  }
+}
+
 __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, long long n, float* __restrict__ out, float beta) {
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 4;
   for (long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
@@ -417,6 +450,15 @@ struct npair_ctx {
   CUtensorMap tm_fB, tm_fS;      // fused gradient kernel: X^T pieces with 32-wide K boxes, 128-row fp32 boxes of S
   bool fused_grad = false;
   bool rs_gathered = false;
+  // peer-memory record exchange (opt-in)
+  bool p2p_rec = false;
+  float* p2p_buf = nullptr;            // [2][N][8] records of the whole world, written by every rank
+  uint32_t* p2p_flags = nullptr;       // [2][world] step number of rank r's last push
+  float** p2p_peer_buf = nullptr;      // device array [world] of the ranks' p2p_buf
+  uint32_t** p2p_peer_flags = nullptr; // device array [world] of the ranks' p2p_flags
+  unsigned int* p2p_ticket = nullptr;
+  std::vector<void*> p2p_opened;
+  uint32_t p2p_epoch = 0;
   int2* sym_tiles = nullptr;     // world == 1: (m_blk, n_blk) of the similarity tiles touching the upper triangle
   int n_sym_tiles = 0;
   float* part = nullptr;         // split-K partial products of the gradient GEMM
@@ -535,6 +577,8 @@ int npair_nccl_unique_id(void* out) {
 void npair_destroy(npair_ctx* c) {
   if (!c) return;
   if (c->device >= 0) cudaSetDevice(c->device);
+  for (void* q : c->p2p_opened) cudaIpcCloseMemHandle(q);
+  cudaFree(c->p2p_buf); cudaFree(c->p2p_flags); cudaFree(c->p2p_peer_buf); cudaFree(c->p2p_peer_flags); cudaFree(c->p2p_ticket);
   if (c->comm && c->own_comm) { NcclApi* api = nccl_api(); if (api->CommDestroy) api->CommDestroy(c->comm); }
   cudaFree(c->Xtot_buf); cudaFree(c->labtot_buf); cudaFree(c->S); cudaFree(c->Xs); cudaFree(c->XsT); cudaFree(c->XlT);
   cudaFree(c->H); cudaFree(c->HT); cudaFree(c->OUT2); cudaFree(c->part); cudaFree(c->sym_tiles); cudaFree(c->sym_tiles2); cudaFree(c->sk_ws); cudaFree(c->sk_flags); cudaFree(c->lse_tile_list); cudaFree(c->lse_prep); cudaFree(c->lse_part); cudaFree(c->lse_cnt); cudaFree(c->XcatA); cudaFree(c->XcatB); cudaFree(c->rs_total); cudaFree(c->row_block); cudaFree(c->bs); cudaFree(c->partial); cudaFree(c->ghist);
@@ -751,6 +795,49 @@ static int create_impl(const npair_config* cfg, const void* id128, void* ext_com
       c->own_comm = true;
     }
   }
+  {
+    const char* ep = getenv("NPAIR_P2P_RECORDS");
+    if (ep && ep[0] == '1' && c->comm && c->world > 1 && c->world <= 32 && c->bwd_mode == NPAIR_BWDMODE_ROW_SCALARS) {
+      // map every rank's record buffer and flags into this process (cudaIpc over the NCCL bootstrap: one tiny all-gather of handles)
+      NcclApi* api = nccl_api();
+      const int W = c->world;
+      CREATE_TRY(cudaMalloc(&c->p2p_buf, sizeof(float) * 2ull * 8ull * N));
+      CREATE_TRY(cudaMalloc(&c->p2p_flags, sizeof(uint32_t) * 2ull * W));
+      CREATE_TRY(cudaMemset(c->p2p_flags, 0, sizeof(uint32_t) * 2ull * W));
+      CREATE_TRY(cudaMalloc(&c->p2p_ticket, sizeof(unsigned int)));
+      CREATE_TRY(cudaMemset(c->p2p_ticket, 0, sizeof(unsigned int)));
+      struct Handles { cudaIpcMemHandle_t buf, flags; };
+      static_assert(sizeof(Handles) == 128, "two 64-byte IPC handles");
+      Handles mine;
+      CREATE_TRY(cudaIpcGetMemHandle(&mine.buf, c->p2p_buf));
+      CREATE_TRY(cudaIpcGetMemHandle(&mine.flags, c->p2p_flags));
+      float *d_mine = nullptr, *d_all = nullptr;
+      CREATE_TRY(cudaMalloc(&d_mine, 128));
+      CREATE_TRY(cudaMalloc(&d_all, 128ull * W));
+      CREATE_TRY(cudaMemcpy(d_mine, &mine, 128, cudaMemcpyHostToDevice));
+      int r = api->AllGather(d_mine, d_all, 32, NCCL_FLOAT32, c->comm, nullptr);
+      if (r != 0) { g_create_err = fmt("ncclAllGather(ipc handles): %s", api->GetErrorString(r)); cudaFree(d_mine); cudaFree(d_all); npair_destroy(c); return NPAIR_E_NCCL; }
+      CREATE_TRY(cudaStreamSynchronize(nullptr));
+      std::vector<Handles> all(W);
+      CREATE_TRY(cudaMemcpy(all.data(), d_all, 128ull * W, cudaMemcpyDeviceToHost));
+      cudaFree(d_mine); cudaFree(d_all);
+      std::vector<float*> pb(W); std::vector<uint32_t*> pf(W);
+      for (int q = 0; q < W; ++q) {
+        if (q == c->rank) { pb[q] = c->p2p_buf; pf[q] = c->p2p_flags; continue; }
+        void *a = nullptr, *b = nullptr;
+        CREATE_TRY(cudaIpcOpenMemHandle(&a, all[q].buf, cudaIpcMemLazyEnablePeerAccess));
+        c->p2p_opened.push_back(a);
+        CREATE_TRY(cudaIpcOpenMemHandle(&b, all[q].flags, cudaIpcMemLazyEnablePeerAccess));
+        c->p2p_opened.push_back(b);
+        pb[q] = static_cast<float*>(a); pf[q] = static_cast<uint32_t*>(b);
+      }
+      CREATE_TRY(cudaMalloc(&c->p2p_peer_buf, sizeof(float*) * W));
+      CREATE_TRY(cudaMalloc(&c->p2p_peer_flags, sizeof(uint32_t*) * W));
+      CREATE_TRY(cudaMemcpy(c->p2p_peer_buf, pb.data(), sizeof(float*) * W, cudaMemcpyHostToDevice));
+      CREATE_TRY(cudaMemcpy(c->p2p_peer_flags, pf.data(), sizeof(uint32_t*) * W, cudaMemcpyHostToDevice));
+      c->p2p_rec = true;
+    }
+  }
 #undef CREATE_TRY
   *out = c;
   return NPAIR_OK;
@@ -873,8 +960,17 @@ static int forward_impl(npair_ctx* c, const float* d_feat, const float* d_label,
   // NPAIR_RS_GATHER_FWD=1 enqueues the row-record exchange here instead of at the start of npair_backward.  Measured on
   // 8 x B200 (profiles/r01_bench_v6_n8.json): with the collective in front of the forward's host synchronisation the step is
   // SLOWER (0.293 ms against 0.218 ms with it in the backward, where its rendezvous overlaps the host's return), so it is opt-in.
+  if (c->p2p_rec) {
+    // peer-memory exchange: push this rank's records to every rank now; the backward only waits for the flags
+    PhaseTimer pt(c, 8, st);
+    ++c->p2p_epoch;
+    int nb = (2 * Q + 255) / 256; if (nb > 64) nb = 64; if (nb < 1) nb = 1;
+    p2p_push_records_kernel<<<nb, 256, 0, st>>>(reinterpret_cast<const float4*>(c->ra.rowscal), c->p2p_peer_buf, c->p2p_peer_flags, c->world, c->rank,
+                                                Q, N, static_cast<int>(c->p2p_epoch & 1u), c->p2p_epoch, c->p2p_ticket);
+    count_launch();
+  }
   static const bool gather_in_fwd = [] { const char* e = getenv("NPAIR_RS_GATHER_FWD"); return e && e[0] == '1'; }();
-  if (gather_in_fwd && c->bwd_mode == NPAIR_BWDMODE_ROW_SCALARS && c->comm) {
+  if (gather_in_fwd && !c->p2p_rec && c->bwd_mode == NPAIR_BWDMODE_ROW_SCALARS && c->comm) {
     // The only backward exchange (8*Q floats per rank, replaces the N x D MPI_Allreduce of .cu:462-489) does not depend on
     // the loss weight, so it is enqueued here: it runs while the host wakes up from the synchronisation below.
     PhaseTimer pt(c, 8, st);
@@ -955,7 +1051,12 @@ static int backward_impl(npair_ctx* c, float loss_weight, float* d_diff, float* 
     bw_mode = BW_ROWSCAL;
     if (d_rs_ext) rs_total = d_rs_ext;
     else {
-      if (!c->rs_gathered) {
+      if (c->p2p_rec) {
+        PhaseTimer pt(c, 8, st);
+        p2p_wait_records_kernel<<<1, 32, 0, st>>>(c->p2p_flags, c->world, static_cast<int>(c->p2p_epoch & 1u), c->p2p_epoch);
+        count_launch();
+        rs_total = c->p2p_buf + 8ll * static_cast<long long>(c->p2p_epoch & 1u) * N;
+      } else if (!c->rs_gathered) {
         // the only backward exchange: 8*Q floats per rank (replaces the N x D MPI_Allreduce of .cu:462-489)
         if (!c->comm) { c->err = "no communicator: use npair_backward_gathered with externally gathered row records"; return NPAIR_E_STATE; }
         PhaseTimer pt(c, 8, st);
@@ -963,8 +1064,8 @@ static int backward_impl(npair_ctx* c, float loss_weight, float* d_diff, float* 
         int r = api->AllGather(c->ra.rowscal, c->rs_total, 8ull * Q, NCCL_FLOAT32, c->comm, st);
         if (r != 0) { c->err = fmt("ncclAllGather(row records): %s", api->GetErrorString(r)); return NPAIR_E_NCCL; }
         c->rs_gathered = true;
-      }
-      rs_total = c->rs_total;
+        rs_total = c->rs_total;
+      } else rs_total = c->rs_total;
     }
   } else if (c->bwd_mode == NPAIR_BWDMODE_REDUCE_SCATTER) bw_mode = BW_SPLIT;
   if (tc && c->fused_grad) {

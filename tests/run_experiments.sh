@@ -20,3 +20,7 @@ timeout 400 python bench.py --steps 100 --warmup 10 --e2e-prefetch --no-cpu-base
 import sys, json
 d = json.loads(sys.stdin.read().strip().splitlines()[-1])
 print('value', d['value'], 'ms', d['ms_per_step'], 'e2e', d['e2e'], 'e2e_prefetch', d.get('e2e_prefetch'))"
+# multi-GPU (separate gpurun --gpus 2 call):
+#   NPAIR_P2P_RECORDS=1 timeout 600 python -m pytest tests/test_multi_gpu.py -q
+#   for v in NPAIR_NONE=1 NPAIR_P2P_RECORDS=1; do env $v timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 \
+#       --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 200 --warmup 20 --no-cpu-baseline | cut -c1-300; done
