@@ -437,7 +437,7 @@ struct npair_ctx {
   int2* sym_tiles2 = nullptr;       // world == 1: (pair_m, n_blk) list of the pair kernel
   int n_sym_tiles2 = 0;
   // tile row pass (world == 1, NPAIR_LSE_TILES=1): upper-triangular 128 x 128 tile list, per-row prologue records, partials
-  bool lse_tiles = false;
+  bool lse_tiles = false, lse_sym = false;
   int2* lse_tile_list = nullptr; int n_lse_tiles = 0;
   float* lse_prep = nullptr; float4* lse_part = nullptr; int* lse_cnt = nullptr; int lse_qpad = 0;
   CUtensorMap tm_lseS;
@@ -737,22 +737,25 @@ static int create_impl(const npair_config* cfg, const void* id128, void* ext_com
     CREATE_TRY(cudaMalloc(&c->sym_tiles2, sizeof(int2) * tl2.size()));
     CREATE_TRY(cudaMemcpy(c->sym_tiles2, tl2.data(), sizeof(int2) * tl2.size(), cudaMemcpyHostToDevice));
   }
-  if (c->world == 1 && cfg->gemm_backend == NPAIR_GEMM_TCGEN05) {
+  if (cfg->gemm_backend == NPAIR_GEMM_TCGEN05) {
+    // tile row pass (opt-in): NPAIR_LSE_TILES=1 -> symmetric walk at world 1 (upper triangle only), plain tile walk otherwise;
+    // NPAIR_LSE_TILES=2 -> plain tile walk even at world 1 (for A/B measurements)
     const char* et = getenv("NPAIR_LSE_TILES");
-    if (et && et[0] == '1') {
-      // tile row pass: reads only the upper triangle of the symmetric S (see kernels.cu); last row blocks first (still in L2)
-      const int tb = (N + 127) / 128;
+    if (et && (et[0] == '1' || et[0] == '2')) {
+      const bool sym = (c->world == 1 && et[0] == '1');
+      const int tbc = (N + 127) / 128, tbr = (Q + 127) / 128;
       std::vector<int2> tl;
-      for (int I = tb - 1; I >= 0; --I)
-        for (int J = I; J < tb; ++J) tl.push_back(make_int2(I, J));
+      for (int I = tbr - 1; I >= 0; --I)                        // last row blocks first: their tiles are the ones still in L2
+        for (int J = sym ? I : 0; J < tbc; ++J) tl.push_back(make_int2(I, J));
       c->n_lse_tiles = static_cast<int>(tl.size());
-      c->lse_qpad = tb * 128;
+      c->lse_qpad = tbr * 128;
+      c->lse_sym = sym;
       CREATE_TRY(cudaMalloc(&c->lse_tile_list, sizeof(int2) * tl.size()));
       CREATE_TRY(cudaMemcpy(c->lse_tile_list, tl.data(), sizeof(int2) * tl.size(), cudaMemcpyHostToDevice));
       CREATE_TRY(cudaMalloc(&c->lse_prep, sizeof(float) * 8ull * Q));
-      CREATE_TRY(cudaMalloc(&c->lse_part, sizeof(float4) * static_cast<size_t>(tb) * c->lse_qpad));
-      CREATE_TRY(cudaMalloc(&c->lse_cnt, sizeof(int) * tb));
-      CREATE_TRY(cudaMemset(c->lse_cnt, 0, sizeof(int) * tb));
+      CREATE_TRY(cudaMalloc(&c->lse_part, sizeof(float4) * static_cast<size_t>(tbc) * c->lse_qpad));
+      CREATE_TRY(cudaMalloc(&c->lse_cnt, sizeof(int) * tbr));
+      CREATE_TRY(cudaMemset(c->lse_cnt, 0, sizeof(int) * tbr));
       std::string te;
       if (!make_tmap_f32_store(&c->tm_lseS, c->S, N, Q, c->ldS, &te, 128)) { g_create_err = te; npair_destroy(c); return NPAIR_E_CUDA; }
       c->lse_tiles = true;
@@ -951,8 +954,8 @@ static int forward_impl(npair_ctx* c, const float* d_feat, const float* d_label,
   {
     PhaseTimer pt(c, 4, st);
     if (c->lse_tiles)
-      launch_lse_tiles(c->tm_lseS, c->lse_tile_list, c->n_lse_tiles, Q, N, c->lab_total, mp, c->ra, c->bs, c->lse_prep, c->lse_part, c->lse_qpad,
-                       c->lse_cnt, c->cfg.num_tops, c->tops_dev, st);
+      launch_lse_tiles(c->tm_lseS, c->lse_tile_list, c->n_lse_tiles, Q, N, d_label, c->lab_total, self_off, c->lse_sym ? 1 : 0, mp, c->ra, c->bs,
+                       c->lse_prep, c->lse_part, c->lse_qpad, c->lse_cnt, c->cfg.num_tops, c->tops_dev, st);
     else
       launch_lse_rows(c->S, c->ldS, Q, N, d_label, c->lab_total, self_off, mp, c->ra, c->bs, c->cfg.num_tops, c->tops_dev, st);
   }

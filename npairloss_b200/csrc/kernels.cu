@@ -918,9 +918,12 @@ __device__ __forceinline__ void tile_finish_row(int i, int Q, int N, float A, fl
 }
 
 __global__ void __launch_bounds__(256, 3)
-lse_tiles_kernel(const __grid_constant__ CUtensorMap tmS, const int2* __restrict__ tiles, int Q, int N, const float* __restrict__ lab,
+lse_tiles_kernel(const __grid_constant__ CUtensorMap tmS, const int2* __restrict__ tiles, int Q, int N, const float* __restrict__ lab_rows,
+                 const float* __restrict__ lab_cols, int self_offset, int symmetric,
                  const float* __restrict__ prep, float sgn_p, float sgn_n, float4* __restrict__ part /*[TB][Qpad]*/, int Qpad,
-                 int* __restrict__ blk_cnt /*[TB]*/, RowArrays ra, BlockScalars* bs, int num_tops, float* __restrict__ tops) {
+                 int* __restrict__ blk_cnt /*[row blocks]*/, RowArrays ra, BlockScalars* bs, int num_tops, float* __restrict__ tops) {
+  // symmetric = 1: world == 1, tiles = upper triangle, both walks (see above).  symmetric = 0: any world, tiles = every
+  // (row block, column block) of the Q x N block, direct walk only -- the same TMA-fed tile pass without the halved traffic.
   extern __shared__ uint8_t tl_smem_raw[];
   uint8_t* tile = tl_smem_raw + ((1024u - (ptx::smem_u32(tl_smem_raw) & 1023u)) & 1023u);   // 4 boxes of 128 rows x 128 B, 128B-swizzled
   float* labI = reinterpret_cast<float*>(tile + 65536);       // [128] labels of the tile's rows
@@ -931,7 +934,8 @@ lse_tiles_kernel(const __grid_constant__ CUtensorMap tmS, const int2* __restrict
   const int t = threadIdx.x;
   const int2 ij = tiles[blockIdx.x];
   const int I = ij.x, J = ij.y;
-  const int TB = (N + 127) / 128;
+  const int TB = (N + 127) / 128;                              // column blocks = partial slots per row = contributions per row block
+  const int RB = (Q + 127) / 128;                              // row blocks
   if (t == 0) {
     ptx::mbar_init(bar, 1);
     ptx::fence_mbar_init();
@@ -939,8 +943,8 @@ lse_tiles_kernel(const __grid_constant__ CUtensorMap tmS, const int2* __restrict
 #pragma unroll
     for (int b = 0; b < 4; ++b) ptx::tma_load_2d(tile + b * 16384, &tmS, bar, J * 128 + 32 * b, I * 128);
   }
-  if (t < 128) labI[t] = (I * 128 + t < Q) ? lab[I * 128 + t] : 0.f;
-  else labJ[t - 128] = (J * 128 + (t - 128) < N) ? lab[J * 128 + (t - 128)] : 0.f;
+  if (t < 128) labI[t] = (I * 128 + t < Q) ? lab_rows[I * 128 + t] : 0.f;
+  else labJ[t - 128] = (J * 128 + (t - 128) < N) ? lab_cols[J * 128 + (t - 128)] : 0.f;
   const int x = t & 127, half = t >> 7;
   // pass 1 row = I*128 + x, pass 2 "row" = J*128 + x
   TileRow r1 = {0.f, -INFINITY, 0.f, INFINITY, -INFINITY}, r2 = r1;
@@ -949,7 +953,8 @@ lse_tiles_kernel(const __grid_constant__ CUtensorMap tmS, const int2* __restrict
     const float4 a = *reinterpret_cast<const float4*>(prep + 8ll * gi);
     r1.m2 = a.x; r1.thr_n = a.y; r1.li = a.z; r1.scut = a.w; r1.thr_p = prep[8ll * gi + 4];
   }
-  if (I < J && gj < Q) {
+  const bool walk2 = symmetric && I < J;                        // transposed walk for the rows of block J
+  if (walk2 && gj < Q) {
     const float4 a = *reinterpret_cast<const float4*>(prep + 8ll * gj);
     r2.m2 = a.x; r2.thr_n = a.y; r2.li = a.z; r2.scut = a.w; r2.thr_p = prep[8ll * gj + 4];
   }
@@ -967,8 +972,9 @@ lse_tiles_kernel(const __grid_constant__ CUtensorMap tmS, const int2* __restrict
         const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
         const float ll[4] = {l4.x, l4.y, l4.z, l4.w};
         const int j0 = J * 128 + co;
-        const bool plain = (j0 + 3 < N) && !(I == J && gi >= j0 && gi <= j0 + 3);
-        tile_group4(vv, ll, r1, sgn_p, sgn_n, plain, j0, N, (I == J) ? gi : -1, A, T, c);
+        const int self_col = gi + self_offset;                   // global column of this row's self pair (.cu:54)
+        const bool plain = (j0 + 3 < N) && (self_col < j0 || self_col > j0 + 3);
+        tile_group4(vv, ll, r1, sgn_p, sgn_n, plain, j0, N, self_col, A, T, c);
       }
     }
     if (half == 1) { red[3 * x] = A; red[3 * x + 1] = T; red[3 * x + 2] = __int_as_float(c); }
@@ -978,7 +984,7 @@ lse_tiles_kernel(const __grid_constant__ CUtensorMap tmS, const int2* __restrict
     __syncthreads();                                           // red is reused by pass 2
   }
   // ------------------------------ pass 2: rows of block J against the ROWS of block I (transposed walk) ------------------------------
-  if (I < J) {
+  if (walk2) {
     float A = 0.f, T = 0.f; int c = 0;
     if (gj < Q) {
       const uint8_t* colbase = tile + (x >> 5) * 16384 + ((x & 3) << 2);
@@ -1006,7 +1012,7 @@ lse_tiles_kernel(const __grid_constant__ CUtensorMap tmS, const int2* __restrict
   if (t == 0) {
     int fin = 0;
     if (atomicAdd(&blk_cnt[I], 1) == TB - 1) fin |= 1;
-    if (I < J && atomicAdd(&blk_cnt[J], 1) == TB - 1) fin |= 2;
+    if (walk2 && atomicAdd(&blk_cnt[J], 1) == TB - 1) fin |= 2;
     s_fin = fin;
   }
   __syncthreads();
@@ -1031,7 +1037,7 @@ lse_tiles_kernel(const __grid_constant__ CUtensorMap tmS, const int2* __restrict
   }
   __threadfence();
   __syncthreads();
-  if (t == 0) s_fin = (atomicAdd(&bs->ticket, static_cast<unsigned>(finished_blocks)) + finished_blocks == static_cast<unsigned>(TB)) ? 1 : 0;
+  if (t == 0) s_fin = (atomicAdd(&bs->ticket, static_cast<unsigned>(finished_blocks)) + finished_blocks == static_cast<unsigned>(RB)) ? 1 : 0;
   __syncthreads();
   if (!s_fin) return;
   // ------------------------------ the very last CTA: tops (same reduction as lse_rows_kernel's last block) ------------------------------
@@ -1052,7 +1058,7 @@ lse_tiles_kernel(const __grid_constant__ CUtensorMap tmS, const int2* __restrict
   const int w = t >> 5;
   if (lane == 0) { s_l[w] = ls; s_h[0][w] = h[0]; s_h[1][w] = h[1]; s_h[2][w] = h[2]; }
   __syncthreads();
-  for (int b = t; b < TB; b += blockDim.x) blk_cnt[b] = 0;    // ready for the next step
+  for (int b = t; b < RB; b += blockDim.x) blk_cnt[b] = 0;    // ready for the next step
   if (t == 0) {
     ls = 0.0; h[0] = h[1] = h[2] = 0;
     for (int k = 0; k < (blockDim.x >> 5); ++k) { ls += s_l[k]; h[0] += s_h[0][k]; h[1] += s_h[1][k]; h[2] += s_h[2][k]; }
@@ -1067,14 +1073,15 @@ lse_tiles_kernel(const __grid_constant__ CUtensorMap tmS, const int2* __restrict
   }
 }
 
-void launch_lse_tiles(const CUtensorMap& tmS, const int2* tiles, int num_tiles, int Q, int N, const float* lab, MiningParams mp, RowArrays ra,
+void launch_lse_tiles(const CUtensorMap& tmS, const int2* tiles, int num_tiles, int Q, int N, const float* lab_rows, const float* lab_cols,
+                      int self_offset, int symmetric, MiningParams mp, RowArrays ra,
                       BlockScalars* bs, float* prep, float4* part, int Qpad, int* blk_cnt, int num_tops, float* tops_dev, cudaStream_t st) {
-  row_prep_kernel<<<(Q + 7) / 8, 256, 0, st>>>(Q, lab, mp, ra, bs, prep);
+  row_prep_kernel<<<(Q + 7) / 8, 256, 0, st>>>(Q, lab_rows, mp, ra, bs, prep);
   count_launch();
   constexpr int SMEM = 65536 + 128 * 4 * 2 + 384 * 4 + 16 + 1024;
   static bool attr_set = false;
   if (!attr_set) { cudaFuncSetAttribute(lse_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); attr_set = true; }
-  lse_tiles_kernel<<<num_tiles, 256, SMEM, st>>>(tmS, tiles, Q, N, lab, prep, ap_sign(mp.ap_method), an_sign(mp.an_method), part, Qpad,
+  lse_tiles_kernel<<<num_tiles, 256, SMEM, st>>>(tmS, tiles, Q, N, lab_rows, lab_cols, self_offset, symmetric, prep, ap_sign(mp.ap_method), an_sign(mp.an_method), part, Qpad,
                                                  blk_cnt, ra, bs, num_tops, tops_dev);
   count_launch();
 }

@@ -4,7 +4,7 @@
 # Every step runs under its own timeout: the stream-K kernel spins on flags, a bug there must not hang the box.
 cd "$(dirname "$0")/.."
 echo "== per-phase timings (HL: B=8192, D=512, fp16x2) =="
-for v in "NPAIR_NONE=1" "NPAIR_LSE_TILES=1" "NPAIR_GRAD_ONE_EX2=1" "NPAIR_GRAD_STREAMK=1" "NPAIR_GRAD_STREAMK=1 NPAIR_GRAD_ONE_EX2=1" \
+for v in "NPAIR_NONE=1" "NPAIR_LSE_TILES=1" "NPAIR_LSE_TILES=2" "NPAIR_GRAD_ONE_EX2=1" "NPAIR_GRAD_STREAMK=1" "NPAIR_GRAD_STREAMK=1 NPAIR_GRAD_ONE_EX2=1" \
          "NPAIR_LSE_TILES=1 NPAIR_GRAD_STREAMK=1 NPAIR_GRAD_ONE_EX2=1"; do
   echo "--- $v"
   env $v timeout 120 python tests/tune_phases.py || echo "FAILED/timeout: $v"

@@ -32,12 +32,13 @@ def _run(B, D, mining, env):
 
 @pytest.mark.parametrize("B,D", [(256, 64), (1000, 200), (2048, 128), (8192, 512)])
 @pytest.mark.parametrize("mining", ["usage", "default", "hard"])
-def test_tile_row_pass_matches_row_pass(B, D, mining):
+@pytest.mark.parametrize("tiles_mode", ["1", "2"])          # 1: symmetric walk (upper triangle), 2: plain tile walk
+def test_tile_row_pass_matches_row_pass(B, D, mining, tiles_mode):
     from npairloss_b200 import synth
     m = {"usage": synth.USAGE_MINING, "default": synth.DEFAULT_MINING,
          "hard": dict(synth.DEFAULT_MINING, ap_method=synth.HARD, an_method=synth.HARD)}[mining]
     t0, t0b, A0, T0, g0 = _run(B, D, m, {"NPAIR_LSE_TILES": "0"})
-    t1, t1b, A1, T1, g1 = _run(B, D, m, {"NPAIR_LSE_TILES": "1"})
+    t1, t1b, A1, T1, g1 = _run(B, D, m, {"NPAIR_LSE_TILES": tiles_mode})
     np.testing.assert_allclose(t1, t0, rtol=2e-6, atol=1e-7)        # other summation order of T only
     np.testing.assert_allclose(t1b, t1, rtol=0, atol=0)             # deterministic, state reset between steps
     np.testing.assert_allclose(A1, A0, rtol=2e-6, atol=1e-30)
