@@ -99,7 +99,7 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, 
 // exponential 2^(s*log2e - m2_j) is formed as e1 * 2^(m2_i) * 2^(-m2_j) from the row term's e1, a per-row constant and a
 // per-column constant that lanes 0..7 of the warp evaluate once per K block (9 instead of 16 MUFU warp instructions per
 // K block and warp: the MUFU pipe is the busiest producer pipe).  Falls back to the two-exponential form for a whole warp
-// and K block whenever a row or column maximum is outside |m2| <= 60 (2^60 products stay far from fp32 overflow).
+// and K block whenever a row or column maximum is outside |m2| <= 30 or a column constant is huge (tiny T).
 template <int NSPLIT, bool BF16, int NCTA = 1, bool ONE_EX2 = false>
 __global__ void __launch_bounds__(640, 1)
 fused_grad_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ CUtensorMap tmapS, const FusedGradParams p) {
@@ -235,7 +235,7 @@ fused_grad_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_consta
       float r_R = 0.f;                             // ONE_EX2: 2^(m2_i)
       bool row_slow = false;
       if (ONE_EX2) {
-        row_slow = !(fabsf(r_m2) <= 60.f);
+        row_slow = !(fabsf(r_m2) <= 30.f);
         if (!row_slow) asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r_R) : "f"(r_m2));
       }
       for (int kb = kb0; kb < kb1; ++kb) {
@@ -259,7 +259,9 @@ fused_grad_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_consta
           const float4 cl = crec[2 * (lane & 7)];                    // lane l evaluates column l & 7 of this warp's eight
           asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(myC) : "f"(-cl.x));
           myC *= cl.z * p.inv_world;                                 // 2^(-m2_j) * cT_j / world
-          one_ex2 = !__any_sync(0xffffffffu, row_slow || !(fabsf(cl.x) <= 60.f));
+          // |m2| <= 30 on both sides: the row/column constants stay within 2^+-30, and an e1 that underflows (s*log2e - m2_i
+          // < -126) belongs to a pair whose true e2 is below 2^-66; the 1e18 bound keeps r_R * cj finite when a row's T is tiny
+          one_ex2 = !__any_sync(0xffffffffu, row_slow || !(fabsf(cl.x) <= 30.f) || !(fabsf(myC) <= 1e18f));
         }
         if (ONE_EX2 && one_ex2) {
 #pragma unroll

@@ -173,7 +173,7 @@ fused_grad_sk_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_con
       float r_R = 0.f;                             // ONE_EX2: 2^(m2_i)
       bool row_slow = false;
       if (ONE_EX2) {
-        row_slow = !(fabsf(r_m2) <= 60.f);
+        row_slow = !(fabsf(r_m2) <= 30.f);
         if (!row_slow) asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r_R) : "f"(r_m2));
       }
       for (int kb = kb0; kb < kb1; ++kb) {
@@ -197,7 +197,9 @@ fused_grad_sk_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_con
           const float4 cl = crec[2 * (lane & 7)];                    // lane l evaluates column l & 7 of this warp's eight
           asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(myC) : "f"(-cl.x));
           myC *= cl.z * p.inv_world;                                 // 2^(-m2_j) * cT_j / world
-          one_ex2 = !__any_sync(0xffffffffu, row_slow || !(fabsf(cl.x) <= 60.f));
+          // |m2| <= 30 on both sides: the row/column constants stay within 2^+-30, and an e1 that underflows (s*log2e - m2_i
+          // < -126) belongs to a pair whose true e2 is below 2^-66; the 1e18 bound keeps r_R * cj finite when a row's T is tiny
+          one_ex2 = !__any_sync(0xffffffffu, row_slow || !(fabsf(cl.x) <= 30.f) || !(fabsf(myC) <= 1e18f));
         }
         if (ONE_EX2 && one_ex2) {
 #pragma unroll
