@@ -175,6 +175,9 @@ def main():
     # extra, opt-in measurement (adds the key "e2e_prefetch"; "e2e" is unchanged): double-buffered host bottoms whose H2D copy
     # for step k+1 runs on a copy stream while step k computes -- what Caffe's prefetching data layers do
     ap.add_argument("--e2e-prefetch", action="store_true")
+    # opt-in: the device-resident step calls npair_forward_backward (one host synchronisation per step) instead of
+    # npair_forward + npair_backward
+    ap.add_argument("--fused-step", action="store_true")
     args = ap.parse_args()
 
     from npairloss_b200 import synth
@@ -241,6 +244,8 @@ def main():
         torch.cuda.synchronize()
 
     def step_device():
+        if args.fused_step:
+            return ctx.forward_backward(d_x, d_l, 1.0, d_g)
         tops = ctx.forward(d_x, d_l)
         ctx.backward(1.0, d_g)
         return tops
@@ -459,6 +464,7 @@ def main():
                "config": {"workload": f"HL: B={B}, D={D}, {B // 2} classes x 2, {args.mining_desc}, loss_weight 1",
                           "global_batch": B, "feature_dim": D,
                           "rows_per_rank": Q, "sharding": f"anchor-sharded x{world}", "precision": args.precision, "noise": noise,
+                          "step_call": "npair_forward_backward (one host sync)" if args.fused_step else "npair_forward + npair_backward",
                           "l2": (f"flushed: a {2 * L2_BYTES >> 20} MB device buffer is rewritten before every timed step (per-rank S = "
                                  f"{4 * Q * N / 1e6:.0f} MB fp32 would otherwise stay in the 126 MB L2); steps timed one by one, flush excluded"
                                  if need_flush else

@@ -111,6 +111,12 @@ int npair_forward(npair_ctx* ctx, const float* d_feat, const float* d_label, flo
  * (bottom[0]->mutable_gpu_diff(); beta = 0 at .cu:448, propagate_down ignored).  Asynchronous on `stream`. */
 int npair_backward(npair_ctx* ctx, float loss_weight, float* d_feat_diff, void* stream);
 
+/* npair_forward + npair_backward with a single host synchronisation: the backward is enqueued behind the forward's kernels (the
+ * loss weight -- top[0]'s diff, reference .cu:435 -- is a constant of the net), then the call waits for the five tops.  Same
+ * results; saves the host round trip during which the GPU idles.  On a forward error the gradient buffer is unspecified. */
+int npair_forward_backward(npair_ctx* ctx, const float* d_feat, const float* d_label, float loss_weight, float* d_feat_diff,
+                           float tops_host[5], void* stream);
+
 /* External-collectives variants for host frameworks that keep their own communication layer (and for emulating all
  * ranks on one GPU in tests).  A context for world > 1 created with npair_create(cfg, NULL, ..) has no communicator
  * and only accepts these two calls.

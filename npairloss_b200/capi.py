@@ -25,7 +25,7 @@ class NpairConfig(C.Structure):
 
 
 EXPORTS = ["npair_config_default", "npair_workspace_bytes", "npair_nccl_unique_id", "npair_create", "npair_create_with_comm",
-           "npair_destroy", "npair_forward", "npair_backward", "npair_forward_gathered", "npair_backward_partial", "npair_bwd_exchange_mode", "npair_row_scalars", "npair_backward_gathered", "npair_profile_enable", "npair_profile_read", "npair_kernel_launches", "npair_util_f64_to_f32", "npair_util_f32_to_f64", "npair_last_error", "npair_version", "npair_debug_read",
+           "npair_destroy", "npair_forward", "npair_backward", "npair_forward_backward", "npair_forward_gathered", "npair_backward_partial", "npair_bwd_exchange_mode", "npair_row_scalars", "npair_backward_gathered", "npair_profile_enable", "npair_profile_read", "npair_kernel_launches", "npair_util_f64_to_f32", "npair_util_f32_to_f64", "npair_last_error", "npair_version", "npair_debug_read",
            "npair_debug_gemm"]
 
 _LIB = None
@@ -128,6 +128,20 @@ class Context:
 
     def backward_ptr(self, loss_weight: float, diff_ptr: int, stream: int = 0):
         self._check(lib().npair_backward(self._h, C.c_float(loss_weight), diff_ptr, stream))
+
+    def forward_backward_ptr(self, feat_ptr: int, label_ptr: int, loss_weight: float, diff_ptr: int, stream: int = 0):
+        tops = (C.c_float * 5)()
+        f = lib().npair_forward_backward
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.POINTER(C.c_float), C.c_void_p]
+        self._check(f(self._h, feat_ptr, label_ptr, C.c_float(loss_weight), diff_ptr, tops, stream))
+        return [tops[i] for i in range(5)]
+
+    def forward_backward(self, feat, label, loss_weight, diff):
+        """npair_forward_backward: both passes, one host synchronisation."""
+        import torch
+        assert feat.is_cuda and label.is_cuda and diff.is_cuda and feat.is_contiguous() and label.is_contiguous() and diff.is_contiguous()
+        assert feat.dtype == torch.float32 and label.dtype == torch.float32 and diff.dtype == torch.float32
+        return self.forward_backward_ptr(feat.data_ptr(), label.data_ptr(), loss_weight, diff.data_ptr(), torch.cuda.current_stream().cuda_stream)
 
     def forward(self, feat, label):
         import torch

@@ -15,6 +15,10 @@ for v in "NPAIR_NONE=1" "NPAIR_GRAD_STREAMK=1 NPAIR_GRAD_ONE_EX2=1"; do
 done
 echo "== correctness against the default path =="
 NPAIR_RUN_EXPERIMENTAL=1 timeout 1200 python -m pytest tests/test_gpu_experimental.py -q 2>&1 | tail -15
+echo "== device-resident step: two calls vs npair_forward_backward =="
+for f in "" "--fused-step"; do timeout 300 python bench.py --steps 200 --warmup 20 --no-cpu-baseline $f 2>/dev/null | python -c "
+import sys, json
+d = json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['config']['step_call'], 'ms/step', d['ms_per_step'], 'samples/s', d['value'])"; done
 echo "== e2e: serial H2D vs prefetch (double-buffered bottoms) =="
 timeout 400 python bench.py --steps 100 --warmup 10 --e2e-prefetch --no-cpu-baseline 2>/dev/null | python -c "
 import sys, json

@@ -156,3 +156,26 @@ def test_full_size_properties_headline():
     t3, g3 = step(x, lab, lw=-0.5)
     np.testing.assert_array_equal(t3, t0)
     assert np.linalg.norm(g3 + 0.5 * g0) <= 1e-6 * np.linalg.norm(g0)
+
+
+def test_forward_backward_single_sync_matches_two_calls():
+    """npair_forward_backward against npair_forward + npair_backward: bit-identical tops and gradient, error codes preserved."""
+    import torch
+    from npairloss_b200 import capi, synth
+    for B, D in ((512, 128), (2048, 512)):
+        x, lab = synth.make_inputs(B, D, 5, noise=2.5)
+        ctx = capi.Context(capi.make_config(B, D, **synth.USAGE_MINING))
+        dx, dl = torch.from_numpy(x).cuda(), torch.from_numpy(lab).cuda()
+        g0, g1 = torch.empty_like(dx), torch.empty_like(dx)
+        t0 = ctx.forward(dx, dl); ctx.backward(0.7, g0)
+        t1 = ctx.forward_backward(dx, dl, 0.7, g1)
+        assert t0 == t1 and torch.equal(g0, g1)
+        t2 = ctx.forward(dx, dl); ctx.backward(0.7, g0)             # the two-call path still works afterwards
+        assert t2 == t0
+        ctx.close()
+    ctx = capi.Context(capi.make_config(16, 8, ap_method=capi.RELATIVE_HARD))   # identsn = -1 -> pos out of range
+    x, lab = synth.make_inputs(16, 8, 1)
+    dx, dl = torch.from_numpy(x).cuda(), torch.from_numpy(lab).cuda()
+    with pytest.raises(capi.NpairError) as e:
+        ctx.forward_backward(dx, dl, 1.0, torch.empty_like(dx))
+    assert e.value.code == -5
