@@ -19,7 +19,6 @@
 #include "../../include/npair_b200.h"
 #include "gemm_tcgen05.cuh"
 #include "grad_fused.cuh"
-#include "grad_streamk.cuh"
 #include "kernels.cuh"
 
 namespace npair {
@@ -154,7 +153,7 @@ static cudaError_t launch_pair_gemm_t(const CUtensorMap& a, const CUtensorMap& b
   }
   const int tiles = p.tile_list ? p.num_tiles_list : p.tiles_m * p.tiles_n * p.splits;
   const int pairs = sms / 2;
-  cudaLaunchConfig_t lc; memset(&lc, 0, sizeof(lc));
+  cudaLaunchConfig_t lc = {};
   lc.gridDim = dim3(2 * (tiles < pairs ? tiles : pairs));
   lc.blockDim = dim3(Cfg::THREADS);
   lc.dynamicSmemBytes = Cfg::SMEM_BYTES;
@@ -200,10 +199,10 @@ static cudaError_t launch_fused_grad_t(const CUtensorMap& b, const CUtensorMap& 
   return cudaGetLastError();
 }
 // CTA-pair launch of the fused gradient kernel (cluster dimension 2); p.tiles_m counts 256-row pair blocks, `b` has 128-row boxes
-template <int NSPLIT, bool BF16, bool ONE_EX2 = false>
+template <int NSPLIT, bool BF16>
 static cudaError_t launch_fused_grad_pair_t(const CUtensorMap& b, const CUtensorMap& sm, const FusedGradParams& p, int sms, cudaStream_t st) {
   using Cfg = FusedCfg<NSPLIT, 2>;
-  auto kern = fused_grad_kernel<NSPLIT, BF16, 2, ONE_EX2>;
+  auto kern = fused_grad_kernel<NSPLIT, BF16, 2>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -212,7 +211,7 @@ static cudaError_t launch_fused_grad_pair_t(const CUtensorMap& b, const CUtensor
   }
   const int tiles = p.tiles_m * p.tiles_n * p.splits;
   const int pairs = sms / 2;
-  cudaLaunchConfig_t lc; memset(&lc, 0, sizeof(lc));
+  cudaLaunchConfig_t lc = {};
   lc.gridDim = dim3(2 * (tiles < pairs ? tiles : pairs));
   lc.blockDim = dim3(Cfg::THREADS);
   lc.dynamicSmemBytes = Cfg::SMEM_BYTES;
@@ -225,50 +224,9 @@ static cudaError_t launch_fused_grad_pair_t(const CUtensorMap& b, const CUtensor
   return cudaLaunchKernelEx(&lc, kern, b, sm, p);
 }
 static cudaError_t launch_fused_grad_pair(int prec, const CUtensorMap& b, const CUtensorMap& sm, const FusedGradParams& p, int sms, cudaStream_t st) {
-  static const bool one_ex2 = [] { const char* e = getenv("NPAIR_GRAD_ONE_EX2"); return e && e[0] == '1'; }();
-  if (one_ex2) {       // opt-in producer variant, see grad_fused.cuh
-    if (prec == PREC_BF16) return launch_fused_grad_pair_t<1, true, true>(b, sm, p, sms, st);
-    if (prec == PREC_FP16X2) return launch_fused_grad_pair_t<2, false, true>(b, sm, p, sms, st);
-    return launch_fused_grad_pair_t<3, true, true>(b, sm, p, sms, st);
-  }
   if (prec == PREC_BF16) return launch_fused_grad_pair_t<1, true>(b, sm, p, sms, st);
   if (prec == PREC_FP16X2) return launch_fused_grad_pair_t<2, false>(b, sm, p, sms, st);
   return launch_fused_grad_pair_t<3, true>(b, sm, p, sms, st);
-}
-// Stream-K launch of the CTA-pair gradient kernel (opt-in, grad_streamk.cuh).  `clusters` must all be co-resident.
-template <int NSPLIT, bool BF16, bool ONE_EX2>
-static cudaError_t launch_fused_grad_sk_t(const CUtensorMap& b, const CUtensorMap& sm, const FusedGradParams& p, const StreamKParams& sk,
-                                          int clusters, cudaStream_t st) {
-  using Cfg = FusedCfg<NSPLIT, 2>;
-  auto kern = fused_grad_sk_kernel<NSPLIT, BF16, ONE_EX2>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
-  cudaLaunchConfig_t lc; memset(&lc, 0, sizeof(lc));
-  lc.gridDim = dim3(2 * clusters);
-  lc.blockDim = dim3(Cfg::THREADS);
-  lc.dynamicSmemBytes = Cfg::SMEM_BYTES;
-  lc.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  lc.attrs = at; lc.numAttrs = 1;
-  count_launch();
-  return cudaLaunchKernelEx(&lc, kern, b, sm, p, sk);
-}
-static cudaError_t launch_fused_grad_sk(int prec, bool one_ex2, const CUtensorMap& b, const CUtensorMap& sm, const FusedGradParams& p,
-                                        const StreamKParams& sk, int clusters, cudaStream_t st) {
-  if (one_ex2) {
-    if (prec == PREC_BF16) return launch_fused_grad_sk_t<1, true, true>(b, sm, p, sk, clusters, st);
-    if (prec == PREC_FP16X2) return launch_fused_grad_sk_t<2, false, true>(b, sm, p, sk, clusters, st);
-    return launch_fused_grad_sk_t<3, true, true>(b, sm, p, sk, clusters, st);
-  }
-  if (prec == PREC_BF16) return launch_fused_grad_sk_t<1, true, false>(b, sm, p, sk, clusters, st);
-  if (prec == PREC_FP16X2) return launch_fused_grad_sk_t<2, false, false>(b, sm, p, sk, clusters, st);
-  return launch_fused_grad_sk_t<3, true, false>(b, sm, p, sk, clusters, st);
 }
 static cudaError_t launch_fused_grad(int prec, const CUtensorMap& b, const CUtensorMap& sm, const FusedGradParams& p, int sms, cudaStream_t st) {
   if (prec == PREC_BF16) return launch_fused_grad_t<1, true>(b, sm, p, sms, st);
@@ -436,15 +394,6 @@ struct npair_ctx {
   bool sim_pair = false;            // similarity GEMM runs in CTA-pair mode (cta_group::2)
   int2* sym_tiles2 = nullptr;       // world == 1: (pair_m, n_blk) list of the pair kernel
   int n_sym_tiles2 = 0;
-  // tile row pass (world == 1, NPAIR_LSE_TILES=1): upper-triangular 128 x 128 tile list, per-row prologue records, partials
-  bool lse_tiles = false, lse_sym = false;
-  int2* lse_tile_list = nullptr; int n_lse_tiles = 0;
-  float* lse_prep = nullptr; float4* lse_part = nullptr; int* lse_cnt = nullptr; int lse_qpad = 0;
-  CUtensorMap tm_lseS;
-  // stream-K gradient kernel (opt-in NPAIR_GRAD_STREAMK=1): equal runs of (block, K block) units per cluster
-  bool grad_sk = false, grad_one_ex2 = false;
-  int sk_clusters = 0, sk_upc = 0, sk_max_slots = 0;
-  float* sk_ws = nullptr; uint32_t* sk_flags = nullptr; uint32_t sk_epoch = 0;
   CUtensorMap tm_fB2;            // 128-row boxes of X^T for the CTA-pair gradient kernel
   bool grad_pair = false;        // fused gradient kernel runs in CTA-pair mode
   CUtensorMap tm_fB, tm_fS;      // fused gradient kernel: X^T pieces with 32-wide K boxes, 128-row fp32 boxes of S
@@ -582,7 +531,7 @@ void npair_destroy(npair_ctx* c) {
   cudaFree(c->p2p_buf); cudaFree(c->p2p_flags); cudaFree(c->p2p_peer_buf); cudaFree(c->p2p_peer_flags); cudaFree(c->p2p_ticket);
   if (c->comm && c->own_comm) { NcclApi* api = nccl_api(); if (api->CommDestroy) api->CommDestroy(c->comm); }
   cudaFree(c->Xtot_buf); cudaFree(c->labtot_buf); cudaFree(c->S); cudaFree(c->Xs); cudaFree(c->XsT); cudaFree(c->XlT);
-  cudaFree(c->H); cudaFree(c->HT); cudaFree(c->OUT2); cudaFree(c->part); cudaFree(c->sym_tiles); cudaFree(c->sym_tiles2); cudaFree(c->sk_ws); cudaFree(c->sk_flags); cudaFree(c->lse_tile_list); cudaFree(c->lse_prep); cudaFree(c->lse_part); cudaFree(c->lse_cnt); cudaFree(c->XcatA); cudaFree(c->XcatB); cudaFree(c->rs_total); cudaFree(c->row_block); cudaFree(c->bs); cudaFree(c->partial); cudaFree(c->ghist);
+  cudaFree(c->H); cudaFree(c->HT); cudaFree(c->OUT2); cudaFree(c->part); cudaFree(c->sym_tiles); cudaFree(c->sym_tiles2); cudaFree(c->XcatA); cudaFree(c->XcatB); cudaFree(c->rs_total); cudaFree(c->row_block); cudaFree(c->bs); cudaFree(c->partial); cudaFree(c->ghist);
   if (c->tops_pinned) cudaFreeHost(c->tops_pinned);
   if (c->ev_made) for (int i = 0; i < NPAIR_PROF_PHASES; ++i) { cudaEventDestroy(c->ev[i][0]); cudaEventDestroy(c->ev[i][1]); }
   delete c;
@@ -738,54 +687,12 @@ static int create_impl(const npair_config* cfg, const void* id128, void* ext_com
     CREATE_TRY(cudaMalloc(&c->sym_tiles2, sizeof(int2) * tl2.size()));
     CREATE_TRY(cudaMemcpy(c->sym_tiles2, tl2.data(), sizeof(int2) * tl2.size(), cudaMemcpyHostToDevice));
   }
-  if (cfg->gemm_backend == NPAIR_GEMM_TCGEN05) {
-    // tile row pass (opt-in): NPAIR_LSE_TILES=1 -> symmetric walk at world 1 (upper triangle only), plain tile walk otherwise;
-    // NPAIR_LSE_TILES=2 -> plain tile walk even at world 1 (for A/B measurements)
-    const char* et = getenv("NPAIR_LSE_TILES");
-    if (et && (et[0] == '1' || et[0] == '2')) {
-      const bool sym = (c->world == 1 && et[0] == '1');
-      const int tbc = (N + 127) / 128, tbr = (Q + 127) / 128;
-      std::vector<int2> tl;
-      for (int I = tbr - 1; I >= 0; --I)                        // last row blocks first: their tiles are the ones still in L2
-        for (int J = sym ? I : 0; J < tbc; ++J) tl.push_back(make_int2(I, J));
-      c->n_lse_tiles = static_cast<int>(tl.size());
-      c->lse_qpad = tbr * 128;
-      c->lse_sym = sym;
-      CREATE_TRY(cudaMalloc(&c->lse_tile_list, sizeof(int2) * tl.size()));
-      CREATE_TRY(cudaMemcpy(c->lse_tile_list, tl.data(), sizeof(int2) * tl.size(), cudaMemcpyHostToDevice));
-      CREATE_TRY(cudaMalloc(&c->lse_prep, sizeof(float) * 8ull * Q));
-      CREATE_TRY(cudaMalloc(&c->lse_part, sizeof(float4) * static_cast<size_t>(tbc) * c->lse_qpad));
-      CREATE_TRY(cudaMalloc(&c->lse_cnt, sizeof(int) * tbr));
-      CREATE_TRY(cudaMemset(c->lse_cnt, 0, sizeof(int) * tbr));
-      std::string te;
-      if (!make_tmap_f32_store(&c->tm_lseS, c->S, N, Q, c->ldS, &te, 128)) { g_create_err = te; npair_destroy(c); return NPAIR_E_CUDA; }
-      c->lse_tiles = true;
-    }
-  }
   {
     // CTA-pair similarity GEMM whenever there are at least two 128-row blocks (NPAIR_SIM_1CTA=1 keeps the single-CTA kernel)
     const char* e1 = getenv("NPAIR_SIM_1CTA");
     c->sim_pair = cfg->gemm_backend == NPAIR_GEMM_TCGEN05 && Q > 128 && !(e1 && e1[0] == '1');
     const char* e2 = getenv("NPAIR_GRAD_1CTA");
     c->grad_pair = c->fused_grad && Q > 128 && !(e2 && e2[0] == '1');
-    const char* e3 = getenv("NPAIR_GRAD_STREAMK");
-    const char* e4 = getenv("NPAIR_GRAD_ONE_EX2");
-    c->grad_one_ex2 = e4 && e4[0] == '1';
-    if (c->grad_pair && e3 && e3[0] == '1') {
-      const long long blocks = static_cast<long long>((Q + 255) / 256) * ((D + 255) / 256);
-      const int nkb = (N + 31) / 32;
-      const long long total = blocks * nkb;
-      long long clusters = c->sms / 2;                          // one cluster per TPC: all co-resident on an otherwise idle GPU
-      if (clusters > total) clusters = total;
-      const long long upc = (total + clusters - 1) / clusters;
-      c->sk_upc = static_cast<int>(upc);
-      c->sk_clusters = static_cast<int>((total + upc - 1) / upc);
-      c->sk_max_slots = static_cast<int>((nkb + upc - 1) / upc) + 1;
-      CREATE_TRY(cudaMalloc(&c->sk_ws, sizeof(float) * static_cast<size_t>(blocks) * c->sk_max_slots * 2 * 128 * 256));
-      CREATE_TRY(cudaMalloc(&c->sk_flags, sizeof(uint32_t) * static_cast<size_t>(blocks) * c->sk_max_slots * 32));
-      CREATE_TRY(cudaMemset(c->sk_flags, 0, sizeof(uint32_t) * static_cast<size_t>(blocks) * c->sk_max_slots * 32));
-      c->grad_sk = true;
-    }
   }
   // ---- NCCL ----
   if (c->world > 1 && (id128 || ext_comm)) {
@@ -954,11 +861,7 @@ static int forward_impl(npair_ctx* c, const float* d_feat, const float* d_label,
   // ---- selection + counts + exp + masked sums + log + retrieval in one pass (.cu:343-398) ----
   {
     PhaseTimer pt(c, 4, st);
-    if (c->lse_tiles)
-      launch_lse_tiles(c->tm_lseS, c->lse_tile_list, c->n_lse_tiles, Q, N, d_label, c->lab_total, self_off, c->lse_sym ? 1 : 0, mp, c->ra, c->bs,
-                       c->lse_prep, c->lse_part, c->lse_qpad, c->lse_cnt, c->cfg.num_tops, c->tops_dev, st);
-    else
-      launch_lse_rows(c->S, c->ldS, Q, N, d_label, c->lab_total, self_off, mp, c->ra, c->bs, c->cfg.num_tops, c->tops_dev, st);
+    launch_lse_rows(c->S, c->ldS, Q, N, d_label, c->lab_total, self_off, mp, c->ra, c->bs, c->cfg.num_tops, c->tops_dev, st);
   }
   c->rs_gathered = false;
   // NPAIR_RS_GATHER_FWD=1 enqueues the row-record exchange here instead of at the start of npair_backward.  Measured on
@@ -1123,11 +1026,7 @@ static int backward_impl(npair_ctx* c, float loss_weight, float* d_diff, float* 
     }
     {
       PhaseTimer pt(c, 6, st);
-      if (c->grad_sk) {
-        StreamKParams sk; sk.ws = c->sk_ws; sk.flags = c->sk_flags; sk.epoch = ++c->sk_epoch; sk.upc = c->sk_upc; sk.max_slots = c->sk_max_slots;
-        fp.splits = 1; fp.kb_per_split = fp.num_kblocks;        // stream-K replaces split-K and its reduce kernel
-        CUDA_TRY(c, launch_fused_grad_sk(c->prec, c->grad_one_ex2, c->tm_fB2, c->tm_fS, fp, sk, c->sk_clusters, st));
-      } else if (c->grad_pair) CUDA_TRY(c, launch_fused_grad_pair(c->prec, c->tm_fB2, c->tm_fS, fp, c->sms, st));
+      if (c->grad_pair) CUDA_TRY(c, launch_fused_grad_pair(c->prec, c->tm_fB2, c->tm_fS, fp, c->sms, st));
       else CUDA_TRY(c, launch_fused_grad(c->prec, c->tm_fB, c->tm_fS, fp, c->sms, st));
       if (fp.splits > 1) {
         const long long n = static_cast<long long>(Q) * D;

@@ -95,12 +95,10 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, 
                : "memory");
 }
 
-// ONE_EX2 (opt-in, NPAIR_GRAD_ONE_EX2=1; written after round 1's GPU budget ran out, not measured yet): the transposed term's
-// exponential 2^(s*log2e - m2_j) is formed as e1 * 2^(m2_i) * 2^(-m2_j) from the row term's e1, a per-row constant and a
-// per-column constant that lanes 0..7 of the warp evaluate once per K block (9 instead of 16 MUFU warp instructions per
-// K block and warp: the MUFU pipe is the busiest producer pipe).  Falls back to the two-exponential form for a whole warp
-// and K block whenever a row or column maximum is outside |m2| <= 30 or a column constant is huge (tiny T).
-template <int NSPLIT, bool BF16, int NCTA = 1, bool ONE_EX2 = false>
+// Measured and dropped (round 2, profiles/r02_experiments.md): forming the transposed term's exponential from the row term's
+// (one ex2 per pair plus per-row / per-column constants) was SLOWER (180 vs 166 us): the extra shuffles and selects cost more
+// than the saved MUFU issue slots.
+template <int NSPLIT, bool BF16, int NCTA = 1>
 __global__ void __launch_bounds__(640, 1)
 fused_grad_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ CUtensorMap tmapS, const FusedGradParams p) {
   using Cfg = FusedCfg<NSPLIT, NCTA>;
@@ -232,12 +230,6 @@ fused_grad_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_consta
         r_m2 = a.x; r_tn = a.y; r_cT = a.z; r_lab = a.w; r_tp = b.x; r_cA = b.y;
       }
       const int self_col = row + p.self_offset;
-      float r_R = 0.f;                             // ONE_EX2: 2^(m2_i)
-      bool row_slow = false;
-      if (ONE_EX2) {
-        row_slow = !(fabsf(r_m2) <= 30.f);
-        if (!row_slow) asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r_R) : "f"(r_m2));
-      }
       for (int kb = kb0; kb < kb1; ++kb) {
         ptx::mbar_wait(&full_bar[stage], phase);
         uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
@@ -253,31 +245,6 @@ fused_grad_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_consta
         const int m0 = kb * BK + 8 * qt;         // global column of sv[0]
         float g[8];
         bool any_same = false;
-        bool one_ex2 = false;
-        float myC = 0.f;
-        if (ONE_EX2) {
-          const float4 cl = crec[2 * (lane & 7)];                    // lane l evaluates column l & 7 of this warp's eight
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(myC) : "f"(-cl.x));
-          myC *= cl.z * p.inv_world;                                 // 2^(-m2_j) * cT_j / world
-          // |m2| <= 30 on both sides: the row/column constants stay within 2^+-30, and an e1 that underflows (s*log2e - m2_i
-          // < -126) belongs to a pair whose true e2 is below 2^-66; the 1e18 bound keeps r_R * cj finite when a row's T is tiny
-          one_ex2 = !__any_sync(0xffffffffu, row_slow || !(fabsf(cl.x) <= 30.f) || !(fabsf(myC) <= 1e18f));
-        }
-        if (ONE_EX2 && one_ex2) {
-#pragma unroll
-          for (int cc = 0; cc < 8; ++cc) {
-            const float4 ca = crec[2 * cc];
-            const float s = sv[cc];
-            float e1;
-            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(s, NPAIR_LOG2E_F, -r_m2)));
-            const float key = s * p.sgn_n;
-            const float cj = __shfl_sync(0xffffffffu, myC, cc);
-            const float a = (key <= r_tn) ? r_cT : 0.f;
-            const float b = (key <= ca.y) ? r_R * cj : 0.f;
-            g[cc] = e1 * (a + b);
-            any_same |= (ca.w == r_lab);
-          }
-        } else
 #pragma unroll
         for (int cc = 0; cc < 8; ++cc) {
           const float4 ca = crec[2 * cc];        // {m2, thr_n, cT, label}: everything a diff-label pair needs

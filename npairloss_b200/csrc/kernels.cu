@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ x,
   uint16_t p[8][3];
   float v[8];
   const bool rowok = n < N;
-  if (rowok && d + 7 < D && (D & 3) == 0) {
+  if (rowok && d + 7 < D && (D & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {   // 16-byte loads need an aligned base
     const float4 a = *reinterpret_cast<const float4*>(x + static_cast<long long>(n) * D + d);
     const float4 b4 = *reinterpret_cast<const float4*>(x + static_cast<long long>(n) * D + d + 4);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b4.x; v[5] = b4.y; v[6] = b4.z; v[7] = b4.w;
@@ -325,8 +325,8 @@ __global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ x,
   // D is ragged: the excess elements are zeros (v = 0 above) and lie beyond the TMA extent anyway
   if (rowok && d < Dp) {
     const long long ps = static_cast<long long>(N) * ldXs;
-#pragma unroll
     if (Xs)      // NULL when the similarity GEMM reads the K-concatenated operands below
+#pragma unroll
       for (int s = 0; s < NS; ++s) *reinterpret_cast<uint4*>(Xs + s * ps + static_cast<long long>(n) * ldXs + d) = pk[s];
     // K-concatenated operands of the bitwise-symmetric similarity GEMM (one MMA pass over K_cat):
     //   fp16x2 : A row = [ hi | hi(8) lo(8) ... ]                         B row = [ hi | lo(8) hi(8) ... ]                  K_cat = 3*Dp
@@ -842,250 +842,8 @@ void launch_lse_rows(const float* S, long long ldS, int Q, int N, const float* l
   count_launch();
 }
 
-// --------------------------------------------------------------------------------------------
-// Tile row pass (world == 1 only; opt-in with NPAIR_LSE_TILES=1 until measured -- written in round 1 after the GPU budget ran
-// out).  S = X X^T is bitwise symmetric, so the row pass reads only the 128 x 128 tiles of the UPPER triangle (half the
-// HBM bytes of lse_rows_kernel): tile (I, J) is loaded once by TMA and walked twice from shared memory -- row-wise for the
-// rows of block I ("direct") and column-wise for the rows of block J ("transposed", I < J).  Every (row, column-block) pair
-// gets exactly one partial {A, T, count}; the CTA that delivers the last partial of a 128-row block sums that block's
-// partials in slot order (deterministic) and runs the per-row finalisation of lse_rows_kernel; the CTA that finalises the
-// last block reduces the tops.  Same outputs as lse_rows_kernel (ra.A/T/logv/hits/rowscal, tops), other summation order.
-//   row_prep_kernel   one warp per row: {m2, thr_n', label, retrieval cut | thr_p', cnt_same} -> prep[Q][8]
-//   lse_tiles_kernel  256 threads per tile, 3 CTAs per SM (66 KB smem)
-// --------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) row_prep_kernel(int Q, const float* __restrict__ lab_rows, MiningParams mp, RowArrays ra,
-                                                       const BlockScalars* __restrict__ bs, float* __restrict__ prep) {
-  const int lane = threadIdx.x & 31;
-  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (i >= Q) return;
-  const float li = lab_rows[i];
-  const float max_all = ord2f(ra.st_maxall[i]);
-  const float m2 = max_all * NPAIR_LOG2E;
-  const float posi = mp.ap_region == REGION_GLOBAL ? bs->posi_global : ra.posi_thr[i];
-  const float nega = mp.an_region == REGION_GLOBAL ? bs->nega_global : ra.nega_thr[i];
-  const float tp = posi + mp.margin_ident;                    // fp32 add as in .cu:81
-  const float tn = nega + mp.margin_diff;                     // .cu:102
-  const float thr_p = ap_thr(tp, mp.ap_method), thr_n = an_thr(tn, mp.an_method);
-  const int cs = ra.cnt_same[i];
-  const float scut = cs > 0 ? retrieval_cut(ord2f(ra.st_maxw[i]), max_all, lane) : INFINITY;
-  __syncwarp();
-  if (lane == 0) {
-    ra.posi_thr[i] = posi; ra.nega_thr[i] = nega;             // kept per row for inspection (npair_debug_read)
-    float4* rec = reinterpret_cast<float4*>(prep + 8ll * i);
-    rec[0] = make_float4(m2, thr_n, li, scut);
-    rec[1] = make_float4(thr_p, __int_as_float(cs), 0.f, 0.f);
-  }
-}
-
-struct TileRow { float m2, thr_n, li, scut, thr_p; };
-
-// four consecutive pairs of one row against four labels; `valid` / `skip` handle ragged edges and the self pair
-__device__ __forceinline__ void tile_group4(const float (&vv)[4], const float (&ll)[4], const TileRow& r, float sgn_p, float sgn_n,
-                                            bool all_plain, int first_idx, int limit, int self_idx, float& A, float& T, int& c) {
-  if (all_plain && ll[0] != r.li && ll[1] != r.li && ll[2] != r.li && ll[3] != r.li) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      c += (vv[q] >= r.scut) ? 1 : 0;
-      const float e = fast_exp_m2(vv[q], r.m2);
-      if (vv[q] * sgn_n <= r.thr_n) T += e;
-    }
-  } else if (all_plain) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) lse_elem(vv[q], ll[q], r.li, r.scut, r.m2, sgn_p, r.thr_p, sgn_n, r.thr_n, A, T, c);
-  } else {
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      if (first_idx + q < limit && first_idx + q != self_idx) lse_elem(vv[q], ll[q], r.li, r.scut, r.m2, sgn_p, r.thr_p, sgn_n, r.thr_n, A, T, c);
-  }
-}
-
-// per-row finalisation shared with lse_rows_kernel's epilogue (.cu:162-169, :173-206, :410-415)
-__device__ __forceinline__ void tile_finish_row(int i, int Q, int N, float A, float T, int c, const float* __restrict__ prep, RowArrays ra) {
-  const float4 p0 = __ldcg(reinterpret_cast<const float4*>(prep + 8ll * i));
-  const float4 p1 = __ldcg(reinterpret_cast<const float4*>(prep + 8ll * i) + 1);
-  const int cs = __float_as_int(p1.y);
-  ra.A[i] = A; ra.T[i] = T;
-  ra.logv[i] = (A == 0.f || T == 0.f) ? 0.f : logf(A / T);
-  const int lim = N - 2;
-  ra.hits[i] = (cs > 0 && c <= min(1, lim)) ? 1 : 0;
-  ra.hits[Q + i] = (cs > 0 && c <= min(5, lim)) ? 1 : 0;
-  ra.hits[2 * Q + i] = (cs > 0 && c <= min(10, lim)) ? 1 : 0;
-  const float invA = A == 0.f ? 0.f : 1.f / A;
-  const float invT = T == 0.f ? 0.f : 1.f / T;
-  float4* rec = reinterpret_cast<float4*>(ra.rowscal + 8ll * i);
-  rec[0] = make_float4(p0.x, p0.y, invT, p0.z);               // {m2, thr_n', 1/T, label}
-  rec[1] = make_float4(p1.x, invT - invA, 0.f, 0.f);          // {thr_p', 1/T - 1/A}
-}
-
-__global__ void __launch_bounds__(256, 3)
-lse_tiles_kernel(const __grid_constant__ CUtensorMap tmS, const int2* __restrict__ tiles, int Q, int N, const float* __restrict__ lab_rows,
-                 const float* __restrict__ lab_cols, int self_offset, int symmetric,
-                 const float* __restrict__ prep, float sgn_p, float sgn_n, float4* __restrict__ part /*[TB][Qpad]*/, int Qpad,
-                 int* __restrict__ blk_cnt /*[row blocks]*/, RowArrays ra, BlockScalars* bs, int num_tops, float* __restrict__ tops) {
-  // symmetric = 1: world == 1, tiles = upper triangle, both walks (see above).  symmetric = 0: any world, tiles = every
-  // (row block, column block) of the Q x N block, direct walk only -- the same TMA-fed tile pass without the halved traffic.
-  extern __shared__ uint8_t tl_smem_raw[];
-  uint8_t* tile = tl_smem_raw + ((1024u - (ptx::smem_u32(tl_smem_raw) & 1023u)) & 1023u);   // 4 boxes of 128 rows x 128 B, 128B-swizzled
-  float* labI = reinterpret_cast<float*>(tile + 65536);       // [128] labels of the tile's rows
-  float* labJ = labI + 128;                                    // [128] labels of the tile's columns
-  float* red = labJ + 128;                                     // [128][3] second half's partial sums
-  uint64_t* bar = reinterpret_cast<uint64_t*>(red + 384);
-  __shared__ int s_fin;
-  const int t = threadIdx.x;
-  const int2 ij = tiles[blockIdx.x];
-  const int I = ij.x, J = ij.y;
-  const int TB = (N + 127) / 128;                              // column blocks = partial slots per row = contributions per row block
-  const int RB = (Q + 127) / 128;                              // row blocks
-  if (t == 0) {
-    ptx::mbar_init(bar, 1);
-    ptx::fence_mbar_init();
-    ptx::mbar_arrive_expect_tx(bar, 65536);
-#pragma unroll
-    for (int b = 0; b < 4; ++b) ptx::tma_load_2d(tile + b * 16384, &tmS, bar, J * 128 + 32 * b, I * 128);
-  }
-  if (t < 128) labI[t] = (I * 128 + t < Q) ? lab_rows[I * 128 + t] : 0.f;
-  else labJ[t - 128] = (J * 128 + (t - 128) < N) ? lab_cols[J * 128 + (t - 128)] : 0.f;
-  const int x = t & 127, half = t >> 7;
-  // pass 1 row = I*128 + x, pass 2 "row" = J*128 + x
-  TileRow r1 = {0.f, -INFINITY, 0.f, INFINITY, -INFINITY}, r2 = r1;
-  const int gi = I * 128 + x, gj = J * 128 + x;
-  if (gi < Q) {
-    const float4 a = *reinterpret_cast<const float4*>(prep + 8ll * gi);
-    r1.m2 = a.x; r1.thr_n = a.y; r1.li = a.z; r1.scut = a.w; r1.thr_p = prep[8ll * gi + 4];
-  }
-  const bool walk2 = symmetric && I < J;                        // transposed walk for the rows of block J
-  if (walk2 && gj < Q) {
-    const float4 a = *reinterpret_cast<const float4*>(prep + 8ll * gj);
-    r2.m2 = a.x; r2.thr_n = a.y; r2.li = a.z; r2.scut = a.w; r2.thr_p = prep[8ll * gj + 4];
-  }
-  __syncthreads();                                             // labels + barrier init visible
-  ptx::mbar_wait(bar, 0);
-  // ------------------------------ pass 1: rows of block I against the columns of block J ------------------------------
-  {
-    float A = 0.f, T = 0.f; int c = 0;
-    if (gi < Q) {
-#pragma unroll 4
-      for (int g = 0; g < 16; ++g) {
-        const int co = half * 64 + 4 * g;                      // column inside the tile
-        const float4 v4 = *reinterpret_cast<const float4*>(tile + (co >> 5) * 16384 + x * 128 + ((((co & 31) >> 2) ^ (x & 7)) << 4));
-        const float4 l4 = *reinterpret_cast<const float4*>(labJ + co);
-        const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
-        const float ll[4] = {l4.x, l4.y, l4.z, l4.w};
-        const int j0 = J * 128 + co;
-        const int self_col = gi + self_offset;                   // global column of this row's self pair (.cu:54)
-        const bool plain = (j0 + 3 < N) && (self_col < j0 || self_col > j0 + 3);
-        tile_group4(vv, ll, r1, sgn_p, sgn_n, plain, j0, N, self_col, A, T, c);
-      }
-    }
-    if (half == 1) { red[3 * x] = A; red[3 * x + 1] = T; red[3 * x + 2] = __int_as_float(c); }
-    __syncthreads();
-    if (half == 0 && gi < Q)
-      part[static_cast<long long>(J) * Qpad + gi] = make_float4(A + red[3 * x], T + red[3 * x + 1], __int_as_float(c + __float_as_int(red[3 * x + 2])), 0.f);
-    __syncthreads();                                           // red is reused by pass 2
-  }
-  // ------------------------------ pass 2: rows of block J against the ROWS of block I (transposed walk) ------------------------------
-  if (walk2) {
-    float A = 0.f, T = 0.f; int c = 0;
-    if (gj < Q) {
-      const uint8_t* colbase = tile + (x >> 5) * 16384 + ((x & 3) << 2);
-      const int cw = (x & 31) >> 2;
-#pragma unroll 4
-      for (int g = 0; g < 16; ++g) {
-        const int r0 = half * 64 + 4 * g;                      // tile row of the first of four elements
-        float vv[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) vv[q] = *reinterpret_cast<const float*>(colbase + (r0 + q) * 128 + ((cw ^ ((r0 + q) & 7)) << 4));
-        const float4 l4 = *reinterpret_cast<const float4*>(labI + r0);
-        const float ll[4] = {l4.x, l4.y, l4.z, l4.w};
-        const int i0 = I * 128 + r0;
-        tile_group4(vv, ll, r2, sgn_p, sgn_n, i0 + 3 < Q, i0, Q, -1, A, T, c);
-      }
-    }
-    if (half == 1) { red[3 * x] = A; red[3 * x + 1] = T; red[3 * x + 2] = __int_as_float(c); }
-    __syncthreads();
-    if (half == 0 && gj < Q)
-      part[static_cast<long long>(I) * Qpad + gj] = make_float4(A + red[3 * x], T + red[3 * x + 1], __int_as_float(c + __float_as_int(red[3 * x + 2])), 0.f);
-  }
-  // ------------------------------ completion: last contributor of a row block finalises it ------------------------------
-  __threadfence();
-  __syncthreads();
-  if (t == 0) {
-    int fin = 0;
-    if (atomicAdd(&blk_cnt[I], 1) == TB - 1) fin |= 1;
-    if (walk2 && atomicAdd(&blk_cnt[J], 1) == TB - 1) fin |= 2;
-    s_fin = fin;
-  }
-  __syncthreads();
-  const int fin = s_fin;
-  if (fin == 0) return;
-  __threadfence();
-  int finished_blocks = 0;
-#pragma unroll 1
-  for (int which = 0; which < 2; ++which) {
-    if (!(fin & (1 << which))) continue;
-    const int X = which == 0 ? I : J;
-    ++finished_blocks;
-    const int row = X * 128 + t;
-    if (t < 128 && row < Q) {
-      float A = 0.f, T = 0.f; int c = 0;
-      for (int y = 0; y < TB; ++y) {                           // fixed slot order -> deterministic
-        const float4 p4 = __ldcg(&part[static_cast<long long>(y) * Qpad + row]);
-        A += p4.x; T += p4.y; c += __float_as_int(p4.z);
-      }
-      tile_finish_row(row, Q, N, A, T, c, prep, ra);
-    }
-  }
-  __threadfence();
-  __syncthreads();
-  if (t == 0) s_fin = (atomicAdd(&bs->ticket, static_cast<unsigned>(finished_blocks)) + finished_blocks == static_cast<unsigned>(RB)) ? 1 : 0;
-  __syncthreads();
-  if (!s_fin) return;
-  // ------------------------------ the very last CTA: tops (same reduction as lse_rows_kernel's last block) ------------------------------
-  __threadfence();
-  __shared__ double s_l[8];
-  __shared__ int s_h[3][8];
-  const int lane = t & 31;
-  double ls = 0.0; int h[3] = {0, 0, 0};
-  for (int r = t; r < Q; r += blockDim.x) {
-    ls += __ldcg(&ra.logv[r]);
-    h[0] += __ldcg(&ra.hits[r]); h[1] += __ldcg(&ra.hits[Q + r]); h[2] += __ldcg(&ra.hits[2 * Q + r]);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    ls += __shfl_xor_sync(0xffffffffu, ls, o);
-    h[0] += __shfl_xor_sync(0xffffffffu, h[0], o); h[1] += __shfl_xor_sync(0xffffffffu, h[1], o); h[2] += __shfl_xor_sync(0xffffffffu, h[2], o);
-  }
-  const int w = t >> 5;
-  if (lane == 0) { s_l[w] = ls; s_h[0][w] = h[0]; s_h[1][w] = h[1]; s_h[2][w] = h[2]; }
-  __syncthreads();
-  for (int b = t; b < RB; b += blockDim.x) blk_cnt[b] = 0;    // ready for the next step
-  if (t == 0) {
-    ls = 0.0; h[0] = h[1] = h[2] = 0;
-    for (int k = 0; k < (blockDim.x >> 5); ++k) { ls += s_l[k]; h[0] += s_h[0][k]; h[1] += s_h[1][k]; h[2] += s_h[2][k]; }
-    float out[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-    out[0] = static_cast<float>(ls) / static_cast<float>(-Q);                       // .cu:384-385
-    for (int k = 1; k <= num_tops - 2 && k <= 3; ++k) out[k] = static_cast<float>(h[k - 1]) / static_cast<float>(Q);   // .cu:205
-    out[num_tops - 1] = bs->asum / static_cast<float>(Q);                           // .cu:400-401 (always the LAST top)
-    for (int k = 0; k < 5; ++k) tops[k] = out[k];
-    reinterpret_cast<int*>(tops)[5] = bs->err;
-    bs->ticket = 0;
-    __threadfence_system();
-  }
-}
-
-void launch_lse_tiles(const CUtensorMap& tmS, const int2* tiles, int num_tiles, int Q, int N, const float* lab_rows, const float* lab_cols,
-                      int self_offset, int symmetric, MiningParams mp, RowArrays ra,
-                      BlockScalars* bs, float* prep, float4* part, int Qpad, int* blk_cnt, int num_tops, float* tops_dev, cudaStream_t st) {
-  row_prep_kernel<<<(Q + 7) / 8, 256, 0, st>>>(Q, lab_rows, mp, ra, bs, prep);
-  count_launch();
-  constexpr int SMEM = 65536 + 128 * 4 * 2 + 384 * 4 + 16 + 1024;
-  static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(lse_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); attr_set = true; }
-  lse_tiles_kernel<<<num_tiles, 256, SMEM, st>>>(tmS, tiles, Q, N, lab_rows, lab_cols, self_offset, symmetric, prep, ap_sign(mp.ap_method), an_sign(mp.an_method), part, Qpad,
-                                                 blk_cnt, ra, bs, num_tops, tops_dev);
-  count_launch();
-}
-
+// Measured and dropped (round 2, profiles/r02_experiments.md): a TMA-fed tile pass that walked only the upper triangle of the
+// symmetric S (half the HBM bytes) ran in 84 us against 80 us for lse_rows_kernel -- the pass is issue-bound, not byte-bound.
 // --------------------------------------------------------------------------------------------
 // Backward weight builder: replaces Get_Query_Diff_Part x3 (.cu:405-419, :438-446).  The reference
 // materialises W1,W2,W3 in fp32 and runs six GEMMs; here one pass over S produces the unit gradient

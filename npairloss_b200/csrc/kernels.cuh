@@ -81,11 +81,6 @@ void launch_global_select(const float* S, long long ldS, int Q, int N, const flo
 void launch_lse_rows(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
                      int self_offset, MiningParams mp, RowArrays ra, BlockScalars* bs, int num_tops, float* tops_dev /*[5]+err*/,
                      cudaStream_t st);
-// Tile row pass (world == 1, bitwise symmetric S; opt-in NPAIR_LSE_TILES=1): row_prep_kernel + lse_tiles_kernel, see kernels.cu
-void launch_lse_tiles(const CUtensorMap& tmS /*fp32 S, box {32 cols, 128 rows}, 128B swizzle*/, const int2* tiles, int num_tiles, int Q, int N,
-                      const float* lab_rows, const float* lab_cols, int self_offset, int symmetric /*1: upper-triangle tiles, both walks*/,
-                      MiningParams mp, RowArrays ra, BlockScalars* bs, float* prep /*[Q][8]*/, float4* part /*[ceil(N/128)][Qpad]*/,
-                      int Qpad, int* blk_cnt /*[ceil(Q/128)], zero*/, int num_tops, float* tops_dev, cudaStream_t st);
 // mode: BW_SPLIT (world > 1, reduce-scatter form: H and HT), BW_SYM (world == 1), BW_ROWSCAL (world > 1, row-scalar
 // exchange: rs_total = all-gathered [world][5][Q] row scalars)
 enum { BW_SPLIT = 0, BW_SYM = 1, BW_ROWSCAL = 2 };

@@ -1,0 +1,21 @@
+"""Diagnostic (not a test): gradient / loss error of the CUDA path against the oracle (on the GPU's own S) as the database grows.
+   python tests/diag_grad_error.py [D]"""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import numpy as np
+from npairloss_b200 import capi, synth
+from oracle import oracle_lib as o
+from gpu_harness import gpu_step_world
+D = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+for B in (1024, 2048, 4096, 8192):
+    x, lab = synth.make_inputs(B, D, 20171225 + 5, noise=2.5)
+    for prec, name in ((2, "fp16x2"), (0, "bf16x3")):
+        g = gpu_step_world(x, lab, B, 1, synth.USAGE_MINING, prec, capi.GEMM_TCGEN05)
+        t0 = time.time()
+        cfg = o.make_config(B, D, faithful_sorts=0, **synth.USAGE_MINING)
+        tops_o, dx_o = o.step_world(x, lab, cfg, 1.0, S_inject_all=g["S"])
+        rel = np.linalg.norm(g["dx"] - dx_o) / np.linalg.norm(dx_o)
+        proj = float((g["dx"].astype(np.float64) * dx_o).sum() / (dx_o.astype(np.float64) ** 2).sum())
+        print(f"B={B} D={D} {name}: loss_rel={abs(g['tops'][0,0]-tops_o[0,0])/abs(tops_o[0,0]):.2e} grad_rel={rel:.2e} shrink={proj-1:+.2e} "
+              f"tops_gpu={g['tops'][0,1:4]} tops_o={tops_o[0,1:4]} oracle_s={time.time()-t0:.1f}", flush=True)
