@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NPAIR_ABI_VERSION 1
+#define NPAIR_ABI_VERSION 2
 
 /* caffe.proto:8-11 */
 enum { NPAIR_GLOBAL = 0, NPAIR_LOCAL = 1 };
@@ -74,17 +74,36 @@ typedef struct {
   int32_t sim_precision; /* NPAIR_PREC_*  */
   int32_t gemm_backend;  /* NPAIR_GEMM_*  */
   int32_t device;        /* CUDA device ordinal; -1 = current device */
-  int32_t bwd_exchange;  /* world > 1 only.  NPAIR_BWD_AUTO: row-scalar exchange when the operand format gives a bitwise
-                            symmetric similarity GEMM (fp16x2, bf16), else reduce-scatter.  NPAIR_BWD_REDUCE_SCATTER forces the
-                            reference's form (all-reduce of the N x D transposed product, .cu:455-497). */
+  int32_t bwd_exchange;  /* world > 1 only.  NPAIR_BWD_AUTO: row-record exchange (every operand format is laid out so that the
+                            similarity GEMM is bitwise symmetric; npair_create verifies that on the device and falls back to the
+                            reduce-scatter form if the check fails).  NPAIR_BWD_REDUCE_SCATTER forces the reference's form
+                            (all-reduce of the N x D transposed product, .cu:455-497). */
+  /* ---- ABI 2: extensions beyond the reference layer (all 0 = reference behaviour) ---- */
+  int32_t global_scope;    /* 1: GLOBAL-region mining lists and the loss / gradient normaliser span the WORLD's N x N pairs, so the
+                              result does not depend on how the batch is sharded.  0: per rank, as the reference
+                              (.cu:225-268 builds the lists from the rank's own Q x N block, :385/:427 divide by Q). */
+  int32_t normalize_input; /* 1: the L2Normalize producer layer (usage/def.prototxt:115-120) is fused in: bottom[0] holds raw
+                              embeddings, the layer works on x / ||x||_2 and returns the gradient w.r.t. the raw embeddings. */
+  int32_t grad_chunk_cols; /* accumulation chunk of the gradient GEMM in database columns (multiple of 32); 0 = default (1024).
+                              The tensor core truncates its fp32 accumulator on every MMA; chunks bound that error, see DESIGN 5 */
+  int32_t flags;           /* NPAIR_FLAG_* */
 } npair_config;
+
+/* tuning / diagnostic switches (were environment variables in ABI 1) */
+enum {
+  NPAIR_FLAG_NO_FUSED_GRAD = 1,   /* materialise the gradient weights and run the plain split GEMM (cross-check path)        */
+  NPAIR_FLAG_SIM_1CTA = 2,        /* similarity GEMM without CTA pairs                                                       */
+  NPAIR_FLAG_GRAD_1CTA = 4,       /* gradient GEMM without CTA pairs                                                         */
+  NPAIR_FLAG_NCCL_RECORDS = 8,    /* world > 1: exchange the row records with ncclAllGather instead of NVLink peer stores    */
+  NPAIR_FLAG_NCCL_FEATURES = 16   /* world > 1: gather the features with ncclAllGather instead of NVLink peer loads          */
+};
 
 enum { NPAIR_BWD_AUTO = 0, NPAIR_BWD_REDUCE_SCATTER = 1 };
 /* what a context actually uses: 0 = single rank (symmetric tiles), 1 = reduce-scatter, 2 = row-scalar exchange */
 enum { NPAIR_BWDMODE_SINGLE = 0, NPAIR_BWDMODE_REDUCE_SCATTER = 1, NPAIR_BWDMODE_ROW_SCALARS = 2 };
 int npair_bwd_exchange_mode(const npair_ctx* ctx);
 
-/* fills proto defaults (caffe.proto:4-7,19-22), world=1, rank=0, num_tops=5, fp32-faithful fp16x2, tcgen05 */
+/* fills proto defaults (caffe.proto:4-7,19-22), world=1, rank=0, num_tops=5, fp32-faithful fp16x2, tcgen05, extensions off */
 void npair_config_default(npair_config* cfg, int32_t Q, int32_t D);
 
 /* Workspace the context will allocate on the device for this configuration (bytes). */
@@ -137,6 +156,13 @@ int npair_backward_partial(npair_ctx* ctx, float loss_weight, float* d_local_hal
  *   npair_backward_gathered : d_rs_total = [N][8] records of all ranks in global row order; writes the complete bottom.diff */
 int npair_row_scalars(npair_ctx* ctx, float* d_out_8Q, void* stream);
 int npair_backward_gathered(npair_ctx* ctx, float loss_weight, const float* d_rs_total, float* d_feat_diff, void* stream);
+
+/* The L2Normalize producer layer of the reference net (usage/def.prototxt:115-120; its source is not part of the reference tree):
+ * y[r][:] = x[r][:] / ||x[r][:]||_2 (a zero row stays zero), and its backward dx = (dy - y (y . dy)) / ||x||.  Stand-alone entry
+ * points for a host framework's own L2Normalize layer; npair_config.normalize_input = 1 runs the same kernels inside
+ * npair_forward / npair_backward.  d_inv_norm: rows floats (1 / ||x||, 0 for a zero row). */
+int npair_l2normalize_forward(const float* d_x, int rows, int dim, float* d_y, float* d_inv_norm, void* stream);
+int npair_l2normalize_backward(const float* d_y, const float* d_inv_norm, const float* d_dy, int rows, int dim, float* d_dx, void* stream);
 
 const char* npair_last_error(const npair_ctx* ctx);   /* ctx may be NULL: last create() error of this thread */
 const char* npair_version(void);

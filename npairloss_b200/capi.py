@@ -21,12 +21,17 @@ class NpairConfig(C.Structure):
     _fields_ = [("Q", C.c_int32), ("D", C.c_int32), ("world", C.c_int32), ("rank", C.c_int32), ("num_tops", C.c_int32),
                 ("margin_ident", C.c_float), ("margin_diff", C.c_float), ("identsn", C.c_float), ("diffsn", C.c_float),
                 ("ap_region", C.c_int32), ("ap_method", C.c_int32), ("an_region", C.c_int32), ("an_method", C.c_int32),
-                ("sim_precision", C.c_int32), ("gemm_backend", C.c_int32), ("device", C.c_int32), ("bwd_exchange", C.c_int32)]
+                ("sim_precision", C.c_int32), ("gemm_backend", C.c_int32), ("device", C.c_int32), ("bwd_exchange", C.c_int32),
+                # ABI 2 extensions (0 = reference behaviour)
+                ("global_scope", C.c_int32), ("normalize_input", C.c_int32), ("grad_chunk_cols", C.c_int32), ("flags", C.c_int32)]
+
+
+FLAG_NO_FUSED_GRAD, FLAG_SIM_1CTA, FLAG_GRAD_1CTA, FLAG_NCCL_RECORDS, FLAG_NCCL_FEATURES = 1, 2, 4, 8, 16
 
 
 EXPORTS = ["npair_config_default", "npair_workspace_bytes", "npair_nccl_unique_id", "npair_create", "npair_create_with_comm",
            "npair_destroy", "npair_forward", "npair_backward", "npair_forward_backward", "npair_forward_gathered", "npair_backward_partial", "npair_bwd_exchange_mode", "npair_row_scalars", "npair_backward_gathered", "npair_profile_enable", "npair_profile_read", "npair_kernel_launches", "npair_util_f64_to_f32", "npair_util_f32_to_f64", "npair_last_error", "npair_version", "npair_debug_read",
-           "npair_debug_gemm"]
+           "npair_debug_gemm", "npair_l2normalize_forward", "npair_l2normalize_backward"]
 
 _LIB = None
 
@@ -75,15 +80,19 @@ def lib():
         L.npair_version.restype = C.c_char_p
         L.npair_debug_read.argtypes = [vp, C.c_int, fp, C.c_size_t]
         L.npair_debug_gemm.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
+        L.npair_l2normalize_forward.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
+        L.npair_l2normalize_backward.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp]
         _LIB = L
     return _LIB
 
 
 def make_config(Q, D, world=1, rank=0, num_tops=5, margin_ident=0.0, margin_diff=0.0, identsn=-1.0, diffsn=-1.0,
                 ap_region=LOCAL, ap_method=RAND, an_region=LOCAL, an_method=RAND, sim_precision=PREC_FP32_FP16X2,
-                gemm_backend=GEMM_TCGEN05, device=-1, bwd_exchange=0) -> NpairConfig:
+                gemm_backend=GEMM_TCGEN05, device=-1, bwd_exchange=0, global_scope=0, normalize_input=0, grad_chunk_cols=0,
+                flags=0) -> NpairConfig:
     return NpairConfig(Q, D, world, rank, num_tops, margin_ident, margin_diff, identsn, diffsn, ap_region, ap_method,
-                       an_region, an_method, sim_precision, gemm_backend, device, bwd_exchange)
+                       an_region, an_method, sim_precision, gemm_backend, device, bwd_exchange, global_scope, normalize_input,
+                       grad_chunk_cols, flags)
 
 
 def nccl_unique_id() -> bytes:
@@ -207,3 +216,25 @@ def debug_gemm(precision, backend, A, B):
     if rc:
         raise NpairError(rc, lib().npair_last_error(None).decode())
     return Cout
+
+
+def l2normalize_forward(x):
+    """y = x / ||x||_2 per row (npair_l2normalize_forward); returns (y, inv_norm) as CUDA tensors."""
+    import torch
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 2
+    y = torch.empty_like(x)
+    inv = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+    rc = lib().npair_l2normalize_forward(x.data_ptr(), x.shape[0], x.shape[1], y.data_ptr(), inv.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    if rc:
+        raise NpairError(rc, lib().npair_last_error(None).decode())
+    return y, inv
+
+
+def l2normalize_backward(y, inv, dy):
+    import torch
+    dx = torch.empty_like(dy)
+    rc = lib().npair_l2normalize_backward(y.data_ptr(), inv.data_ptr(), dy.data_ptr(), y.shape[0], y.shape[1], dx.data_ptr(),
+                                          torch.cuda.current_stream().cuda_stream)
+    if rc:
+        raise NpairError(rc, lib().npair_last_error(None).decode())
+    return dx

@@ -396,6 +396,8 @@ struct npair_ctx {
   int n_sym_tiles2 = 0;
   CUtensorMap tm_fB2;            // 128-row boxes of X^T for the CTA-pair gradient kernel
   bool grad_pair = false;        // fused gradient kernel runs in CTA-pair mode
+  float *Ynorm = nullptr, *dY = nullptr, *inv_norm = nullptr;   // normalize_input: x / ||x||, gradient w.r.t. it, 1 / ||x||
+  int grad_chunk_kb = 32;        // accumulation chunk of the gradient GEMM in 32-column K blocks (grad_fused.cuh); 0 = unchunked
   CUtensorMap tm_fB, tm_fS;      // fused gradient kernel: X^T pieces with 32-wide K boxes, 128-row fp32 boxes of S
   bool fused_grad = false;
   bool rs_gathered = false;
@@ -417,7 +419,8 @@ struct npair_ctx {
   RowArrays ra;
   BlockScalars* bs = nullptr;
   float* partial = nullptr;
-  unsigned long long* ghist = nullptr;
+  unsigned long long* ghist = nullptr;   // [2][2048] 64-bit digit counts of the GLOBAL radix select
+  uint32_t* gcand = nullptr; unsigned int gcand_cap = 0;   // [2][cap] compacted candidates of the GLOBAL radix select
   float* tops_pinned = nullptr;  // host-mapped: 5 tops + err(int) + inv_scale
   float* tops_dev = nullptr;
   CUtensorMap tm_simA, tm_simB, tm_S, tm_b1A, tm_b1B, tm_b2A, tm_b2B;
@@ -425,6 +428,7 @@ struct npair_ctx {
   void* comm = nullptr; bool own_comm = false;
   // per-step state
   const float* cur_feat = nullptr; const float* cur_label = nullptr;
+  const float* y_local = nullptr;   // normalize_input: this rank's normalised rows
   const float *x_total = nullptr, *lab_total = nullptr;
   bool fwd_done = false;
   cudaStream_t last_stream = nullptr;
@@ -456,6 +460,7 @@ struct PhaseTimer {
     }                                                                                                    \
   } while (0)
 
+static inline bool is_rel_cfg(int m) { return m == NPAIR_RELATIVE_HARD || m == NPAIR_RELATIVE_EASY; }
 static int validate(const npair_config* c, std::string* err) {
   if (!c) { *err = "null config"; return NPAIR_E_ARG; }
   if (c->Q < 1 || c->D < 1) { *err = "Q and D must be >= 1"; return NPAIR_E_ARG; }
@@ -467,6 +472,8 @@ static int validate(const npair_config* c, std::string* err) {
   if (c->gemm_backend < 0 || c->gemm_backend > 1) { *err = "bad gemm_backend"; return NPAIR_E_ARG; }
   if (c->bwd_exchange < 0 || c->bwd_exchange > 1) { *err = "bad bwd_exchange"; return NPAIR_E_ARG; }
   if (static_cast<long long>(c->Q) * c->world > 0x7fffffffLL) { *err = "N = Q*world exceeds int32"; return NPAIR_E_ARG; }
+  if (c->global_scope < 0 || c->global_scope > 1 || c->normalize_input < 0 || c->normalize_input > 1) { *err = "global_scope / normalize_input must be 0 or 1"; return NPAIR_E_ARG; }
+  if (c->grad_chunk_cols > 0 && (c->grad_chunk_cols & 31)) { *err = "grad_chunk_cols must be a multiple of 32"; return NPAIR_E_ARG; }
   return NPAIR_OK;
 }
 
@@ -487,6 +494,12 @@ static Sizes sizes_of(const npair_config* c) {
   if (!fused) t += 2ull * s.ns * c->Q * s.Np;                                       // materialised gradient weights
   if (rs) { t += 2ull * s.ns * c->D * s.Qp + 2ull * s.ns * s.N * s.Qp + sizeof(float) * s.N * c->D; }
   if (c->world > 1 && !rs) t += sizeof(float) * 8ull * s.N;                         // gathered row records
+  if (c->normalize_input) t += sizeof(float) * (2ull * c->Q * c->D + c->Q) + (c->world > 1 ? 0 : 0);   // y, dy, 1/||x||
+  if (tc) {                                                                         // split-K partials of the gradient GEMM
+    const int tiles = ((c->Q + 127) / 128) * ((c->D + 255) / 256);
+    int smax = 148 / (tiles > 0 ? tiles : 1); if (smax > 16) smax = 16;
+    if (smax > 1) t += sizeof(float) * static_cast<size_t>(smax) * c->Q * c->D;
+  }
   t += 4ull * 21 * c->Q + 65536;                                                    // row arrays, records, scalars
   s.total = t;
   return s;
@@ -503,6 +516,7 @@ void npair_config_default(npair_config* c, int32_t Q, int32_t D) {
   c->margin_ident = 0.f; c->margin_diff = 0.f; c->identsn = -1.f; c->diffsn = -1.f;       // caffe.proto:4-7
   c->ap_region = NPAIR_LOCAL; c->ap_method = NPAIR_RAND; c->an_region = NPAIR_LOCAL; c->an_method = NPAIR_RAND;   // :19-22
   c->sim_precision = NPAIR_PREC_FP32_FP16X2; c->gemm_backend = NPAIR_GEMM_TCGEN05; c->device = -1; c->bwd_exchange = NPAIR_BWD_AUTO;
+  c->global_scope = 0; c->normalize_input = 0; c->grad_chunk_cols = 0; c->flags = 0;
 }
 
 size_t npair_workspace_bytes(const npair_config* cfg) {
@@ -531,7 +545,7 @@ void npair_destroy(npair_ctx* c) {
   cudaFree(c->p2p_buf); cudaFree(c->p2p_flags); cudaFree(c->p2p_peer_buf); cudaFree(c->p2p_peer_flags); cudaFree(c->p2p_ticket);
   if (c->comm && c->own_comm) { NcclApi* api = nccl_api(); if (api->CommDestroy) api->CommDestroy(c->comm); }
   cudaFree(c->Xtot_buf); cudaFree(c->labtot_buf); cudaFree(c->S); cudaFree(c->Xs); cudaFree(c->XsT); cudaFree(c->XlT);
-  cudaFree(c->H); cudaFree(c->HT); cudaFree(c->OUT2); cudaFree(c->part); cudaFree(c->sym_tiles); cudaFree(c->sym_tiles2); cudaFree(c->XcatA); cudaFree(c->XcatB); cudaFree(c->rs_total); cudaFree(c->row_block); cudaFree(c->bs); cudaFree(c->partial); cudaFree(c->ghist);
+  cudaFree(c->H); cudaFree(c->HT); cudaFree(c->OUT2); cudaFree(c->part); cudaFree(c->sym_tiles); cudaFree(c->sym_tiles2); cudaFree(c->XcatA); cudaFree(c->XcatB); cudaFree(c->rs_total); cudaFree(c->row_block); cudaFree(c->bs); cudaFree(c->partial); cudaFree(c->ghist); cudaFree(c->gcand); cudaFree(c->Ynorm); cudaFree(c->dY); cudaFree(c->inv_norm);
   if (c->tops_pinned) cudaFreeHost(c->tops_pinned);
   if (c->ev_made) for (int i = 0; i < NPAIR_PROF_PHASES; ++i) { cudaEventDestroy(c->ev[i][0]); cudaEventDestroy(c->ev[i][1]); }
   delete c;
@@ -576,6 +590,11 @@ static int create_impl(const npair_config* cfg, const void* id128, void* ext_com
     CREATE_TRY(cudaMalloc(&c->Xtot_buf, sizeof(float) * static_cast<size_t>(N) * D));
     CREATE_TRY(cudaMalloc(&c->labtot_buf, sizeof(float) * N));
   }
+  if (cfg->normalize_input) {
+    CREATE_TRY(cudaMalloc(&c->Ynorm, sizeof(float) * static_cast<size_t>(Q) * D));
+    CREATE_TRY(cudaMalloc(&c->dY, sizeof(float) * static_cast<size_t>(Q) * D));
+    CREATE_TRY(cudaMalloc(&c->inv_norm, sizeof(float) * Q));
+  }
   CREATE_TRY(cudaMalloc(&c->S, sizeof(float) * static_cast<size_t>(Q) * c->ldS));
   CREATE_TRY(cudaMemset(c->S, 0, sizeof(float) * static_cast<size_t>(Q) * c->ldS));
   CREATE_TRY(cudaMalloc(&c->Xs, 2ull * ns * N * c->Dp));
@@ -586,7 +605,7 @@ static int create_impl(const npair_config* cfg, const void* id128, void* ext_com
   // (reduce-scatter exchange, SIMT cross-check backend, NPAIR_NO_FUSED_GRAD)
   {
     const bool multi_rs = c->world > 1 && cfg->bwd_exchange != NPAIR_BWD_AUTO;
-    c->fused_grad = cfg->gemm_backend == NPAIR_GEMM_TCGEN05 && !multi_rs && !getenv("NPAIR_NO_FUSED_GRAD");
+    c->fused_grad = cfg->gemm_backend == NPAIR_GEMM_TCGEN05 && !multi_rs && !(cfg->flags & NPAIR_FLAG_NO_FUSED_GRAD);
   }
   if (!c->fused_grad) {
     CREATE_TRY(cudaMalloc(&c->H, 2ull * ns * Q * c->Np));
@@ -635,8 +654,19 @@ static int create_impl(const npair_config* cfg, const void* id128, void* ext_com
   CREATE_TRY(cudaMalloc(&c->bs, sizeof(BlockScalars)));
   CREATE_TRY(cudaMemset(c->bs, 0, sizeof(BlockScalars)));
   CREATE_TRY(cudaMalloc(&c->partial, sizeof(float) * 2048));
-  CREATE_TRY(cudaMalloc(&c->ghist, sizeof(unsigned long long) * 2048));
-  CREATE_TRY(cudaMemset(c->ghist, 0, sizeof(unsigned long long) * 2048));
+  CREATE_TRY(cudaMalloc(&c->ghist, sizeof(unsigned long long) * 4096));
+  CREATE_TRY(cudaMemset(c->ghist, 0, sizeof(unsigned long long) * 4096));
+  {
+    // GLOBAL relative select with a general SN: candidate lists of the chosen first-digit bucket (1/8 of the block, at most
+    // 32 M entries per side; a bigger bucket -- heavily tied data -- takes the three-sweep path)
+    const bool need = (is_rel_cfg(cfg->ap_method) && cfg->ap_region == NPAIR_GLOBAL) || (is_rel_cfg(cfg->an_method) && cfg->an_region == NPAIR_GLOBAL);
+    if (need) {
+      unsigned long long cap = static_cast<unsigned long long>(Q) * N / 8 + 4096;
+      if (cap > (32ull << 20)) cap = 32ull << 20;
+      c->gcand_cap = static_cast<unsigned int>(cap);
+      CREATE_TRY(cudaMalloc(&c->gcand, sizeof(uint32_t) * 2ull * cap));
+    }
+  }
   CREATE_TRY(cudaHostAlloc(&c->tops_pinned, 64, cudaHostAllocMapped));
   memset(c->tops_pinned, 0, 64);
   CREATE_TRY(cudaHostGetDevicePointer(&c->tops_dev, c->tops_pinned, 0));
@@ -689,10 +719,10 @@ static int create_impl(const npair_config* cfg, const void* id128, void* ext_com
   }
   {
     // CTA-pair similarity GEMM whenever there are at least two 128-row blocks (NPAIR_SIM_1CTA=1 keeps the single-CTA kernel)
-    const char* e1 = getenv("NPAIR_SIM_1CTA");
-    c->sim_pair = cfg->gemm_backend == NPAIR_GEMM_TCGEN05 && Q > 128 && !(e1 && e1[0] == '1');
-    const char* e2 = getenv("NPAIR_GRAD_1CTA");
-    c->grad_pair = c->fused_grad && Q > 128 && !(e2 && e2[0] == '1');
+    c->sim_pair = cfg->gemm_backend == NPAIR_GEMM_TCGEN05 && Q > 128 && !(cfg->flags & NPAIR_FLAG_SIM_1CTA);
+    c->grad_pair = c->fused_grad && Q > 128 && !(cfg->flags & NPAIR_FLAG_GRAD_1CTA);
+    c->grad_chunk_kb = cfg->grad_chunk_cols > 0 ? (cfg->grad_chunk_cols + 31) / 32 : 32;     // default: 1024 database columns
+    if (cfg->grad_chunk_cols < 0) c->grad_chunk_kb = 0;                                        // negative: one accumulator for the whole K range (diagnostic)
   }
   // ---- NCCL ----
   if (c->world > 1 && (id128 || ext_comm)) {
@@ -707,8 +737,8 @@ static int create_impl(const npair_config* cfg, const void* id128, void* ext_com
     }
   }
   {
-    const char* ep = getenv("NPAIR_P2P_RECORDS");
-    if (ep && ep[0] == '1' && c->comm && c->world > 1 && c->world <= 32 && c->bwd_mode == NPAIR_BWDMODE_ROW_SCALARS) {
+    const char* ep = getenv("NPAIR_P2P_RECORDS");     // A/B switch while the peer-memory exchange is being qualified
+    if (ep && ep[0] == '1' && !(cfg->flags & NPAIR_FLAG_NCCL_RECORDS) && c->comm && c->world > 1 && c->world <= 32 && c->bwd_mode == NPAIR_BWDMODE_ROW_SCALARS) {
       // map every rank's record buffer and flags into this process (cudaIpc over the NCCL bootstrap: one tiny all-gather of handles)
       NcclApi* api = nccl_api();
       const int W = c->world;
@@ -778,6 +808,11 @@ int npair_forward(npair_ctx* c, const float* d_feat, const float* d_label, float
   CUDA_TRY(c, cudaSetDevice(c->device));
   c->fwd_done = false; c->last_stream = st;
   const int Q = c->Q, D = c->D;
+  if (c->cfg.normalize_input) {               // fused L2Normalize producer (usage/def.prototxt:115-120): the layer works on x / ||x||
+    PhaseTimer pt(c, 1, st);
+    launch_l2norm_fwd(d_feat, Q, D, c->Ynorm, c->inv_norm, st);
+    d_feat = c->Ynorm; c->y_local = c->Ynorm;
+  }
   // ---- GatherFeatureAndLabel (.cu:17-43): one NCCL group, device to device over NVLink ----
   if (c->world > 1) {
     if (!c->comm) { c->err = "context was created without a communicator: use npair_forward_gathered"; return NPAIR_E_STATE; }
@@ -802,6 +837,14 @@ int npair_forward_gathered(npair_ctx* c, const float* d_feat_total, const float*
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CUDA_TRY(c, cudaSetDevice(c->device));
   c->fwd_done = false; c->last_stream = st;
+  if (c->cfg.normalize_input) {               // the gathered bottoms are raw embeddings: normalise all N rows (1 / ||x|| kept for the local ones)
+    PhaseTimer pt(c, 1, st);
+    float* dst = c->world > 1 ? c->Xtot_buf : c->Ynorm;
+    launch_l2norm_fwd(d_feat_total, c->N, c->D, dst, nullptr, st);
+    launch_l2norm_fwd(d_feat_total + static_cast<long long>(c->rank) * c->Q * c->D, c->Q, c->D, c->Ynorm, c->inv_norm, st);
+    c->y_local = c->Ynorm;
+    d_feat_total = dst;
+  }
   c->x_total = d_feat_total; c->lab_total = d_label_total;
   return forward_impl(c, d_feat_total + static_cast<long long>(c->rank) * c->Q * c->D, d_label_total + static_cast<long long>(c->rank) * c->Q, tops_host, st);
 }
@@ -849,19 +892,19 @@ static int forward_impl(npair_ctx* c, const float* d_feat, const float* d_label,
   {
   PhaseTimer pt(c, 3, st);
   launch_thresholds(c->ra, Q, N, mp, c->bs, c->partial, st);
-  if (is_rel_m(mp.ap_method) && !sn_max(mp.identsn)) {
-    if (mp.ap_region == NPAIR_LOCAL) launch_local_select(c->S, c->ldS, Q, N, d_label, c->lab_total, self_off, 0, mp.identsn, c->ra, c->bs, st);
-    else launch_global_select(c->S, c->ldS, Q, N, d_label, c->lab_total, self_off, 0, mp.identsn, c->ra, c->ghist, c->bs, st);
-  }
-  if (is_rel_m(mp.an_method) && !sn_max(mp.diffsn)) {
-    if (mp.an_region == NPAIR_LOCAL) launch_local_select(c->S, c->ldS, Q, N, d_label, c->lab_total, self_off, 1, mp.diffsn, c->ra, c->bs, st);
-    else launch_global_select(c->S, c->ldS, Q, N, d_label, c->lab_total, self_off, 1, mp.diffsn, c->ra, c->ghist, c->bs, st);
+  {
+    // general relative SN: radix selects; both sides of a region share one sweep of S
+    int local_mask = 0, global_mask = 0;
+    if (is_rel_m(mp.ap_method) && !sn_max(mp.identsn)) (mp.ap_region == NPAIR_LOCAL ? local_mask : global_mask) |= 1;
+    if (is_rel_m(mp.an_method) && !sn_max(mp.diffsn)) (mp.an_region == NPAIR_LOCAL ? local_mask : global_mask) |= 2;
+    if (global_mask) launch_global_select(c->S, c->ldS, Q, N, d_label, c->lab_total, self_off, global_mask, c->ra, c->ghist, c->gcand, c->gcand_cap, c->bs, c->sms, st);
+    if (local_mask) launch_local_select(c->S, c->ldS, Q, N, d_label, c->lab_total, self_off, local_mask, mp.identsn, mp.diffsn, c->ra, c->bs, c->sms, st);
   }
   }
   // ---- selection + counts + exp + masked sums + log + retrieval in one pass (.cu:343-398) ----
   {
     PhaseTimer pt(c, 4, st);
-    launch_lse_rows(c->S, c->ldS, Q, N, d_label, c->lab_total, self_off, mp, c->ra, c->bs, c->cfg.num_tops, c->tops_dev, st);
+    launch_lse_rows(c->S, c->ldS, Q, N, d_label, c->lab_total, self_off, mp, c->ra, c->bs, c->cfg.num_tops, c->tops_dev, c->world, st);
   }
   c->rs_gathered = false;
   // NPAIR_RS_GATHER_FWD=1 enqueues the row-record exchange here instead of at the start of npair_backward.  Measured on
@@ -876,7 +919,7 @@ static int forward_impl(npair_ctx* c, const float* d_feat, const float* d_label,
                                                 Q, N, static_cast<int>(c->p2p_epoch & 1u), c->p2p_epoch, c->p2p_ticket);
     count_launch();
   }
-  static const bool gather_in_fwd = [] { const char* e = getenv("NPAIR_RS_GATHER_FWD"); return e && e[0] == '1'; }();
+  const bool gather_in_fwd = false;      // measured slower on 8 GPUs (profiles/r01_bench_v6_n8.json): the gather stays in the backward
   if (gather_in_fwd && !c->p2p_rec && c->bwd_mode == NPAIR_BWDMODE_ROW_SCALARS && c->comm) {
     // The only backward exchange (8*Q floats per rank, replaces the N x D MPI_Allreduce of .cu:462-489) does not depend on
     // the loss weight, so it is enqueued here: it runs while the host wakes up from the synchronisation below.
@@ -897,7 +940,17 @@ static int forward_impl(npair_ctx* c, const float* d_feat, const float* d_label,
   return NPAIR_OK;
 }
 
-static int backward_impl(npair_ctx* c, float loss_weight, float* d_diff, float* d_total_ext, const float* d_rs_ext, cudaStream_t st);
+static int backward_core(npair_ctx* c, float loss_weight, float* d_diff, float* d_total_ext, const float* d_rs_ext, cudaStream_t st);
+// Backward_gpu (+ the projection of the fused L2Normalize producer: the kernels produce d loss / d y, the caller gets d loss / d x)
+static int backward_impl(npair_ctx* c, float loss_weight, float* d_diff, float* d_total_ext, const float* d_rs_ext, cudaStream_t st) {
+  if (!c->cfg.normalize_input) return backward_core(c, loss_weight, d_diff, d_total_ext, d_rs_ext, st);
+  if (d_total_ext) { c->err = "normalize_input: the partial (pre-all-reduce) backward is not available, its sum over ranks would have to be projected"; return NPAIR_E_STATE; }
+  const int rc = backward_core(c, loss_weight, c->dY, nullptr, d_rs_ext, st);
+  if (rc != NPAIR_OK) return rc;
+  PhaseTimer pt(c, 5, st);
+  launch_l2norm_bwd(c->y_local, c->inv_norm, c->dY, c->Q, c->D, d_diff, st);
+  return NPAIR_OK;
+}
 
 int npair_bwd_exchange_mode(const npair_ctx* c) { return c ? c->bwd_mode : NPAIR_E_ARG; }
 
@@ -973,7 +1026,7 @@ int npair_backward_gathered(npair_ctx* c, float loss_weight, const float* d_rs_t
   return backward_impl(c, loss_weight, d_diff, nullptr, d_rs_total, st);
 }
 
-static int backward_impl(npair_ctx* c, float loss_weight, float* d_diff, float* d_total_ext, const float* d_rs_ext, cudaStream_t st) {
+static int backward_core(npair_ctx* c, float loss_weight, float* d_diff, float* d_total_ext, const float* d_rs_ext, cudaStream_t st) {
   const int Q = c->Q, N = c->N, D = c->D;
   const MiningParams mp = mining_of(c->cfg);
   const int self_off = c->rank * Q;
@@ -1008,11 +1061,12 @@ static int backward_impl(npair_ctx* c, float loss_weight, float* d_diff, float* 
     fp.Q = Q; fp.N = N; fp.D = D; fp.num_kblocks = (N + 31) / 32;
     fp.tiles_m = (Q + 127) / 128; fp.tiles_n = (D + 255) / 256;
     fp.rowrec = c->ra.rowscal; fp.colrec = rs_total ? rs_total : c->ra.rowscal;
-    fp.self_offset = self_off; fp.inv_world = 1.f / static_cast<float>(c->world);
+    fp.self_offset = self_off; fp.inv_world = 1.f / static_cast<float>(c->world); fp.log2_world = log2f(static_cast<float>(c->world));
     fp.sgn_p = (mp.ap_method == M_EASY || mp.ap_method == M_RELATIVE_EASY) ? -1.f : 1.f;
     fp.sgn_n = (mp.an_method == M_HARD || mp.an_method == M_RELATIVE_HARD) ? -1.f : 1.f;
     fp.out = d_diff; fp.ldo = D; fp.alpha = 0.5f * lw_over_q; fp.beta = 0.f; fp.dev_scale = &c->bs->x_inv_scale;
     fp.part = c->part; fp.splits = 1; fp.kb_per_split = fp.num_kblocks;
+    fp.chunk_kb = c->grad_chunk_kb;
     if (c->grad_pair) fp.tiles_m = (fp.tiles_m + 1) / 2;       // 256-row pair blocks, one cluster of two CTAs each
     if (c->part) {
       const int tiles = fp.tiles_m * fp.tiles_n;
@@ -1186,6 +1240,17 @@ int npair_util_f32_to_f64(const float* d_src, double* d_dst, size_t n, void* str
   int nb = static_cast<int>((n + 255) / 256); if (nb > 148 * 16) nb = 148 * 16;
   cvt_f2d_kernel<<<nb, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_src, d_dst, n);
   count_launch();
+  return cudaGetLastError() == cudaSuccess ? NPAIR_OK : NPAIR_E_CUDA;
+}
+
+int npair_l2normalize_forward(const float* d_x, int rows, int dim, float* d_y, float* d_inv_norm, void* stream) {
+  if (!d_x || !d_y || rows < 1 || dim < 1) { g_create_err = "bad argument"; return NPAIR_E_ARG; }
+  launch_l2norm_fwd(d_x, rows, dim, d_y, d_inv_norm, static_cast<cudaStream_t>(stream));
+  return cudaGetLastError() == cudaSuccess ? NPAIR_OK : NPAIR_E_CUDA;
+}
+int npair_l2normalize_backward(const float* d_y, const float* d_inv_norm, const float* d_dy, int rows, int dim, float* d_dx, void* stream) {
+  if (!d_y || !d_inv_norm || !d_dy || !d_dx || rows < 1 || dim < 1) { g_create_err = "bad argument"; return NPAIR_E_ARG; }
+  launch_l2norm_bwd(d_y, d_inv_norm, d_dy, rows, dim, d_dx, static_cast<cudaStream_t>(stream));
   return cudaGetLastError() == cudaSuccess ? NPAIR_OK : NPAIR_E_CUDA;
 }
 

@@ -10,9 +10,19 @@
 // pass re-reads its operands from smem, so keeping A out of smem removes a third of that traffic).  Requires a bitwise
 // symmetric S (EPI_SIM_SYM tiles at world == 1, K-concatenated operands across ranks) -- see gemm_tcgen05.cuh / kernels.cu.
 //
-// CTA = 640 threads: warp 0 TMA producer (B pieces of X^T, S tile, column records), warp 1 MMA issuer, warp 2 TMEM
-// allocator, warps 4-19 weight producers (warp w: TMEM lanes 32*(w%4), 8 of the 32 K columns), which also run the
-// epilogue (TMEM -> alpha*acc -> out / split-K partial).  NCTA = 2: CTA-pair mode, see FusedCfg.
+// Chunked accumulation.  Every tcgen05.mma TRUNCATES the fp32 accumulator (measured: a bias of about -0.45 * 2^-24 * |acc| per
+// accumulating instruction, tests/diag_gemm_error.py), and this GEMM's K is the database size: at N = 8192 the 1536 instructions
+// per output element put the gradient 2.4e-5 (normwise) from the exact value -- over the 1e-5 parity bar, and growing with N.  The
+// K range is therefore cut into chunks of `chunk_kb` K blocks: each chunk accumulates in tensor memory from zero, the producer
+// warps drain it and ADD it to the output in fp32 round-to-nearest (first chunk: plain store, later chunks: red.global.add.v4.f32
+// by the same thread to the same addresses, hence in program order and deterministic).  The error is then bounded by the chunk
+// length (2.7e-6 measured at 32 K blocks) for any N.  The drain is done by four DEDICATED warps: when the weight producers did it
+// themselves every drain cost ~6 us (they idled until the tensor pipe had caught up, then the pipe idled until they had refilled
+// the ring; polling for the accumulator between K blocks was worse still: the producers are the critical path of this kernel).
+//
+// CTA = 704 threads: warp 0 TMA producer (B pieces of X^T, S tile, column records), warp 1 MMA issuer, warps 4-19 weight
+// producers (warp w: TMEM lanes 32*(w%4), 8 of the 32 K columns), warps 2, 3, 20, 21 accumulator drain (one per TMEM lane
+// quarter; warp 2 also allocates the tensor memory).  NCTA = 2: CTA-pair mode, see FusedCfg.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -32,12 +42,13 @@ struct FusedGradParams {
   int num_kblocks;              // ceil(N / 32)
   int tiles_m, tiles_n;         // 128-row blocks, 256-column tiles of D
   int splits, kb_per_split;     // split-K over the sample index (few row blocks when Q = B / world is small)
+  int chunk_kb;                 // accumulation chunk in K blocks (0 = the whole K range in one accumulator), see below
   float* part;                  // split-K partials [split][Q][ldo]
   const float* S;               // only for address checks; tiles come through the tensor map
-  const float* rowrec;          // [Q][8]  this rank's row records {m2, thr_n, cT, label | thr_p, cA, 0, 0}
+  const float* rowrec;          // [Q][8]  this rank's row records {m2c, thr_n, m2, label | thr_p, cA, cT, 0} (lse_rows_kernel)
   const float* colrec;          // [N][8]  records of every column's row (== rowrec when world == 1)
   int self_offset;              // global column of local row 0
-  float inv_world;
+  float inv_world, log2_world;
   float sgn_p, sgn_n;           // +-1: direction of the same-/diff-label selection compare
   float* out; long long ldo;
   float alpha, beta;
@@ -62,7 +73,7 @@ struct FusedCfg {
   static constexpr int A_COLS = BK / 2;
   static constexpr int NPASS = (NSPLIT == 1) ? 1 : (NSPLIT == 2 ? 3 : 6);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*barriers*/ + 1024 /*alignment*/;
-  static constexpr int THREADS = 640;                         // 4 control warps + 16 producer / epilogue warps
+  static constexpr int THREADS = 704;                         // 22 warps: TMA, MMA, 16 weight producers (4..19), 4 drain warps (2, 3, 20, 21)
 };
 
 // two fp32 weights -> packed 2-byte pieces (lo 16 bits = first value)
@@ -89,17 +100,57 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t (&out)[3])
   }
 }
 
+// fp32 round-to-nearest adds performed at the L2 (REDG.E.ADD.F32x4.RN): same thread, same address => program order
+__device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void red_add_f32(float* dst, float a) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst), "f"(a) : "memory");
+}
+
 __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(ptx::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(ptx::smem_u32(bar))
                : "memory");
 }
 
+// End of the accumulation chunk that starts at K block c0 of the range [kb0, kb1).  The FIRST chunk of a tile is shortened by a
+// per-cluster amount so that the clusters do not all drain at the same moment: the drains are bursts of 128 KB of L2 atomics per
+// SM, and when all 148 SMs issued them together the operand loads stalled behind them (~4.4 us per chunk, measured).
+__device__ __forceinline__ int chunk_end(int c0, int kb0, int kb1, int ch, int worker) {
+  if (ch <= 0) return kb1;
+  if (c0 == kb0) { const int first = max(1, (((worker & 7) + 1) * ch) >> 3); return min(kb1, kb0 + first); }
+  return min(kb1, c0 + ch);
+}
+
+// Weights of 8 consecutive diff-label pairs of one row (the common case): per pair TWO exponentials whose arguments already carry
+// the factors 1/T (and 1/world for the transposed term) -- see lse_rows_kernel -- switched off by a -inf argument when the pair
+// is not selected.  NEG: the diff-label rule compares -s (HARD / RELATIVE_HARD negatives), folded into the compare's operand sign.
+template <bool NEG>
+__device__ __forceinline__ bool produce8(const float (&sv)[8], const float4* __restrict__ crec, float r_m2r, float r_tn, float r_lab, float (&g)[8]) {
+  bool any_same = false;
+#pragma unroll
+  for (int cc = 0; cc < 8; ++cc) {
+    const float4 ca = crec[2 * cc];              // {m2c, thr_n, m2, label} of the column's row
+    const float s = sv[cc];
+    const float a1 = fmaf(s, NPAIR_LOG2E_F, -r_m2r);
+    const float a2 = fmaf(s, NPAIR_LOG2E_F, -ca.x);
+    const bool s1 = NEG ? (-s <= r_tn) : (s <= r_tn);
+    const bool s2 = NEG ? (-s <= ca.y) : (s <= ca.y);
+    float e1, e2;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(s1 ? a1 : -INFINITY));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(s2 ? a2 : -INFINITY));
+    g[cc] = e1 + e2;
+    any_same |= (ca.w == r_lab);
+  }
+  return any_same;
+}
+
 // Measured and dropped (round 2, profiles/r02_experiments.md): forming the transposed term's exponential from the row term's
 // (one ex2 per pair plus per-row / per-column constants) was SLOWER (180 vs 166 us): the extra shuffles and selects cost more
 // than the saved MUFU issue slots.
 template <int NSPLIT, bool BF16, int NCTA = 1>
-__global__ void __launch_bounds__(640, 1)
+__global__ void __launch_bounds__(704, 1)
 fused_grad_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ CUtensorMap tmapS, const FusedGradParams p) {
   using Cfg = FusedCfg<NSPLIT, NCTA>;
   static_assert(Cfg::TMEM_A0 + Cfg::STAGES * NSPLIT * Cfg::A_COLS <= 512, "A pieces do not fit behind the accumulator");
@@ -127,7 +178,7 @@ fused_grad_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_consta
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&bfull_bar[s], 1); ptx::mbar_init(&aready_bar[s], 16 * NCTA); ptx::mbar_init(&empty_bar[s], 1);
     }
-    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 16 * NCTA); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 4 * NCTA); }
     ptx::fence_mbar_init();
   }
   if (warp == 2) { ptx::tmem_alloc<512>(tmem_ptr); ptx::tmem_relinquish(); }
@@ -176,60 +227,62 @@ fused_grad_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_consta
     if (lane == 0 && cta_rank == 0) {
       constexpr uint32_t idesc = ptx::make_idesc_f16(BF16, BM * NCTA, BN);
       int stage = 0; uint32_t phase = 0;
-      int it = 0;
-      for (int tile = worker; tile < num_tiles; tile += num_workers, ++it) {
-        const int acc = 0;                       // one accumulator: the producers run the epilogue themselves
-        const uint32_t acc_phase = it & 1;
-        ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-        ptx::tc_fence_after();
+      uint32_t gen = 0;                          // accumulator generations (one per chunk), drained by warps 2, 3, 20, 21
+      for (int tile = worker; tile < num_tiles; tile += num_workers) {
         const uint32_t d_tmem = tmem_base;
         const int split = tile % p.splits;
         const int kb0 = split * p.kb_per_split, kb1 = min(p.num_kblocks, kb0 + p.kb_per_split);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          ptx::mbar_wait(NCTA == 1 ? &full_bar[stage] : &bfull_bar[stage], phase);
-          ptx::mbar_wait(&aready_bar[stage], phase);
+        const int ch = p.chunk_kb;
+        for (int c0 = kb0, c1; c0 < kb1; c0 = c1, ++gen) {
+          c1 = chunk_end(c0, kb0, kb1, ch, worker);
+          ptx::mbar_wait(&tempty_bar[0], (gen & 1u) ^ 1u);
           ptx::tc_fence_after();
-          const uint32_t b0 = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint32_t a_t = tmem_base + Cfg::TMEM_A0 + stage * NSPLIT * Cfg::A_COLS;
+          for (int kb = c0; kb < c1; ++kb) {
+            ptx::mbar_wait(NCTA == 1 ? &full_bar[stage] : &bfull_bar[stage], phase);
+            ptx::mbar_wait(&aready_bar[stage], phase);
+            ptx::tc_fence_after();
+            const uint32_t b0 = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
+            const uint32_t a_t = tmem_base + Cfg::TMEM_A0 + stage * NSPLIT * Cfg::A_COLS;
 #pragma unroll
-          for (int ps = 0; ps < Cfg::NPASS; ++ps) {
-            int sa, sb;
-            pass_pieces(NSPLIT, ps, sa, sb);
+            for (int ps = 0; ps < Cfg::NPASS; ++ps) {
+              int sa, sb;
+              pass_pieces(NSPLIT, ps, sa, sb);
 #pragma unroll
-            for (int k2 = 0; k2 < BK / 16; ++k2) {
-              const uint64_t bd = ptx::make_kmajor_desc(b0 + sb * Cfg::B_PIECE + k2 * 32, 512u, 4u);   // SWIZZLE_64B, 8 rows = 512 B
-              if (NCTA == 1) ptx::mma_f16_ts(d_tmem, a_t + sa * Cfg::A_COLS + k2 * 8, bd, idesc, ((kb - kb0) | ps | k2) != 0 ? 1u : 0u);
-              else ptx::mma_f16_ts_pair(d_tmem, a_t + sa * Cfg::A_COLS + k2 * 8, bd, idesc, ((kb - kb0) | ps | k2) != 0 ? 1u : 0u);
+              for (int k2 = 0; k2 < BK / 16; ++k2) {
+                const uint64_t bd = ptx::make_kmajor_desc(b0 + sb * Cfg::B_PIECE + k2 * 32, 512u, 4u);   // SWIZZLE_64B, 8 rows = 512 B
+                if (NCTA == 1) ptx::mma_f16_ts(d_tmem, a_t + sa * Cfg::A_COLS + k2 * 8, bd, idesc, ((kb - c0) | ps | k2) != 0 ? 1u : 0u);
+                else ptx::mma_f16_ts_pair(d_tmem, a_t + sa * Cfg::A_COLS + k2 * 8, bd, idesc, ((kb - c0) | ps | k2) != 0 ? 1u : 0u);
+              }
             }
+            if (NCTA == 1) ptx::mma_commit(&empty_bar[stage]); else ptx::mma_commit_pair(&empty_bar[stage], 3);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          if (NCTA == 1) ptx::mma_commit(&empty_bar[stage]); else ptx::mma_commit_pair(&empty_bar[stage], 3);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (NCTA == 1) ptx::mma_commit(&tfull_bar[0]); else ptx::mma_commit_pair(&tfull_bar[0], 3);
         }
-        if (NCTA == 1) ptx::mma_commit(&tfull_bar[acc]); else ptx::mma_commit_pair(&tfull_bar[acc], 3);
       }
     }
-  } else if (warp >= 4) {
-    // ===================================== weight producers + epilogue =====================================
+  } else if (warp >= 4 && warp < 20) {
+    // ===================================== weight producers =====================================
     const int ew = (warp - 4) & 3;               // TMEM lane group / 32-row group
-    const int qt = (warp - 4) >> 2;              // quarter: 8 of the 32 K columns while producing, 64 of the 256 D columns in the epilogue
+    const int qt = (warp - 4) >> 2;              // quarter: 8 of the 32 K columns
     int stage = 0; uint32_t phase = 0;
-    int it = 0;
+    int prev_stage = -1;                         // stage whose tcgen05.st are issued but not yet published to the MMA issuer
     const uint32_t lead_aready = (NCTA == 2) ? ptx::mapa_u32(ptx::smem_u32(&aready_bar[0]), 0) : 0u;
-    const uint32_t lead_tempty = (NCTA == 2) ? ptx::mapa_u32(ptx::smem_u32(&tempty_bar[0]), 0) : 0u;
-    for (int tile = worker; tile < num_tiles; tile += num_workers, ++it) {
+    for (int tile = worker; tile < num_tiles; tile += num_workers) {
       const int mn = tile / p.splits, split = tile - mn * p.splits;
-      const int m_blk = (mn / p.tiles_n) * NCTA + cta_rank, n_blk = mn % p.tiles_n;
+      const int m_blk = (mn / p.tiles_n) * NCTA + cta_rank;
       const int kb0 = split * p.kb_per_split, kb1 = min(p.num_kblocks, kb0 + p.kb_per_split);
       const int rl = ew * 32 + lane;             // row inside the tile
       const int row = m_blk * BM + rl;
       // row record (neutral when the row does not exist: thresholds -inf -> nothing selected)
-      float r_m2 = 0.f, r_tp = -INFINITY, r_tn = -INFINITY, r_cA = 0.f, r_cT = 0.f, r_lab = 0.f;
+      float r_m2 = 0.f, r_m2r = INFINITY, r_tp = -INFINITY, r_tn = -INFINITY, r_cA = 0.f, r_lab = 0.f;
       if (row < p.Q) {
         const float4 a = *reinterpret_cast<const float4*>(p.rowrec + 8ll * row);
         const float4 b = *reinterpret_cast<const float4*>(p.rowrec + 8ll * row + 4);
-        r_m2 = a.x; r_tn = a.y; r_cT = a.z; r_lab = a.w; r_tp = b.x; r_cA = b.y;
+        r_m2r = a.x - p.log2_world; r_tn = a.y; r_m2 = a.z; r_lab = a.w; r_tp = b.x; r_cA = b.y;   // the row term carries no 1/world
       }
       const int self_col = row + p.self_offset;
+      const bool neg_n = p.sgn_n < 0.f;
       for (int kb = kb0; kb < kb1; ++kb) {
         ptx::mbar_wait(&full_bar[stage], phase);
         uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
@@ -244,30 +297,17 @@ fused_grad_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_consta
         }
         const int m0 = kb * BK + 8 * qt;         // global column of sv[0]
         float g[8];
-        bool any_same = false;
-#pragma unroll
-        for (int cc = 0; cc < 8; ++cc) {
-          const float4 ca = crec[2 * cc];        // {m2, thr_n, cT, label}: everything a diff-label pair needs
-          const float s = sv[cc];
-          float e1, e2;                          // same formula as the forward row pass (fast_exp_m2)
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(s, NPAIR_LOG2E_F, -r_m2)));
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(fmaf(s, NPAIR_LOG2E_F, -ca.x)));
-          const float key = s * p.sgn_n;
-          const float w1 = (key <= r_tn) ? e1 * r_cT : 0.f;
-          const float w2 = (key <= ca.y) ? e2 * ca.z : 0.f;
-          g[cc] = fmaf(w2, p.inv_world, w1);
-          any_same |= (ca.w == r_lab);
-        }
+        const bool any_same = neg_n ? produce8<true>(sv, crec, r_m2r, r_tn, r_lab, g) : produce8<false>(sv, crec, r_m2r, r_tn, r_lab, g);
         // rare fix-ups: same-label pairs (the other selection rule and weight), the self pair, columns beyond N
         if (any_same || (self_col >= m0 && self_col < m0 + 8) || m0 + 8 > p.N) {
 #pragma unroll
           for (int cc = 0; cc < 8; ++cc) {
-            const float4 ca = crec[2 * cc], cb = crec[2 * cc + 1];   // cb = {thr_p, cA, -, -}
+            const float4 ca = crec[2 * cc], cb = crec[2 * cc + 1];   // cb = {thr_p, cA, cT, -}
             if (ca.w == r_lab) {
               const float s = sv[cc];
-              float e1, e2;
+              float e1, e2;                      // same exponential as the forward row pass (fast_exp_m2)
               asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(s, NPAIR_LOG2E_F, -r_m2)));
-              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(fmaf(s, NPAIR_LOG2E_F, -ca.x)));
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(fmaf(s, NPAIR_LOG2E_F, -ca.z)));
               const float key = s * p.sgn_p;
               const float w1 = (key <= r_tp) ? e1 * r_cA : 0.f;
               const float w2 = (key <= cb.x) ? e2 * cb.y : 0.f;
@@ -285,56 +325,99 @@ fused_grad_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_consta
 #pragma unroll
           for (int s = 0; s < NSPLIT; ++s) pk[s][q] = o[s];
         }
+        // the previous K block's tensor-memory stores have had this block's arithmetic to complete: publish them now
+        if (prev_stage >= 0) {
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before();                 // order the tcgen05.st before the arrive that releases the MMA issuer
+          __syncwarp();
+          if (lane == 0) { if (NCTA == 1) ptx::mbar_arrive(&aready_bar[prev_stage]); else ptx::mbar_arrive_cluster(lead_aready + 8u * prev_stage); }
+        }
         const uint32_t a_t = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + Cfg::TMEM_A0 + stage * NSPLIT * Cfg::A_COLS + 4 * qt;
 #pragma unroll
         for (int s = 0; s < NSPLIT; ++s) ptx::tmem_st_32x32b_x4(a_t + s * Cfg::A_COLS, pk[s][0], pk[s][1], pk[s][2], pk[s][3]);
-        ptx::tmem_st_wait();
-        ptx::tc_fence_before();                   // order the tcgen05.st before the arrive that releases the MMA issuer
-        __syncwarp();
-        if (lane == 0) { if (NCTA == 1) ptx::mbar_arrive(&aready_bar[stage]); else ptx::mbar_arrive_cluster(lead_aready + 8u * stage); }
+        prev_stage = stage;
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      // ---- epilogue of this tile: TMEM -> alpha * acc (+ beta * out) ----
-      const int acc = 0;
-      const uint32_t acc_phase = it & 1;
-      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
-      ptx::tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
+    }
+    if (prev_stage >= 0) {
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { if (NCTA == 1) ptx::mbar_arrive(&aready_bar[prev_stage]); else ptx::mbar_arrive_cluster(lead_aready + 8u * prev_stage); }
+    }
+  }
+  if (warp == 2 || warp == 3 || warp >= 20) {
+    // ===================================== accumulator drain (4 warps, one per TMEM lane quarter) =====================================
+    // Dedicated warps, so that the producers never wait for the tensor pipe: they hand every accumulator generation (one per
+    // chunk) back to the MMA issuer as soon as its 128 x 256 values are in flight to the output.
+    const int ew = warp & 3;                      // TMEM lane quarter this warp may access (warp id % 4)
+    const uint32_t lead_tempty = (NCTA == 2) ? ptx::mapa_u32(ptx::smem_u32(&tempty_bar[0]), 0) : 0u;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
+    uint32_t gen = 0;
+    for (int tile = worker; tile < num_tiles; tile += num_workers) {
+      const int mn = tile / p.splits, split = tile - mn * p.splits;
+      const int m_blk = (mn / p.tiles_n) * NCTA + cta_rank, n_blk = mn % p.tiles_n;
+      const int kb0 = split * p.kb_per_split, kb1 = min(p.num_kblocks, kb0 + p.kb_per_split);
+      const int row = m_blk * BM + ew * 32 + lane;
       float* obase = p.splits > 1 ? p.part + static_cast<long long>(split) * p.Q * p.ldo : p.out;
       const float beta = p.splits > 1 ? 0.f : p.beta;
+      for (int c0 = kb0, c1; c0 < kb1; c0 = c1, ++gen) {
+        c1 = chunk_end(c0, kb0, kb1, p.chunk_kb, worker);
+        const bool first = (c0 == kb0);          // first chunk of the tile stores (+ beta * out), later chunks add (fp32 RN)
+        ptx::mbar_wait(&tfull_bar[0], gen & 1u);
+        ptx::tc_fence_after();
+#ifndef NPAIR_DBG_DRAIN
+#define NPAIR_DBG_DRAIN 0          // timing experiments only: 1 = no global writes for later chunks, 2 = release the accumulator at once
+#endif
+        if (NPAIR_DBG_DRAIN == 2) {
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) { if (NCTA == 1) ptx::mbar_arrive(&tempty_bar[0]); else ptx::mbar_arrive_cluster(lead_tempty); }
+        }
 #pragma unroll 1
-      for (int ch = qt * 2; ch < qt * 2 + 2; ++ch) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(t_row + ch * 32, r);
-        ptx::tmem_ld_wait();
-        const int col0 = n_blk * BN + ch * 32;
-        if (row < p.Q) {
-          float* dst = obase + static_cast<long long>(row) * p.ldo + col0;
-          if (col0 + 32 <= p.D && (p.ldo & 3) == 0) {
+        for (int ch = 0; ch < BN / 32; ++ch) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(t_row + ch * 32, r);
+          ptx::tmem_ld_wait();
+          if (NPAIR_DBG_DRAIN != 2 && ch == BN / 32 - 1) {   // everything is in registers / in flight: the MMA issuer may start the next chunk
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (NCTA == 1) ptx::mbar_arrive(&tempty_bar[0]); else ptx::mbar_arrive_cluster(lead_tempty); }
+          }
+          const int col0 = n_blk * BN + ch * 32;
+          if (NPAIR_DBG_DRAIN == 1 && !first) continue;
+          if (row < p.Q) {
+            float* dst = obase + static_cast<long long>(row) * p.ldo + col0;
+            if (col0 + 32 <= p.D && (p.ldo & 3) == 0) {
+              if (first) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              float4 o = make_float4(alpha * __uint_as_float(r[4 * q]), alpha * __uint_as_float(r[4 * q + 1]),
-                                     alpha * __uint_as_float(r[4 * q + 2]), alpha * __uint_as_float(r[4 * q + 3]));
-              if (beta != 0.f) {
-                const float4 old = reinterpret_cast<float4*>(dst)[q];
-                o.x += beta * old.x; o.y += beta * old.y; o.z += beta * old.z; o.w += beta * old.w;
+                for (int q = 0; q < 8; ++q) {
+                  float4 o = make_float4(alpha * __uint_as_float(r[4 * q]), alpha * __uint_as_float(r[4 * q + 1]),
+                                         alpha * __uint_as_float(r[4 * q + 2]), alpha * __uint_as_float(r[4 * q + 3]));
+                  if (beta != 0.f) {
+                    const float4 old = reinterpret_cast<float4*>(dst)[q];
+                    o.x += beta * old.x; o.y += beta * old.y; o.z += beta * old.z; o.w += beta * old.w;
+                  }
+                  reinterpret_cast<float4*>(dst)[q] = o;
+                }
+              } else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                  red_add_v4(dst + 4 * q, alpha * __uint_as_float(r[4 * q]), alpha * __uint_as_float(r[4 * q + 1]),
+                             alpha * __uint_as_float(r[4 * q + 2]), alpha * __uint_as_float(r[4 * q + 3]));
               }
-              reinterpret_cast<float4*>(dst)[q] = o;
+            } else {
+#pragma unroll
+              for (int c = 0; c < 32; ++c)
+                if (col0 + c < p.D) {
+                  const float o = alpha * __uint_as_float(r[c]);
+                  if (first) dst[c] = (beta != 0.f) ? o + beta * dst[c] : o;
+                  else red_add_f32(dst + c, o);
+                }
             }
-          } else {
-#pragma unroll
-            for (int c = 0; c < 32; ++c)
-              if (col0 + c < p.D) {
-                float o = alpha * __uint_as_float(r[c]);
-                if (beta != 0.f) o += beta * dst[c];
-                dst[c] = o;
-              }
           }
         }
       }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) { if (NCTA == 1) ptx::mbar_arrive(&tempty_bar[acc]); else ptx::mbar_arrive_cluster(lead_tempty + 8u * acc); }
     }
   }
   ptx::tc_fence_before();

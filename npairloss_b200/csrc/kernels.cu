@@ -216,7 +216,8 @@ __global__ void __launch_bounds__(256) prep_reduce_kernel(const float* __restric
       sc = ldexpf(1.f, -e); inv = ldexpf(1.f, e);
     }
     bs->x_scale = sc; bs->x_inv_scale = inv;
-    bs->err = 0; bs->ticket = 0; bs->ticket2 = 0; bs->ticket0 = 0; bs->sel_active[0] = 0; bs->sel_active[1] = 0;
+    bs->err = 0; bs->ticket = 0; bs->ticket2 = 0; bs->ticket0 = 0; bs->ticket3 = 0; bs->sel_active[0] = 0; bs->sel_active[1] = 0;
+    bs->cand_n[0] = 0; bs->cand_n[1] = 0;
     bs->n_same = 0; bs->n_diff = 0;
   }
 }
@@ -510,137 +511,334 @@ void launch_thresholds(RowArrays ra, int Q, int N, MiningParams mp, BlockScalars
 }
 
 // --------------------------------------------------------------------------------------------
-// LOCAL relative thresholds: k-th smallest masked element of each row by 4 x 8-bit MSB radix select
-// (replaces the per-row std::sort + index of .cu:270-273, :282-290, :313-321).  One block per row; the
-// row is re-read from L1/L2, HBM sees it once.
+// Relative thresholds = order statistics of the masked similarities (replaces the unconditional std::sorts of .cu:266-273
+// and the list indexing of .cu:282-290, :300-304, :313-321, :331-335).  MSB-first radix select on the order-preserving
+// uint32 keys, digits of 11 / 11 / 10 bits.  Similarities of one row are clustered (a few binades), so the first digit
+// already narrows the k-th element down to a few percent of the row: those CANDIDATES are compacted (21-bit remainders) and the
+// last two digits are decided on the compact list -- S is read once from HBM (LOCAL: one more time from L1/L2; GLOBAL: twice).
+// Both sides (same-label list for AP, diff-label list for AN) are handled in the same sweep when both are relative.
+// The self pair is counted by the vectorised sweep and taken out again by one thread (it is always a same-label entry).
 // --------------------------------------------------------------------------------------------
-__global__ void local_select_kernel(const float* __restrict__ S, long long ldS, int Q, int N, const float* __restrict__ lab_rows,
-                                    const float* __restrict__ lab_cols, int self_offset, int side, float sn, RowArrays ra,
-                                    BlockScalars* bs) {
-  __shared__ unsigned int hist[256];
-  __shared__ uint32_t s_prefix, s_mask;
-  __shared__ unsigned int s_rank;
-  __shared__ int s_ok;
-  const int i = blockIdx.x;
-  const float li = lab_rows[i];
-  const int self_col = i + self_offset;
-  const float* row = S + static_cast<long long>(i) * ldS;
-  float* out = side == 0 ? ra.posi_thr : ra.nega_thr;
-  if (threadIdx.x == 0) {
-    const int cs = ra.cnt_same[i];
-    const unsigned long long size = side == 0 ? cs : (N - 1 - cs);
-    unsigned long long pos = 0;
-    s_ok = 1;
-    if (size == 0) { atomicOr(&bs->err, DERR_EMPTY_LIST); s_ok = 0; }
-    else if (!pos_index(sn, size, pos)) { atomicOr(&bs->err, DERR_POS_RANGE); s_ok = 0; }
-    s_rank = static_cast<unsigned int>(pos); s_prefix = 0; s_mask = 0;
-  }
-  __syncthreads();
-  if (!s_ok) { if (threadIdx.x == 0) out[i] = 0.f; return; }
-  for (int shift = 24; shift >= 0; shift -= 8) {
-    for (int b = threadIdx.x; b < 256; b += blockDim.x) hist[b] = 0;
-    __syncthreads();
-    const uint32_t prefix = s_prefix, mask = s_mask;
-    for (int j = threadIdx.x; j < N; j += blockDim.x) {
-      if (j == self_col) continue;
-      const bool same = lab_cols[j] == li;
-      if (same != (side == 0)) continue;
-      const uint32_t key = f2ord(row[j]);
-      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+#define NPAIR_SEL_BINS 2048
+
+// Sweep of one row: calls f(key, j, side) for every column j < N with side = 0 (same label as the row) or 1 (different);
+// the self pair is NOT excluded here.  16-byte loads of S (row stride is a multiple of 32 floats) and of the labels.
+template <class F>
+__device__ __forceinline__ void sweep_row(const float* __restrict__ row, int N, const float* __restrict__ lab_cols, float li, bool lab_aligned,
+                                          bool want_same, bool want_diff, F f) {
+  for (int j4 = threadIdx.x * 4; j4 < N; j4 += blockDim.x * 4) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(row + j4));
+    float ll[4];
+    if (lab_aligned && j4 + 3 < N) {
+      const float4 l = __ldg(reinterpret_cast<const float4*>(lab_cols + j4));
+      ll[0] = l.x; ll[1] = l.y; ll[2] = l.z; ll[3] = l.w;
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) ll[c] = (j4 + c < N) ? __ldg(lab_cols + j4 + c) : li;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned int r = s_rank, cum = 0; int d = 0;
-      for (; d < 256; ++d) { if (cum + hist[d] > r) break; cum += hist[d]; }
-      s_rank = r - cum; s_prefix = prefix | (static_cast<uint32_t>(d) << shift); s_mask = mask | (255u << shift);
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+    if (j4 + 3 < N && ll[0] != li && ll[1] != li && ll[2] != li && ll[3] != li) {
+      if (want_diff) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) f(f2ord(vv[c]), j4 + c, 1);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (j4 + c >= N) continue;
+        const int side = (ll[c] == li) ? 0 : 1;
+        if (side == 0 ? want_same : want_diff) f(f2ord(vv[c]), j4 + c, side);
+      }
     }
-    __syncthreads();
   }
-  if (threadIdx.x == 0) out[i] = clamp_thr(ord2f(s_prefix));
-}
-void launch_local_select(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
-                         int self_offset, int side, float sn, RowArrays ra, BlockScalars* bs, cudaStream_t st) {
-  local_select_kernel<<<Q, 256, 0, st>>>(S, ldS, Q, N, lab_rows, lab_cols, self_offset, side, sn, ra, bs);
-  count_launch();
 }
 
-// --------------------------------------------------------------------------------------------
-// GLOBAL relative thresholds: k-th smallest of ALL same (or diff) similarities of this rank's Q x N block
-// (replaces the std::sort of ident/diff_prod_global_list, .cu:267-268, and the index at .cu:300-304/:331-335).
-// Three digit passes (11/11/10 bits) of a multi-block histogram radix select with 64-bit counts.
-// --------------------------------------------------------------------------------------------
-__global__ void global_hist_kernel(const float* __restrict__ S, long long ldS, int Q, int N, const float* __restrict__ lab_rows,
-                                   const float* __restrict__ lab_cols, int self_offset, int side, int shift, int nbits,
-                                   unsigned long long* __restrict__ ghist, const BlockScalars* __restrict__ bs) {
-  __shared__ unsigned int hist[2048];
-  if (!bs->sel_active[side]) return;
-  const uint32_t prefix = bs->sel_prefix[side], mask = bs->sel_mask[side];
-  const uint32_t dmask = (1u << nbits) - 1u;
-  for (int b = threadIdx.x; b < 2048; b += blockDim.x) hist[b] = 0;
+// Block-parallel search of the bin that holds 0-based rank r in hist[0..nbins): returns the bin (or nbins when r is out of range),
+// the rank inside it and its population.  nbins <= 2048, blockDim.x threads (a multiple of 32, <= 1024).  All threads get the result.
+template <class CT>
+__device__ __forceinline__ int find_bin(const CT* hist, int nbins, unsigned long long r, unsigned long long* r_in, unsigned long long* pop,
+                                        unsigned long long* s_scan /*[33]*/, int* s_res /*[1]*/, unsigned long long* s_out /*[2]*/) {
+  const int per = (nbins + blockDim.x - 1) / blockDim.x;
+  const int b0 = threadIdx.x * per;
+  unsigned long long mine = 0;
+  for (int b = b0; b < b0 + per && b < nbins; ++b) mine += hist[b];
+  unsigned long long incl = mine;                                 // inclusive scan over the block
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  if (lane == 31) s_scan[w] = incl;
+  if (threadIdx.x == 0) *s_res = nbins;
   __syncthreads();
+  if (w == 0) {
+    unsigned long long x = (lane < static_cast<int>(blockDim.x >> 5)) ? s_scan[lane] : 0ull;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += t; }
+    s_scan[lane] = x;                                             // inclusive warp totals
+  }
+  __syncthreads();
+  const unsigned long long before = (w ? s_scan[w - 1] : 0ull) + incl - mine;
+  if (mine && r >= before && r < before + mine) {                 // exactly one thread
+    unsigned long long cum = before;
+    int b = b0;
+    for (; b < b0 + per && b < nbins; ++b) { const unsigned long long h = hist[b]; if (cum + h > r) break; cum += h; }
+    *s_res = b; s_out[0] = r - cum; s_out[1] = hist[b];
+  }
+  __syncthreads();
+  *r_in = s_out[0]; *pop = s_out[1];
+  return *s_res;
+}
+
+// ---- LOCAL: one block per row (persistent over rows), per side: digit 1 from the row, candidates -> smem, digits 2 and 3 there ----
+#define NPAIR_LSEL_CAP 3072            // candidate capacity per side (21-bit remainders); larger buckets fall back to sweeps of the row
+__global__ void __launch_bounds__(256) local_select_kernel(const float* __restrict__ S, long long ldS, int Q, int N, const float* __restrict__ lab_rows,
+                                                           const float* __restrict__ lab_cols, int self_offset, int side_mask /*1 AP, 2 AN*/,
+                                                           float sn_ap, float sn_an, RowArrays ra, BlockScalars* bs) {
+  __shared__ unsigned int hist[2][NPAIR_SEL_BINS];
+  __shared__ uint32_t cand[2][NPAIR_LSEL_CAP];
+  __shared__ unsigned int s_ncand[2];
+  __shared__ unsigned long long s_scan[33], s_out[2];
+  __shared__ int s_res;
+  const bool lab_aligned = (reinterpret_cast<uintptr_t>(lab_cols) & 15) == 0;
+  const bool want_same = side_mask & 1, want_diff = side_mask & 2;
   for (int i = blockIdx.x; i < Q; i += gridDim.x) {
     const float li = lab_rows[i];
     const int self_col = i + self_offset;
     const float* row = S + static_cast<long long>(i) * ldS;
-    for (int j4 = threadIdx.x * 4; j4 < N; j4 += blockDim.x * 4) {
-      const float4 v = *reinterpret_cast<const float4*>(row + j4);
-      const float vv[4] = {v.x, v.y, v.z, v.w};
+    for (int b = threadIdx.x; b < 2 * NPAIR_SEL_BINS; b += blockDim.x) (&hist[0][0])[b] = 0;
+    if (threadIdx.x < 2) s_ncand[threadIdx.x] = 0;
+    __syncthreads();
+    // ---- digit 1 (bits 31..21) of both sides in one sweep ----
+    sweep_row(row, N, lab_cols, li, lab_aligned, want_same, want_diff,
+              [&](uint32_t key, int, int side) { atomicAdd(&hist[side][key >> 21], 1u); });
+    __syncthreads();
+    if (threadIdx.x == 0 && want_same) hist[0][f2ord(row[self_col]) >> 21] -= 1u;     // the self pair is in neither list (.cu:54)
+    __syncthreads();
+    const int cs = ra.cnt_same[i];
+    uint32_t prefix[2] = {0, 0};
+    unsigned long long rank_in[2] = {0, 0}, pop[2] = {0, 0};
+    bool ok[2] = {false, false};
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int j = j4 + c;
-        if (j >= N || j == self_col) continue;
-        const bool same = lab_cols[j] == li;
-        if (same != (side == 0)) continue;
-        const uint32_t key = f2ord(vv[c]);
-        if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & dmask], 1u);
+    for (int side = 0; side < 2; ++side) {
+      if (!(side_mask & (1 << side))) continue;
+      const unsigned long long size = side == 0 ? static_cast<unsigned long long>(cs) : static_cast<unsigned long long>(N - 1 - cs);
+      unsigned long long pos = 0;
+      bool good = true;
+      if (size == 0) { if (threadIdx.x == 0) atomicOr(&bs->err, DERR_EMPTY_LIST); good = false; }
+      else if (!pos_index(side == 0 ? sn_ap : sn_an, size, pos)) { if (threadIdx.x == 0) atomicOr(&bs->err, DERR_POS_RANGE); good = false; }
+      if (good) {                                                 // block-uniform
+        const int d = find_bin(hist[side], NPAIR_SEL_BINS, pos, &rank_in[side], &pop[side], s_scan, &s_res, s_out);
+        prefix[side] = static_cast<uint32_t>(d) << 21;
+        ok[side] = d < NPAIR_SEL_BINS;
+        __syncthreads();
       }
     }
+    // ---- candidates of the chosen first digits -> shared memory (second read of the row: L1 / L2) ----
+    const bool fit0 = ok[0] && pop[0] <= NPAIR_LSEL_CAP, fit1 = ok[1] && pop[1] <= NPAIR_LSEL_CAP;
+    if (fit0 || fit1) {
+      const uint32_t p0 = prefix[0] >> 21, p1 = prefix[1] >> 21;
+      sweep_row(row, N, lab_cols, li, lab_aligned, fit0, fit1, [&](uint32_t key, int j, int side) {
+        if ((key >> 21) == (side == 0 ? p0 : p1) && j != self_col) cand[side][atomicAdd(&s_ncand[side], 1u)] = key & 0x1FFFFFu;
+      });
+    }
+    __syncthreads();
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+      if (!(side_mask & (1 << side))) continue;
+      float* out = side == 0 ? ra.posi_thr : ra.nega_thr;
+      if (!ok[side]) { if (threadIdx.x == 0) out[i] = 0.f; continue; }
+      const bool fit = side == 0 ? fit0 : fit1;
+      uint32_t pre = prefix[side], msk = 0xFFE00000u;
+      unsigned long long r = rank_in[side];
+      const int shifts[2] = {10, 0}, bits[2] = {11, 10};
+#pragma unroll
+      for (int pss = 0; pss < 2; ++pss) {
+        const int nb = 1 << bits[pss];
+        for (int b = threadIdx.x; b < nb; b += blockDim.x) hist[side][b] = 0;
+        __syncthreads();
+        const uint32_t dm = static_cast<uint32_t>(nb - 1);
+        if (fit) {
+          const unsigned int nc = s_ncand[side];
+          const uint32_t lowpre = pre & 0x1FFFFFu, lowmsk = msk & 0x1FFFFFu;
+          for (unsigned int e = threadIdx.x; e < nc; e += blockDim.x) {
+            const uint32_t k = cand[side][e];
+            if ((k & lowmsk) == lowpre) atomicAdd(&hist[side][(k >> shifts[pss]) & dm], 1u);
+          }
+        } else {                                                   // oversized bucket (heavily tied data): sweep the row again
+          sweep_row(row, N, lab_cols, li, lab_aligned, side == 0, side == 1, [&](uint32_t key, int j, int) {
+            if ((key & msk) == pre && j != self_col) atomicAdd(&hist[side][(key >> shifts[pss]) & dm], 1u);
+          });
+        }
+        __syncthreads();
+        unsigned long long r2, pp;
+        const int d = find_bin(hist[side], nb, r, &r2, &pp, s_scan, &s_res, s_out);
+        pre |= static_cast<uint32_t>(d < nb ? d : 0) << shifts[pss]; msk |= dm << shifts[pss]; r = r2;
+        __syncthreads();
+      }
+      if (threadIdx.x == 0) out[i] = clamp_thr(ord2f(pre));          // .cu:288 / :319
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  for (int b = threadIdx.x; b < 2048; b += blockDim.x)
-    if (hist[b]) atomicAdd(&ghist[b], static_cast<unsigned long long>(hist[b]));
 }
-__global__ void global_pick_kernel(unsigned long long* __restrict__ ghist, int side, int shift, int nbits, int last,
-                                   RowArrays ra, int Q, BlockScalars* bs) {
-  __shared__ float s_thr;
-  __shared__ int s_done;
-  if (threadIdx.x == 0) {
-    s_done = 0;
-    if (bs->sel_active[side]) {
-      const int nb = 1 << nbits;
-      unsigned long long r = bs->sel_rank[side], cum = 0; int d = 0;
-      for (; d < nb; ++d) { if (cum + ghist[d] > r) break; cum += ghist[d]; }
-      if (d == nb) { bs->err |= DERR_POS_RANGE; bs->sel_active[side] = 0; d = 0; }
-      bs->sel_rank[side] = r - cum;
-      bs->sel_prefix[side] |= static_cast<uint32_t>(d) << shift;
-      bs->sel_mask[side] |= ((1u << nbits) - 1u) << shift;
-      if (last) {
-        const float thr = clamp_thr(ord2f(bs->sel_prefix[side]));
-        if (side == 0) bs->posi_global = thr; else bs->nega_global = thr;
-        s_thr = thr; s_done = 1;
+void launch_local_select(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
+                         int self_offset, int side_mask, float sn_ap, float sn_an, RowArrays ra, BlockScalars* bs, int sms, cudaStream_t st) {
+  int grid = sms * 5; if (grid > Q) grid = Q;                      // 41 KB of shared memory per block: 5 blocks per SM
+  local_select_kernel<<<grid, 256, 0, st>>>(S, ldS, Q, N, lab_rows, lab_cols, self_offset, side_mask, sn_ap, sn_an, ra, bs);
+  count_launch();
+}
+
+// ---- GLOBAL: the rank's whole Q x N block.  Three kernels, each finished by its last block (ticket):
+//   A  digit 1 histogram over S (64-bit global counts)                       -> bucket, rank inside, population
+//   B  second sweep of S: digit 2 histogram of the bucket's elements, and -- when the bucket fits the candidate buffer -- their
+//      21-bit remainders are compacted (per-block staging, one global atomic per flush)
+//   C  digit 3 histogram over the candidates (or, oversized bucket, over S once more) -> threshold, written to all rows
+struct GlobalSelectBufs {
+  unsigned long long* hist;   // [2][2048]
+  uint32_t* cand;             // [2][cap]
+  unsigned int cap;
+};
+#define NPAIR_GSEL_STAGE 2048
+__global__ void __launch_bounds__(512) global_select_kernel(const float* __restrict__ S, long long ldS, int Q, int N, const float* __restrict__ lab_rows,
+                                                            const float* __restrict__ lab_cols, int self_offset, int side_mask, int pass /*0,1,2*/,
+                                                            GlobalSelectBufs gb, RowArrays ra, BlockScalars* bs) {
+  __shared__ unsigned int hist[2][NPAIR_SEL_BINS];
+  __shared__ uint32_t stage[2][NPAIR_GSEL_STAGE];
+  __shared__ unsigned int s_nst[2], s_base[2];
+  __shared__ unsigned long long s_scan[33], s_out[2];
+  __shared__ int s_res, s_last;
+  const bool act0 = (side_mask & 1) && bs->sel_active[0], act1 = (side_mask & 2) && bs->sel_active[1];
+  if (!act0 && !act1) return;
+  const bool lab_aligned = (reinterpret_cast<uintptr_t>(lab_cols) & 15) == 0;
+  const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
+  const int nbits = pass == 2 ? 10 : 11;
+  const uint32_t dm = (1u << nbits) - 1u;
+  const uint32_t pre0 = bs->sel_prefix[0], pre1 = bs->sel_prefix[1], msk = pass == 0 ? 0u : (pass == 1 ? 0xFFE00000u : 0xFFFFFC00u);
+  const bool comp0 = act0 && pass == 1 && bs->sel_cnt[0] <= gb.cap, comp1 = act1 && pass == 1 && bs->sel_cnt[1] <= gb.cap;   // compaction this pass
+  const bool list0 = act0 && pass == 2 && bs->sel_cnt[0] <= gb.cap, list1 = act1 && pass == 2 && bs->sel_cnt[1] <= gb.cap;   // read the list this pass
+  for (int b = threadIdx.x; b < 2 * NPAIR_SEL_BINS; b += blockDim.x) (&hist[0][0])[b] = 0;
+  if (threadIdx.x < 2) s_nst[threadIdx.x] = 0;
+  __syncthreads();
+  const bool sweep0 = act0 && !list0, sweep1 = act1 && !list1;
+  if (sweep0 || sweep1) {
+    for (int i = blockIdx.x; i < Q; i += gridDim.x) {
+      const float li = lab_rows[i];
+      const int self_col = i + self_offset;
+      const float* row = S + static_cast<long long>(i) * ldS;
+      if (pass == 0) {
+        sweep_row(row, N, lab_cols, li, lab_aligned, sweep0, sweep1, [&](uint32_t key, int, int side) { atomicAdd(&hist[side][key >> 21], 1u); });
+        if (threadIdx.x == 0 && sweep0) atomicSub(&hist[0][f2ord(row[self_col]) >> 21], 1u);      // the self pair (modular: order-free)
+      } else {
+        sweep_row(row, N, lab_cols, li, lab_aligned, sweep0, sweep1, [&](uint32_t key, int j, int side) {
+          if ((key & msk) == (side == 0 ? pre0 : pre1) && j != self_col) {
+            atomicAdd(&hist[side][(key >> shift) & dm], 1u);
+            if (side == 0 ? comp0 : comp1) {
+              const unsigned int slot = atomicAdd(&s_nst[side], 1u);
+              if (slot < NPAIR_GSEL_STAGE) stage[side][slot] = key & 0x1FFFFFu;
+              else {                                               // staging full (rare): straight to the global list
+                const unsigned int g = atomicAdd(&bs->cand_n[side], 1u);
+                if (g < gb.cap) gb.cand[static_cast<size_t>(side) * gb.cap + g] = key & 0x1FFFFFu;
+              }
+            }
+          }
+        });
+      }
+      if (pass == 1 && (comp0 || comp1)) {                         // flush a staging area that is at least half full
+        __syncthreads();
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+          const unsigned int n = min(s_nst[side], static_cast<unsigned int>(NPAIR_GSEL_STAGE));
+          if (n >= NPAIR_GSEL_STAGE / 2) {
+            if (threadIdx.x == 0) s_base[side] = atomicAdd(&bs->cand_n[side], n);
+            __syncthreads();
+            for (unsigned int e = threadIdx.x; e < n; e += blockDim.x)
+              if (s_base[side] + e < gb.cap) gb.cand[static_cast<size_t>(side) * gb.cap + s_base[side] + e] = stage[side][e];
+            __syncthreads();
+            if (threadIdx.x == 0) s_nst[side] = 0;
+          }
+        }
+        __syncthreads();
+      }
+    }
+  }
+  if (list0 || list1) {                                            // pass 2 over the compact candidate lists
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+      if (!(side == 0 ? list0 : list1)) continue;
+      const unsigned int n = bs->cand_n[side];
+      const uint32_t lowpre = (side == 0 ? pre0 : pre1) & 0x1FFFFFu, lowmsk = msk & 0x1FFFFFu;
+      const uint32_t* cl = gb.cand + static_cast<size_t>(side) * gb.cap;
+      for (unsigned int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const uint32_t k = cl[e];
+        if ((k & lowmsk) == lowpre) atomicAdd(&hist[side][k & dm], 1u);
       }
     }
   }
   __syncthreads();
-  for (int b = threadIdx.x; b < 2048; b += blockDim.x) ghist[b] = 0ull;
-  if (s_done) {
-    float* out = side == 0 ? ra.posi_thr : ra.nega_thr;
-    for (int i = threadIdx.x; i < Q; i += blockDim.x) out[i] = s_thr;
+  if (pass == 1) {                                                 // remaining staged candidates
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+      const unsigned int n = min(s_nst[side], static_cast<unsigned int>(NPAIR_GSEL_STAGE));
+      if (n) {
+        if (threadIdx.x == 0) s_base[side] = atomicAdd(&bs->cand_n[side], n);
+        __syncthreads();
+        for (unsigned int e = threadIdx.x; e < n; e += blockDim.x)
+          if (s_base[side] + e < gb.cap) gb.cand[static_cast<size_t>(side) * gb.cap + s_base[side] + e] = stage[side][e];
+        __syncthreads();
+      }
+    }
+  }
+  for (int b = threadIdx.x; b < 2 * NPAIR_SEL_BINS; b += blockDim.x) {
+    const unsigned int h = (&hist[0][0])[b];
+    if (h) atomicAdd(&gb.hist[b], static_cast<unsigned long long>(h));
+  }
+  // ---- last block: decide this digit ----
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&bs->ticket3, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+#pragma unroll
+  for (int side = 0; side < 2; ++side) {
+    if (!(side == 0 ? act0 : act1)) continue;
+    unsigned long long r2, pp;
+    const unsigned long long* gh = gb.hist + side * NPAIR_SEL_BINS;
+    const int nb = 1 << nbits;
+    const int d = find_bin(gh, nb, bs->sel_rank[side], &r2, &pp, s_scan, &s_res, s_out);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (d >= nb) { bs->err |= DERR_POS_RANGE; bs->sel_active[side] = 0; }
+      else {
+        bs->sel_rank[side] = r2;
+        bs->sel_prefix[side] |= static_cast<uint32_t>(d) << shift;
+        if (pass == 0) { bs->sel_cnt[side] = pp; bs->cand_n[side] = 0; }
+        if (pass == 2) {
+          const float thr = clamp_thr(ord2f(bs->sel_prefix[side]));      // .cu:303 / :334
+          if (side == 0) bs->posi_global = thr; else bs->nega_global = thr;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  for (int b = threadIdx.x; b < 2 * NPAIR_SEL_BINS; b += blockDim.x) gb.hist[b] = 0ull;
+  if (threadIdx.x == 0) bs->ticket3 = 0;
+  if (pass == 2) {
+    __syncthreads();
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+      if (!(side == 0 ? act0 : act1) || !bs->sel_active[side]) continue;
+      const float thr = side == 0 ? bs->posi_global : bs->nega_global;
+      float* out = side == 0 ? ra.posi_thr : ra.nega_thr;
+      for (int i = threadIdx.x; i < Q; i += blockDim.x) out[i] = thr;
+    }
   }
 }
 void launch_global_select(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
-                          int self_offset, int side, float sn, RowArrays ra, unsigned long long* hist, BlockScalars* bs,
-                          cudaStream_t st) {
-  (void)sn;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int grid = sms * 4; if (grid > Q) grid = Q;
-  const int shifts[3] = {21, 10, 0}, bits[3] = {11, 11, 10};
-  for (int p = 0; p < 3; ++p) {
-    global_hist_kernel<<<grid, 512, 0, st>>>(S, ldS, Q, N, lab_rows, lab_cols, self_offset, side, shifts[p], bits[p], hist, bs);
-    count_launch();
-    global_pick_kernel<<<1, 1024, 0, st>>>(hist, side, shifts[p], bits[p], p == 2, ra, Q, bs);
+                          int self_offset, int side_mask, RowArrays ra, unsigned long long* hist, uint32_t* cand, unsigned int cand_cap,
+                          BlockScalars* bs, int sms, cudaStream_t st) {
+  int grid = sms * 2; if (grid > Q) grid = Q;
+  GlobalSelectBufs gb; gb.hist = hist; gb.cand = cand; gb.cap = cand_cap;
+  for (int pass = 0; pass < 3; ++pass) {
+    global_select_kernel<<<grid, 512, 0, st>>>(S, ldS, Q, N, lab_rows, lab_cols, self_offset, side_mask, pass, gb, ra, bs);
     count_launch();
   }
 }
@@ -701,7 +899,7 @@ __device__ __forceinline__ void lse_elem(float sv, float lab, float li, float sc
 __global__ void __launch_bounds__(256, NPAIR_LSE_MINB) lse_rows_kernel(const float* __restrict__ S, long long ldS, int Q, int N,
                                                        const float* __restrict__ lab_rows, const float* __restrict__ lab_cols,
                                                        int self_offset, MiningParams mp, RowArrays ra, BlockScalars* bs,
-                                                       int num_tops, float* __restrict__ tops) {
+                                                       int num_tops, float* __restrict__ tops, float log2_world) {
   const int lane = threadIdx.x & 31;
   // NPAIR_LSE_REV: walk the rows from the last to the first.  The similarity GEMM produced the high row blocks last, so
   // their tiles are the ones still resident in the 126 MB L2 when this kernel starts.
@@ -787,11 +985,13 @@ __global__ void __launch_bounds__(256, NPAIR_LSE_MINB) lse_rows_kernel(const flo
       ra.hits[2 * Q + i] = (cs > 0 && c <= min(10, lim)) ? 1 : 0;
       const float invA = A == 0.f ? 0.f : 1.f / A;              // Get_Query_Diff_Part zero rules (.cu:410-415)
       const float invT = T == 0.f ? 0.f : 1.f / T;
-      // first 16 bytes = all a diff-label pair needs: {max_all*log2(e) (the backward uses the same exponential), an_thr-transformed
-      // threshold, diff-label weight 1/T, label}; second 16 bytes = the same-label rule: {ap_thr threshold, weight -1/A + 1/T}
+      // first 16 bytes = all a diff-label pair needs.  Its backward weight exp(s - max) / T / world is evaluated by the gradient
+      // kernel as ONE exponential 2^(s*log2(e) - m2c) with m2c = max*log2(e) + log2(T) + log2(world) (T == 0: +inf, weight 0):
+      // {m2c, an_thr-transformed threshold, max*log2(e), label}; second 16 bytes = the same-label rule and the plain factors:
+      // {ap_thr threshold, weight 1/T - 1/A, 1/T, 0}
       float4* rec = reinterpret_cast<float4*>(ra.rowscal + 8ll * i);
-      rec[0] = make_float4(m2, thr_n, invT, li);
-      rec[1] = make_float4(thr_p, invT - invA, 0.f, 0.f);
+      rec[0] = make_float4(T == 0.f ? INFINITY : m2 + log2f(T) + log2_world, thr_n, m2, li);
+      rec[1] = make_float4(thr_p, invT - invA, invT, 0.f);
     }
   }
   // ---- grid-level completion: the last block reduces the row results (fixed order -> deterministic) ----
@@ -831,14 +1031,13 @@ __global__ void __launch_bounds__(256, NPAIR_LSE_MINB) lse_rows_kernel(const flo
   }
 }
 void launch_lse_rows(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
-                     int self_offset, MiningParams mp, RowArrays ra, BlockScalars* bs, int num_tops, float* tops_dev, cudaStream_t st) {
+                     int self_offset, MiningParams mp, RowArrays ra, BlockScalars* bs, int num_tops, float* tops_dev, int world, cudaStream_t st) {
   // 8 warps per block, 4 blocks per SM.  Measured at Q = 8192 (1.73 waves): 7 warps (1.98 waves, less idle tail) is SLOWER
   // (81.3 vs 78.7 us; 6: 83.7, 5: 87.6) -- the pass is latency-bound, more resident warps win.  NPAIR_LSE_WPB overrides.
   int wpb = 8;
-  if (const char* e = getenv("NPAIR_LSE_WPB")) { const int w = atoi(e); if (w >= 1 && w <= 8) wpb = w; }
   while (wpb > 1 && (Q + wpb - 1) / wpb < 296) wpb >>= 1;     // keep >= 2 blocks per SM when the rank has few rows
   const int grid = (Q + wpb - 1) / wpb;
-  lse_rows_kernel<<<grid, wpb * 32, 0, st>>>(S, ldS, Q, N, lab_rows, lab_cols, self_offset, mp, ra, bs, num_tops, tops_dev);
+  lse_rows_kernel<<<grid, wpb * 32, 0, st>>>(S, ldS, Q, N, lab_rows, lab_cols, self_offset, mp, ra, bs, num_tops, tops_dev, log2f(static_cast<float>(world)));
   count_launch();
 }
 
@@ -906,17 +1105,17 @@ __global__ void __launch_bounds__(256, 4) build_weights_kernel(const float* __re
   if (t < TS) {
     const int j = a0 + t;
     RowScal r = {0.f, -INFINITY, -INFINITY, 0.f, 0.f, 0.f};
-    if (j < Q) { const float* b = ra.rowscal + 8ll * j; r.maxall = b[0]; r.tn = b[1]; r.cT = b[2]; r.lab = b[3]; r.tp = b[4]; r.cA = b[5]; }
+    if (j < Q) { const float* b = ra.rowscal + 8ll * j; r.maxall = b[2]; r.tn = b[1]; r.cT = b[6]; r.lab = b[3]; r.tp = b[4]; r.cA = b[5]; }
     sc_a[t] = r;
   } else if (t < 2 * TS) {
     const int mm = t - TS, m = b0 + mm;
     RowScal r = {0.f, -INFINITY, -INFINITY, 0.f, 0.f, 0.f};
     if (MODE == BW_SYM) {   // world == 1: column m is also a local row
-      if (m < Q) { const float* b = ra.rowscal + 8ll * m; r.maxall = b[0]; r.tn = b[1]; r.cT = b[2]; r.lab = b[3]; r.tp = b[4]; r.cA = b[5]; }
+      if (m < Q) { const float* b = ra.rowscal + 8ll * m; r.maxall = b[2]; r.tn = b[1]; r.cT = b[6]; r.lab = b[3]; r.tp = b[4]; r.cA = b[5]; }
     } else if (MODE == BW_ROWSCAL) {   // all-gathered [N][8] row records; the 1/world of .cu:474 folded into the weights
       if (m < N) {
         const float* b = rs_total + 8ll * m;
-        r.maxall = b[0]; r.tn = b[1]; r.cT = b[2] * inv_world; r.lab = b[3]; r.tp = b[4]; r.cA = b[5] * inv_world;
+        r.maxall = b[2]; r.tn = b[1]; r.cT = b[6] * inv_world; r.lab = b[3]; r.tp = b[4]; r.cA = b[5] * inv_world;
       }
     } else if (m < N) r.lab = lab_cols[m];
     sc_b[mm] = r;
@@ -986,6 +1185,61 @@ __global__ void axpy_kernel(float* __restrict__ dst, const float* __restrict__ s
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] += a * src[i];
 }
+// --------------------------------------------------------------------------------------------
+// L2Normalize producer (usage/def.prototxt:115-120; the layer's source is not in the reference tree, so the semantics are
+// stated here): y = x / ||x||_2 per sample, a zero row stays zero; backward dx = (dy - y (y . dy)) / ||x||.
+// One warp per row, 16-byte loads, fixed summation order (lane-strided partial sums, then the shuffle tree).
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) l2norm_fwd_kernel(const float* __restrict__ x, int rows, int dim, float* __restrict__ y,
+                                                         float* __restrict__ inv_norm) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const float* xr = x + static_cast<long long>(r) * dim;
+  float* yr = y + static_cast<long long>(r) * dim;
+  const bool vec = (dim & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+  float ss = 0.f;
+  if (vec) for (int d = lane * 4; d < dim; d += 128) { const float4 v = *reinterpret_cast<const float4*>(xr + d); ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss); }
+  else for (int d = lane; d < dim; d += 32) ss = fmaf(xr[d], xr[d], ss);
+  ss = warp_sum(ss);
+  const float nrm = sqrtf(ss);
+  const float inv = nrm > 0.f ? 1.f / nrm : 0.f;
+  if (lane == 0 && inv_norm) inv_norm[r] = inv;
+  if (vec) for (int d = lane * 4; d < dim; d += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + d);
+    *reinterpret_cast<float4*>(yr + d) = nrm > 0.f ? make_float4(v.x / nrm, v.y / nrm, v.z / nrm, v.w / nrm) : make_float4(0.f, 0.f, 0.f, 0.f);
+  } else for (int d = lane; d < dim; d += 32) yr[d] = nrm > 0.f ? xr[d] / nrm : 0.f;
+}
+__global__ void __launch_bounds__(256) l2norm_bwd_kernel(const float* __restrict__ y, const float* __restrict__ inv_norm, const float* __restrict__ dy,
+                                                         int rows, int dim, float* __restrict__ dx) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const float* yr = y + static_cast<long long>(r) * dim;
+  const float* gr = dy + static_cast<long long>(r) * dim;
+  float* dr = dx + static_cast<long long>(r) * dim;
+  const bool vec = (dim & 3) == 0 && ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0;
+  float dot = 0.f;
+  if (vec) for (int d = lane * 4; d < dim; d += 128) {
+    const float4 a = *reinterpret_cast<const float4*>(yr + d), g = *reinterpret_cast<const float4*>(gr + d);
+    dot = fmaf(a.x, g.x, dot); dot = fmaf(a.y, g.y, dot); dot = fmaf(a.z, g.z, dot); dot = fmaf(a.w, g.w, dot);
+  } else for (int d = lane; d < dim; d += 32) dot = fmaf(yr[d], gr[d], dot);
+  dot = warp_sum(dot);
+  const float inv = inv_norm[r];
+  if (vec) for (int d = lane * 4; d < dim; d += 128) {
+    const float4 a = *reinterpret_cast<const float4*>(yr + d), g = *reinterpret_cast<const float4*>(gr + d);
+    *reinterpret_cast<float4*>(dr + d) = make_float4((g.x - a.x * dot) * inv, (g.y - a.y * dot) * inv, (g.z - a.z * dot) * inv, (g.w - a.w * dot) * inv);
+  } else for (int d = lane; d < dim; d += 32) dr[d] = (gr[d] - yr[d] * dot) * inv;
+}
+void launch_l2norm_fwd(const float* x, int rows, int dim, float* y, float* inv_norm, cudaStream_t st) {
+  l2norm_fwd_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, rows, dim, y, inv_norm);
+  count_launch();
+}
+void launch_l2norm_bwd(const float* y, const float* inv_norm, const float* dy, int rows, int dim, float* dx, cudaStream_t st) {
+  l2norm_bwd_kernel<<<(rows + 7) / 8, 256, 0, st>>>(y, inv_norm, dy, rows, dim, dx);
+  count_launch();
+}
+
 void launch_axpy_rows(float* dst, const float* src, long long n, float a, cudaStream_t st) {
   int nb = static_cast<int>((n + 255) / 256); if (nb > 148 * 8) nb = 148 * 8; if (nb < 1) nb = 1;
   axpy_kernel<<<nb, 256, 0, st>>>(dst, src, n, a);

@@ -31,6 +31,9 @@ struct BlockScalars {
   uint32_t sel_prefix[2];                  // ordered-uint prefix decided so far
   uint32_t sel_mask[2];                    // which bits of the prefix are decided
   int sel_active[2];                       // 1 while a GLOBAL relative select is in flight
+  unsigned long long sel_cnt[2];           // population of the chosen first-digit bucket (GLOBAL select)
+  unsigned int cand_n[2];                  // entries of the compact candidate lists (GLOBAL select)
+  unsigned int ticket3;                    // block-completion counter of the GLOBAL select kernels
   float asum;                              // sum |x| over the local features (.cu:400)
   float x_absmax;                          // max |x| over x_total (operand pre-scale for PREC_FP16X2)
   float x_scale, x_inv_scale;              // power of two s.t. max|x*scale| in [0.5,1]; 1 for other precisions
@@ -50,7 +53,7 @@ struct RowArrays {
   // forward row results
   float *A, *T, *logv;
   int* hits;                 // [3][Q] retrieval hit flags for k=1,5,10
-  // row scalars consumed by the backward: [Q][8] floats {max_all*log2e, thr_n', cT, label | thr_p', cA, 0, 0}
+  // row scalars consumed by the backward: [Q][8] floats {m2c, thr_n', max_all*log2e, label | thr_p', cA, cT, 0} (see lse_rows_kernel)
   // (one 32-byte record per row: all-gathered as is when world > 1, bulk-copied per K block by the fused gradient kernel)
   float* rowscal;
 };
@@ -72,21 +75,23 @@ void launch_split(const float* x_total, int N, int D, int prec, const BlockScala
 void launch_row_stats_ref(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
                           int self_offset, RowArrays ra, cudaStream_t st);
 void launch_thresholds(RowArrays ra, int Q, int N, MiningParams mp, BlockScalars* bs, float* scratch /*>= 2 KB*/, cudaStream_t st);
+// side_mask: bit 0 = AP threshold over the same-label list, bit 1 = AN threshold over the diff-label list
 void launch_local_select(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
-                         int self_offset, int side /*0 AP same, 1 AN diff*/, float sn, RowArrays ra, BlockScalars* bs,
-                         cudaStream_t st);
+                         int self_offset, int side_mask, float sn_ap, float sn_an, RowArrays ra, BlockScalars* bs, int sms, cudaStream_t st);
 void launch_global_select(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
-                          int self_offset, int side, float sn, RowArrays ra, unsigned long long* hist /*[2048]*/,
-                          BlockScalars* bs, cudaStream_t st);
+                          int self_offset, int side_mask, RowArrays ra, unsigned long long* hist /*[2][2048], zero*/,
+                          uint32_t* cand /*[2][cand_cap]*/, unsigned int cand_cap, BlockScalars* bs, int sms, cudaStream_t st);
 void launch_lse_rows(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
                      int self_offset, MiningParams mp, RowArrays ra, BlockScalars* bs, int num_tops, float* tops_dev /*[5]+err*/,
-                     cudaStream_t st);
+                     int world, cudaStream_t st);
 // mode: BW_SPLIT (world > 1, reduce-scatter form: H and HT), BW_SYM (world == 1), BW_ROWSCAL (world > 1, row-scalar
 // exchange: rs_total = all-gathered [world][5][Q] row scalars)
 enum { BW_SPLIT = 0, BW_SYM = 1, BW_ROWSCAL = 2 };
 void launch_build_weights(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
                           int self_offset, int world, int mode, const float* rs_total, MiningParams mp, RowArrays ra, int prec,
                           uint16_t* H, long long ldH /*Np*/, uint16_t* HT, long long ldHT /*Qp*/, cudaStream_t st);
+void launch_l2norm_fwd(const float* x, int rows, int dim, float* y, float* inv_norm, cudaStream_t st);
+void launch_l2norm_bwd(const float* y, const float* inv_norm, const float* dy, int rows, int dim, float* dx, cudaStream_t st);
 void launch_axpy_rows(float* dst, const float* src, long long n, float a, cudaStream_t st);
 
 }  // namespace npair

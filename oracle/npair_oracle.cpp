@@ -501,6 +501,30 @@ int npo_backward_partial(const npo_config* cfg, const float* x_total, const npo_
   return NPO_OK;
 }
 
+void npo_l2normalize_forward(const float* x, int rows, int dim, float* y, float* inv_norm) {
+#pragma omp parallel for schedule(static)
+  for (int r = 0; r < rows; ++r) {
+    const float* xr = x + (size_t)r * dim;
+    double ss = 0.0;
+    for (int d = 0; d < dim; ++d) ss += (double)xr[d] * (double)xr[d];
+    const float nrm = sqrtf((float)ss);
+    if (inv_norm) inv_norm[r] = nrm > 0.f ? 1.f / nrm : 0.f;
+    for (int d = 0; d < dim; ++d) y[(size_t)r * dim + d] = nrm > 0.f ? xr[d] / nrm : 0.f;
+  }
+}
+
+void npo_l2normalize_backward(const float* y, const float* inv_norm, const float* dy, int rows, int dim, float* dx) {
+#pragma omp parallel for schedule(static)
+  for (int r = 0; r < rows; ++r) {
+    const float* yr = y + (size_t)r * dim;
+    const float* gr = dy + (size_t)r * dim;
+    double dot = 0.0;
+    for (int d = 0; d < dim; ++d) dot += (double)yr[d] * (double)gr[d];
+    const float dotf = (float)dot, inv = inv_norm[r];
+    for (int d = 0; d < dim; ++d) dx[(size_t)r * dim + d] = (gr[d] - yr[d] * dotf) * inv;
+  }
+}
+
 int npo_step_world(const npo_config* cfg0, const float* x_total, const float* label_total,
                    const float* S_inject_all, float loss_weight, float* tops_out, float* dx_out) {
   if (!cfg0 || !x_total || !label_total || !tops_out) return NPO_ERR_ARG;

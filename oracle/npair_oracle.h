@@ -99,6 +99,14 @@ int npo_step_world(const npo_config* cfg_rank0, const float* x_total, const floa
  * value / >= size when out of range (caller decides).  Exposed for the known-answer tests. */
 long long npo_pos(float sn, size_t size);
 
+/* The L2Normalize producer layer in front of the loss (usage/def.prototxt:115-120).  Its source is NOT in the reference tree
+ * (a layer of the private Caffe fork), so this is the textbook definition, stated rather than restated:
+ *   forward : y[r][:] = x[r][:] / sqrt(sum_d x[r][d]^2)      (a zero row stays zero)
+ *   backward: dx[r][:] = (dy[r][:] - y[r][:] * (y[r][:] . dy[r][:])) / ||x[r]||
+ * inv_norm: rows floats, 1/||x|| (0 for a zero row).  Sums in double, rounded to fp32 on store. */
+void npo_l2normalize_forward(const float* x, int rows, int dim, float* y, float* inv_norm);
+void npo_l2normalize_backward(const float* y, const float* inv_norm, const float* dy, int rows, int dim, float* dx);
+
 const char* npo_version(void);
 
 #ifdef __cplusplus

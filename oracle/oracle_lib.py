@@ -52,6 +52,10 @@ def lib():
         L.npo_pos.restype = C.c_longlong
         L.npo_pos.argtypes = [C.c_float, C.c_size_t]
         L.npo_version.restype = C.c_char_p
+        L.npo_l2normalize_forward.argtypes = [fp, C.c_int, C.c_int, fp, fp]
+        L.npo_l2normalize_forward.restype = None
+        L.npo_l2normalize_backward.argtypes = [fp, fp, fp, C.c_int, C.c_int, fp]
+        L.npo_l2normalize_backward.restype = None
         _LIB = L
     return _LIB
 
@@ -122,3 +126,20 @@ def step_world(x_total, label_total, cfg: NpoConfig, loss_weight=1.0, S_inject_a
 
 def pos(sn, size):
     return int(lib().npo_pos(C.c_float(sn), C.c_size_t(size)))
+
+
+def l2normalize_forward(x):
+    """(y, inv_norm) of the L2Normalize producer layer (usage/def.prototxt:115-120)."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    y = np.empty_like(x)
+    inv = np.empty(x.shape[0], dtype=np.float32)
+    lib().npo_l2normalize_forward(_fp(x), x.shape[0], x.shape[1], _fp(y), _fp(inv))
+    return y, inv
+
+
+def l2normalize_backward(y, inv, dy):
+    y = np.ascontiguousarray(y, dtype=np.float32); dy = np.ascontiguousarray(dy, dtype=np.float32)
+    inv = np.ascontiguousarray(inv, dtype=np.float32)
+    dx = np.empty_like(dy)
+    lib().npo_l2normalize_backward(_fp(y), _fp(inv), _fp(dy), y.shape[0], y.shape[1], _fp(dx))
+    return dx

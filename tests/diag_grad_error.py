@@ -1,5 +1,5 @@
 """Diagnostic (not a test): gradient / loss error of the CUDA path against the oracle (on the GPU's own S) as the database grows.
-   python tests/diag_grad_error.py [D]"""
+   python tests/diag_grad_error.py [D] [B,B,...]"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
@@ -8,7 +8,8 @@ from npairloss_b200 import capi, synth
 from oracle import oracle_lib as o
 from gpu_harness import gpu_step_world
 D = int(sys.argv[1]) if len(sys.argv) > 1 else 512
-for B in (1024, 2048, 4096, 8192):
+Bs = [int(b) for b in sys.argv[2].split(",")] if len(sys.argv) > 2 else [1024, 2048, 4096, 8192]
+for B in Bs:
     x, lab = synth.make_inputs(B, D, 20171225 + 5, noise=2.5)
     for prec, name in ((2, "fp16x2"), (0, "bf16x3")):
         g = gpu_step_world(x, lab, B, 1, synth.USAGE_MINING, prec, capi.GEMM_TCGEN05)

@@ -158,3 +158,28 @@ def test_multirank_loss_is_per_rank_and_grad_blend(oracle):
         G[r * Q:(r + 1) * Q] = onp.grad_weights(st, Q, 1.0)
     ref = 0.5 * G @ x.astype(np.float64) + 0.5 / k * G.T @ x.astype(np.float64)
     assert np.linalg.norm(dx - ref) <= 2e-6 * np.linalg.norm(ref)
+
+
+def test_l2normalize_statement(oracle):
+    """The L2Normalize producer (usage/def.prototxt:115-120; source not in the reference tree): unit rows, zero rows kept,
+    backward = the Jacobian of x / ||x|| (finite differences in fp64)."""
+    rng = np.random.default_rng(3)
+    x = (rng.standard_normal((6, 9)) * rng.uniform(0.1, 50, size=(6, 1))).astype(np.float32)
+    x[4] = 0
+    y, inv = oracle.l2normalize_forward(x)
+    np.testing.assert_allclose(np.linalg.norm(y[[0, 1, 2, 3, 5]].astype(np.float64), axis=1), 1.0, rtol=1e-6)
+    assert not y[4].any() and inv[4] == 0
+    dy = rng.standard_normal((6, 9)).astype(np.float32)
+    dx = oracle.l2normalize_backward(y, inv, dy)
+
+    def f(xx):
+        n = np.linalg.norm(xx, axis=1, keepdims=True)
+        return float((np.where(n > 0, xx / np.where(n > 0, n, 1), 0) * dy).sum())
+    x64 = x.astype(np.float64)
+    for i in (0, 1, 2, 3, 5):
+        for j in range(9):
+            h = 1e-6 * max(1.0, abs(x64[i, j]))
+            e = np.zeros_like(x64); e[i, j] = h
+            fd = (f(x64 + e) - f(x64 - e)) / (2 * h)
+            assert abs(fd - dx[i, j]) <= 1e-5 * max(1e-3, abs(fd)) + 1e-7, (i, j, fd, dx[i, j])
+    assert not dx[4].any()
