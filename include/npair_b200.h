@@ -84,7 +84,7 @@ typedef struct {
                               (.cu:225-268 builds the lists from the rank's own Q x N block, :385/:427 divide by Q). */
   int32_t normalize_input; /* 1: the L2Normalize producer layer (usage/def.prototxt:115-120) is fused in: bottom[0] holds raw
                               embeddings, the layer works on x / ||x||_2 and returns the gradient w.r.t. the raw embeddings. */
-  int32_t grad_chunk_cols; /* accumulation chunk of the gradient GEMM in database columns (multiple of 32); 0 = default (1024).
+  int32_t grad_chunk_cols; /* accumulation chunk of the gradient GEMM in database columns (multiple of 32); 0 = default (2048: gradient 5e-6 from exact at any N; 1024 halves that for +8 % kernel time), < 0 = one accumulator.
                               The tensor core truncates its fp32 accumulator on every MMA; chunks bound that error, see DESIGN 5 */
   int32_t flags;           /* NPAIR_FLAG_* */
 } npair_config;

@@ -42,10 +42,14 @@ void NPairMultiClassLossLayer<Dtype>::LayerSetUp(const vector<Blob<Dtype>*>& bot
   cfg.num_tops = static_cast<int32_t>(top.size());
   if (sim_precision_ >= 0) cfg.sim_precision = sim_precision_;
   if (const char* e = getenv("NPAIR_SIM_PRECISION")) cfg.sim_precision = atoi(e);
-  if (ctx_) { npair_destroy(ctx_); ctx_ = nullptr; }
-  const int rc = npair_create(&cfg, Caffe::NUM_GPU > 1 ? Caffe::nccl_unique_id() : nullptr, &ctx_);
-  CHECK_EQ(rc, NPAIR_OK) << "npair_create: " << npair_last_error(nullptr);
   if (cfg.world > 1) CHECK(Caffe::nccl_unique_id() != nullptr) << "NUM_GPU > 1 needs Caffe::set_nccl_unique_id()";
+  npair_ctx* old = ctx_;                   // destroyed AFTER the new context exists: the shared communicator stays referenced
+  ctx_ = nullptr;
+  // every layer instance of this process passes the same id: the library keeps ONE communicator per (process, id), so a second
+  // instance (TRAIN + TEST nets) or a repeated LayerSetUp does not consume the ncclUniqueId again
+  const int rc = npair_create(&cfg, Caffe::NUM_GPU > 1 ? Caffe::nccl_unique_id() : nullptr, &ctx_);
+  if (old) npair_destroy(old);
+  CHECK_EQ(rc, NPAIR_OK) << "npair_create: " << npair_last_error(nullptr);
   if (sizeof(Dtype) == 8) {
     CUDA_CHECK(cudaMalloc(&f32_feat_, sizeof(float) * static_cast<size_t>(num_) * dim_));
     CUDA_CHECK(cudaMalloc(&f32_label_, sizeof(float) * num_));

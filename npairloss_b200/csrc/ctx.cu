@@ -13,6 +13,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -72,6 +74,36 @@ static NcclApi* nccl_api() {
   return &api;
 }
 enum { NCCL_FLOAT32 = 7, NCCL_SUM = 0 };
+
+// One communicator per (process, unique id): a second context created with the same 128-byte id -- a solver's TRAIN and TEST nets,
+// a repeated LayerSetUp, a wrapper that rebuilds its context for a new batch size -- shares the communicator of the first
+// (an ncclUniqueId can only be consumed once by ncclCommInitRank).  Reference-counted; destroyed with its last context.
+struct SharedComm { void* comm; int refs; };
+static std::mutex g_comm_mu;
+static std::map<std::string, SharedComm> g_comms;
+static int acquire_comm(const void* id128, int world, int rank, void** out, std::string* err) {
+  NcclApi* api = nccl_api();
+  const std::string key(static_cast<const char*>(id128), 128);
+  std::lock_guard<std::mutex> lk(g_comm_mu);
+  auto it = g_comms.find(key);
+  if (it != g_comms.end()) { ++it->second.refs; *out = it->second.comm; return 0; }
+  NcclId id; memcpy(&id, id128, 128);
+  void* comm = nullptr;
+  const int r = api->CommInitRank(&comm, world, id, rank);
+  if (r != 0) { *err = fmt("ncclCommInitRank: %s", api->GetErrorString(r)); return r; }
+  g_comms[key] = SharedComm{comm, 1};
+  *out = comm;
+  return 0;
+}
+static void release_comm(void* comm) {
+  NcclApi* api = nccl_api();
+  std::lock_guard<std::mutex> lk(g_comm_mu);
+  for (auto it = g_comms.begin(); it != g_comms.end(); ++it)
+    if (it->second.comm == comm) {
+      if (--it->second.refs == 0) { if (api->CommDestroy) api->CommDestroy(comm); g_comms.erase(it); }
+      return;
+    }
+}
 
 // ------------------------------------------------------------------------------------------------ TMA maps
 static PFN_cuTensorMapEncodeTiled_v12000 tmap_encode_fn() {
@@ -303,18 +335,29 @@ static cudaError_t launch_simt_gemm(int prec, int epi, const uint16_t* A, long l
 }
 
 // out = sum_s part[s] + beta*out, fixed summation order (deterministic split-K)
-// ---- opt-in peer-memory exchange of the row records (NPAIR_P2P_RECORDS=1; written after round 1's GPU budget, not run yet) ----
-// Every rank PUSHES its [Q][8] records into all ranks' buffers with plain stores over NVLink (cudaIpc-mapped peer memory), then
-// raises one flag per peer; the backward waits for the world's flags.  Replaces the ~20 us NCCL all-gather of 256 KB.
-// Buffers and flags are double-buffered by the parity of the step counter; flags carry the step number, never reset.
-__global__ void p2p_push_records_kernel(const float4* __restrict__ rec, float* const* __restrict__ peer_buf, uint32_t* const* __restrict__ peer_flags,
-                                        int world, int rank, int Q, long long N, int parity, uint32_t epoch, unsigned int* ticket) {
-  const long long n4 = 2ll * Q;                                  // float4s of this rank's records
-  const long long off = 2ll * (static_cast<long long>(parity) * N + static_cast<long long>(rank) * Q);
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const float4 v = rec[i];
-    for (int r = 0; r < world; ++r) reinterpret_cast<float4*>(peer_buf[r])[off + i] = v;
+// ---- peer-memory exchange (world > 1, one process per GPU, NVLink / NVSwitch) ----
+// Every rank owns one exported region (cudaIpc-mapped into all ranks):
+//     X[2][N][D] fp32 | LAB[2][N] | REC[2][N][8] | FLAGS[2 kinds][2][world] uint32
+// and PUSHES its own rows into every rank's region with plain stores over NVLink, then raises one flag per peer (release.sys);
+// consumers wait for the world's flags (acquire.sys).  Replaces GatherFeatureAndLabel's MPI_Allgather (reference .cu:17-43) and the
+// backward's exchange (row records instead of the N x D all-reduce, .cu:462-489) without a collective rendezvous: nothing
+// waits for a slower rank until its data is really needed.  Buffers are double-buffered by the parity of the step counter and
+// the flags carry the step number (never reset), so a rank that runs one step ahead never overwrites data still in use;
+// like any collective this requires all ranks to issue the same sequence of forward / backward calls.
+__global__ void p2p_push_kernel(const float* __restrict__ srcA, long long nA, long long offA, const float* __restrict__ srcB, long long nB, long long offB,
+                                float* const* __restrict__ peer_base, long long flags_off /*in floats*/, int flag_index, int world, uint32_t epoch,
+                                unsigned int* ticket) {
+  const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x, nth = static_cast<long long>(gridDim.x) * blockDim.x;
+  const bool vecA = (nA & 3) == 0 && (offA & 3) == 0 && (reinterpret_cast<uintptr_t>(srcA) & 15) == 0;
+  if (vecA) {
+    for (long long i = tid; i < (nA >> 2); i += nth) {
+      const float4 v = reinterpret_cast<const float4*>(srcA)[i];
+      for (int r = 0; r < world; ++r) reinterpret_cast<float4*>(peer_base[r] + offA)[i] = v;
+    }
+  } else {
+    for (long long i = tid; i < nA; i += nth) { const float v = srcA[i]; for (int r = 0; r < world; ++r) peer_base[r][offA + i] = v; }
   }
+  for (long long i = tid; i < nB; i += nth) { const float v = srcB[i]; for (int r = 0; r < world; ++r) peer_base[r][offB + i] = v; }
   __threadfence_system();
   __syncthreads();
   __shared__ int s_last;
@@ -323,16 +366,15 @@ __global__ void p2p_push_records_kernel(const float4* __restrict__ rec, float* c
   if (!s_last) return;
   __threadfence_system();
   if (static_cast<int>(threadIdx.x) < world) {
-    uint32_t* f = peer_flags[threadIdx.x] + parity * world + rank;
+    uint32_t* f = reinterpret_cast<uint32_t*>(peer_base[threadIdx.x] + flags_off) + flag_index;
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
   }
   if (threadIdx.x == 0) *ticket = 0;
 }
-__global__ void p2p_wait_records_kernel(const uint32_t* __restrict__ flags, int world, int parity, uint32_t epoch) {
+__global__ void p2p_wait_kernel(const uint32_t* __restrict__ flags /*[world]*/, int world, uint32_t epoch) {
   if (static_cast<int>(threadIdx.x) < world) {
-    const uint32_t* f = flags + parity * world + threadIdx.x;
     uint32_t v;
-    do { asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory"); } while (v != epoch);
+    do { asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + threadIdx.x) : "memory"); } while (static_cast<int32_t>(v - epoch) < 0);
   }
 }
 
@@ -397,20 +439,20 @@ struct npair_ctx {
   CUtensorMap tm_fB2;            // 128-row boxes of X^T for the CTA-pair gradient kernel
   bool grad_pair = false;        // fused gradient kernel runs in CTA-pair mode
   float *Ynorm = nullptr, *dY = nullptr, *inv_norm = nullptr;   // normalize_input: x / ||x||, gradient w.r.t. it, 1 / ||x||
-  int grad_chunk_kb = 32;        // accumulation chunk of the gradient GEMM in 32-column K blocks (grad_fused.cuh); 0 = unchunked
+  int grad_chunk_kb = 64;        // accumulation chunk of the gradient GEMM in 32-column K blocks (grad_fused.cuh); 0 = unchunked
   CUtensorMap tm_fB, tm_fS;      // fused gradient kernel: X^T pieces with 32-wide K boxes, 128-row fp32 boxes of S
   bool fused_grad = false;
   bool rs_gathered = false;
+  bool ext_gathered = false;      // the current forward came through npair_forward_gathered (external collectives)
   bool defer_sync = false;        // npair_forward_backward: the forward returns after enqueueing, the caller synchronises later
-  // peer-memory record exchange (opt-in)
-  bool p2p_rec = false;
-  float* p2p_buf = nullptr;            // [2][N][8] records of the whole world, written by every rank
-  uint32_t* p2p_flags = nullptr;       // [2][world] step number of rank r's last push
-  float** p2p_peer_buf = nullptr;      // device array [world] of the ranks' p2p_buf
-  uint32_t** p2p_peer_flags = nullptr; // device array [world] of the ranks' p2p_flags
+  // peer-memory exchange (world > 1 with a communicator; NPAIR_FLAG_NCCL_FEATURES / _RECORDS fall back to NCCL)
+  bool p2p_feat = false, p2p_rec = false;
+  float* p2p_region = nullptr;         // X[2][N][D] | LAB[2][N] | REC[2][N][8] | FLAGS
+  long long p2p_offX = 0, p2p_offLab = 0, p2p_offRec = 0, p2p_offFlags = 0;   // in floats
+  float** p2p_peer_base = nullptr;     // device array [world] of the ranks' regions
   unsigned int* p2p_ticket = nullptr;
   std::vector<void*> p2p_opened;
-  uint32_t p2p_epoch = 0;
+  uint32_t p2p_fwd_epoch = 0, p2p_rec_epoch = 0;
   int2* sym_tiles = nullptr;     // world == 1: (m_blk, n_blk) of the similarity tiles touching the upper triangle
   int n_sym_tiles = 0;
   float* part = nullptr;         // split-K partial products of the gradient GEMM
@@ -542,8 +584,8 @@ void npair_destroy(npair_ctx* c) {
   if (!c) return;
   if (c->device >= 0) cudaSetDevice(c->device);
   for (void* q : c->p2p_opened) cudaIpcCloseMemHandle(q);
-  cudaFree(c->p2p_buf); cudaFree(c->p2p_flags); cudaFree(c->p2p_peer_buf); cudaFree(c->p2p_peer_flags); cudaFree(c->p2p_ticket);
-  if (c->comm && c->own_comm) { NcclApi* api = nccl_api(); if (api->CommDestroy) api->CommDestroy(c->comm); }
+  cudaFree(c->p2p_region); cudaFree(c->p2p_peer_base); cudaFree(c->p2p_ticket);
+  if (c->comm && c->own_comm) release_comm(c->comm);
   cudaFree(c->Xtot_buf); cudaFree(c->labtot_buf); cudaFree(c->S); cudaFree(c->Xs); cudaFree(c->XsT); cudaFree(c->XlT);
   cudaFree(c->H); cudaFree(c->HT); cudaFree(c->OUT2); cudaFree(c->part); cudaFree(c->sym_tiles); cudaFree(c->sym_tiles2); cudaFree(c->XcatA); cudaFree(c->XcatB); cudaFree(c->rs_total); cudaFree(c->row_block); cudaFree(c->bs); cudaFree(c->partial); cudaFree(c->ghist); cudaFree(c->gcand); cudaFree(c->Ynorm); cudaFree(c->dY); cudaFree(c->inv_norm);
   if (c->tops_pinned) cudaFreeHost(c->tops_pinned);
@@ -721,7 +763,7 @@ static int create_impl(const npair_config* cfg, const void* id128, void* ext_com
     // CTA-pair similarity GEMM whenever there are at least two 128-row blocks (NPAIR_SIM_1CTA=1 keeps the single-CTA kernel)
     c->sim_pair = cfg->gemm_backend == NPAIR_GEMM_TCGEN05 && Q > 128 && !(cfg->flags & NPAIR_FLAG_SIM_1CTA);
     c->grad_pair = c->fused_grad && Q > 128 && !(cfg->flags & NPAIR_FLAG_GRAD_1CTA);
-    c->grad_chunk_kb = cfg->grad_chunk_cols > 0 ? (cfg->grad_chunk_cols + 31) / 32 : 32;     // default: 1024 database columns
+    c->grad_chunk_kb = cfg->grad_chunk_cols > 0 ? (cfg->grad_chunk_cols + 31) / 32 : 64;     // default: 2048 database columns
     if (cfg->grad_chunk_cols < 0) c->grad_chunk_kb = 0;                                        // negative: one accumulator for the whole K range (diagnostic)
   }
   // ---- NCCL ----
@@ -730,53 +772,55 @@ static int create_impl(const npair_config* cfg, const void* id128, void* ext_com
     if (!api->h || !api->err.empty()) { g_create_err = api->err; npair_destroy(c); return NPAIR_E_NCCL; }
     if (ext_comm) { c->comm = ext_comm; c->own_comm = false; }
     else {
-      NcclId id; memcpy(&id, id128, 128);
-      int r = api->CommInitRank(&c->comm, c->world, id, c->rank);
-      if (r != 0) { g_create_err = fmt("ncclCommInitRank: %s", api->GetErrorString(r)); c->comm = nullptr; npair_destroy(c); return NPAIR_E_NCCL; }
+      std::string ce;
+      if (acquire_comm(id128, c->world, c->rank, &c->comm, &ce) != 0) { g_create_err = ce; c->comm = nullptr; npair_destroy(c); return NPAIR_E_NCCL; }
       c->own_comm = true;
     }
   }
-  {
-    const char* ep = getenv("NPAIR_P2P_RECORDS");     // A/B switch while the peer-memory exchange is being qualified
-    if (ep && ep[0] == '1' && !(cfg->flags & NPAIR_FLAG_NCCL_RECORDS) && c->comm && c->world > 1 && c->world <= 32 && c->bwd_mode == NPAIR_BWDMODE_ROW_SCALARS) {
-      // map every rank's record buffer and flags into this process (cudaIpc over the NCCL bootstrap: one tiny all-gather of handles)
+  if (c->comm && c->world > 1 && c->world <= 32 && !getenv("NPAIR_NO_P2P")) {
+    const bool want_feat = !(cfg->flags & NPAIR_FLAG_NCCL_FEATURES);
+    const bool want_rec = !(cfg->flags & NPAIR_FLAG_NCCL_RECORDS) && c->bwd_mode == NPAIR_BWDMODE_ROW_SCALARS;
+    if (want_feat || want_rec) {
+      // one exported region per rank; handles travel over the NCCL communicator once (a 64-byte all-gather)
       NcclApi* api = nccl_api();
       const int W = c->world;
-      CREATE_TRY(cudaMalloc(&c->p2p_buf, sizeof(float) * 2ull * 8ull * N));
-      CREATE_TRY(cudaMalloc(&c->p2p_flags, sizeof(uint32_t) * 2ull * W));
-      CREATE_TRY(cudaMemset(c->p2p_flags, 0, sizeof(uint32_t) * 2ull * W));
+      const long long nX = static_cast<long long>(N) * D, nL = round_up(N, 4), nR = 8ll * N;
+      c->p2p_offX = 0; c->p2p_offLab = 2 * nX; c->p2p_offRec = c->p2p_offLab + 2 * nL; c->p2p_offFlags = c->p2p_offRec + 2 * nR;
+      const long long total = c->p2p_offFlags + round_up(4ll * W, 4);
+      CREATE_TRY(cudaMalloc(&c->p2p_region, sizeof(float) * static_cast<size_t>(total)));
+      CREATE_TRY(cudaMemset(c->p2p_region, 0, sizeof(float) * static_cast<size_t>(total)));
       CREATE_TRY(cudaMalloc(&c->p2p_ticket, sizeof(unsigned int)));
       CREATE_TRY(cudaMemset(c->p2p_ticket, 0, sizeof(unsigned int)));
-      struct Handles { cudaIpcMemHandle_t buf, flags; };
-      static_assert(sizeof(Handles) == 128, "two 64-byte IPC handles");
-      Handles mine;
-      CREATE_TRY(cudaIpcGetMemHandle(&mine.buf, c->p2p_buf));
-      CREATE_TRY(cudaIpcGetMemHandle(&mine.flags, c->p2p_flags));
+      cudaIpcMemHandle_t mine;
+      static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+      CREATE_TRY(cudaIpcGetMemHandle(&mine, c->p2p_region));
       float *d_mine = nullptr, *d_all = nullptr;
-      CREATE_TRY(cudaMalloc(&d_mine, 128));
-      CREATE_TRY(cudaMalloc(&d_all, 128ull * W));
-      CREATE_TRY(cudaMemcpy(d_mine, &mine, 128, cudaMemcpyHostToDevice));
-      int r = api->AllGather(d_mine, d_all, 32, NCCL_FLOAT32, c->comm, nullptr);
+      CREATE_TRY(cudaMalloc(&d_mine, 64));
+      CREATE_TRY(cudaMalloc(&d_all, 64ull * W));
+      CREATE_TRY(cudaMemcpy(d_mine, &mine, 64, cudaMemcpyHostToDevice));
+      CREATE_TRY(cudaDeviceSynchronize());                       // the memset above has landed before any peer can write into the region
+      int r = api->AllGather(d_mine, d_all, 16, NCCL_FLOAT32, c->comm, nullptr);
       if (r != 0) { g_create_err = fmt("ncclAllGather(ipc handles): %s", api->GetErrorString(r)); cudaFree(d_mine); cudaFree(d_all); npair_destroy(c); return NPAIR_E_NCCL; }
       CREATE_TRY(cudaStreamSynchronize(nullptr));
-      std::vector<Handles> all(W);
-      CREATE_TRY(cudaMemcpy(all.data(), d_all, 128ull * W, cudaMemcpyDeviceToHost));
+      std::vector<cudaIpcMemHandle_t> all(W);
+      CREATE_TRY(cudaMemcpy(all.data(), d_all, 64ull * W, cudaMemcpyDeviceToHost));
       cudaFree(d_mine); cudaFree(d_all);
-      std::vector<float*> pb(W); std::vector<uint32_t*> pf(W);
-      for (int q = 0; q < W; ++q) {
-        if (q == c->rank) { pb[q] = c->p2p_buf; pf[q] = c->p2p_flags; continue; }
-        void *a = nullptr, *b = nullptr;
-        CREATE_TRY(cudaIpcOpenMemHandle(&a, all[q].buf, cudaIpcMemLazyEnablePeerAccess));
+      std::vector<float*> pb(W);
+      bool mapped = true;
+      for (int q = 0; q < W && mapped; ++q) {
+        if (q == c->rank) { pb[q] = c->p2p_region; continue; }
+        void* a = nullptr;
+        if (cudaIpcOpenMemHandle(&a, all[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); mapped = false; break; }
         c->p2p_opened.push_back(a);
-        CREATE_TRY(cudaIpcOpenMemHandle(&b, all[q].flags, cudaIpcMemLazyEnablePeerAccess));
-        c->p2p_opened.push_back(b);
-        pb[q] = static_cast<float*>(a); pf[q] = static_cast<uint32_t*>(b);
+        pb[q] = static_cast<float*>(a);
       }
-      CREATE_TRY(cudaMalloc(&c->p2p_peer_buf, sizeof(float*) * W));
-      CREATE_TRY(cudaMalloc(&c->p2p_peer_flags, sizeof(uint32_t*) * W));
-      CREATE_TRY(cudaMemcpy(c->p2p_peer_buf, pb.data(), sizeof(float*) * W, cudaMemcpyHostToDevice));
-      CREATE_TRY(cudaMemcpy(c->p2p_peer_flags, pf.data(), sizeof(uint32_t*) * W, cudaMemcpyHostToDevice));
-      c->p2p_rec = true;
+      if (mapped) {
+        CREATE_TRY(cudaMalloc(&c->p2p_peer_base, sizeof(float*) * W));
+        CREATE_TRY(cudaMemcpy(c->p2p_peer_base, pb.data(), sizeof(float*) * W, cudaMemcpyHostToDevice));
+        c->p2p_feat = want_feat; c->p2p_rec = want_rec;
+      }
+      // (no peer access between some pair of GPUs: the NCCL paths are used; every rank takes the same decision only if the
+      // topology is symmetric, which holds on an NVSwitch box -- a mixed outcome is reported by the first exchange's timeout)
     }
   }
 #undef CREATE_TRY
@@ -806,7 +850,7 @@ int npair_forward(npair_ctx* c, const float* d_feat, const float* d_label, float
   if (!d_feat || !d_label || !tops_host) { c->err = "null pointer argument"; return NPAIR_E_ARG; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CUDA_TRY(c, cudaSetDevice(c->device));
-  c->fwd_done = false; c->last_stream = st;
+  c->fwd_done = false; c->last_stream = st; c->ext_gathered = false;
   const int Q = c->Q, D = c->D;
   if (c->cfg.normalize_input) {               // fused L2Normalize producer (usage/def.prototxt:115-120): the layer works on x / ||x||
     PhaseTimer pt(c, 1, st);
@@ -814,7 +858,21 @@ int npair_forward(npair_ctx* c, const float* d_feat, const float* d_label, float
     d_feat = c->Ynorm; c->y_local = c->Ynorm;
   }
   // ---- GatherFeatureAndLabel (.cu:17-43): one NCCL group, device to device over NVLink ----
-  if (c->world > 1) {
+  if (c->world > 1 && c->p2p_feat) {
+    PhaseTimer pt(c, 0, st);
+    const uint32_t ep = ++c->p2p_fwd_epoch;
+    const long long par = ep & 1u, N = c->N;
+    const long long offX = c->p2p_offX + par * N * D + static_cast<long long>(c->rank) * Q * D;
+    const long long offL = c->p2p_offLab + par * round_up(N, 4) + static_cast<long long>(c->rank) * Q;
+    int nb = static_cast<int>((static_cast<long long>(Q) * D / 4 + 255) / 256); if (nb > 2 * c->sms) nb = 2 * c->sms; if (nb < 1) nb = 1;
+    p2p_push_kernel<<<nb, 256, 0, st>>>(d_feat, static_cast<long long>(Q) * D, offX, d_label, Q, offL, c->p2p_peer_base, c->p2p_offFlags,
+                                        static_cast<int>(par) * c->world + c->rank, c->world, ep, c->p2p_ticket);
+    count_launch();
+    p2p_wait_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const uint32_t*>(c->p2p_region + c->p2p_offFlags) + par * c->world, c->world, ep);
+    count_launch();
+    c->x_total = c->p2p_region + c->p2p_offX + par * N * D;
+    c->lab_total = c->p2p_region + c->p2p_offLab + par * round_up(N, 4);
+  } else if (c->world > 1) {
     if (!c->comm) { c->err = "context was created without a communicator: use npair_forward_gathered"; return NPAIR_E_STATE; }
     PhaseTimer pt(c, 0, st);
     NcclApi* api = nccl_api();
@@ -836,7 +894,7 @@ int npair_forward_gathered(npair_ctx* c, const float* d_feat_total, const float*
   if (!d_feat_total || !d_label_total || !tops_host) { c->err = "null pointer argument"; return NPAIR_E_ARG; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CUDA_TRY(c, cudaSetDevice(c->device));
-  c->fwd_done = false; c->last_stream = st;
+  c->fwd_done = false; c->last_stream = st; c->ext_gathered = true;
   if (c->cfg.normalize_input) {               // the gathered bottoms are raw embeddings: normalise all N rows (1 / ||x|| kept for the local ones)
     PhaseTimer pt(c, 1, st);
     float* dst = c->world > 1 ? c->Xtot_buf : c->Ynorm;
@@ -910,13 +968,15 @@ static int forward_impl(npair_ctx* c, const float* d_feat, const float* d_label,
   // NPAIR_RS_GATHER_FWD=1 enqueues the row-record exchange here instead of at the start of npair_backward.  Measured on
   // 8 x B200 (profiles/r01_bench_v6_n8.json): with the collective in front of the forward's host synchronisation the step is
   // SLOWER (0.293 ms against 0.218 ms with it in the backward, where its rendezvous overlaps the host's return), so it is opt-in.
-  if (c->p2p_rec) {
-    // peer-memory exchange: push this rank's records to every rank now; the backward only waits for the flags
+  if (c->p2p_rec && c->comm && c->x_total != nullptr && !c->ext_gathered) {
+    // peer-memory exchange: push this rank's 32-byte row records to every rank now; the backward only waits for the flags
     PhaseTimer pt(c, 8, st);
-    ++c->p2p_epoch;
+    const uint32_t ep = ++c->p2p_rec_epoch;
+    const long long par = ep & 1u;
+    const long long offR = c->p2p_offRec + par * 8ll * N + 8ll * c->rank * Q;
     int nb = (2 * Q + 255) / 256; if (nb > 64) nb = 64; if (nb < 1) nb = 1;
-    p2p_push_records_kernel<<<nb, 256, 0, st>>>(reinterpret_cast<const float4*>(c->ra.rowscal), c->p2p_peer_buf, c->p2p_peer_flags, c->world, c->rank,
-                                                Q, N, static_cast<int>(c->p2p_epoch & 1u), c->p2p_epoch, c->p2p_ticket);
+    p2p_push_kernel<<<nb, 256, 0, st>>>(c->ra.rowscal, 8ll * Q, offR, nullptr, 0, 0, c->p2p_peer_base, c->p2p_offFlags,
+                                        2 * c->world + static_cast<int>(par) * c->world + c->rank, c->world, ep, c->p2p_ticket);
     count_launch();
   }
   const bool gather_in_fwd = false;      // measured slower on 8 GPUs (profiles/r01_bench_v6_n8.json): the gather stays in the backward
@@ -1038,11 +1098,13 @@ static int backward_core(npair_ctx* c, float loss_weight, float* d_diff, float* 
     bw_mode = BW_ROWSCAL;
     if (d_rs_ext) rs_total = d_rs_ext;
     else {
-      if (c->p2p_rec) {
+      if (c->p2p_rec && !c->ext_gathered) {
         PhaseTimer pt(c, 8, st);
-        p2p_wait_records_kernel<<<1, 32, 0, st>>>(c->p2p_flags, c->world, static_cast<int>(c->p2p_epoch & 1u), c->p2p_epoch);
+        const uint32_t ep = c->p2p_rec_epoch;
+        const long long par = ep & 1u;
+        p2p_wait_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const uint32_t*>(c->p2p_region + c->p2p_offFlags) + 2 * c->world + par * c->world, c->world, ep);
         count_launch();
-        rs_total = c->p2p_buf + 8ll * static_cast<long long>(c->p2p_epoch & 1u) * N;
+        rs_total = c->p2p_region + c->p2p_offRec + par * 8ll * N;
       } else if (!c->rs_gathered) {
         // the only backward exchange: 8*Q floats per rank (replaces the N x D MPI_Allreduce of .cu:462-489)
         if (!c->comm) { c->err = "no communicator: use npair_backward_gathered with externally gathered row records"; return NPAIR_E_STATE; }

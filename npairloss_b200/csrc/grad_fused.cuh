@@ -72,7 +72,8 @@ struct FusedCfg {
   static constexpr int TMEM_A0 = 256;
   static constexpr int A_COLS = BK / 2;
   static constexpr int NPASS = (NSPLIT == 1) ? 1 : (NSPLIT == 2 ? 3 : 6);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*barriers*/ + 1024 /*alignment*/;
+  static constexpr int DRAIN_STAGE = 4 * 4096;            // one 32 x 32 fp32 transposition tile per drain warp
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + DRAIN_STAGE + 1024 /*barriers*/ + 1024 /*alignment*/;
   static constexpr int THREADS = 704;                         // 22 warps: TMA, MMA, 16 weight producers (4..19), 4 drain warps (2, 3, 20, 21)
 };
 
@@ -115,8 +116,7 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, 
 }
 
 // End of the accumulation chunk that starts at K block c0 of the range [kb0, kb1).  The FIRST chunk of a tile is shortened by a
-// per-cluster amount so that the clusters do not all drain at the same moment: the drains are bursts of 128 KB of L2 atomics per
-// SM, and when all 148 SMs issued them together the operand loads stalled behind them (~4.4 us per chunk, measured).
+// per-cluster amount so that the clusters do not all drain at the same moment (bursts of 128 KB of L2 reductions per SM).
 __device__ __forceinline__ int chunk_end(int c0, int kb0, int kb1, int ch, int worker) {
   if (ch <= 0) return kb1;
   if (c0 == kb0) { const int first = max(1, (((worker & 7) + 1) * ch) >> 3); return min(kb1, kb0 + first); }
@@ -150,7 +150,7 @@ __device__ __forceinline__ bool produce8(const float (&sv)[8], const float4* __r
 // (one ex2 per pair plus per-row / per-column constants) was SLOWER (180 vs 166 us): the extra shuffles and selects cost more
 // than the saved MUFU issue slots.
 template <int NSPLIT, bool BF16, int NCTA = 1>
-__global__ void __launch_bounds__(704, 1)
+__global__ void __launch_bounds__(704, 1)     // 22 warps x 80 registers (88 would not fit: the register file is handed out in 512-register units per warp)
 fused_grad_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ CUtensorMap tmapS, const FusedGradParams p) {
   using Cfg = FusedCfg<NSPLIT, NCTA>;
   static_assert(Cfg::TMEM_A0 + Cfg::STAGES * NSPLIT * Cfg::A_COLS <= 512, "A pieces do not fit behind the accumulator");
@@ -159,7 +159,8 @@ fused_grad_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_consta
   constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* aux = smem + STAGES * Cfg::STAGE_BYTES;
+  uint8_t* drain_stage = smem + STAGES * Cfg::STAGE_BYTES;
+  uint8_t* aux = drain_stage + Cfg::DRAIN_STAGE;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);            // [STAGES] TMA bytes landed (B, S tile, column records)
   uint64_t* bfull_bar = full_bar + STAGES;                           // [STAGES] pair mode: both CTAs' B halves landed (leader's copy is used)
   uint64_t* aready_bar = bfull_bar + STAGES;                         // [STAGES] producers wrote the A pieces (pair mode: of both CTAs, leader's copy)
@@ -353,12 +354,13 @@ fused_grad_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_consta
     const int ew = warp & 3;                      // TMEM lane quarter this warp may access (warp id % 4)
     const uint32_t lead_tempty = (NCTA == 2) ? ptx::mapa_u32(ptx::smem_u32(&tempty_bar[0]), 0) : 0u;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
+    uint8_t* const stg = drain_stage + ew * 4096;       // this warp's 32 x 32 fp32 transposition tile
     uint32_t gen = 0;
     for (int tile = worker; tile < num_tiles; tile += num_workers) {
       const int mn = tile / p.splits, split = tile - mn * p.splits;
       const int m_blk = (mn / p.tiles_n) * NCTA + cta_rank, n_blk = mn % p.tiles_n;
       const int kb0 = split * p.kb_per_split, kb1 = min(p.num_kblocks, kb0 + p.kb_per_split);
-      const int row = m_blk * BM + ew * 32 + lane;
+      const int row0 = m_blk * BM + ew * 32, row = row0 + lane;
       float* obase = p.splits > 1 ? p.part + static_cast<long long>(split) * p.Q * p.ldo : p.out;
       const float beta = p.splits > 1 ? 0.f : p.beta;
       for (int c0 = kb0, c1; c0 < kb1; c0 = c1, ++gen) {
@@ -366,55 +368,50 @@ fused_grad_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_consta
         const bool first = (c0 == kb0);          // first chunk of the tile stores (+ beta * out), later chunks add (fp32 RN)
         ptx::mbar_wait(&tfull_bar[0], gen & 1u);
         ptx::tc_fence_after();
-#ifndef NPAIR_DBG_DRAIN
-#define NPAIR_DBG_DRAIN 0          // timing experiments only: 1 = no global writes for later chunks, 2 = release the accumulator at once
-#endif
-        if (NPAIR_DBG_DRAIN == 2) {
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) { if (NCTA == 1) ptx::mbar_arrive(&tempty_bar[0]); else ptx::mbar_arrive_cluster(lead_tempty); }
-        }
 #pragma unroll 1
         for (int ch = 0; ch < BN / 32; ++ch) {
           uint32_t r[32];
           ptx::tmem_ld_32x32b_x32(t_row + ch * 32, r);
           ptx::tmem_ld_wait();
-          if (NPAIR_DBG_DRAIN != 2 && ch == BN / 32 - 1) {   // everything is in registers / in flight: the MMA issuer may start the next chunk
+          if (ch == BN / 32 - 1) {                // everything is in registers / on its way out: the MMA issuer may start the next chunk
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) { if (NCTA == 1) ptx::mbar_arrive(&tempty_bar[0]); else ptx::mbar_arrive_cluster(lead_tempty); }
           }
           const int col0 = n_blk * BN + ch * 32;
-          if (NPAIR_DBG_DRAIN == 1 && !first) continue;
-          if (row < p.Q) {
-            float* dst = obase + static_cast<long long>(row) * p.ldo + col0;
-            if (col0 + 32 <= p.D && (p.ldo & 3) == 0) {
-              if (first) {
+          if (col0 + 32 <= p.D && (p.ldo & 3) == 0) {
+            // lane = row in registers -> 128B-swizzled 32 x 32 staging tile -> lane = (row / 4 groups, 16-byte column chunk): every
+            // global request covers whole 128-byte lines (4 rows x 128 B per instruction instead of 32 half-used sectors)
+            __syncwarp();                         // the previous tile's reads of the staging tile are complete
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                  float4 o = make_float4(alpha * __uint_as_float(r[4 * q]), alpha * __uint_as_float(r[4 * q + 1]),
-                                         alpha * __uint_as_float(r[4 * q + 2]), alpha * __uint_as_float(r[4 * q + 3]));
-                  if (beta != 0.f) {
-                    const float4 old = reinterpret_cast<float4*>(dst)[q];
-                    o.x += beta * old.x; o.y += beta * old.y; o.z += beta * old.z; o.w += beta * old.w;
-                  }
-                  reinterpret_cast<float4*>(dst)[q] = o;
-                }
-              } else {
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<float4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+                  make_float4(alpha * __uint_as_float(r[4 * q]), alpha * __uint_as_float(r[4 * q + 1]), alpha * __uint_as_float(r[4 * q + 2]),
+                              alpha * __uint_as_float(r[4 * q + 3]));
+            __syncwarp();
+            const int cq = lane & 7;
 #pragma unroll
-                for (int q = 0; q < 8; ++q)
-                  red_add_v4(dst + 4 * q, alpha * __uint_as_float(r[4 * q]), alpha * __uint_as_float(r[4 * q + 1]),
-                             alpha * __uint_as_float(r[4 * q + 2]), alpha * __uint_as_float(r[4 * q + 3]));
+            for (int i = 0; i < 8; ++i) {
+              const int rr = 4 * i + (lane >> 3);
+              const int grow = row0 + rr;
+              float4 o = *reinterpret_cast<const float4*>(stg + rr * 128 + ((cq ^ (rr & 7)) << 4));
+              if (grow < p.Q) {
+                float* dst = obase + static_cast<long long>(grow) * p.ldo + col0 + 4 * cq;
+                if (first) {
+                  if (beta != 0.f) { const float4 old = *reinterpret_cast<const float4*>(dst); o.x += beta * old.x; o.y += beta * old.y; o.z += beta * old.z; o.w += beta * old.w; }
+                  *reinterpret_cast<float4*>(dst) = o;
+                } else red_add_v4(dst, o.x, o.y, o.z, o.w);
               }
-            } else {
-#pragma unroll
-              for (int c = 0; c < 32; ++c)
-                if (col0 + c < p.D) {
-                  const float o = alpha * __uint_as_float(r[c]);
-                  if (first) dst[c] = (beta != 0.f) ? o + beta * dst[c] : o;
-                  else red_add_f32(dst + c, o);
-                }
             }
+          } else if (row < p.Q) {                 // ragged D / unaligned rows: lane = row, element by element
+            float* dst = obase + static_cast<long long>(row) * p.ldo + col0;
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+              if (col0 + c < p.D) {
+                const float o = alpha * __uint_as_float(r[c]);
+                if (first) dst[c] = (beta != 0.f) ? o + beta * dst[c] : o;
+                else red_add_f32(dst + c, o);
+              }
           }
         }
       }

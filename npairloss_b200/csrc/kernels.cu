@@ -588,115 +588,273 @@ __device__ __forceinline__ int find_bin(const CT* hist, int nbins, unsigned long
   return *s_res;
 }
 
-// ---- LOCAL: one block per row (persistent over rows), per side: digit 1 from the row, candidates -> smem, digits 2 and 3 there ----
-#define NPAIR_LSEL_CAP 3072            // candidate capacity per side (21-bit remainders); larger buckets fall back to sweeps of the row
-__global__ void __launch_bounds__(256) local_select_kernel(const float* __restrict__ S, long long ldS, int Q, int N, const float* __restrict__ lab_rows,
-                                                           const float* __restrict__ lab_cols, int self_offset, int side_mask /*1 AP, 2 AN*/,
-                                                           float sn_ap, float sn_an, RowArrays ra, BlockScalars* bs) {
-  __shared__ unsigned int hist[2][NPAIR_SEL_BINS];
-  __shared__ uint32_t cand[2][NPAIR_LSEL_CAP];
-  __shared__ unsigned int s_ncand[2];
-  __shared__ unsigned long long s_scan[33], s_out[2];
-  __shared__ int s_res;
-  const bool lab_aligned = (reinterpret_cast<uintptr_t>(lab_cols) & 15) == 0;
+// ---- LOCAL: ONE WARP per row, warp-private histogram -- no block barriers, no block-wide scans ----
+// sweep 1  digit 1 (top 10 bits of the RAW float bits: 3 instructions per element, no label branch) of every column into the warp's
+//          histogram; the few same-label entries (and the self pair) are kept in a small list on the side
+// pick     the excluded keys (same-label entries, self pair) are taken out of the histogram again; bins are walked in value order
+//          (negative floats: descending raw digit) to find the bin of the wanted rank
+// sweep 2  (L1 / L2) elements of that bin -> per-LANE private candidate lists in shared memory (two predicated instructions per
+//          match: no ballots, no atomics); 22-bit remainders
+// tail     three more digits (8 + 7 + 7 bits) over the candidate lists, excluded keys subtracted per digit
+// Anything that does not fit the fast path (more than 128 same-label entries, a lane with more than 48 candidates) is redone
+// by slow_select_row: plain sweeps of the row, one digit per sweep, label test per element.
+#define NPAIR_LSEL_WARPS 8
+#define NPAIR_LSEL_D1 1024                 // bins of the first digit
+#define NPAIR_LSEL_LCAP 48                 // candidates per lane
+#define NPAIR_LSEL_SCAP 128                // same-label entries kept per row
+#define NPAIR_LSEL_U 4                     // 16-byte loads in flight per lane and array
+struct LselWarp {
+  unsigned int hist[NPAIR_LSEL_D1];
+  uint32_t cand[32 * NPAIR_LSEL_LCAP];     // [slot][lane]: lane-private lists, bank = lane
+  uint32_t same[NPAIR_LSEL_SCAP];          // raw bits of the same-label entries (self pair excluded)
+  unsigned int n_same, pad_[3];            // keeps sizeof a multiple of 16 (16-byte stores into hist)
+};
+static_assert(sizeof(LselWarp) % 16 == 0, "LselWarp must keep 16-byte alignment in an array");
+// value order <-> raw 10-bit digit (sign, 8 exponent bits, 1 mantissa bit): order o in [0,512) are the negative floats, descending raw
+__device__ __forceinline__ uint32_t d1_raw_of_order(uint32_t o) { return o < 512u ? 1023u - o : o - 512u; }
+__device__ __forceinline__ uint32_t d1_order_of_raw(uint32_t r) { return r >= 512u ? 1023u - r : r + 512u; }
+
+// rank r (0-based) within bins[0..nb) taken in index order; nb a multiple of 32.  Returns the bin, *r_in, *pop (warp-uniform); nb if out of range.
+__device__ __forceinline__ int warp_find_bin(const unsigned int* bins, int nb, unsigned int r, unsigned int* r_in, unsigned int* pop, int lane) {
+  const int per = nb >> 5;
+  unsigned int mine = 0;
+  for (int b = 0; b < per; ++b) mine += bins[lane * per + b];
+  unsigned int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  const unsigned int before = incl - mine;
+  const unsigned int hit = __ballot_sync(0xffffffffu, mine && r >= before && r < before + mine);
+  if (!hit) return nb;
+  const int src = __ffs(hit) - 1;
+  int bin = 0; unsigned int ri = 0, pp = 0;
+  if (lane == src) {
+    unsigned int cum = before;
+    int b = 0;
+    for (; b < per; ++b) { const unsigned int h = bins[lane * per + b]; if (cum + h > r) { pp = h; break; } cum += h; }
+    bin = lane * per + b; ri = r - cum;
+  }
+  *r_in = __shfl_sync(0xffffffffu, ri, src); *pop = __shfl_sync(0xffffffffu, pp, src);
+  return __shfl_sync(0xffffffffu, bin, src);
+}
+
+// Generic (slow) select of one side of one row by a warp: 32-bit ordered keys, digits of 10/10/10/2 bits, one sweep of the row per digit.
+__device__ __noinline__ uint32_t slow_select_row(const float* __restrict__ row, int N, const float* __restrict__ lab_cols, float li, int self_col,
+                                                 int side, unsigned int rank, unsigned int* hist /*[1024]*/, int lane) {
+  uint32_t prefix = 0, mask = 0;
+  int shift = 22;
+  for (int pass = 0; pass < 4; ++pass) {
+    const int bits = pass < 3 ? 10 : 2;
+    if (pass == 3) shift = 0;
+    const int nb = 1 << bits;
+    for (int b = lane; b < 1024; b += 32) hist[b] = 0;
+    __syncwarp();
+    for (int j = lane; j < N; j += 32) {
+      if (j == self_col) continue;
+      if ((lab_cols[j] == li) != (side == 0)) continue;
+      const uint32_t key = f2ord(row[j]);
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & (nb - 1)], 1u);
+    }
+    __syncwarp();
+    unsigned int r2, pp;
+    const int d = warp_find_bin(hist, nb < 32 ? 32 : nb, rank, &r2, &pp, lane);
+    prefix |= static_cast<uint32_t>(d) << shift; mask |= static_cast<uint32_t>(nb - 1) << shift; rank = r2;
+    shift -= 10;
+    __syncwarp();
+  }
+  return prefix;
+}
+
+__global__ void __launch_bounds__(32 * NPAIR_LSEL_WARPS) local_select_kernel(const float* __restrict__ S, long long ldS, int Q, int N,
+                                                                              const float* __restrict__ lab_rows, const float* __restrict__ lab_cols,
+                                                                              int self_offset, int side_mask /*1 AP, 2 AN*/, float sn_ap, float sn_an,
+                                                                              RowArrays ra, BlockScalars* bs) {
+  extern __shared__ __align__(16) unsigned char lsel_smem[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  LselWarp& W = reinterpret_cast<LselWarp*>(lsel_smem)[w];
   const bool want_same = side_mask & 1, want_diff = side_mask & 2;
-  for (int i = blockIdx.x; i < Q; i += gridDim.x) {
+  const bool lab_aligned = (reinterpret_cast<uintptr_t>(lab_cols) & 15) == 0;
+  const int nwarps = gridDim.x * NPAIR_LSEL_WARPS;
+  for (int i = blockIdx.x * NPAIR_LSEL_WARPS + w; i < Q; i += nwarps) {
     const float li = lab_rows[i];
     const int self_col = i + self_offset;
     const float* row = S + static_cast<long long>(i) * ldS;
-    for (int b = threadIdx.x; b < 2 * NPAIR_SEL_BINS; b += blockDim.x) (&hist[0][0])[b] = 0;
-    if (threadIdx.x < 2) s_ncand[threadIdx.x] = 0;
-    __syncthreads();
-    // ---- digit 1 (bits 31..21) of both sides in one sweep ----
-    sweep_row(row, N, lab_cols, li, lab_aligned, want_same, want_diff,
-              [&](uint32_t key, int, int side) { atomicAdd(&hist[side][key >> 21], 1u); });
-    __syncthreads();
-    if (threadIdx.x == 0 && want_same) hist[0][f2ord(row[self_col]) >> 21] -= 1u;     // the self pair is in neither list (.cu:54)
-    __syncthreads();
     const int cs = ra.cnt_same[i];
-    uint32_t prefix[2] = {0, 0};
-    unsigned long long rank_in[2] = {0, 0}, pop[2] = {0, 0};
-    bool ok[2] = {false, false};
+    // ---------------- sweep 1 ----------------
+    for (int b = lane * 4; b < NPAIR_LSEL_D1; b += 128) *reinterpret_cast<uint4*>(&W.hist[b]) = make_uint4(0u, 0u, 0u, 0u);
+    if (lane == 0) W.n_same = 0;
+    __syncwarp();
+    const int n_vec = lab_aligned ? (N & ~127) : 0;               // whole 128-column groups with aligned labels: 16-byte loads
+    for (int j4 = lane * 4; j4 < n_vec; j4 += 128 * NPAIR_LSEL_U) {   // NPAIR_LSEL_U groups (16-byte loads of S and of the labels) in flight per lane
+      uint4 v[NPAIR_LSEL_U]; float4 l[NPAIR_LSEL_U];
 #pragma unroll
-    for (int side = 0; side < 2; ++side) {
-      if (!(side_mask & (1 << side))) continue;
-      const unsigned long long size = side == 0 ? static_cast<unsigned long long>(cs) : static_cast<unsigned long long>(N - 1 - cs);
-      unsigned long long pos = 0;
-      bool good = true;
-      if (size == 0) { if (threadIdx.x == 0) atomicOr(&bs->err, DERR_EMPTY_LIST); good = false; }
-      else if (!pos_index(side == 0 ? sn_ap : sn_an, size, pos)) { if (threadIdx.x == 0) atomicOr(&bs->err, DERR_POS_RANGE); good = false; }
-      if (good) {                                                 // block-uniform
-        const int d = find_bin(hist[side], NPAIR_SEL_BINS, pos, &rank_in[side], &pop[side], s_scan, &s_res, s_out);
-        prefix[side] = static_cast<uint32_t>(d) << 21;
-        ok[side] = d < NPAIR_SEL_BINS;
-        __syncthreads();
+      for (int u = 0; u < NPAIR_LSEL_U; ++u) {
+        const int jj = j4 + 128 * u;
+        if (jj < n_vec) { v[u] = __ldg(reinterpret_cast<const uint4*>(row + jj)); l[u] = __ldg(reinterpret_cast<const float4*>(lab_cols + jj)); }
       }
-    }
-    // ---- candidates of the chosen first digits -> shared memory (second read of the row: L1 / L2) ----
-    const bool fit0 = ok[0] && pop[0] <= NPAIR_LSEL_CAP, fit1 = ok[1] && pop[1] <= NPAIR_LSEL_CAP;
-    if (fit0 || fit1) {
-      const uint32_t p0 = prefix[0] >> 21, p1 = prefix[1] >> 21;
-      sweep_row(row, N, lab_cols, li, lab_aligned, fit0, fit1, [&](uint32_t key, int j, int side) {
-        if ((key >> 21) == (side == 0 ? p0 : p1) && j != self_col) cand[side][atomicAdd(&s_ncand[side], 1u)] = key & 0x1FFFFFu;
-      });
-    }
-    __syncthreads();
 #pragma unroll
-    for (int side = 0; side < 2; ++side) {
-      if (!(side_mask & (1 << side))) continue;
-      float* out = side == 0 ? ra.posi_thr : ra.nega_thr;
-      if (!ok[side]) { if (threadIdx.x == 0) out[i] = 0.f; continue; }
-      const bool fit = side == 0 ? fit0 : fit1;
-      uint32_t pre = prefix[side], msk = 0xFFE00000u;
-      unsigned long long r = rank_in[side];
-      const int shifts[2] = {10, 0}, bits[2] = {11, 10};
+      for (int u = 0; u < NPAIR_LSEL_U; ++u) {
+        const int jj = j4 + 128 * u;
+        if (jj >= n_vec) continue;
+        const uint32_t vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+        const float ll[4] = {l[u].x, l[u].y, l[u].z, l[u].w};
+        if (want_diff) {
 #pragma unroll
-      for (int pss = 0; pss < 2; ++pss) {
-        const int nb = 1 << bits[pss];
-        for (int b = threadIdx.x; b < nb; b += blockDim.x) hist[side][b] = 0;
-        __syncthreads();
-        const uint32_t dm = static_cast<uint32_t>(nb - 1);
-        if (fit) {
-          const unsigned int nc = s_ncand[side];
-          const uint32_t lowpre = pre & 0x1FFFFFu, lowmsk = msk & 0x1FFFFFu;
-          for (unsigned int e = threadIdx.x; e < nc; e += blockDim.x) {
-            const uint32_t k = cand[side][e];
-            if ((k & lowmsk) == lowpre) atomicAdd(&hist[side][(k >> shifts[pss]) & dm], 1u);
-          }
-        } else {                                                   // oversized bucket (heavily tied data): sweep the row again
-          sweep_row(row, N, lab_cols, li, lab_aligned, side == 0, side == 1, [&](uint32_t key, int j, int) {
-            if ((key & msk) == pre && j != self_col) atomicAdd(&hist[side][(key >> shifts[pss]) & dm], 1u);
-          });
+          for (int c = 0; c < 4; ++c) atomicAdd(reinterpret_cast<unsigned int*>(reinterpret_cast<unsigned char*>(W.hist) + ((vv[c] >> 20) & 0xFFCu)), 1u);
         }
-        __syncthreads();
-        unsigned long long r2, pp;
-        const int d = find_bin(hist[side], nb, r, &r2, &pp, s_scan, &s_res, s_out);
-        pre |= static_cast<uint32_t>(d < nb ? d : 0) << shifts[pss]; msk |= dm << shifts[pss]; r = r2;
-        __syncthreads();
+        if (ll[0] == li || ll[1] == li || ll[2] == li || ll[3] == li) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (ll[c] == li && jj + c != self_col) { const unsigned int k = atomicAdd(&W.n_same, 1u); if (k < NPAIR_LSEL_SCAP) W.same[k] = vv[c]; }
+        }
       }
-      if (threadIdx.x == 0) out[i] = clamp_thr(ord2f(pre));          // .cu:288 / :319
     }
-    __syncthreads();
+    for (int j = n_vec + lane; j < N; j += 32) {                  // ragged tail / unaligned labels
+      const uint32_t b = __float_as_uint(row[j]);
+      if (want_diff) atomicAdd(&W.hist[b >> 22], 1u);
+      if (lab_cols[j] == li && j != self_col) { const unsigned int k = atomicAdd(&W.n_same, 1u); if (k < NPAIR_LSEL_SCAP) W.same[k] = b; }
+    }
+    __syncwarp();
+    const unsigned int ns = W.n_same;                             // == cs
+    const uint32_t self_bits = __float_as_uint(row[self_col]);
+    // ---------------- AP side: the same-label list is short ----------------
+    if (want_same) {
+      unsigned long long pos = 0;
+      float thr = 0.f;
+      if (cs == 0) { if (lane == 0) atomicOr(&bs->err, DERR_EMPTY_LIST); }
+      else if (!pos_index(sn_ap, static_cast<unsigned long long>(cs), pos)) { if (lane == 0) atomicOr(&bs->err, DERR_POS_RANGE); }
+      else if (ns <= 32) {                                        // rank by counting inside the warp
+        const uint32_t key = lane < static_cast<int>(ns) ? f2ord(__uint_as_float(W.same[lane])) : 0xFFFFFFFFu;
+        unsigned int rk = 0;
+        for (unsigned int t = 0; t < ns; ++t) { const uint32_t kt = __shfl_sync(0xffffffffu, key, t); rk += (kt < key || (kt == key && static_cast<int>(t) < lane)) ? 1u : 0u; }
+        const unsigned int hit = __ballot_sync(0xffffffffu, lane < static_cast<int>(ns) && rk == static_cast<unsigned int>(pos));
+        thr = clamp_thr(ord2f(__shfl_sync(0xffffffffu, key, __ffs(hit) - 1)));
+      } else {
+        thr = clamp_thr(ord2f(slow_select_row(row, N, lab_cols, li, self_col, 0, static_cast<unsigned int>(pos), W.hist + 0, lane)));
+        // the slow path used the histogram: rebuild digit 1 for the diff side below by falling into its slow path as well
+        if (want_diff && lane == 0) W.n_same = NPAIR_LSEL_SCAP + 1;
+      }
+      if (lane == 0) ra.posi_thr[i] = thr;                        // .cu:288
+      __syncwarp();
+    }
+    // ---------------- AN side ----------------
+    if (want_diff) {
+      const unsigned long long size = static_cast<unsigned long long>(N - 1 - cs);
+      unsigned long long pos = 0;
+      float thr = 0.f;
+      if (size == 0) { if (lane == 0) atomicOr(&bs->err, DERR_EMPTY_LIST); }
+      else if (!pos_index(sn_an, size, pos)) { if (lane == 0) atomicOr(&bs->err, DERR_POS_RANGE); }
+      else if (W.n_same > NPAIR_LSEL_SCAP) {
+        thr = clamp_thr(ord2f(slow_select_row(row, N, lab_cols, li, self_col, 1, static_cast<unsigned int>(pos), W.hist, lane)));
+      } else {
+        // excluded keys (same-label entries + the self pair) leave the histogram; then walk the bins in value order
+        for (unsigned int e = lane; e <= ns; e += 32) atomicSub(&W.hist[(e < ns ? W.same[e] : self_bits) >> 22], 1u);
+        __syncwarp();
+        // permute into value order in place is not needed: lanes own 32 consecutive ORDER positions and read the raw bins they map to
+        unsigned int mine = 0;
+        for (int b = 0; b < 32; ++b) mine += W.hist[d1_raw_of_order(lane * 32 + b)];
+        unsigned int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        const unsigned int before = incl - mine, r0 = static_cast<unsigned int>(pos);
+        const unsigned int hit = __ballot_sync(0xffffffffu, mine && r0 >= before && r0 < before + mine);
+        const int src = __ffs(hit) - 1;                           // exists: pos < size = sum of the bins
+        // the winning lane's 32 bins, one per lane: a second warp scan instead of a serial walk
+        const unsigned int base = __shfl_sync(0xffffffffu, before, src);
+        const uint32_t my_raw = d1_raw_of_order(src * 32 + lane);
+        const unsigned int h1 = W.hist[my_raw];
+        unsigned int inc2 = h1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned int t = __shfl_up_sync(0xffffffffu, inc2, o); if (lane >= o) inc2 += t; }
+        const unsigned int bef2 = base + inc2 - h1;
+        const int src2 = __ffs(__ballot_sync(0xffffffffu, h1 && r0 >= bef2 && r0 < bef2 + h1)) - 1;
+        const uint32_t raw = __shfl_sync(0xffffffffu, my_raw, src2);
+        unsigned int rank = r0 - __shfl_sync(0xffffffffu, bef2, src2);
+        const bool negative = raw >= 512u;                        // remainders of negative floats sort descending
+        // ---------------- sweep 2: that bin's elements -> lane-private candidate lists ----------------
+        unsigned int cnt = 0;
+        for (int j4 = lane * 4; j4 < n_vec; j4 += 128 * NPAIR_LSEL_U) {
+          uint4 v[NPAIR_LSEL_U];
+#pragma unroll
+          for (int u = 0; u < NPAIR_LSEL_U; ++u) if (j4 + 128 * u < n_vec) v[u] = __ldg(reinterpret_cast<const uint4*>(row + j4 + 128 * u));
+#pragma unroll
+          for (int u = 0; u < NPAIR_LSEL_U; ++u) {
+            if (j4 + 128 * u >= n_vec) continue;
+            const uint32_t vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              if ((vv[c] >> 22) == raw) { if (cnt < NPAIR_LSEL_LCAP) W.cand[cnt * 32 + lane] = vv[c] & 0x3FFFFFu; ++cnt; }
+          }
+        }
+        for (int j = n_vec + lane; j < N; j += 32) {
+          const uint32_t b = __float_as_uint(row[j]);
+          if ((b >> 22) == raw) { if (cnt < NPAIR_LSEL_LCAP) W.cand[cnt * 32 + lane] = b & 0x3FFFFFu; ++cnt; }
+        }
+        if (__any_sync(0xffffffffu, cnt > NPAIR_LSEL_LCAP)) {
+          thr = clamp_thr(ord2f(slow_select_row(row, N, lab_cols, li, self_col, 1, static_cast<unsigned int>(pos), W.hist, lane)));
+        } else {
+          // ---------------- tail: 8 + 7 + 7 bits over the candidates; excluded keys of this bin are subtracted per digit ----------------
+          // in remainder space the order is ascending for positive floats and descending for negative ones: flip the remainders of negatives
+          const uint32_t flip = negative ? 0x3FFFFFu : 0u;
+          uint32_t pre = 0, msk = 0;
+          const int shifts[3] = {14, 7, 0}, nbits[3] = {8, 7, 7};
+#pragma unroll
+          for (int ps = 0; ps < 3; ++ps) {
+            const int nb = 1 << nbits[ps];
+            for (int b = lane * 4; b < nb; b += 128) *reinterpret_cast<uint4*>(&W.hist[b]) = make_uint4(0u, 0u, 0u, 0u);
+            __syncwarp();
+            for (unsigned int e = 0; e < cnt; ++e) {
+              const uint32_t k = W.cand[e * 32 + lane] ^ flip;
+              if ((k & msk) == pre) atomicAdd(&W.hist[(k >> shifts[ps]) & (nb - 1)], 1u);
+            }
+            __syncwarp();
+            for (unsigned int e = lane; e <= ns; e += 32) {
+              const uint32_t b = e < ns ? W.same[e] : self_bits;
+              const uint32_t k = (b & 0x3FFFFFu) ^ flip;
+              if ((b >> 22) == raw && (k & msk) == pre) atomicSub(&W.hist[(k >> shifts[ps]) & (nb - 1)], 1u);
+            }
+            __syncwarp();
+            unsigned int r2, p2;
+            const int d = warp_find_bin(W.hist, nb, rank, &r2, &p2, lane);
+            pre |= static_cast<uint32_t>(d & (nb - 1)) << shifts[ps]; msk |= static_cast<uint32_t>(nb - 1) << shifts[ps]; rank = r2;
+            __syncwarp();
+          }
+          thr = clamp_thr(__uint_as_float((raw << 22) | (pre ^ flip)));
+        }
+      }
+      if (lane == 0) ra.nega_thr[i] = thr;                        // .cu:319
+      __syncwarp();
+    }
   }
 }
 void launch_local_select(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
                          int self_offset, int side_mask, float sn_ap, float sn_an, RowArrays ra, BlockScalars* bs, int sms, cudaStream_t st) {
-  int grid = sms * 5; if (grid > Q) grid = Q;                      // 41 KB of shared memory per block: 5 blocks per SM
-  local_select_kernel<<<grid, 256, 0, st>>>(S, ldS, Q, N, lab_rows, lab_cols, self_offset, side_mask, sn_ap, sn_an, ra, bs);
+  const int smem = static_cast<int>(sizeof(LselWarp)) * NPAIR_LSEL_WARPS;
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(local_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
+  const int per_sm = (227 * 1024) / (smem + 1024);
+  int grid = sms * (per_sm < 1 ? 1 : per_sm);
+  const int need = (Q + NPAIR_LSEL_WARPS - 1) / NPAIR_LSEL_WARPS;
+  if (grid > need) grid = need;
+  local_select_kernel<<<grid, 32 * NPAIR_LSEL_WARPS, smem, st>>>(S, ldS, Q, N, lab_rows, lab_cols, self_offset, side_mask, sn_ap, sn_an, ra, bs);
   count_launch();
 }
 
 // ---- GLOBAL: the rank's whole Q x N block.  Three kernels, each finished by its last block (ticket):
-//   A  digit 1 histogram over S (64-bit global counts)                       -> bucket, rank inside, population
-//   B  second sweep of S: digit 2 histogram of the bucket's elements, and -- when the bucket fits the candidate buffer -- their
-//      21-bit remainders are compacted (per-block staging, one global atomic per flush)
-//   C  digit 3 histogram over the candidates (or, oversized bucket, over S once more) -> threshold, written to all rows
+//   A  digit 1 (top 11 bits of the RAW float bits; three instructions per element on the all-different-label fast path) histogram
+//      over S, 64-bit global counts; the last block walks the bins in value order -> bin, rank inside, population
+//   B  second sweep of S: elements of that bin only (a shift and a compare per element): digit 2 histogram of their 21-bit
+//      remainders, and -- when the bin fits the candidate buffer -- the remainders are compacted (per-block staging, one global
+//      atomic per flush)
+//   C  digit 3 over the candidates (or, oversized bin, over S once more) -> threshold, written to all rows
+// Remainders of negative floats sort descending, so they are stored complemented ("flipped"): ascending everywhere.
 struct GlobalSelectBufs {
   unsigned long long* hist;   // [2][2048]
   uint32_t* cand;             // [2][cap]
   unsigned int cap;
 };
 #define NPAIR_GSEL_STAGE 2048
+__device__ __forceinline__ uint32_t d11_raw_of_order(uint32_t o) { return o < 1024u ? 2047u - o : o - 1024u; }
+
 __global__ void __launch_bounds__(512) global_select_kernel(const float* __restrict__ S, long long ldS, int Q, int N, const float* __restrict__ lab_rows,
                                                             const float* __restrict__ lab_cols, int self_offset, int side_mask, int pass /*0,1,2*/,
                                                             GlobalSelectBufs gb, RowArrays ra, BlockScalars* bs) {
@@ -708,38 +866,81 @@ __global__ void __launch_bounds__(512) global_select_kernel(const float* __restr
   const bool act0 = (side_mask & 1) && bs->sel_active[0], act1 = (side_mask & 2) && bs->sel_active[1];
   if (!act0 && !act1) return;
   const bool lab_aligned = (reinterpret_cast<uintptr_t>(lab_cols) & 15) == 0;
-  const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
+  const int shift = pass == 1 ? 10 : 0;
   const int nbits = pass == 2 ? 10 : 11;
   const uint32_t dm = (1u << nbits) - 1u;
-  const uint32_t pre0 = bs->sel_prefix[0], pre1 = bs->sel_prefix[1], msk = pass == 0 ? 0u : (pass == 1 ? 0xFFE00000u : 0xFFFFFC00u);
+  // sel_prefix after pass 0: raw digit << 21; after pass 1: | flipped-remainder digit << 10
+  const uint32_t raw0 = bs->sel_prefix[0] >> 21, raw1 = bs->sel_prefix[1] >> 21;
+  const uint32_t flip0 = raw0 >= 1024u ? 0x1FFFFFu : 0u, flip1 = raw1 >= 1024u ? 0x1FFFFFu : 0u;
+  const uint32_t mid0 = (bs->sel_prefix[0] >> 10) & 0x7FFu, mid1 = (bs->sel_prefix[1] >> 10) & 0x7FFu;   // pass 2: decided second digit
   const bool comp0 = act0 && pass == 1 && bs->sel_cnt[0] <= gb.cap, comp1 = act1 && pass == 1 && bs->sel_cnt[1] <= gb.cap;   // compaction this pass
   const bool list0 = act0 && pass == 2 && bs->sel_cnt[0] <= gb.cap, list1 = act1 && pass == 2 && bs->sel_cnt[1] <= gb.cap;   // read the list this pass
   for (int b = threadIdx.x; b < 2 * NPAIR_SEL_BINS; b += blockDim.x) (&hist[0][0])[b] = 0;
   if (threadIdx.x < 2) s_nst[threadIdx.x] = 0;
   __syncthreads();
   const bool sweep0 = act0 && !list0, sweep1 = act1 && !list1;
+
+  // one element of the bin of `side` (passes 1 and 2): its flipped remainder goes to the digit histogram / the staging list
+  auto take = [&](uint32_t bits, int side) {
+    const uint32_t k = (bits & 0x1FFFFFu) ^ (side == 0 ? flip0 : flip1);
+    if (pass == 2 && ((k >> 10) != (side == 0 ? mid0 : mid1))) return;
+    atomicAdd(&hist[side][(k >> shift) & dm], 1u);
+    if (side == 0 ? comp0 : comp1) {
+      const unsigned int slot = atomicAdd(&s_nst[side], 1u);
+      if (slot < NPAIR_GSEL_STAGE) stage[side][slot] = k;
+      else {                                                     // staging full (rare): straight to the global list
+        const unsigned int g = atomicAdd(&bs->cand_n[side], 1u);
+        if (g < gb.cap) gb.cand[static_cast<size_t>(side) * gb.cap + g] = k;
+      }
+    }
+  };
+
   if (sweep0 || sweep1) {
     for (int i = blockIdx.x; i < Q; i += gridDim.x) {
       const float li = lab_rows[i];
       const int self_col = i + self_offset;
       const float* row = S + static_cast<long long>(i) * ldS;
-      if (pass == 0) {
-        sweep_row(row, N, lab_cols, li, lab_aligned, sweep0, sweep1, [&](uint32_t key, int, int side) { atomicAdd(&hist[side][key >> 21], 1u); });
-        if (threadIdx.x == 0 && sweep0) atomicSub(&hist[0][f2ord(row[self_col]) >> 21], 1u);      // the self pair (modular: order-free)
-      } else {
-        sweep_row(row, N, lab_cols, li, lab_aligned, sweep0, sweep1, [&](uint32_t key, int j, int side) {
-          if ((key & msk) == (side == 0 ? pre0 : pre1) && j != self_col) {
-            atomicAdd(&hist[side][(key >> shift) & dm], 1u);
-            if (side == 0 ? comp0 : comp1) {
-              const unsigned int slot = atomicAdd(&s_nst[side], 1u);
-              if (slot < NPAIR_GSEL_STAGE) stage[side][slot] = key & 0x1FFFFFu;
-              else {                                               // staging full (rare): straight to the global list
-                const unsigned int g = atomicAdd(&bs->cand_n[side], 1u);
-                if (g < gb.cap) gb.cand[static_cast<size_t>(side) * gb.cap + g] = key & 0x1FFFFFu;
-              }
+      // two 16-byte groups per thread in flight (S and labels): the sweeps are latency-bound otherwise
+      for (int j0 = threadIdx.x * 4; j0 < N; j0 += blockDim.x * 8) {
+        uint4 vq[2]; float lq[2][4];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int j4 = j0 + u * blockDim.x * 4;
+          if (j4 >= N) continue;
+          vq[u] = __ldg(reinterpret_cast<const uint4*>(row + j4));              // row stride is a multiple of 32 floats: in bounds
+          if (lab_aligned && j4 + 3 < N) { const float4 l = __ldg(reinterpret_cast<const float4*>(lab_cols + j4)); lq[u][0] = l.x; lq[u][1] = l.y; lq[u][2] = l.z; lq[u][3] = l.w; }
+          else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) lq[u][c] = (j4 + c < N) ? __ldg(lab_cols + j4 + c) : li;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+        const int j4 = j0 + u * blockDim.x * 4;
+        if (j4 >= N) continue;
+        const uint32_t vv[4] = {vq[u].x, vq[u].y, vq[u].z, vq[u].w};
+        const float* ll = lq[u];
+        if (j4 + 3 < N && ll[0] != li && ll[1] != li && ll[2] != li && ll[3] != li) {     // four diff-label pairs: the common case
+          if (sweep1) {
+            if (pass == 0) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) atomicAdd(reinterpret_cast<unsigned int*>(reinterpret_cast<unsigned char*>(hist[1]) + ((vv[c] >> 19) & 0x1FFCu)), 1u);
+            } else if ((vv[0] >> 21) == raw1 || (vv[1] >> 21) == raw1 || (vv[2] >> 21) == raw1 || (vv[3] >> 21) == raw1) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) if ((vv[c] >> 21) == raw1) take(vv[c], 1);
             }
           }
-        });
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (j4 + c >= N || j4 + c == self_col) continue;                    // the self pair is in neither list (.cu:54)
+            const int side = (ll[c] == li) ? 0 : 1;
+            if (!(side == 0 ? sweep0 : sweep1)) continue;
+            if (pass == 0) atomicAdd(&hist[side][vv[c] >> 21], 1u);
+            else if ((vv[c] >> 21) == (side == 0 ? raw0 : raw1)) take(vv[c], side);
+          }
+        }
+        }
       }
       if (pass == 1 && (comp0 || comp1)) {                         // flush a staging area that is at least half full
         __syncthreads();
@@ -759,16 +960,16 @@ __global__ void __launch_bounds__(512) global_select_kernel(const float* __restr
       }
     }
   }
-  if (list0 || list1) {                                            // pass 2 over the compact candidate lists
+  if (list0 || list1) {                                            // pass 2 over the compact candidate lists (flipped remainders)
 #pragma unroll
     for (int side = 0; side < 2; ++side) {
       if (!(side == 0 ? list0 : list1)) continue;
       const unsigned int n = bs->cand_n[side];
-      const uint32_t lowpre = (side == 0 ? pre0 : pre1) & 0x1FFFFFu, lowmsk = msk & 0x1FFFFFu;
+      const uint32_t mid = side == 0 ? mid0 : mid1;
       const uint32_t* cl = gb.cand + static_cast<size_t>(side) * gb.cap;
       for (unsigned int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
         const uint32_t k = cl[e];
-        if ((k & lowmsk) == lowpre) atomicAdd(&hist[side][k & dm], 1u);
+        if ((k >> 10) == mid) atomicAdd(&hist[side][k & dm], 1u);
       }
     }
   }
@@ -797,22 +998,29 @@ __global__ void __launch_bounds__(512) global_select_kernel(const float* __restr
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  unsigned long long* ordered = reinterpret_cast<unsigned long long*>(&hist[0][0]);       // 2048 x 8 bytes: reuses the block histograms
 #pragma unroll
   for (int side = 0; side < 2; ++side) {
     if (!(side == 0 ? act0 : act1)) continue;
-    unsigned long long r2, pp;
     const unsigned long long* gh = gb.hist + side * NPAIR_SEL_BINS;
     const int nb = 1 << nbits;
-    const int d = find_bin(gh, nb, bs->sel_rank[side], &r2, &pp, s_scan, &s_res, s_out);
+    __syncthreads();
+    // pass 0 counted RAW digits: walk them in value order (negative floats: descending raw digit)
+    for (int o = threadIdx.x; o < nb; o += blockDim.x) ordered[o] = __ldcg(&gh[pass == 0 ? d11_raw_of_order(o) : static_cast<uint32_t>(o)]);
+    __syncthreads();
+    unsigned long long r2, pp;
+    const int d = find_bin(ordered, nb, bs->sel_rank[side], &r2, &pp, s_scan, &s_res, s_out);
     __syncthreads();
     if (threadIdx.x == 0) {
       if (d >= nb) { bs->err |= DERR_POS_RANGE; bs->sel_active[side] = 0; }
       else {
         bs->sel_rank[side] = r2;
-        bs->sel_prefix[side] |= static_cast<uint32_t>(d) << shift;
-        if (pass == 0) { bs->sel_cnt[side] = pp; bs->cand_n[side] = 0; }
+        if (pass == 0) { bs->sel_prefix[side] = d11_raw_of_order(static_cast<uint32_t>(d)) << 21; bs->sel_cnt[side] = pp; bs->cand_n[side] = 0; }
+        else bs->sel_prefix[side] |= static_cast<uint32_t>(d) << shift;
         if (pass == 2) {
-          const float thr = clamp_thr(ord2f(bs->sel_prefix[side]));      // .cu:303 / :334
+          const uint32_t p = bs->sel_prefix[side];
+          const uint32_t bits = (p & 0xFFE00000u) | ((p & 0x1FFFFFu) ^ ((p >> 21) >= 1024u ? 0x1FFFFFu : 0u));     // un-flip the remainder
+          const float thr = clamp_thr(__uint_as_float(bits));                    // .cu:303 / :334
           if (side == 0) bs->posi_global = thr; else bs->nega_global = thr;
         }
       }
@@ -835,7 +1043,7 @@ __global__ void __launch_bounds__(512) global_select_kernel(const float* __restr
 void launch_global_select(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
                           int self_offset, int side_mask, RowArrays ra, unsigned long long* hist, uint32_t* cand, unsigned int cand_cap,
                           BlockScalars* bs, int sms, cudaStream_t st) {
-  int grid = sms * 2; if (grid > Q) grid = Q;
+  int grid = sms * 4; if (grid > Q) grid = Q;
   GlobalSelectBufs gb; gb.hist = hist; gb.cand = cand; gb.cap = cand_cap;
   for (int pass = 0; pass < 3; ++pass) {
     global_select_kernel<<<grid, 512, 0, st>>>(S, ldS, Q, N, lab_rows, lab_cols, self_offset, side_mask, pass, gb, ra, bs);

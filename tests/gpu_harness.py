@@ -18,7 +18,7 @@ S_REL = {capi.PREC_FP32_BF16X3: 3e-5, capi.PREC_FP32_FP16X2: 1.5e-5, capi.PREC_B
 G_TOL = {capi.PREC_FP32_BF16X3: 1e-5, capi.PREC_FP32_FP16X2: 1e-5, capi.PREC_BF16: 2e-2}
 
 
-def gpu_step_world(x, lab, Q, world, mining, prec, backend, loss_weight=1.0, num_tops=5, want_grad=True, bwd_exchange=0):
+def gpu_step_world(x, lab, Q, world, mining, prec, backend, loss_weight=1.0, num_tops=5, want_grad=True, bwd_exchange=0, **cfg_extra):
     """Emulates every rank on one GPU through the external-collectives API (the test plays NCCL's role).
     Returns dict(tops[world,5], dx[N,D], S[N,N], posi[N], nega[N], mode)."""
     N, D = x.shape
@@ -35,7 +35,7 @@ def gpu_step_world(x, lab, Q, world, mining, prec, backend, loss_weight=1.0, num
     try:
         for r in range(world):
             cfg = capi.make_config(Q, D, world=world, rank=r, num_tops=num_tops, sim_precision=prec, gemm_backend=backend,
-                                   bwd_exchange=bwd_exchange, **mining)
+                                   bwd_exchange=bwd_exchange, **mining, **cfg_extra)
             ctx = capi.Context(cfg)
             ctxs.append(ctx)
             tops[r] = ctx.forward_gathered(xt, lt)

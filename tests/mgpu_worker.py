@@ -19,6 +19,7 @@ def main():
     dev = torch.device("cuda", lr)
     dist.init_process_group("nccl", device_id=dev)
     ok = True
+    cfg_flags = int(os.environ.get("NPAIR_TEST_FLAGS", "0"))       # 24 = NCCL exchange instead of peer memory
     for (B, D, mining_name, prec) in [(256 * world, 128, "usage", capi.PREC_FP32_FP16X2), (120 * world, 1024, "usage", capi.PREC_FP32_BF16X3),
                                       (512 * world, 256, "default", capi.PREC_FP32_FP16X2), (64 * world, 96, "local_rel", capi.PREC_FP32_FP16X2)]:
         mining = {"usage": synth.USAGE_MINING, "default": synth.DEFAULT_MINING,
@@ -26,10 +27,15 @@ def main():
         x, lab = synth.make_inputs(B, D, seed=B + D, noise=2.5)
         Q, rows = dist_util.shard_rows(B, world, rank)
         nid = dist_util.broadcast_bytes(capi.nccl_unique_id() if rank == 0 else None, 128, device=dev)
-        ctx = capi.Context(capi.make_config(Q, D, world=world, rank=rank, sim_precision=prec, device=lr, **mining), nid)
+        ctx = capi.Context(capi.make_config(Q, D, world=world, rank=rank, sim_precision=prec, device=lr, flags=cfg_flags, **mining), nid)
         d_x = torch.from_numpy(np.ascontiguousarray(x[rows])).to(dev)
         d_l = torch.from_numpy(np.ascontiguousarray(lab[rows])).to(dev)
         d_g = torch.full_like(d_x, float("nan"))
+        for _ in range(3):                      # several steps: the exchange buffers are double-buffered by step parity
+            tops = ctx.forward(d_x, d_l)
+            ctx.backward(0.7, d_g)
+        tops2 = ctx.forward(d_x, d_l)           # forward-only steps in between (evaluation pattern)
+        assert tops2 == tops, (tops2, tops)
         tops = ctx.forward(d_x, d_l)
         ctx.backward(0.7, d_g)
         torch.cuda.synchronize()
@@ -50,7 +56,7 @@ def main():
             rel = np.linalg.norm(dx - dx_o) / max(np.linalg.norm(dx_o), 1e-30)
             lerr = np.abs(tg[:, 0] - tops_o[:, 0]).max() / max(np.abs(tops_o[:, 0]).max(), 1e-30)
             good = np.isfinite(dx).all() and rel <= 1e-5 and lerr <= 1e-5 and np.abs(tg[:, 1:4] - tops_o[:, 1:4]).max() * Q <= 1.001
-            print(f"[mgpu] world={world} B={B} D={D} {mining_name} prec={prec}: grad_rel={rel:.2e} loss_rel={lerr:.2e} {'OK' if good else 'FAIL'}", flush=True)
+            print(f"[mgpu] flags={cfg_flags} world={world} B={B} D={D} {mining_name} prec={prec}: grad_rel={rel:.2e} loss_rel={lerr:.2e} {'OK' if good else 'FAIL'}", flush=True)
             ok = ok and good
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)

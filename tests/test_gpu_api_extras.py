@@ -24,6 +24,30 @@ def test_torch_api_matches_capi():
     np.testing.assert_allclose(xr.grad.cpu().numpy(), dg.cpu().numpy(), rtol=0, atol=0)
 
 
+def test_torch_true_gradient_is_the_derivative_of_the_loss():
+    """true_gradient=True: central differences of the module's own loss (RAND mining: every pair selected, the loss is smooth)."""
+    import torch
+    from npairloss_b200 import synth, torch_api
+    B, D = 32, 16
+    x, lab = synth.make_inputs(B, D, 3, noise=1.0)
+    m = torch_api.NPairLoss(true_gradient=True, sim_precision=0, **synth.DEFAULT_MINING)      # bf16x3: no pre-scale step to perturb
+    xt = torch.from_numpy(x).cuda().requires_grad_(True)
+    lt = torch.from_numpy(lab).cuda()
+    loss, _ = m(xt, lt)
+    loss.backward()
+    g = xt.grad.cpu().numpy()
+    rng = np.random.default_rng(0)
+    for _ in range(6):
+        i, j = int(rng.integers(B)), int(rng.integers(D))
+        h = 2e-2
+        xp, xm = x.copy(), x.copy()
+        xp[i, j] += h; xm[i, j] -= h
+        lp = m(torch.from_numpy(xp).cuda(), lt)[0].item()
+        lm = m(torch.from_numpy(xm).cuda(), lt)[0].item()
+        fd = (lp - lm) / (2 * h)
+        assert abs(fd - g[i, j]) <= 2e-3 * max(abs(fd), 1e-2), (i, j, fd, g[i, j])
+
+
 def test_full_size_properties_headline():
     """BASELINE.json's full size (B=8192, D=512, usage-block mining; the oracle comparison at this size is
     tests/test_gpu_baseline_configs.py): the domain's size-independent properties -- S bitwise symmetric, sample-permutation

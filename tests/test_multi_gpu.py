@@ -9,14 +9,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.gpu
-def test_nccl_sharded_step_matches_oracle():
+@pytest.mark.parametrize("flags", [0, 24])          # 0: peer-memory exchange over NVLink (default), 24: NCCL all-gathers
+def test_nccl_sharded_step_matches_oracle(flags):
     import torch
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     world = 2 if n < 4 else (4 if n < 8 else 8)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", "29517", os.path.join(ROOT, "tests", "mgpu_worker.py")]
-    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+           "--master-port", str(29517 + flags), os.path.join(ROOT, "tests", "mgpu_worker.py")]
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600, env=dict(os.environ, NPAIR_TEST_FLAGS=str(flags)))
     print(r.stdout[-3000:], r.stderr[-3000:])
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

@@ -50,3 +50,33 @@ def test_rejects_other_dtypes():
     except TypeError:
         return
     raise AssertionError("fp64 embeddings must be rejected")
+
+
+def test_second_forward_invalidates_the_first_graph():
+    """The library context holds ONE batch: backward of an older forward must fail loudly, not return the wrong batch's gradient."""
+    m = torch_api.NPairLoss(_context_factory=lambda c, n: FakeContext(c, n))
+    x1 = torch.randn(6, 4, requires_grad=True)
+    x2 = torch.randn(6, 4, requires_grad=True)
+    lab = torch.tensor([0, 0, 1, 1, 2, 2])
+    l1, _ = m(x1, lab)
+    l2, _ = m(x2, lab)
+    l2.backward()                                              # the newest graph is fine
+    try:
+        l1.backward()
+    except RuntimeError as e:
+        assert "another forward" in str(e)
+    else:
+        raise AssertionError("stale backward must raise")
+
+
+def test_true_gradient_doubles_the_reference_value():
+    m = torch_api.NPairLoss(true_gradient=True, _context_factory=lambda c, n: FakeContext(c, n))
+    x = torch.randn(4, 3, requires_grad=True)
+    loss, _ = m(x, torch.tensor([0, 0, 1, 1]))
+    loss.backward()
+    np.testing.assert_allclose(x.grad.numpy(), np.full((4, 3), 4.0, np.float32))      # FakeContext: 2 * loss_weight, doubled
+    try:
+        torch_api.NPairLoss(world=2, true_gradient=True)
+    except ValueError:
+        return
+    raise AssertionError("true_gradient with world > 1 must be rejected")
