@@ -232,6 +232,7 @@ def main():
     ap.add_argument("--mining", default="config", choices=["config", "usage", "rand", "relative"])
     ap.add_argument("--no-extras", action="store_true", help="skip the other_minings / e2e variants / parity_check legs")
     ap.add_argument("--fused-step", action="store_true", help="device-resident step through npair_forward_backward (one host sync)")
+    ap.add_argument("--no-flush", action="store_true", help="diagnostic: never flush the L2 between steps (sharded runs)")
     ap.add_argument("--cfg-flags", type=int, default=0, help="npair_config.flags (NPAIR_FLAG_*), e.g. 24 = exchange through NCCL instead of peer memory")
     ap.add_argument("--grad-chunk", type=int, default=0, help="npair_config.grad_chunk_cols (0 = library default)")
     args = ap.parse_args()
@@ -304,7 +305,7 @@ def main():
     # L2 nothing survives from one step to the next (N = 1: 268 MB); otherwise (sharded runs) a 252 MB device buffer is rewritten
     # before every step and the steps are timed one by one with their own event pair (the flush is outside the pairs).
     L2_BYTES = 126 << 20
-    need_flush = 4 * Q * N < 2 * L2_BYTES
+    need_flush = 4 * Q * N < 2 * L2_BYTES and not args.no_flush
     flush_buf = torch.empty(2 * L2_BYTES, dtype=torch.uint8, device=dev) if need_flush else None
 
     def timed_steps(c, steps):
@@ -362,6 +363,25 @@ def main():
     tops = step_device()
     torch.cuda.synchronize()
     grad_dev = d_g.cpu().numpy()
+
+    # ---------------- sharded runs: the same step without the per-step L2 flush, and through npair_forward_backward ----------------
+    variants = None
+    if world > 1 and not args.no_extras:
+        def plain_loop(fn, steps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for _ in range(3):
+                fn()
+            barrier()
+            e0.record(stream)
+            for _ in range(steps):
+                fn()
+            e1.record(stream)
+            barrier()
+            return max_over_ranks(e0.elapsed_time(e1) / steps)
+        ms_nf = plain_loop(lambda: step_device(), args.steps)
+        ms_fu = plain_loop(lambda: ctx.forward_backward(d_x, d_l, 1.0, d_g), args.steps)
+        variants = {"no_l2_flush": {"ms_per_step": ms_nf, "value": B / (ms_nf * 1e-3), "note": "npair_forward + npair_backward back to back, one event pair around the loop, L2 not flushed"},
+                    "fused_call_no_l2_flush": {"ms_per_step": ms_fu, "value": B / (ms_fu * 1e-3), "note": "npair_forward_backward: the backward is enqueued behind the forward, one host synchronisation per step"}}
 
     # ---------------- end-to-end through the plugin surface with host buffers ----------------
     # The Caffe-style layer (npairloss_b200/caffe_shim) on HOST blobs: a data layer hands a new batch through mutable_cpu_data()
@@ -597,7 +617,7 @@ def main():
                                  if need_flush else
                                  f"not flushed: per-step working set (S {4 * Q * N / 1e6:.0f} MB fp32 + operand pieces) is more than twice the 126 MB L2")},
                "clocks": clocks, "roofline": roofline, "roofline_other": roofline_other, "phase_ms": phase_ms, "hbm_kernels": hbm,
-               "other_minings": other, "parity_check": parity, "cpu_baseline": cpu, "e2e": e2e, **e2e_variants,
+               "other_minings": other, "sharded_variants": variants, "parity_check": parity, "cpu_baseline": cpu, "e2e": e2e, **e2e_variants,
                "gpu_launches": launches_timed,
                "tops": {"loss": tops[0], "top1": tops[1], "top5": tops[2], "top10": tops[3], "feature_asum": tops[4]}}
         emit(out)

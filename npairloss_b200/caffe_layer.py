@@ -49,6 +49,8 @@ def lib():
         L.npc_set_cpu_diff.argtypes = [vp, C.c_int]
         L.npc_set_cpu_diff.restype = fp
         L.npc_parse_only.argtypes = [C.c_char_p, fp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p, C.c_int]
+        L.npc_solver_run.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_float, fp, C.c_int]
+        L.npc_solver_last_error.restype = C.c_char_p
         _LIB = L
     return _LIB
 
@@ -192,3 +194,16 @@ class Layer:
         if read_gradient:
             self.bottom_diff()
         return tops
+
+
+def solver_run(net_prototxt: str, solver_prototxt: str, feature_dim: int, num_identities: int, imgs_per_identity: int = 4, iters: int = 0,
+               seed: int = 1, noise: float = 2.5, max_rows: int = 4096):
+    """Synthetic training loop inside the shim: MultibatchData -> [synthetic trunk] -> L2Normalize -> NPairMultiClassLoss
+    driven like `caffe train` with the solver prototxt's SGD settings.  Returns an array of rows
+    [iter, weighted loss, top0 (loss), top1, top5, top10, feature_asum] logged every `display` iterations."""
+    log = np.zeros((max_rows, 7), dtype=np.float32)
+    n = lib().npc_solver_run(net_prototxt.encode(), solver_prototxt.encode(), feature_dim, num_identities, imgs_per_identity, iters, seed,
+                             C.c_float(noise), log.ctypes.data_as(C.POINTER(C.c_float)), max_rows)
+    if n < 0:
+        raise LayerError(lib().npc_solver_last_error().decode())
+    return log[:n]

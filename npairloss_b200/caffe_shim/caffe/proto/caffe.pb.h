@@ -6,6 +6,7 @@
 #ifndef CAFFE_PROTO_CAFFE_PB_H_
 #define CAFFE_PROTO_CAFFE_PB_H_
 
+#include <map>
 #include <string>
 #include <vector>
 
@@ -72,7 +73,12 @@ class LayerParameter {
   void add_bottom(const std::string& s) { bottom_.push_back(s); }
   void add_top(const std::string& s) { top_.push_back(s); }
   void add_loss_weight(float w) { loss_weight_.push_back(w); }
+  // scalar fields of the layer's OTHER nested messages, kept as text under "message.field" (first occurrence), e.g.
+  // "multi_batch_data_param.identity_num_per_batch" or "include.phase": enough for the synthetic data layer of the harness
+  const std::string* extra(const std::string& key) const { std::map<std::string, std::string>::const_iterator it = extra_.find(key); return it == extra_.end() ? 0 : &it->second; }
+  void set_extra(const std::string& key, const std::string& v) { if (!extra_.count(key)) extra_[key] = v; }
  private:
+  std::map<std::string, std::string> extra_;
   std::string name_, type_;
   std::vector<std::string> bottom_, top_;
   std::vector<float> loss_weight_;
@@ -84,6 +90,8 @@ class LayerParameter {
 // fields and nested messages are skipped; `#` comments and the literal "." placeholder lines of usage/def.prototxt are
 // ignored.  Unknown enum identifiers inside npair_loss_param are an error.
 bool ReadLayersFromText(const std::string& text, std::vector<LayerParameter>* layers, std::string* error);
+// top-level "key: value" pairs (solver prototxt)
+bool ReadScalarsFromText(const std::string& text, std::map<std::string, std::string>* out, std::string* error);
 
 }  // namespace caffe
 #endif

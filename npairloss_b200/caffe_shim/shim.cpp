@@ -3,6 +3,7 @@
 
 #include <cctype>
 #include <cstring>
+#include <map>
 
 #include "caffe/blob.hpp"
 #include "caffe/common.hpp"
@@ -163,6 +164,22 @@ bool parse_npair(Lexer& lx, NPairLossParameter* p, std::string* err) {
   }
 }
 
+// nested message of a layer other than npair_loss_param: its scalar fields are kept as text ("message.field"), deeper levels skipped
+bool capture_message(Lexer& lx, const std::string& name, LayerParameter* L, std::string* err) {
+  for (;;) {
+    Tok k = lx.next();
+    if (k.kind == Tok::RBRACE) return true;
+    if (k.kind == Tok::END) { *err = "unterminated message " + name; return false; }
+    if (k.kind != Tok::IDENT) continue;
+    Tok c = lx.next();
+    if (c.kind == Tok::LBRACE) { if (!skip_message(lx, err)) return false; continue; }
+    if (c.kind != Tok::COLON) { *err = name + ": expected ':' after " + k.text; return false; }
+    Tok v = lx.next();
+    if (v.kind == Tok::LBRACE) { if (!skip_message(lx, err)) return false; continue; }
+    L->set_extra(name + "." + k.text, v.text);
+  }
+}
+
 bool parse_layer(Lexer& lx, LayerParameter* L, std::string* err) {
   for (;;) {
     Tok k = lx.next();
@@ -172,14 +189,14 @@ bool parse_layer(Lexer& lx, LayerParameter* L, std::string* err) {
     Tok c = lx.next();
     if (c.kind == Tok::LBRACE) {
       if (k.text == "npair_loss_param") { if (!parse_npair(lx, L->mutable_npair_loss_param(), err)) return false; }
-      else if (!skip_message(lx, err)) return false;
+      else if (!capture_message(lx, k.text, L, err)) return false;
       continue;
     }
     if (c.kind != Tok::COLON) { *err = "layer: expected ':' or '{' after " + k.text; return false; }
     Tok v = lx.next();
     if (v.kind == Tok::LBRACE) {   // "field: { ... }" form
       if (k.text == "npair_loss_param") { if (!parse_npair(lx, L->mutable_npair_loss_param(), err)) return false; }
-      else if (!skip_message(lx, err)) return false;
+      else if (!capture_message(lx, k.text, L, err)) return false;
       continue;
     }
     if (k.text == "name") L->set_name(v.text);
@@ -212,6 +229,23 @@ bool ReadLayersFromText(const std::string& text, std::vector<LayerParameter>* la
       if (!parse_layer(lx, &L, &err)) { if (error) *error = err; return false; }
       layers->push_back(L);
     } else if (!skip_message(lx, &err)) { if (error) *error = err; return false; }
+  }
+}
+
+// top-level "key: value" pairs of a prototxt (the solver file, usage/solver.prototxt); nested messages are skipped
+bool ReadScalarsFromText(const std::string& text, std::map<std::string, std::string>* out, std::string* error) {
+  Lexer lx(text);
+  std::string err;
+  for (;;) {
+    Tok k = lx.next();
+    if (k.kind == Tok::END) return true;
+    if (k.kind != Tok::IDENT) continue;
+    Tok c = lx.next();
+    if (c.kind == Tok::LBRACE) { if (!skip_message(lx, &err)) { if (error) *error = err; return false; } continue; }
+    if (c.kind != Tok::COLON) continue;
+    Tok v = lx.next();
+    if (v.kind == Tok::LBRACE) { if (!skip_message(lx, &err)) { if (error) *error = err; return false; } continue; }
+    if (!out->count(k.text)) (*out)[k.text] = v.text;
   }
 }
 

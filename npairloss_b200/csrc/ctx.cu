@@ -337,7 +337,7 @@ static cudaError_t launch_simt_gemm(int prec, int epi, const uint16_t* A, long l
 // out = sum_s part[s] + beta*out, fixed summation order (deterministic split-K)
 // ---- peer-memory exchange (world > 1, one process per GPU, NVLink / NVSwitch) ----
 // Every rank owns one exported region (cudaIpc-mapped into all ranks):
-//     X[2][N][D] fp32 | LAB[2][N] | REC[2][N][8] | FLAGS[2 kinds][2][world] uint32
+//     X[2][N][D] fp32 | LAB[2][N] | REC[2][N][8] | XCH[2][world][8192] (small world-scope reductions) | FLAGS[3 kinds][2][world] uint32
 // and PUSHES its own rows into every rank's region with plain stores over NVLink, then raises one flag per peer (release.sys);
 // consumers wait for the world's flags (acquire.sys).  Replaces GatherFeatureAndLabel's MPI_Allgather (reference .cu:17-43) and the
 // backward's exchange (row records instead of the N x D all-reduce, .cu:462-489) without a collective rendezvous: nothing
@@ -416,6 +416,7 @@ static inline long long round_up(long long v, long long m) { return (v + m - 1) 
 using namespace npair;
 
 #define NPAIR_PROF_PHASES 9
+#define NPAIR_XCH_FLOATS 8192          // largest small exchange: two sides x 2048 64-bit digit counts
 
 // ------------------------------------------------------------------------------------------------ context
 struct npair_ctx {
@@ -448,7 +449,10 @@ struct npair_ctx {
   // peer-memory exchange (world > 1 with a communicator; NPAIR_FLAG_NCCL_FEATURES / _RECORDS fall back to NCCL)
   bool p2p_feat = false, p2p_rec = false;
   float* p2p_region = nullptr;         // X[2][N][D] | LAB[2][N] | REC[2][N][8] | FLAGS
-  long long p2p_offX = 0, p2p_offLab = 0, p2p_offRec = 0, p2p_offFlags = 0;   // in floats
+  long long p2p_offX = 0, p2p_offLab = 0, p2p_offRec = 0, p2p_offXch = 0, p2p_offFlags = 0;   // in floats
+  uint32_t xch_epoch = 0;              // small exchanges of the world-scope mode (several per step)
+  float* xch_src = nullptr;            // [8192] staging of this rank's contribution
+  float* xch_all = nullptr;            // NCCL fallback: gathered [world][8192]
   float** p2p_peer_base = nullptr;     // device array [world] of the ranks' regions
   unsigned int* p2p_ticket = nullptr;
   std::vector<void*> p2p_opened;
@@ -463,7 +467,8 @@ struct npair_ctx {
   float* partial = nullptr;
   unsigned long long* ghist = nullptr;   // [2][2048] 64-bit digit counts of the GLOBAL radix select
   uint32_t* gcand = nullptr; unsigned int gcand_cap = 0;   // [2][cap] compacted candidates of the GLOBAL radix select
-  float* tops_pinned = nullptr;  // host-mapped: 5 tops + err(int) + inv_scale
+  float* tops_pinned = nullptr;  // host-mapped: 5 tops + err(int) + sequence number of the forward that wrote them
+  unsigned int tops_seq = 0;
   float* tops_dev = nullptr;
   CUtensorMap tm_simA, tm_simB, tm_S, tm_b1A, tm_b1B, tm_b2A, tm_b2B;
   // nccl
@@ -516,6 +521,9 @@ static int validate(const npair_config* c, std::string* err) {
   if (static_cast<long long>(c->Q) * c->world > 0x7fffffffLL) { *err = "N = Q*world exceeds int32"; return NPAIR_E_ARG; }
   if (c->global_scope < 0 || c->global_scope > 1 || c->normalize_input < 0 || c->normalize_input > 1) { *err = "global_scope / normalize_input must be 0 or 1"; return NPAIR_E_ARG; }
   if (c->grad_chunk_cols > 0 && (c->grad_chunk_cols & 31)) { *err = "grad_chunk_cols must be a multiple of 32"; return NPAIR_E_ARG; }
+  if (c->global_scope && c->world > 1 && (c->bwd_exchange != NPAIR_BWD_AUTO || c->gemm_backend != NPAIR_GEMM_TCGEN05 || (c->flags & NPAIR_FLAG_NO_FUSED_GRAD))) {
+    *err = "global_scope needs the row-record backward (bwd_exchange AUTO, tcgen05 backend, fused gradient kernel)"; return NPAIR_E_ARG;
+  }
   return NPAIR_OK;
 }
 
@@ -587,7 +595,7 @@ void npair_destroy(npair_ctx* c) {
   cudaFree(c->p2p_region); cudaFree(c->p2p_peer_base); cudaFree(c->p2p_ticket);
   if (c->comm && c->own_comm) release_comm(c->comm);
   cudaFree(c->Xtot_buf); cudaFree(c->labtot_buf); cudaFree(c->S); cudaFree(c->Xs); cudaFree(c->XsT); cudaFree(c->XlT);
-  cudaFree(c->H); cudaFree(c->HT); cudaFree(c->OUT2); cudaFree(c->part); cudaFree(c->sym_tiles); cudaFree(c->sym_tiles2); cudaFree(c->XcatA); cudaFree(c->XcatB); cudaFree(c->rs_total); cudaFree(c->row_block); cudaFree(c->bs); cudaFree(c->partial); cudaFree(c->ghist); cudaFree(c->gcand); cudaFree(c->Ynorm); cudaFree(c->dY); cudaFree(c->inv_norm);
+  cudaFree(c->H); cudaFree(c->HT); cudaFree(c->OUT2); cudaFree(c->part); cudaFree(c->sym_tiles); cudaFree(c->sym_tiles2); cudaFree(c->XcatA); cudaFree(c->XcatB); cudaFree(c->rs_total); cudaFree(c->row_block); cudaFree(c->bs); cudaFree(c->partial); cudaFree(c->ghist); cudaFree(c->gcand); cudaFree(c->Ynorm); cudaFree(c->dY); cudaFree(c->inv_norm); cudaFree(c->xch_src); cudaFree(c->xch_all);
   if (c->tops_pinned) cudaFreeHost(c->tops_pinned);
   if (c->ev_made) for (int i = 0; i < NPAIR_PROF_PHASES; ++i) { cudaEventDestroy(c->ev[i][0]); cudaEventDestroy(c->ev[i][1]); }
   delete c;
@@ -785,8 +793,9 @@ static int create_impl(const npair_config* cfg, const void* id128, void* ext_com
       NcclApi* api = nccl_api();
       const int W = c->world;
       const long long nX = static_cast<long long>(N) * D, nL = round_up(N, 4), nR = 8ll * N;
-      c->p2p_offX = 0; c->p2p_offLab = 2 * nX; c->p2p_offRec = c->p2p_offLab + 2 * nL; c->p2p_offFlags = c->p2p_offRec + 2 * nR;
-      const long long total = c->p2p_offFlags + round_up(4ll * W, 4);
+      c->p2p_offX = 0; c->p2p_offLab = 2 * nX; c->p2p_offRec = c->p2p_offLab + 2 * nL; c->p2p_offXch = c->p2p_offRec + 2 * nR;
+      c->p2p_offFlags = c->p2p_offXch + (cfg->global_scope ? 2ll * W * NPAIR_XCH_FLOATS : 0);
+      const long long total = c->p2p_offFlags + round_up(6ll * W, 4);
       CREATE_TRY(cudaMalloc(&c->p2p_region, sizeof(float) * static_cast<size_t>(total)));
       CREATE_TRY(cudaMemset(c->p2p_region, 0, sizeof(float) * static_cast<size_t>(total)));
       CREATE_TRY(cudaMalloc(&c->p2p_ticket, sizeof(unsigned int)));
@@ -823,6 +832,11 @@ static int create_impl(const npair_config* cfg, const void* id128, void* ext_com
       // topology is symmetric, which holds on an NVSwitch box -- a mixed outcome is reported by the first exchange's timeout)
     }
   }
+  if (cfg->global_scope && c->world > 1) {
+    if (!c->comm) { g_create_err = "global_scope with world > 1 needs a communicator (the world-scope reductions are internal)"; npair_destroy(c); return NPAIR_E_ARG; }
+    CREATE_TRY(cudaMalloc(&c->xch_src, sizeof(float) * NPAIR_XCH_FLOATS));
+    if (!c->p2p_region) CREATE_TRY(cudaMalloc(&c->xch_all, sizeof(float) * static_cast<size_t>(NPAIR_XCH_FLOATS) * c->world));
+  }
 #undef CREATE_TRY
   *out = c;
   return NPAIR_OK;
@@ -832,6 +846,30 @@ int npair_create(const npair_config* cfg, const void* id128, npair_ctx** out) { 
 int npair_create_with_comm(const npair_config* cfg, void* comm, npair_ctx** out) {
   if (cfg && cfg->world > 1 && !comm) { g_create_err = "null communicator"; return NPAIR_E_ARG; }
   return create_impl(cfg, nullptr, comm, out);
+}
+
+// World-scope mode: every rank contributes `n` floats (in c->xch_src, or `src` copied there) and gets the world's contributions as
+// [world][NPAIR_XCH_FLOATS]; all ranks then reduce them in rank order, so decisions are identical everywhere.
+static int xchg_small(npair_ctx* c, const float* src, int n, const float** all, cudaStream_t st) {
+  if (src != c->xch_src) CUDA_TRY(c, cudaMemcpyAsync(c->xch_src, src, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+  if (c->p2p_region) {
+    const uint32_t ep = ++c->xch_epoch;
+    const long long par = ep & 1u;
+    const long long off = c->p2p_offXch + (par * c->world + c->rank) * NPAIR_XCH_FLOATS;
+    int nb = (n / 4 + 255) / 256; if (nb > 8) nb = 8; if (nb < 1) nb = 1;
+    p2p_push_kernel<<<nb, 256, 0, st>>>(c->xch_src, n, off, nullptr, 0, 0, c->p2p_peer_base, c->p2p_offFlags,
+                                        4 * c->world + static_cast<int>(par) * c->world + c->rank, c->world, ep, c->p2p_ticket);
+    count_launch();
+    p2p_wait_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const uint32_t*>(c->p2p_region + c->p2p_offFlags) + 4 * c->world + par * c->world, c->world, ep);
+    count_launch();
+    *all = c->p2p_region + c->p2p_offXch + par * c->world * NPAIR_XCH_FLOATS;
+  } else {
+    NcclApi* api = nccl_api();
+    int r = api->AllGather(c->xch_src, c->xch_all, NPAIR_XCH_FLOATS, NCCL_FLOAT32, c->comm, st);
+    if (r != 0) { c->err = fmt("ncclAllGather(world-scope reduction): %s", api->GetErrorString(r)); return NPAIR_E_NCCL; }
+    *all = c->xch_all;
+  }
+  return NPAIR_OK;
 }
 
 static MiningParams mining_of(const npair_config& c) {
@@ -949,20 +987,47 @@ static int forward_impl(npair_ctx* c, const float* d_feat, const float* d_label,
   // ---- thresholds (.cu:275-337) ----
   {
   PhaseTimer pt(c, 3, st);
-  launch_thresholds(c->ra, Q, N, mp, c->bs, c->partial, st);
+  const bool wscope = c->cfg.global_scope && c->world > 1;      // world == 1: the block IS the world
+  launch_thresholds(c->ra, Q, N, mp, c->bs, c->partial, wscope ? c->xch_src : nullptr, st);
+  if (wscope) {
+    const float* all = nullptr;
+    const int rc = xchg_small(c, c->xch_src, 8, &all, st);
+    if (rc != NPAIR_OK) return rc;
+    launch_thresholds_world(all, NPAIR_XCH_FLOATS, c->world, N, mp, c->bs, st);
+  }
   {
     // general relative SN: radix selects; both sides of a region share one sweep of S
     int local_mask = 0, global_mask = 0;
     if (is_rel_m(mp.ap_method) && !sn_max(mp.identsn)) (mp.ap_region == NPAIR_LOCAL ? local_mask : global_mask) |= 1;
     if (is_rel_m(mp.an_method) && !sn_max(mp.diffsn)) (mp.an_region == NPAIR_LOCAL ? local_mask : global_mask) |= 2;
-    if (global_mask) launch_global_select(c->S, c->ldS, Q, N, d_label, c->lab_total, self_off, global_mask, c->ra, c->ghist, c->gcand, c->gcand_cap, c->bs, c->sms, st);
+    if (global_mask) {
+      for (int pass = 0; pass < 3; ++pass) {
+        launch_global_select_pass(c->S, c->ldS, Q, N, d_label, c->lab_total, self_off, global_mask, pass, c->ra, c->ghist, c->gcand, c->gcand_cap,
+                                  wscope ? 1 : 0, c->bs, c->sms, st);
+        if (wscope) {
+          const float* all = nullptr;
+          const int rc = xchg_small(c, reinterpret_cast<const float*>(c->ghist), NPAIR_XCH_FLOATS, &all, st);
+          if (rc != NPAIR_OK) return rc;
+          launch_global_decide(all, NPAIR_XCH_FLOATS, c->world, global_mask, pass, c->ra, Q, c->ghist, c->gcand, c->gcand_cap, c->bs, st);
+        }
+      }
+    }
     if (local_mask) launch_local_select(c->S, c->ldS, Q, N, d_label, c->lab_total, self_off, local_mask, mp.identsn, mp.diffsn, c->ra, c->bs, c->sms, st);
   }
   }
   // ---- selection + counts + exp + masked sums + log + retrieval in one pass (.cu:343-398) ----
   {
     PhaseTimer pt(c, 4, st);
-    launch_lse_rows(c->S, c->ldS, Q, N, d_label, c->lab_total, self_off, mp, c->ra, c->bs, c->cfg.num_tops, c->tops_dev, c->world, st);
+    const bool wscope = c->cfg.global_scope && c->world > 1;
+    ++c->tops_seq;
+    launch_lse_rows(c->S, c->ldS, Q, N, d_label, c->lab_total, self_off, mp, c->ra, c->bs, c->cfg.num_tops, c->tops_dev, c->world,
+                    wscope ? c->xch_src : nullptr, c->tops_seq, st);
+    if (wscope) {       // loss / retrieval / asum over the world's N rows, identical on every rank (the reference's are per rank, .cu:385)
+      const float* all = nullptr;
+      const int rc = xchg_small(c, c->xch_src, 8, &all, st);
+      if (rc != NPAIR_OK) return rc;
+      launch_tops_world(all, NPAIR_XCH_FLOATS, c->world, N, c->cfg.num_tops, c->tops_dev, c->tops_seq, st);
+    }
   }
   c->rs_gathered = false;
   // NPAIR_RS_GATHER_FWD=1 enqueues the row-record exchange here instead of at the start of npair_backward.  Measured on
@@ -991,7 +1056,19 @@ static int forward_impl(npair_ctx* c, const float* d_feat, const float* d_label,
   }
   CUDA_TRY(c, cudaGetLastError());
   if (c->defer_sync) return NPAIR_OK;              // npair_forward_backward enqueues the backward first, then waits once
-  CUDA_TRY(c, cudaStreamSynchronize(st));          // the reference also blocks here (host reads of loss/asum, .cu:384,400)
+  // The reference also blocks here (host reads of loss / asum, .cu:384,400).  The five tops land in mapped pinned memory followed by
+  // this forward's sequence number: polling that word returns a few microseconds earlier than a stream synchronisation and does not
+  // wait for the row-record push behind the row pass.  A fault in a kernel never writes the number: after ~2 s fall back to the
+  // synchronisation, which reports the error.
+  {
+    volatile unsigned int* seqp = reinterpret_cast<volatile unsigned int*>(c->tops_pinned) + 6;
+    unsigned long long spins = 0;
+    while (*seqp != c->tops_seq) {
+      if (++spins > (1ull << 28)) { CUDA_TRY(c, cudaStreamSynchronize(st)); if (*seqp != c->tops_seq) { c->err = "the forward kernels finished without publishing their results"; return NPAIR_E_CUDA; } break; }
+      __builtin_ia32_pause();
+    }
+    __sync_synchronize();
+  }
   const int derr = reinterpret_cast<int*>(c->tops_pinned)[5];
   if (derr & DERR_EMPTY_LIST) { c->err = "an empty same/diff list was indexed (undefined behaviour in the reference, .cu:296/:327/:288)"; return NPAIR_E_EMPTY_LIST; }
   if (derr & DERR_POS_RANGE) { c->err = "identsn/diffsn select a position outside the list (undefined behaviour in the reference, .cu:285-288)"; return NPAIR_E_POS_RANGE; }
@@ -1090,7 +1167,10 @@ static int backward_core(npair_ctx* c, float loss_weight, float* d_diff, float* 
   const int Q = c->Q, N = c->N, D = c->D;
   const MiningParams mp = mining_of(c->cfg);
   const int self_off = c->rank * Q;
-  const float lw_over_q = loss_weight / static_cast<float>(Q);     // loss_weight / dot_normalizer (.cu:427,448)
+  const bool wscope = c->cfg.global_scope && c->world > 1;
+  // loss_weight / dot_normalizer (.cu:427,448); world scope: the normaliser is the world's batch and the transposed term is not
+  // divided by the world size, i.e. exactly what a single rank holding the whole batch computes
+  const float lw_over_q = loss_weight / static_cast<float>(wscope ? N : Q);
   const bool tc = c->cfg.gemm_backend == NPAIR_GEMM_TCGEN05;
   const float* rs_total = nullptr;
   int bw_mode = BW_SYM;
@@ -1123,7 +1203,8 @@ static int backward_core(npair_ctx* c, float loss_weight, float* d_diff, float* 
     fp.Q = Q; fp.N = N; fp.D = D; fp.num_kblocks = (N + 31) / 32;
     fp.tiles_m = (Q + 127) / 128; fp.tiles_n = (D + 255) / 256;
     fp.rowrec = c->ra.rowscal; fp.colrec = rs_total ? rs_total : c->ra.rowscal;
-    fp.self_offset = self_off; fp.inv_world = 1.f / static_cast<float>(c->world); fp.log2_world = log2f(static_cast<float>(c->world));
+    fp.self_offset = self_off; fp.inv_world = wscope ? 1.f : 1.f / static_cast<float>(c->world);
+    fp.log2_world = wscope ? 0.f : log2f(static_cast<float>(c->world));
     fp.sgn_p = (mp.ap_method == M_EASY || mp.ap_method == M_RELATIVE_EASY) ? -1.f : 1.f;
     fp.sgn_n = (mp.an_method == M_HARD || mp.an_method == M_RELATIVE_HARD) ? -1.f : 1.f;
     fp.out = d_diff; fp.ldo = D; fp.alpha = 0.5f * lw_over_q; fp.beta = 0.f; fp.dev_scale = &c->bs->x_inv_scale;

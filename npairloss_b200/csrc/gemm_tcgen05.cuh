@@ -159,6 +159,15 @@ __device__ __forceinline__ void stats32(const float (&v)[32], const float* __res
   }
 }
 
+// Statistics of 32 similarities none of which is a same-label pair (the caller has excluded it by the chunk's label range): only
+// the hardest negative moves.  Eight independent chains, then a tree.
+__device__ __forceinline__ float max32(const float (&v)[32]) {
+  float m[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) m[e] = fmaxf(fmaxf(v[e], v[8 + e]), fmaxf(v[16 + e], v[24 + e]));
+  return fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
+}
+
 // NCTA = 2: launched with cluster dimension 2; p.tiles_m and the tile list count 256-row PAIR blocks, tmapB has 128-row boxes.
 // 256-bit global store (sm_100: STG.E.256): one full 32-byte sector per lane
 __device__ __forceinline__ void st_global_v8(float* dst, const float* v) {
@@ -199,6 +208,7 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* s_lab = reinterpret_cast<float*>(aux + 256);                // [256] column labels of the current tile (EPI_SIM*)
   float* s_labr = reinterpret_cast<float*>(aux + 256 + 1024);        // [128] row labels of the current tile (EPI_SIM_SYM)
+  float2* s_rng = reinterpret_cast<float2*>(aux + 256 + 1024 + 512); // [8] {min, max} label of each 32-column chunk, [8..12) of each 32-row group
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = p.tile_list ? p.num_tiles_list : p.tiles_m * p.tiles_n * p.splits;
@@ -328,6 +338,23 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         if (row < p.M) lab_i = p.lab_rows[row];
         if (EPI == EPI_SIM_SYM && half == 0) s_labr[ew * 32 + lane] = lab_i;
         asm volatile("bar.sync 1, 256;" ::: "memory");
+        // label range of every 32-column chunk (epilogue warp w: chunk w) and of every 32-row group (warps 0..3): a row whose label
+        // lies outside a chunk's range has no same-label pair in it, and its statistics reduce to one running maximum
+        {
+          const float lc = s_lab[(warp - 4) * 32 + lane];
+          float mn = lc, mx = lc;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) { mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+          if (lane == 0) s_rng[warp - 4] = make_float2(mn, mx);
+          if (EPI == EPI_SIM_SYM && warp - 4 < 4) {
+            const float lr = s_labr[(warp - 4) * 32 + lane];
+            float rn = lr, rx = lr;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { rn = fminf(rn, __shfl_xor_sync(0xffffffffu, rn, o)); rx = fmaxf(rx, __shfl_xor_sync(0xffffffffu, rx, o)); }
+            if (lane == 0) s_rng[8 + warp - 4] = make_float2(rn, rx);
+          }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tc_fence_after();
@@ -378,9 +405,16 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
 #endif
           }
           // statistics AFTER issuing the store: the ~200 ALU instructions hide the bulk store's shared-memory read
-          if (NPAIR_DBG_EPI_LEVEL >= 2 && row < p.M && col0 < p.Nn)
-            stats32(v, s_lab + ch * 32, lab_i, col0 + 32 <= p.Nn && (self_col < col0 || self_col >= col0 + 32), col0, p.Nn, self_col,
-                    minw, maxw, maxb, cnt);
+          if (NPAIR_DBG_EPI_LEVEL >= 2 && col0 < p.Nn) {
+            const float2 rg = s_rng[ch];
+            // warp-uniform: every row of this warp is outside the chunk's label range (and the chunk is whole: the self pair is a
+            // same-label pair, so it cannot be in such a chunk)
+            if (__all_sync(0xffffffffu, row >= p.M || lab_i < rg.x || lab_i > rg.y) && col0 + 32 <= p.Nn) {
+              if (row < p.M) maxb = fmaxf(maxb, max32(v));
+            } else if (row < p.M)
+              stats32(v, s_lab + ch * 32, lab_i, col0 + 32 <= p.Nn && (self_col < col0 || self_col >= col0 + 32), col0, p.Nn, self_col,
+                      minw, maxw, maxb, cnt);
+          }
           if (NPAIR_DBG_EPI_LEVEL >= 3 && EPI == EPI_SIM_SYM && cb > m_blk && m_blk * BM + ew * 32 < p.M && col0 < p.Nn) {
             // ---- mirrored store: staging row c holds S[col0 + c][rows of this warp]; box lands at (x = row block, y = col0) ----
             if (!NPAIR_EPI_MSTG && lane == 0) { if (SB == 2) ptx::tma_store_wait_read<1>(); else ptx::tma_store_wait_read<0>(); }
@@ -412,8 +446,13 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
 #pragma unroll
               for (int q = 0; q < 4; ++q) st_global_v8(dst + 8 * q, vt + 8 * q);
             }
-            if (NPAIR_DBG_EPI_LEVEL >= 4 && gc < p.Nn) {
-              stats32(vt, s_labr + ew * 32, s_lab[ch * 32 + lane], r0 + 32 <= p.M, r0, p.M, -1, t_minw, t_maxw, t_maxb, t_cnt);
+            if (NPAIR_DBG_EPI_LEVEL >= 4) {
+              const float lab_c = s_lab[ch * 32 + lane];
+              const float2 rr = s_rng[8 + ew];
+              const bool plain = __all_sync(0xffffffffu, gc >= p.Nn || lab_c < rr.x || lab_c > rr.y) && r0 + 32 <= p.M;
+              if (gc < p.Nn) {
+              if (plain) t_maxb = max32(vt);
+              else stats32(vt, s_labr + ew * 32, lab_c, r0 + 32 <= p.M, r0, p.M, -1, t_minw, t_maxw, t_maxb, t_cnt);
               if (t_cnt) {
                 atomicMin(&p.st_minw[gc], f2ord(t_minw));
                 atomicMax(&p.st_maxw[gc], f2ord(t_maxw));
@@ -421,6 +460,7 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
               }
               atomicMax(&p.st_maxb[gc], f2ord(t_maxb));
               atomicMax(&p.st_maxall[gc], f2ord(fmaxf(t_maxw, t_maxb)));
+              }
             }
           }
         } else {

@@ -149,21 +149,31 @@ __global__ void __launch_bounds__(256) prep_reduce_kernel(const float* __restric
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   const long long t0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   // 16-byte loads, four in flight per thread (cudaMalloc'd / framework blobs are 16-byte aligned; otherwise the scalar loop)
+  const bool same_range = want_scale && xl == xt && nl == ntot;    // world == 1: one sweep gives both the sum and the maximum
   if ((reinterpret_cast<uintptr_t>(xl) & 15) == 0) {
     const float4* x4 = reinterpret_cast<const float4*>(xl);
     const long long n4 = nl >> 2;
     long long i = t0;
     for (; i + 3 * stride < n4; i += 4 * stride) {
       const float4 a = __ldg(x4 + i), b = __ldg(x4 + i + stride), c = __ldg(x4 + i + 2 * stride), d = __ldg(x4 + i + 3 * stride);
-      sum += (fabsf(a.x) + fabsf(a.y)) + (fabsf(a.z) + fabsf(a.w)) + (fabsf(b.x) + fabsf(b.y)) + (fabsf(b.z) + fabsf(b.w)) +
-             (fabsf(c.x) + fabsf(c.y)) + (fabsf(c.z) + fabsf(c.w)) + (fabsf(d.x) + fabsf(d.y)) + (fabsf(d.z) + fabsf(d.w));
+      const float a0 = fabsf(a.x), a1 = fabsf(a.y), a2 = fabsf(a.z), a3 = fabsf(a.w), b0 = fabsf(b.x), b1 = fabsf(b.y), b2 = fabsf(b.z), b3 = fabsf(b.w);
+      const float c0 = fabsf(c.x), c1 = fabsf(c.y), c2 = fabsf(c.z), c3 = fabsf(c.w), d0 = fabsf(d.x), d1 = fabsf(d.y), d2 = fabsf(d.z), d3 = fabsf(d.w);
+      sum += (a0 + a1) + (a2 + a3) + (b0 + b1) + (b2 + b3) + (c0 + c1) + (c2 + c3) + (d0 + d1) + (d2 + d3);
+      if (same_range) {
+        mx = fmaxf(mx, fmaxf(fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)), fmaxf(fmaxf(b0, b1), fmaxf(b2, b3))));
+        mx = fmaxf(mx, fmaxf(fmaxf(fmaxf(c0, c1), fmaxf(c2, c3)), fmaxf(fmaxf(d0, d1), fmaxf(d2, d3))));
+      }
     }
-    for (; i < n4; i += stride) { const float4 a = __ldg(x4 + i); sum += (fabsf(a.x) + fabsf(a.y)) + (fabsf(a.z) + fabsf(a.w)); }
-    for (long long j = (n4 << 2) + t0; j < nl; j += stride) sum += fabsf(xl[j]);
+    for (; i < n4; i += stride) {
+      const float4 a = __ldg(x4 + i);
+      sum += (fabsf(a.x) + fabsf(a.y)) + (fabsf(a.z) + fabsf(a.w));
+      if (same_range) mx = fmaxf(mx, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))));
+    }
+    for (long long j = (n4 << 2) + t0; j < nl; j += stride) { sum += fabsf(xl[j]); if (same_range) mx = fmaxf(mx, fabsf(xl[j])); }
   } else {
-    for (long long i = t0; i < nl; i += stride) sum += fabsf(xl[i]);
+    for (long long i = t0; i < nl; i += stride) { sum += fabsf(xl[i]); if (same_range) mx = fmaxf(mx, fabsf(xl[i])); }
   }
-  if (want_scale) {
+  if (want_scale && !same_range) {
     if ((reinterpret_cast<uintptr_t>(xt) & 15) == 0) {
       const float4* x4 = reinterpret_cast<const float4*>(xt);
       const long long n4 = ntot >> 2;
@@ -428,11 +438,44 @@ void launch_row_stats_ref(const float* S, long long ldS, int Q, int N, const flo
 __device__ __forceinline__ bool is_rel(int m) { return m == M_RELATIVE_HARD || m == M_RELATIVE_EASY; }
 __host__ __device__ inline bool sn_is_max(float sn) { return sn >= 0.f && static_cast<int>(sn) == 0; }   // pos = size-1
 
+// Block-wide (or, world scope, world-wide) sizes / extrema -> GLOBAL-region thresholds and the arming of the radix selects (.cu:292-337)
+__device__ void finish_thresholds(unsigned long long n_same, unsigned long long n_diff, float gmin_w, float gmax_w, float gmax_b, int err,
+                                  const MiningParams& mp, BlockScalars* bs) {
+  float posi_g = 0.f, nega_g = 0.f;
+  bool arm_ap = false, arm_an = false;
+  if (mp.ap_region == REGION_GLOBAL) {
+    if (!is_rel(mp.ap_method)) { if (n_diff == 0) err |= DERR_EMPTY_LIST; posi_g = gmax_b; }              // .cu:296
+    else if (sn_is_max(mp.identsn)) { if (n_same == 0) err |= DERR_EMPTY_LIST; posi_g = clamp_thr(gmax_w); }   // pos = size-1
+    else arm_ap = true;                                                                                    // .cu:300-304
+  }
+  if (mp.an_region == REGION_GLOBAL) {
+    if (!is_rel(mp.an_method)) { if (n_same == 0) err |= DERR_EMPTY_LIST; nega_g = gmin_w; }               // .cu:327
+    else if (sn_is_max(mp.diffsn)) { if (n_diff == 0) err |= DERR_EMPTY_LIST; nega_g = clamp_thr(gmax_b); }
+    else arm_an = true;                                                                                    // .cu:331-335
+  }
+  bs->n_same = n_same; bs->n_diff = n_diff;
+  bs->gmin_within = gmin_w; bs->gmax_within = gmax_w; bs->gmax_between = gmax_b;
+  bs->posi_global = posi_g; bs->nega_global = nega_g;
+  for (int side = 0; side < 2; ++side) {
+    const bool arm = side == 0 ? arm_ap : arm_an;
+    bs->sel_active[side] = 0;
+    if (arm) {
+      unsigned long long pos = 0;
+      const unsigned long long size = side == 0 ? n_same : n_diff;
+      if (size == 0) err |= DERR_EMPTY_LIST;
+      else if (!pos_index(side == 0 ? mp.identsn : mp.diffsn, size, pos)) err |= DERR_POS_RANGE;
+      else { bs->sel_active[side] = 1; bs->sel_rank[side] = pos; bs->sel_prefix[side] = 0; bs->sel_mask[side] = 0; }
+    }
+  }
+  bs->err |= err;
+}
+
 // Multi-block: every block reduces its slice of the row statistics and writes the LOCAL-region thresholds of its rows
 // (they need no global value); the last block to finish (ticket) combines the per-block partials into the block-wide
 // sizes / extrema, the GLOBAL-region thresholds (read directly by the row pass) and the radix-select arming.
 struct ThrPartial { unsigned long long ns; float mn, mxw, mxb; int err; };
-__global__ void __launch_bounds__(256) thresholds_kernel(RowArrays ra, int Q, int N, MiningParams mp, BlockScalars* bs, ThrPartial* part) {
+__global__ void __launch_bounds__(256) thresholds_kernel(RowArrays ra, int Q, int N, MiningParams mp, BlockScalars* bs, ThrPartial* part,
+                                                         float* __restrict__ xout /*world scope: 6 floats of block statistics, else NULL*/) {
   __shared__ unsigned long long s_ns[8];
   __shared__ float s_mn[8], s_mxw[8], s_mxb[8];
   __shared__ int s_err, s_last;
@@ -474,39 +517,33 @@ __global__ void __launch_bounds__(256) thresholds_kernel(RowArrays ra, int Q, in
     const ThrPartial t = part[g];
     n_same += t.ns; gmin_w = fminf(gmin_w, t.mn); gmax_w = fmaxf(gmax_w, t.mxw); gmax_b = fmaxf(gmax_b, t.mxb); err |= t.err;
   }
-  const unsigned long long n_diff = static_cast<unsigned long long>(Q) * static_cast<unsigned long long>(N - 1) - n_same;
-  float posi_g = 0.f, nega_g = 0.f;
-  bool arm_ap = false, arm_an = false;
-  if (mp.ap_region == REGION_GLOBAL) {
-    if (!is_rel(mp.ap_method)) { if (n_diff == 0) err |= DERR_EMPTY_LIST; posi_g = gmax_b; }              // .cu:296
-    else if (sn_is_max(mp.identsn)) { if (n_same == 0) err |= DERR_EMPTY_LIST; posi_g = clamp_thr(gmax_w); }   // pos = size-1
-    else arm_ap = true;                                                                                    // .cu:300-304
-  }
-  if (mp.an_region == REGION_GLOBAL) {
-    if (!is_rel(mp.an_method)) { if (n_same == 0) err |= DERR_EMPTY_LIST; nega_g = gmin_w; }               // .cu:327
-    else if (sn_is_max(mp.diffsn)) { if (n_diff == 0) err |= DERR_EMPTY_LIST; nega_g = clamp_thr(gmax_b); }
-    else arm_an = true;                                                                                    // .cu:331-335
-  }
-  bs->n_same = n_same; bs->n_diff = n_diff;
-  bs->gmin_within = gmin_w; bs->gmax_within = gmax_w; bs->gmax_between = gmax_b;
-  bs->posi_global = posi_g; bs->nega_global = nega_g;
-  for (int side = 0; side < 2; ++side) {
-    const bool arm = side == 0 ? arm_ap : arm_an;
-    bs->sel_active[side] = 0;
-    if (arm) {
-      unsigned long long pos = 0;
-      const unsigned long long size = side == 0 ? n_same : n_diff;
-      if (size == 0) err |= DERR_EMPTY_LIST;
-      else if (!pos_index(side == 0 ? mp.identsn : mp.diffsn, size, pos)) err |= DERR_POS_RANGE;
-      else { bs->sel_active[side] = 1; bs->sel_rank[side] = pos; bs->sel_prefix[side] = 0; bs->sel_mask[side] = 0; }
-    }
-  }
-  bs->err |= err;
   bs->ticket2 = 0;
+  if (xout) {          // world scope: this rank's block statistics go to the exchange; thresholds_world_kernel finishes
+    xout[0] = __uint_as_float(static_cast<uint32_t>(n_same)); xout[1] = __uint_as_float(static_cast<uint32_t>(n_same >> 32));
+    xout[2] = gmin_w; xout[3] = gmax_w; xout[4] = gmax_b; xout[5] = __int_as_float(err);
+    return;
+  }
+  finish_thresholds(n_same, static_cast<unsigned long long>(Q) * static_cast<unsigned long long>(N - 1) - n_same, gmin_w, gmax_w, gmax_b, err, mp, bs);
 }
-void launch_thresholds(RowArrays ra, int Q, int N, MiningParams mp, BlockScalars* bs, float* scratch, cudaStream_t st) {
+// world scope (npair_config.global_scope): every rank reduces the world's block statistics in the same order -> identical thresholds
+__global__ void thresholds_world_kernel(const float* __restrict__ xall /*[world][xstride]*/, int xstride, int world, long long N, MiningParams mp,
+                                        BlockScalars* bs) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  unsigned long long n_same = 0; float gmin_w = FLT_MAX, gmax_w = -FLT_MAX, gmax_b = -FLT_MAX; int err = 0;
+  for (int r = 0; r < world; ++r) {
+    const float* x = xall + static_cast<long long>(r) * xstride;
+    n_same += static_cast<unsigned long long>(__float_as_uint(x[0])) | (static_cast<unsigned long long>(__float_as_uint(x[1])) << 32);
+    gmin_w = fminf(gmin_w, x[2]); gmax_w = fmaxf(gmax_w, x[3]); gmax_b = fmaxf(gmax_b, x[4]); err |= __float_as_int(x[5]);
+  }
+  finish_thresholds(n_same, static_cast<unsigned long long>(N) * static_cast<unsigned long long>(N - 1) - n_same, gmin_w, gmax_w, gmax_b, err, mp, bs);
+}
+void launch_thresholds_world(const float* xall, int xstride, int world, long long N, MiningParams mp, BlockScalars* bs, cudaStream_t st) {
+  thresholds_world_kernel<<<1, 32, 0, st>>>(xall, xstride, world, N, mp, bs);
+  count_launch();
+}
+void launch_thresholds(RowArrays ra, int Q, int N, MiningParams mp, BlockScalars* bs, float* scratch, float* xout, cudaStream_t st) {
   int grid = (Q + 255) / 256; if (grid > 64) grid = 64; if (grid < 1) grid = 1;
-  thresholds_kernel<<<grid, 256, 0, st>>>(ra, Q, N, mp, bs, reinterpret_cast<ThrPartial*>(scratch));
+  thresholds_kernel<<<grid, 256, 0, st>>>(ra, Q, N, mp, bs, reinterpret_cast<ThrPartial*>(scratch), xout);
   count_launch();
 }
 
@@ -851,9 +888,56 @@ struct GlobalSelectBufs {
   unsigned long long* hist;   // [2][2048]
   uint32_t* cand;             // [2][cap]
   unsigned int cap;
+  int world_scope;            // 1: the digit counts are exchanged between the ranks before the decision
 };
 #define NPAIR_GSEL_STAGE 2048
 __device__ __forceinline__ uint32_t d11_raw_of_order(uint32_t o) { return o < 1024u ? 2047u - o : o - 1024u; }
+
+// Decides one digit of the GLOBAL select from the 64-bit counts in gb.hist (one block; `ordered` = 2048 x 8 bytes of shared memory)
+__device__ void global_decide(int pass, bool act0, bool act1, GlobalSelectBufs gb, RowArrays ra, int Q, BlockScalars* bs,
+                              unsigned long long* ordered, unsigned long long* s_scan, int* s_res, unsigned long long* s_out) {
+  const int shift = pass == 1 ? 10 : 0;
+  const int nbits = pass == 2 ? 10 : 11;
+#pragma unroll
+  for (int side = 0; side < 2; ++side) {
+    if (!(side == 0 ? act0 : act1)) continue;
+    const unsigned long long* gh = gb.hist + side * NPAIR_SEL_BINS;
+    const int nb = 1 << nbits;
+    __syncthreads();
+    // pass 0 counted RAW digits: walk them in value order (negative floats: descending raw digit)
+    for (int o = threadIdx.x; o < nb; o += blockDim.x) ordered[o] = __ldcg(&gh[pass == 0 ? d11_raw_of_order(o) : static_cast<uint32_t>(o)]);
+    __syncthreads();
+    unsigned long long r2, pp;
+    const int d = find_bin(ordered, nb, bs->sel_rank[side], &r2, &pp, s_scan, s_res, s_out);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (d >= nb) { bs->err |= DERR_POS_RANGE; bs->sel_active[side] = 0; }
+      else {
+        bs->sel_rank[side] = r2;
+        if (pass == 0) { bs->sel_prefix[side] = d11_raw_of_order(static_cast<uint32_t>(d)) << 21; bs->sel_cnt[side] = pp; bs->cand_n[side] = 0; }
+        else bs->sel_prefix[side] |= static_cast<uint32_t>(d) << shift;
+        if (pass == 2) {
+          const uint32_t p = bs->sel_prefix[side];
+          const uint32_t bits = (p & 0xFFE00000u) | ((p & 0x1FFFFFu) ^ ((p >> 21) >= 1024u ? 0x1FFFFFu : 0u));     // un-flip the remainder
+          const float thr = clamp_thr(__uint_as_float(bits));                    // .cu:303 / :334
+          if (side == 0) bs->posi_global = thr; else bs->nega_global = thr;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  for (int b = threadIdx.x; b < 2 * NPAIR_SEL_BINS; b += blockDim.x) gb.hist[b] = 0ull;
+  if (pass == 2) {
+    __syncthreads();
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+      if (!(side == 0 ? act0 : act1) || !bs->sel_active[side]) continue;
+      const float thr = side == 0 ? bs->posi_global : bs->nega_global;
+      float* out = side == 0 ? ra.posi_thr : ra.nega_thr;
+      for (int i = threadIdx.x; i < Q; i += blockDim.x) out[i] = thr;
+    }
+  }
+}
 
 __global__ void __launch_bounds__(512) global_select_kernel(const float* __restrict__ S, long long ldS, int Q, int N, const float* __restrict__ lab_rows,
                                                             const float* __restrict__ lab_cols, int self_offset, int side_mask, int pass /*0,1,2*/,
@@ -991,64 +1075,49 @@ __global__ void __launch_bounds__(512) global_select_kernel(const float* __restr
     const unsigned int h = (&hist[0][0])[b];
     if (h) atomicAdd(&gb.hist[b], static_cast<unsigned long long>(h));
   }
-  // ---- last block: decide this digit ----
+  // ---- last block: decide this digit (world scope: the counts are exchanged first, global_decide_kernel decides) ----
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) s_last = (atomicAdd(&bs->ticket3, 1u) == gridDim.x - 1) ? 1 : 0;
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  unsigned long long* ordered = reinterpret_cast<unsigned long long*>(&hist[0][0]);       // 2048 x 8 bytes: reuses the block histograms
-#pragma unroll
-  for (int side = 0; side < 2; ++side) {
-    if (!(side == 0 ? act0 : act1)) continue;
-    const unsigned long long* gh = gb.hist + side * NPAIR_SEL_BINS;
-    const int nb = 1 << nbits;
-    __syncthreads();
-    // pass 0 counted RAW digits: walk them in value order (negative floats: descending raw digit)
-    for (int o = threadIdx.x; o < nb; o += blockDim.x) ordered[o] = __ldcg(&gh[pass == 0 ? d11_raw_of_order(o) : static_cast<uint32_t>(o)]);
-    __syncthreads();
-    unsigned long long r2, pp;
-    const int d = find_bin(ordered, nb, bs->sel_rank[side], &r2, &pp, s_scan, &s_res, s_out);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      if (d >= nb) { bs->err |= DERR_POS_RANGE; bs->sel_active[side] = 0; }
-      else {
-        bs->sel_rank[side] = r2;
-        if (pass == 0) { bs->sel_prefix[side] = d11_raw_of_order(static_cast<uint32_t>(d)) << 21; bs->sel_cnt[side] = pp; bs->cand_n[side] = 0; }
-        else bs->sel_prefix[side] |= static_cast<uint32_t>(d) << shift;
-        if (pass == 2) {
-          const uint32_t p = bs->sel_prefix[side];
-          const uint32_t bits = (p & 0xFFE00000u) | ((p & 0x1FFFFFu) ^ ((p >> 21) >= 1024u ? 0x1FFFFFu : 0u));     // un-flip the remainder
-          const float thr = clamp_thr(__uint_as_float(bits));                    // .cu:303 / :334
-          if (side == 0) bs->posi_global = thr; else bs->nega_global = thr;
-        }
-      }
-    }
-    __syncthreads();
-  }
-  for (int b = threadIdx.x; b < 2 * NPAIR_SEL_BINS; b += blockDim.x) gb.hist[b] = 0ull;
   if (threadIdx.x == 0) bs->ticket3 = 0;
-  if (pass == 2) {
-    __syncthreads();
-#pragma unroll
-    for (int side = 0; side < 2; ++side) {
-      if (!(side == 0 ? act0 : act1) || !bs->sel_active[side]) continue;
-      const float thr = side == 0 ? bs->posi_global : bs->nega_global;
-      float* out = side == 0 ? ra.posi_thr : ra.nega_thr;
-      for (int i = threadIdx.x; i < Q; i += blockDim.x) out[i] = thr;
-    }
-  }
+  if (gb.world_scope) return;
+  global_decide(pass, act0, act1, gb, ra, Q, bs, reinterpret_cast<unsigned long long*>(&hist[0][0]), s_scan, &s_res, s_out);
 }
-void launch_global_select(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
-                          int self_offset, int side_mask, RowArrays ra, unsigned long long* hist, uint32_t* cand, unsigned int cand_cap,
-                          BlockScalars* bs, int sms, cudaStream_t st) {
-  int grid = sms * 4; if (grid > Q) grid = Q;
-  GlobalSelectBufs gb; gb.hist = hist; gb.cand = cand; gb.cap = cand_cap;
-  for (int pass = 0; pass < 3; ++pass) {
-    global_select_kernel<<<grid, 512, 0, st>>>(S, ldS, Q, N, lab_rows, lab_cols, self_offset, side_mask, pass, gb, ra, bs);
-    count_launch();
+// world scope: sum the ranks' digit counts (same order on every rank -> identical decisions), then decide like the last block does
+__global__ void __launch_bounds__(512) global_decide_kernel(const float* __restrict__ xall, int xstride, int world, int side_mask, int pass,
+                                                            GlobalSelectBufs gb, RowArrays ra, int Q, BlockScalars* bs) {
+  __shared__ unsigned long long ordered[NPAIR_SEL_BINS];
+  __shared__ unsigned long long s_scan[33], s_out[2];
+  __shared__ int s_res;
+  const bool act0 = (side_mask & 1) && bs->sel_active[0], act1 = (side_mask & 2) && bs->sel_active[1];
+  if (!act0 && !act1) return;
+  for (int b = threadIdx.x; b < 2 * NPAIR_SEL_BINS; b += blockDim.x) {
+    unsigned long long sum = 0;
+    for (int r = 0; r < world; ++r) {
+      const float* x = xall + static_cast<long long>(r) * xstride + 2 * b;
+      sum += static_cast<unsigned long long>(__float_as_uint(x[0])) | (static_cast<unsigned long long>(__float_as_uint(x[1])) << 32);
+    }
+    gb.hist[b] = sum;
   }
+  __syncthreads();
+  global_decide(pass, act0, act1, gb, ra, Q, bs, ordered, s_scan, &s_res, s_out);
+}
+void launch_global_select_pass(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
+                               int self_offset, int side_mask, int pass, RowArrays ra, unsigned long long* hist, uint32_t* cand,
+                               unsigned int cand_cap, int world_scope, BlockScalars* bs, int sms, cudaStream_t st) {
+  int grid = sms * 4; if (grid > Q) grid = Q;
+  GlobalSelectBufs gb; gb.hist = hist; gb.cand = cand; gb.cap = cand_cap; gb.world_scope = world_scope;
+  global_select_kernel<<<grid, 512, 0, st>>>(S, ldS, Q, N, lab_rows, lab_cols, self_offset, side_mask, pass, gb, ra, bs);
+  count_launch();
+}
+void launch_global_decide(const float* xall, int xstride, int world, int side_mask, int pass, RowArrays ra, int Q, unsigned long long* hist,
+                          uint32_t* cand, unsigned int cand_cap, BlockScalars* bs, cudaStream_t st) {
+  GlobalSelectBufs gb; gb.hist = hist; gb.cand = cand; gb.cap = cand_cap; gb.world_scope = 1;
+  global_decide_kernel<<<1, 512, 0, st>>>(xall, xstride, world, side_mask, pass, gb, ra, Q, bs);
+  count_launch();
 }
 
 // --------------------------------------------------------------------------------------------
@@ -1107,39 +1176,50 @@ __device__ __forceinline__ void lse_elem(float sv, float lab, float li, float sc
 __global__ void __launch_bounds__(256, NPAIR_LSE_MINB) lse_rows_kernel(const float* __restrict__ S, long long ldS, int Q, int N,
                                                        const float* __restrict__ lab_rows, const float* __restrict__ lab_cols,
                                                        int self_offset, MiningParams mp, RowArrays ra, BlockScalars* bs,
-                                                       int num_tops, float* __restrict__ tops, float log2_world) {
+                                                       int num_tops, float* __restrict__ tops, float log2_world,
+                                                       float* __restrict__ xout /*world scope: this rank's partial tops, else NULL*/,
+                                                       int wpr /*warps per row: 1, 2, 4 or 8 (few rows per rank: keep the SMs full)*/,
+                                                       unsigned int seq /*written behind the tops: the host polls it*/) {
   const int lane = threadIdx.x & 31;
+  __shared__ float s_pA[8], s_pT[8];
+  __shared__ int s_pc[8];
   // NPAIR_LSE_REV: walk the rows from the last to the first.  The similarity GEMM produced the high row blocks last, so
   // their tiles are the ones still resident in the 126 MB L2 when this kernel starts.
 #ifndef NPAIR_LSE_REV
 #define NPAIR_LSE_REV 1
 #endif
   const int blk = NPAIR_LSE_REV ? static_cast<int>(gridDim.x - 1 - blockIdx.x) : static_cast<int>(blockIdx.x);
-  const int i = blk * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int wib = threadIdx.x >> 5;
+  const int i = blk * ((blockDim.x >> 5) / wpr) + wib / wpr;
+  const int part = wib % wpr;                                   // this warp's column segment of the row
+  float A = 0.f, T = 0.f; int c = 0;
+  float m2 = 0.f, thr_p = 0.f, thr_n = 0.f, li = 0.f; int cs = 0;
   if (i < Q) {
-    const float li = lab_rows[i];
+    li = lab_rows[i];
     const int self_col = i + self_offset;
     const float max_all = ord2f(ra.st_maxall[i]);
-    const float m2 = max_all * NPAIR_LOG2E;
+    m2 = max_all * NPAIR_LOG2E;
     // GLOBAL-region thresholds are block-wide scalars (thresholds_kernel / global_pick_kernel); LOCAL ones are per row
     const float posi = mp.ap_region == REGION_GLOBAL ? bs->posi_global : ra.posi_thr[i];
     const float nega = mp.an_region == REGION_GLOBAL ? bs->nega_global : ra.nega_thr[i];
-    if (lane == 0) { ra.posi_thr[i] = posi; ra.nega_thr[i] = nega; }   // kept per row for inspection (npair_debug_read)
+    if (lane == 0 && part == 0) { ra.posi_thr[i] = posi; ra.nega_thr[i] = nega; }   // kept per row for inspection (npair_debug_read)
     const float tp = posi + mp.margin_ident;                    // fp32 add as in .cu:81
     const float tn = nega + mp.margin_diff;                     // .cu:102
     const float sgn_p = ap_sign(mp.ap_method), sgn_n = an_sign(mp.an_method);
-    const float thr_p = ap_thr(tp, mp.ap_method), thr_n = an_thr(tn, mp.an_method);
-    const int cs = ra.cnt_same[i];
+    thr_p = ap_thr(tp, mp.ap_method); thr_n = an_thr(tn, mp.an_method);
+    cs = ra.cnt_same[i];
     const float scut = cs > 0 ? retrieval_cut(ord2f(ra.st_maxw[i]), max_all, lane) : INFINITY;
     const float* row = S + static_cast<long long>(i) * ldS;
-    float A = 0.f, T = 0.f; int c = 0;
     // ---- full 512-column blocks: unguarded 128-bit loads (4 in flight per lane for S, 4 for the labels) ----
     constexpr int U = NPAIR_LSE_U;
-    const int n_full = N - N % (128 * U);
-    const float4* srow4 = reinterpret_cast<const float4*>(row) + lane;
-    const float4* lab4 = reinterpret_cast<const float4*>(lab_cols) + lane;
+    // this warp's segment [c_lo, c_hi) of the row: multiples of 512 columns
+    const int seg = ((N + wpr - 1) / wpr + 128 * U - 1) / (128 * U) * (128 * U);
+    const int c_lo = min(N, part * seg), c_hi = min(N, c_lo + seg);
+    const int n_full = c_lo + (c_hi - c_lo) / (128 * U) * (128 * U);
+    const float4* srow4 = reinterpret_cast<const float4*>(row + c_lo) + lane;
+    const float4* lab4 = reinterpret_cast<const float4*>(lab_cols + c_lo) + lane;
     const bool lab_aligned = (reinterpret_cast<uintptr_t>(lab_cols) & 15) == 0;
-    int base = 0;
+    int base = c_lo;
     if (lab_aligned) {
       for (; base < n_full; base += 128 * U, srow4 += 32 * U, lab4 += 32 * U) {
         float4 v[U], l[U];
@@ -1171,19 +1251,29 @@ __global__ void __launch_bounds__(256, NPAIR_LSE_MINB) lse_rows_kernel(const flo
       }
     }
     // ---- ragged tail (and the whole row when the label pointer is not 16-byte aligned) ----
-    for (; base < N; base += 512) {
+    for (; base < c_hi; base += 512) {
 #pragma unroll 1
       for (int u = 0; u < 4; ++u) {
         const int j4 = base + u * 128 + lane * 4;
-        if (j4 >= N) continue;
+        if (j4 >= c_hi) continue;
         const float4 v4 = *reinterpret_cast<const float4*>(row + j4);      // row stride ldS is a multiple of 32: in bounds
         const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          if (j4 + q < N && j4 + q != self_col) lse_elem(vv[q], lab_cols[j4 + q], li, scut, m2, sgn_p, thr_p, sgn_n, thr_n, A, T, c);
+          if (j4 + q < c_hi && j4 + q != self_col) lse_elem(vv[q], lab_cols[j4 + q], li, scut, m2, sgn_p, thr_p, sgn_n, thr_n, A, T, c);
       }
     }
     A = warp_sum(A); T = warp_sum(T); c = warp_sum_i(c);
+  }
+  if (wpr > 1) {                                                // the row's segments, added in segment order by its first warp
+    if (lane == 0) { s_pA[wib] = A; s_pT[wib] = T; s_pc[wib] = c; }
+    __syncthreads();
+    if (part == 0) {
+      A = 0.f; T = 0.f; c = 0;
+      for (int q = 0; q < wpr; ++q) { A += s_pA[wib + q]; T += s_pT[wib + q]; c += s_pc[wib + q]; }
+    }
+  }
+  if (i < Q && part == 0) {
     if (lane == 0) {
       ra.A[i] = A; ra.T[i] = T;                                 // T = A + B (.cu:380)
       ra.logv[i] = (A == 0.f || T == 0.f) ? 0.f : logf(A / T);  // .cu:162-169
@@ -1228,6 +1318,14 @@ __global__ void __launch_bounds__(256, NPAIR_LSE_MINB) lse_rows_kernel(const flo
   if (threadIdx.x == 0) {
     ls = 0.0; h[0] = h[1] = h[2] = 0;
     for (int k = 0; k < (blockDim.x >> 5); ++k) { ls += s_l[k]; h[0] += s_h[0][k]; h[1] += s_h[1][k]; h[2] += s_h[2][k]; }
+    if (xout) {        // world scope: sums only; tops_world_kernel divides by the world's N after the exchange
+      const unsigned long long lb = static_cast<unsigned long long>(__double_as_longlong(ls));
+      xout[0] = __uint_as_float(static_cast<uint32_t>(lb)); xout[1] = __uint_as_float(static_cast<uint32_t>(lb >> 32));
+      xout[2] = __int_as_float(h[0]); xout[3] = __int_as_float(h[1]); xout[4] = __int_as_float(h[2]);
+      xout[5] = bs->asum; xout[6] = __int_as_float(bs->err);
+      bs->ticket = 0;
+      return;
+    }
     float out[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
     out[0] = static_cast<float>(ls) / static_cast<float>(-Q);                       // .cu:384-385
     for (int t = 1; t <= num_tops - 2 && t <= 3; ++t) out[t] = static_cast<float>(h[t - 1]) / static_cast<float>(Q);   // .cu:205
@@ -1236,16 +1334,30 @@ __global__ void __launch_bounds__(256, NPAIR_LSE_MINB) lse_rows_kernel(const flo
     reinterpret_cast<int*>(tops)[5] = bs->err;
     bs->ticket = 0;
     __threadfence_system();
+    reinterpret_cast<volatile unsigned int*>(tops)[6] = seq;     // tops are visible on the host before the sequence number
   }
 }
 void launch_lse_rows(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
-                     int self_offset, MiningParams mp, RowArrays ra, BlockScalars* bs, int num_tops, float* tops_dev, int world, cudaStream_t st) {
+                     int self_offset, MiningParams mp, RowArrays ra, BlockScalars* bs, int num_tops, float* tops_dev, int world, float* xout,
+                     unsigned int seq, cudaStream_t st) {
+  // few rows per rank (anchor sharding over many GPUs): several warps share a row so that every SM still holds ~32 warps
+  int wpr = 1;
+  while (wpr < 8 && static_cast<long long>(Q) * wpr < 4096 && N / (2 * wpr) >= 512) wpr *= 2;
+  if (wpr > 1) {
+    const int rows_per_blk = 8 / wpr;
+    const int grid = (Q + rows_per_blk - 1) / rows_per_blk;
+    lse_rows_kernel<<<grid, 256, 0, st>>>(S, ldS, Q, N, lab_rows, lab_cols, self_offset, mp, ra, bs, num_tops, tops_dev,
+                                          xout ? 0.f : log2f(static_cast<float>(world)), xout, wpr, seq);
+    count_launch();
+    return;
+  }
   // 8 warps per block, 4 blocks per SM.  Measured at Q = 8192 (1.73 waves): 7 warps (1.98 waves, less idle tail) is SLOWER
   // (81.3 vs 78.7 us; 6: 83.7, 5: 87.6) -- the pass is latency-bound, more resident warps win.  NPAIR_LSE_WPB overrides.
   int wpb = 8;
   while (wpb > 1 && (Q + wpb - 1) / wpb < 296) wpb >>= 1;     // keep >= 2 blocks per SM when the rank has few rows
   const int grid = (Q + wpb - 1) / wpb;
-  lse_rows_kernel<<<grid, wpb * 32, 0, st>>>(S, ldS, Q, N, lab_rows, lab_cols, self_offset, mp, ra, bs, num_tops, tops_dev, log2f(static_cast<float>(world)));
+  lse_rows_kernel<<<grid, wpb * 32, 0, st>>>(S, ldS, Q, N, lab_rows, lab_cols, self_offset, mp, ra, bs, num_tops, tops_dev,
+                                             xout ? 0.f : log2f(static_cast<float>(world)), xout, 1, seq);
   count_launch();
 }
 
@@ -1439,6 +1551,32 @@ __global__ void __launch_bounds__(256) l2norm_bwd_kernel(const float* __restrict
     *reinterpret_cast<float4*>(dr + d) = make_float4((g.x - a.x * dot) * inv, (g.y - a.y * dot) * inv, (g.z - a.z * dot) * inv, (g.w - a.w * dot) * inv);
   } else for (int d = lane; d < dim; d += 32) dr[d] = (gr[d] - yr[d] * dot) * inv;
 }
+// world scope: tops from the ranks' partial sums, normalised by the world's N (identical on every rank)
+__global__ void tops_world_kernel(const float* __restrict__ xall, int xstride, int world, long long N, int num_tops, float* __restrict__ tops,
+                                  unsigned int seq) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double ls = 0.0; long long h[3] = {0, 0, 0}; double asum = 0.0; int err = 0;
+  for (int r = 0; r < world; ++r) {
+    const float* x = xall + static_cast<long long>(r) * xstride;
+    const unsigned long long lb = static_cast<unsigned long long>(__float_as_uint(x[0])) | (static_cast<unsigned long long>(__float_as_uint(x[1])) << 32);
+    ls += __longlong_as_double(static_cast<long long>(lb));
+    h[0] += __float_as_int(x[2]); h[1] += __float_as_int(x[3]); h[2] += __float_as_int(x[4]);
+    asum += x[5]; err |= __float_as_int(x[6]);
+  }
+  float out[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  out[0] = static_cast<float>(ls) / static_cast<float>(-N);
+  for (int t = 1; t <= num_tops - 2 && t <= 3; ++t) out[t] = static_cast<float>(h[t - 1]) / static_cast<float>(N);
+  out[num_tops - 1] = static_cast<float>(asum) / static_cast<float>(N);
+  for (int t = 0; t < 5; ++t) tops[t] = out[t];
+  reinterpret_cast<int*>(tops)[5] = err;
+  __threadfence_system();
+  reinterpret_cast<volatile unsigned int*>(tops)[6] = seq;
+}
+void launch_tops_world(const float* xall, int xstride, int world, long long N, int num_tops, float* tops_dev, unsigned int seq, cudaStream_t st) {
+  tops_world_kernel<<<1, 32, 0, st>>>(xall, xstride, world, N, num_tops, tops_dev, seq);
+  count_launch();
+}
+
 void launch_l2norm_fwd(const float* x, int rows, int dim, float* y, float* inv_norm, cudaStream_t st) {
   l2norm_fwd_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, rows, dim, y, inv_norm);
   count_launch();

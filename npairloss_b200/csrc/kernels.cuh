@@ -74,16 +74,22 @@ void launch_split(const float* x_total, int N, int D, int prec, const BlockScala
                   uint16_t* XcatA /*or NULL*/, uint16_t* XcatB, long long Dp, cudaStream_t st);
 void launch_row_stats_ref(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
                           int self_offset, RowArrays ra, cudaStream_t st);
-void launch_thresholds(RowArrays ra, int Q, int N, MiningParams mp, BlockScalars* bs, float* scratch /*>= 2 KB*/, cudaStream_t st);
+// xout: NULL, or (world scope) 6 floats receiving this rank's block statistics instead of the final thresholds
+void launch_thresholds(RowArrays ra, int Q, int N, MiningParams mp, BlockScalars* bs, float* scratch /*>= 2 KB*/, float* xout, cudaStream_t st);
+void launch_thresholds_world(const float* xall, int xstride, int world, long long N, MiningParams mp, BlockScalars* bs, cudaStream_t st);
+void launch_tops_world(const float* xall, int xstride, int world, long long N, int num_tops, float* tops_dev, unsigned int seq, cudaStream_t st);
 // side_mask: bit 0 = AP threshold over the same-label list, bit 1 = AN threshold over the diff-label list
 void launch_local_select(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
                          int self_offset, int side_mask, float sn_ap, float sn_an, RowArrays ra, BlockScalars* bs, int sms, cudaStream_t st);
-void launch_global_select(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
-                          int self_offset, int side_mask, RowArrays ra, unsigned long long* hist /*[2][2048], zero*/,
-                          uint32_t* cand /*[2][cand_cap]*/, unsigned int cand_cap, BlockScalars* bs, int sms, cudaStream_t st);
+void launch_global_select_pass(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
+                               int self_offset, int side_mask, int pass /*0,1,2*/, RowArrays ra, unsigned long long* hist /*[2][2048], zero*/,
+                               uint32_t* cand /*[2][cand_cap]*/, unsigned int cand_cap, int world_scope, BlockScalars* bs, int sms, cudaStream_t st);
+// world scope: xall = the ranks' exchanged [2][2048] 64-bit digit counts
+void launch_global_decide(const float* xall, int xstride, int world, int side_mask, int pass, RowArrays ra, int Q, unsigned long long* hist,
+                          uint32_t* cand, unsigned int cand_cap, BlockScalars* bs, cudaStream_t st);
 void launch_lse_rows(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
                      int self_offset, MiningParams mp, RowArrays ra, BlockScalars* bs, int num_tops, float* tops_dev /*[5]+err*/,
-                     int world, cudaStream_t st);
+                     int world, float* xout /*world scope: 7 floats of partial tops, else NULL*/, unsigned int seq, cudaStream_t st);
 // mode: BW_SPLIT (world > 1, reduce-scatter form: H and HT), BW_SYM (world == 1), BW_ROWSCAL (world > 1, row-scalar
 // exchange: rs_total = all-gathered [world][5][Q] row scalars)
 enum { BW_SPLIT = 0, BW_SYM = 1, BW_ROWSCAL = 2 };

@@ -122,3 +122,54 @@ def test_layer_contract(oracle):
         layer.forward_cpu_mode()
     assert "no CPU path" in str(e.value)
     layer.close()
+
+
+REF_TRAIN_NET = '''
+name: "GoogleNet"
+layer {
+    name: "data_mb"
+    type: "MultibatchData"
+    top: "data_mb"
+    top: "label_type_mb"
+    include { phase: TRAIN }
+    multi_batch_data_param {
+        batch_size: 120
+        shuffle: true
+        identity_num_per_batch: 60
+        img_num_per_identity: 2
+        rand_identity: true
+    }
+}
+layer {
+    name: "data_mb"
+    type: "MultibatchData"
+    top: "data_mb"
+    top: "label_type_mb"
+    include { phase: TEST }
+    multi_batch_data_param { batch_size: 30 identity_num_per_batch: 15 img_num_per_identity: 2 }
+}
+.
+.
+''' + REF_USAGE_BLOCK
+
+
+def test_train_net_prototxt_is_parsed():
+    """The data-layer block format of usage/def.prototxt:2-59 next to the loss block: both phases, nested messages captured."""
+    p = caffe_layer.parse_only(REF_TRAIN_NET)
+    assert p["n_layers"] == 4 and p["num_tops"] == 5
+
+
+@pytest.mark.gpu
+def test_solver_loop_trains_through_the_reference_chain():
+    """SURVEY 8f-4: MultibatchData -> [synthetic trunk] -> L2Normalize -> NPairMultiClassLoss for a few hundred SGD iterations with the
+    solver settings of usage/solver.prototxt (momentum 0.9, step policy); the learning rate is scaled for the toy embedding table.
+    The loss must come down and top-1 retrieval must go up: forward, backward and both layers' gradients act together."""
+    solver = "base_lr: 4000\nlr_policy: \"step\"\nstepsize: 200\ngamma: 0.5\nmomentum: 0.9\nweight_decay: 0.00002\ndisplay: 20\nmax_iter: 400\nsolver_mode: GPU\n"
+    log = caffe_layer.solver_run(REF_TRAIN_NET, solver, feature_dim=64, num_identities=240, imgs_per_identity=4, seed=3, noise=2.5)
+    assert len(log) >= 20 and log[0, 0] == 0 and log[-1, 0] == 399
+    first, last = log[:3].mean(axis=0), log[-3:].mean(axis=0)
+    print("solver loop: loss", first[2], "->", last[2], " top1", first[3], "->", last[3])
+    assert np.isfinite(log).all()
+    assert last[2] < 0.8 * first[2], (first[2], last[2])
+    assert last[3] > first[3] + 0.1, (first[3], last[3])
+    assert abs(last[6] - first[6]) < 0.2 * first[6]          # feature_asum of unit rows stays put
