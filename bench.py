@@ -429,7 +429,7 @@ def main():
                    "host every step, gradient left in bottom[0]'s device diff"),
            "timing": "host wall clock around the loop, device synchronised and ranks barriered on both sides, max over ranks",
            "gradient_matches_device_path": e2e_consistent, "loss": tops_p[0]}
-    if not args.no_extras:
+    if not args.no_extras and world == 1:
         # (2) serial: copy, then compute; (3) serial + the gradient copied back to the host every step
         for _ in range(nw):
             layer.step_host(read_gradient=False)
@@ -503,7 +503,7 @@ def main():
 
     # ---------------- the two other mining settings of SURVEY 8d (short runs, N = 1 or sharded alike) ----------------
     other = None
-    if not args.no_extras and args.mining == "config" and name in ("HL", "C4"):
+    if not args.no_extras and args.mining == "config" and name in ("HL", "C4") and world == 1:
         other = {}
         for mname, m in (("rand", dict(synth.DEFAULT_MINING)),
                          ("relative", dict(synth.USAGE_MINING, ap_region=synth.LOCAL, ap_method=synth.RELATIVE_HARD, an_region=synth.LOCAL,

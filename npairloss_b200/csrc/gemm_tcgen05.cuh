@@ -226,9 +226,10 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 8 * NCTA); }
     ptx::fence_mbar_init();
   }
+  if (NCTA == 2) ptx::cluster_sync_all();      // both CTAs of the pair are resident before the pair-wide tensor-memory allocation
   if (warp == 2) {
-    ptx::tmem_alloc<512>(tmem_ptr);
-    ptx::tmem_relinquish();
+    ptx::tmem_alloc<512, NCTA>(tmem_ptr);
+    ptx::tmem_relinquish<NCTA>();
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -513,7 +514,7 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   if (NCTA == 2) ptx::cluster_sync_all();      // no CTA of the pair exits while the other may still signal or read it
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc<512>(tmem_base);
+    ptx::tmem_dealloc<512, NCTA>(tmem_base);
   }
 }
 

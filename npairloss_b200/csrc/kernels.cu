@@ -1152,6 +1152,13 @@ __device__ __forceinline__ float retrieval_cut(float maxw, float max_all, int la
   return ord2f(hi);
 }
 
+// 16-byte streaming load: read-only path, no L1 allocation (S is read exactly once by this kernel)
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
 // One warp per anchor row, branch-free hot loop (12 instructions per element): one retrieval-count compare, one label
 // compare, ONE selection compare with sign/threshold picked by the label predicate, a 2-instruction exponential, and two
 // accumulations (T = A + B for every selected pair, A under the same-label predicate).
@@ -1171,7 +1178,7 @@ __device__ __forceinline__ void lse_elem(float sv, float lab, float li, float sc
 #define NPAIR_LSE_U 4            // 16-byte loads in flight per lane and array (S, labels)
 #endif
 #ifndef NPAIR_LSE_MINB
-#define NPAIR_LSE_MINB 4
+#define NPAIR_LSE_MINB 3
 #endif
 __global__ void __launch_bounds__(256, NPAIR_LSE_MINB) lse_rows_kernel(const float* __restrict__ S, long long ldS, int Q, int N,
                                                        const float* __restrict__ lab_rows, const float* __restrict__ lab_cols,
@@ -1220,11 +1227,21 @@ __global__ void __launch_bounds__(256, NPAIR_LSE_MINB) lse_rows_kernel(const flo
     const float4* lab4 = reinterpret_cast<const float4*>(lab_cols + c_lo) + lane;
     const bool lab_aligned = (reinterpret_cast<uintptr_t>(lab_cols) & 15) == 0;
     int base = c_lo;
-    if (lab_aligned) {
-      for (; base < n_full; base += 128 * U, srow4 += 32 * U, lab4 += 32 * U) {
-        float4 v[U], l[U];
+    if (lab_aligned && base < n_full) {
+      // software pipeline: the 16-byte loads of block k+1 (streamed past the L1: every byte of S is used once) are in flight while
+      // block k is evaluated; the labels (32 KB shared by every row) come from the L1 when they are needed
+      float4 v[U], vn[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) { v[u] = __ldg(srow4 + 32 * u); l[u] = __ldg(lab4 + 32 * u); }
+      for (int u = 0; u < U; ++u) v[u] = ldg_stream(srow4 + 32 * u);
+      for (; base < n_full; base += 128 * U, srow4 += 32 * U, lab4 += 32 * U) {
+        const bool more = base + 128 * U < n_full;
+        if (more) {
+#pragma unroll
+          for (int u = 0; u < U; ++u) vn[u] = ldg_stream(srow4 + 32 * U + 32 * u);
+        }
+        float4 l[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) l[u] = __ldg(lab4 + 32 * u);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int j4 = base + u * 128 + lane * 4;
@@ -1247,6 +1264,10 @@ __global__ void __launch_bounds__(256, NPAIR_LSE_MINB) lse_rows_kernel(const flo
             for (int q = 0; q < 4; ++q)
               if (j4 + q != self_col) lse_elem(vv[q], ll[q], li, scut, m2, sgn_p, thr_p, sgn_n, thr_n, A, T, c);
           }
+        }
+        if (more) {
+#pragma unroll
+          for (int u = 0; u < U; ++u) v[u] = vn[u];
         }
       }
     }

@@ -154,3 +154,23 @@ def test_medium_headline_mining_fp32_faithful(cuda, oracle):
     for prec in (capi.PREC_FP32_FP16X2, capi.PREC_FP32_BF16X3):
         r = check_parity(oracle, x, lab, 2048, 1, synth.USAGE_MINING, prec, capi.GEMM_TCGEN05, tag=f"B2048 {PREC_NAME[prec]}")
         print("B2048", PREC_NAME[prec], r)
+
+
+@pytest.mark.parametrize("B,D,prec", [(1024, 256, capi.PREC_FP32_FP16X2), (2048, 512, capi.PREC_BF16), (640, 200, capi.PREC_FP32_BF16X3)])
+def test_pair_kernels_match_single_cta_bitwise(cuda, B, D, prec):
+    """The CTA-pair (tcgen05 cta_group::2) similarity / gradient kernels against the single-CTA kernels (npair_config.flags): S, the
+    fused row statistics, the tops and the gradient agree bit for bit."""
+    torch = cuda
+    x, lab = synth.make_inputs(B, D, 20171230, noise=2.5)
+    dx, dl = torch.from_numpy(x).cuda(), torch.from_numpy(lab).cuda()
+    res = []
+    for flags in (0, capi.FLAG_SIM_1CTA | capi.FLAG_GRAD_1CTA):
+        ctx = capi.Context(capi.make_config(B, D, sim_precision=prec, flags=flags, **synth.USAGE_MINING))
+        dg = torch.full_like(dx, float("nan"))
+        tops = ctx.forward(dx, dl)
+        ctx.backward(1.0, dg)
+        torch.cuda.synchronize()
+        res.append((np.array(tops, np.float32), ctx.debug_read(0, B * B), np.stack([ctx.debug_read(w, B) for w in (3, 4, 5, 8, 9)]), dg.cpu().numpy()))
+        ctx.close()
+    for a, b in zip(res[0], res[1]):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
