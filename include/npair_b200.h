@@ -188,6 +188,11 @@ int npair_util_f32_to_f64(const float* d_src, double* d_dst, size_t n, void* str
  *        9 = max_within[Q]  10 = operand pre-scale (1 float) */
 int npair_debug_read(npair_ctx* ctx, int which, float* host_dst, size_t n_floats);
 
+/* 1 if a similarity matrix computed on this device with every tile (no mirroring) in operand format `precision` comes out bitwise
+ * symmetric, 0 if not (the row-record backward exchange then falls back to the reduce-scatter form), negative on error.  npair_create
+ * runs and caches this check itself for world > 1. */
+int npair_debug_mma_symmetric(int precision);
+
 /* Stand-alone run of the split-operand GEMM  C[M x Nn] = A[M x K] . B[Nn x K]^T  on device fp32 inputs
  * (unit test of the tcgen05 path; not used by the layer). */
 int npair_debug_gemm(int precision, int backend, int M, int Nn, int K, const float* d_A, const float* d_B, float* d_C,

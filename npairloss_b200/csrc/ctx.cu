@@ -12,6 +12,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -416,6 +417,7 @@ static inline long long round_up(long long v, long long m) { return (v + m - 1) 
 using namespace npair;
 
 #define NPAIR_PROF_PHASES 9
+#define NPAIR_INTERNAL_FULL_TILES (1 << 30)   // npair_config.flags, internal: world == 1 computes every tile (symmetry self-check)
 #define NPAIR_XCH_FLOATS 8192          // largest small exchange: two sides x 2048 64-bit digit counts
 
 // ------------------------------------------------------------------------------------------------ context
@@ -601,6 +603,52 @@ void npair_destroy(npair_ctx* c) {
   delete c;
 }
 
+static int create_impl(const npair_config* cfg, const void* id128, void* ext_comm, npair_ctx** out);
+// One-off device check (per process, device and operand format): a 192 x 192 similarity matrix computed with EVERY tile (no mirroring)
+// must come out bitwise symmetric.
+static bool mma_is_symmetric(int prec, int device) {
+  static std::mutex mu;
+  static std::map<std::pair<int, int>, bool> cache;
+  std::lock_guard<std::mutex> lk(mu);
+  const std::pair<int, int> key(device, prec);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  bool ok = false;
+  const int Q = 192, D = 96;
+  npair_config cfg;
+  npair_config_default(&cfg, Q, D);
+  cfg.sim_precision = prec; cfg.device = device; cfg.flags = NPAIR_INTERNAL_FULL_TILES; cfg.num_tops = 2;
+  npair_ctx* t = nullptr;
+  if (create_impl(&cfg, nullptr, nullptr, &t) == NPAIR_OK) {
+    std::vector<float> x(static_cast<size_t>(Q) * D), lab(Q), S(static_cast<size_t>(Q) * t->ldS);
+    uint32_t rng = 12345u;
+    for (int r = 0; r < Q; ++r) {
+      double nrm = 0.0;
+      for (int d = 0; d < D; ++d) { rng = rng * 1664525u + 1013904223u; const float v = static_cast<float>(static_cast<int32_t>(rng >> 8) % 2001 - 1000) * 1e-3f; x[static_cast<size_t>(r) * D + d] = v; nrm += static_cast<double>(v) * v; }
+      const float inv = static_cast<float>(1.0 / sqrt(nrm > 0 ? nrm : 1.0));
+      for (int d = 0; d < D; ++d) x[static_cast<size_t>(r) * D + d] *= inv;
+      lab[r] = static_cast<float>(r / 2);
+    }
+    float *dx = nullptr, *dl = nullptr;
+    float tops[5];
+    if (cudaMalloc(&dx, sizeof(float) * x.size()) == cudaSuccess && cudaMalloc(&dl, sizeof(float) * Q) == cudaSuccess &&
+        cudaMemcpy(dx, x.data(), sizeof(float) * x.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
+        cudaMemcpy(dl, lab.data(), sizeof(float) * Q, cudaMemcpyHostToDevice) == cudaSuccess &&
+        npair_forward(t, dx, dl, tops, nullptr) == NPAIR_OK && cudaDeviceSynchronize() == cudaSuccess &&
+        cudaMemcpy(S.data(), t->S, sizeof(float) * S.size(), cudaMemcpyDeviceToHost) == cudaSuccess) {
+      ok = true;
+      for (int i = 0; i < Q && ok; ++i)
+        for (int j = 0; j < i; ++j)
+          if (memcmp(&S[static_cast<size_t>(i) * t->ldS + j], &S[static_cast<size_t>(j) * t->ldS + i], 4) != 0) { ok = false; break; }
+    }
+    cudaFree(dx); cudaFree(dl);
+    npair_destroy(t);
+  }
+  cudaGetLastError();
+  cache[key] = ok;
+  return ok;
+}
+
 static int create_impl(const npair_config* cfg, const void* id128, void* ext_comm, npair_ctx** out) {
   if (!out) { g_create_err = "null out"; return NPAIR_E_ARG; }
   *out = nullptr;
@@ -654,15 +702,20 @@ static int create_impl(const npair_config* cfg, const void* id128, void* ext_com
   // gradient weights are only materialised when the fused tensor-memory kernel is not used
   // (reduce-scatter exchange, SIMT cross-check backend, NPAIR_NO_FUSED_GRAD)
   {
-    const bool multi_rs = c->world > 1 && cfg->bwd_exchange != NPAIR_BWD_AUTO;
+    const bool multi_rs = c->world > 1 && (cfg->bwd_exchange != NPAIR_BWD_AUTO ||
+                                           (cfg->gemm_backend == NPAIR_GEMM_TCGEN05 && !mma_is_symmetric(cfg->sim_precision, c->device)));
     c->fused_grad = cfg->gemm_backend == NPAIR_GEMM_TCGEN05 && !multi_rs && !(cfg->flags & NPAIR_FLAG_NO_FUSED_GRAD);
   }
   if (!c->fused_grad) {
     CREATE_TRY(cudaMalloc(&c->H, 2ull * ns * Q * c->Np));
     CREATE_TRY(cudaMemset(c->H, 0, 2ull * ns * Q * c->Np));
   }
+  // The row-record exchange needs S[j][m] on rank r to equal S[m][j] on the rank that owns row m BIT FOR BIT, i.e. a tensor-core
+  // MMA whose result does not change when the operand roles are swapped.  Measured true on B200 for every operand format; checked
+  // once per process and format on this device -- if it ever fails, the reference's reduce-scatter form is used instead.
+  const bool sym_ok = c->world == 1 || cfg->bwd_exchange != NPAIR_BWD_AUTO || cfg->gemm_backend != NPAIR_GEMM_TCGEN05 || mma_is_symmetric(cfg->sim_precision, c->device);
   c->bwd_mode = c->world == 1 ? NPAIR_BWDMODE_SINGLE
-              : (cfg->bwd_exchange == NPAIR_BWD_AUTO ? NPAIR_BWDMODE_ROW_SCALARS : NPAIR_BWDMODE_REDUCE_SCATTER);
+              : ((cfg->bwd_exchange == NPAIR_BWD_AUTO && sym_ok) ? NPAIR_BWDMODE_ROW_SCALARS : NPAIR_BWDMODE_REDUCE_SCATTER);
   if (c->bwd_mode == NPAIR_BWDMODE_ROW_SCALARS) CREATE_TRY(cudaMalloc(&c->rs_total, sizeof(float) * 8ull * N));
   if (c->prec != PREC_BF16 && cfg->gemm_backend == NPAIR_GEMM_TCGEN05) {
     const size_t cat_bytes = 2ull * N * kcat_mult(c->prec) * c->Dp;
@@ -750,7 +803,7 @@ static int create_impl(const npair_config* cfg, const void* id128, void* ext_com
     }
     if (!ok) { g_create_err = te; npair_destroy(c); return NPAIR_E_CUDA; }
   }
-  if (c->world == 1 && cfg->gemm_backend == NPAIR_GEMM_TCGEN05) {
+  if (c->world == 1 && cfg->gemm_backend == NPAIR_GEMM_TCGEN05 && !(cfg->flags & NPAIR_INTERNAL_FULL_TILES)) {
     // S = X X^T is symmetric: only tiles (m_blk, n_blk) whose 256 columns reach the 128-row block's diagonal or beyond
     std::vector<int2> tl;
     const int tm = (Q + 127) / 128, tn = (N + 255) / 256;
@@ -966,6 +1019,9 @@ static int forward_impl(npair_ctx* c, const float* d_feat, const float* d_label,
   gp.S = c->S; gp.ldS = c->ldS; gp.dev_scale = &c->bs->x_inv_scale;
   gp.lab_rows = d_label; gp.lab_cols = c->lab_total; gp.self_offset = self_off;
   gp.st_minw = c->ra.st_minw; gp.st_maxw = c->ra.st_maxw; gp.st_maxb = c->ra.st_maxb; gp.st_maxall = c->ra.st_maxall; gp.cnt_same = c->ra.cnt_same;
+  // the threshold pick rides in the similarity kernel's last CTA unless its result has to be exchanged first (world scope)
+  const bool fuse_thr = c->cfg.gemm_backend == NPAIR_GEMM_TCGEN05 && !(c->cfg.global_scope && c->world > 1);
+  gp.fuse_thr = fuse_thr ? 1 : 0; gp.ra = c->ra; gp.mp = mp; gp.bs = c->bs;
   if (c->cfg.gemm_backend == NPAIR_GEMM_TCGEN05) {
     PhaseTimer pt(c, 2, st);
     if (c->sym_tiles) { gp.tile_list = c->sym_tiles; gp.num_tiles_list = c->n_sym_tiles; }
@@ -988,7 +1044,7 @@ static int forward_impl(npair_ctx* c, const float* d_feat, const float* d_label,
   {
   PhaseTimer pt(c, 3, st);
   const bool wscope = c->cfg.global_scope && c->world > 1;      // world == 1: the block IS the world
-  launch_thresholds(c->ra, Q, N, mp, c->bs, c->partial, wscope ? c->xch_src : nullptr, st);
+  if (!fuse_thr) launch_thresholds(c->ra, Q, N, mp, c->bs, c->partial, wscope ? c->xch_src : nullptr, st);
   if (wscope) {
     const float* all = nullptr;
     const int rc = xchg_small(c, c->xch_src, 8, &all, st);
@@ -1395,6 +1451,13 @@ int npair_l2normalize_backward(const float* d_y, const float* d_inv_norm, const 
   if (!d_y || !d_inv_norm || !d_dy || !d_dx || rows < 1 || dim < 1) { g_create_err = "bad argument"; return NPAIR_E_ARG; }
   launch_l2norm_bwd(d_y, d_inv_norm, d_dy, rows, dim, d_dx, static_cast<cudaStream_t>(stream));
   return cudaGetLastError() == cudaSuccess ? NPAIR_OK : NPAIR_E_CUDA;
+}
+
+int npair_debug_mma_symmetric(int precision) {
+  if (precision < 0 || precision > 2) return NPAIR_E_ARG;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return NPAIR_E_CUDA;
+  return mma_is_symmetric(precision, dev) ? 1 : 0;
 }
 
 int npair_debug_gemm(int precision, int backend, int M, int Nn, int K, const float* dA, const float* dB, float* dC, void* stream) {

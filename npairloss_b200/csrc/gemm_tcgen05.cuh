@@ -26,7 +26,9 @@
 #include <cfloat>
 #include <stdint.h>
 
+#include "kernels.cuh"
 #include "ptx.cuh"
+#include "thresholds.cuh"
 
 namespace npair {
 
@@ -37,24 +39,6 @@ namespace npair {
 //               MIRRORED (second TMA store) and contributes COLUMN statistics (warp redux) to the rows it mirrors into.
 //               S comes out bitwise symmetric, which the backward weight builder relies on.
 enum { EPI_SIM = 0, EPI_OUT = 1, EPI_SIM_SYM = 2 };
-
-// order-preserving float <-> uint32 map so atomicMin/atomicMax work on floats of either sign
-__host__ __device__ __forceinline__ uint32_t f2ord(float f) {
-#ifdef __CUDA_ARCH__
-  uint32_t b = __float_as_uint(f);
-#else
-  union { float f; uint32_t u; } c; c.f = f; uint32_t b = c.u;
-#endif
-  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-}
-__host__ __device__ __forceinline__ float ord2f(uint32_t u) {
-  uint32_t b = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
-#ifdef __CUDA_ARCH__
-  return __uint_as_float(b);
-#else
-  union { float f; uint32_t u; } c; c.u = b; return c.f;
-#endif
-}
 
 struct GemmParams {
   int M, Nn;           // logical output extent
@@ -77,6 +61,11 @@ struct GemmParams {
   uint32_t* st_maxb;
   uint32_t* st_maxall;
   int* cnt_same;           // per-row number of same-label non-self columns
+  // fused threshold pick (.cu:275-337): the last CTA to finish runs thresholds_one_block (thresholds.cuh); fuse_thr = 0: separate kernel
+  int fuse_thr;
+  RowArrays ra;
+  MiningParams mp;
+  BlockScalars* bs;
   // ---- EPI_OUT ----
   float* out;          // [M x ldo]
   long long ldo;
@@ -515,6 +504,19 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<512, NCTA>(tmem_base);
+  }
+  if (EPI != EPI_OUT && p.fuse_thr) {
+    // every CTA's statistics atomics are out; the last CTA to get here picks the thresholds for the whole block of rows
+    __shared__ int s_last_cta;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last_cta = (atomicAdd(&p.bs->ticket2, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (s_last_cta) {
+      __threadfence();
+      thresholds_one_block(p.ra, p.M, p.Nn, p.mp, p.bs, smem);     // the operand ring is idle: reuse its first bytes as scratch
+      if (threadIdx.x == 0) p.bs->ticket2 = 0;
+    }
   }
 }
 

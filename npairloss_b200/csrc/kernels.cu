@@ -8,7 +8,7 @@
 #include <cuda_fp16.h>
 #include <cfloat>
 
-#include "gemm_tcgen05.cuh"   // f2ord / ord2f
+#include "thresholds.cuh"   // f2ord / ord2f come with kernels.cuh
 
 namespace npair {
 unsigned long long g_kernel_launches = 0;
@@ -56,24 +56,6 @@ __device__ __forceinline__ void split3(float v, uint16_t& p0, uint16_t& p1, uint
   }
 }
 __host__ __device__ inline int nsplit_of(int prec) { return prec == PREC_BF16 ? 1 : (prec == PREC_FP16X2 ? 2 : 3); }
-
-// pos(SN,size) of npair_multi_class_loss.cu:285-287: size_t arithmetic for SN>=0, un-fused fp32 otherwise.
-__device__ __forceinline__ bool pos_index(float sn, unsigned long long size, unsigned long long& pos) {
-  if (size == 0) return false;
-  if (sn >= 0.f) {                                    // -0.0f >= 0 is true
-    const unsigned long long p = size - 1ull - static_cast<unsigned long long>(static_cast<long long>(static_cast<int>(sn)));
-    if (p >= size) return false;
-    pos = p; return true;
-  }
-  const float a = __ull2float_rn(size - 1ull);
-  const float b = __fmul_rn(sn, __ull2float_rn(size));
-  const float c = __fadd_rn(a, b);
-  if (!(c > -2147483648.f && c < 2147483648.f)) return false;
-  const int ip = static_cast<int>(c);                 // truncation toward zero
-  if (ip < 0 || static_cast<unsigned long long>(ip) >= size) return false;
-  pos = static_cast<unsigned long long>(ip); return true;
-}
-__device__ __forceinline__ float clamp_thr(float v) { return v >= 0.f ? v : -FLT_MAX; }   // .cu:288,303,319,334
 
 // exp(x) for x <= 0 as one FMUL + MUFU.EX2 (relative error ~ (2 + 1.44|x|) ulp: 3e-7 for the |x| <= 2 of unit-norm
 // embeddings, 1e-5 only beyond |x| ~ 80 where the terms are ~1e-35 anyway).  Cheap enough to evaluate for EVERY pair,
@@ -435,41 +417,6 @@ void launch_row_stats_ref(const float* S, long long ldS, int Q, int N, const flo
 // thresholds (.cu:275-337).  One block.  Non-relative modes and the pos==size-1 relative shortcut are
 // closed forms of the row statistics; general relative modes arm the radix selects below.
 // --------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool is_rel(int m) { return m == M_RELATIVE_HARD || m == M_RELATIVE_EASY; }
-__host__ __device__ inline bool sn_is_max(float sn) { return sn >= 0.f && static_cast<int>(sn) == 0; }   // pos = size-1
-
-// Block-wide (or, world scope, world-wide) sizes / extrema -> GLOBAL-region thresholds and the arming of the radix selects (.cu:292-337)
-__device__ void finish_thresholds(unsigned long long n_same, unsigned long long n_diff, float gmin_w, float gmax_w, float gmax_b, int err,
-                                  const MiningParams& mp, BlockScalars* bs) {
-  float posi_g = 0.f, nega_g = 0.f;
-  bool arm_ap = false, arm_an = false;
-  if (mp.ap_region == REGION_GLOBAL) {
-    if (!is_rel(mp.ap_method)) { if (n_diff == 0) err |= DERR_EMPTY_LIST; posi_g = gmax_b; }              // .cu:296
-    else if (sn_is_max(mp.identsn)) { if (n_same == 0) err |= DERR_EMPTY_LIST; posi_g = clamp_thr(gmax_w); }   // pos = size-1
-    else arm_ap = true;                                                                                    // .cu:300-304
-  }
-  if (mp.an_region == REGION_GLOBAL) {
-    if (!is_rel(mp.an_method)) { if (n_same == 0) err |= DERR_EMPTY_LIST; nega_g = gmin_w; }               // .cu:327
-    else if (sn_is_max(mp.diffsn)) { if (n_diff == 0) err |= DERR_EMPTY_LIST; nega_g = clamp_thr(gmax_b); }
-    else arm_an = true;                                                                                    // .cu:331-335
-  }
-  bs->n_same = n_same; bs->n_diff = n_diff;
-  bs->gmin_within = gmin_w; bs->gmax_within = gmax_w; bs->gmax_between = gmax_b;
-  bs->posi_global = posi_g; bs->nega_global = nega_g;
-  for (int side = 0; side < 2; ++side) {
-    const bool arm = side == 0 ? arm_ap : arm_an;
-    bs->sel_active[side] = 0;
-    if (arm) {
-      unsigned long long pos = 0;
-      const unsigned long long size = side == 0 ? n_same : n_diff;
-      if (size == 0) err |= DERR_EMPTY_LIST;
-      else if (!pos_index(side == 0 ? mp.identsn : mp.diffsn, size, pos)) err |= DERR_POS_RANGE;
-      else { bs->sel_active[side] = 1; bs->sel_rank[side] = pos; bs->sel_prefix[side] = 0; bs->sel_mask[side] = 0; }
-    }
-  }
-  bs->err |= err;
-}
-
 // Multi-block: every block reduces its slice of the row statistics and writes the LOCAL-region thresholds of its rows
 // (they need no global value); the last block to finish (ticket) combines the per-block partials into the block-wide
 // sizes / extrema, the GLOBAL-region thresholds (read directly by the row pass) and the radix-select arming.

@@ -58,6 +58,24 @@ struct RowArrays {
   float* rowscal;
 };
 
+// order-preserving float <-> uint32 map so atomicMin/atomicMax work on floats of either sign
+__host__ __device__ __forceinline__ uint32_t f2ord(float f) {
+#ifdef __CUDA_ARCH__
+  uint32_t b = __float_as_uint(f);
+#else
+  union { float f; uint32_t u; } c; c.f = f; uint32_t b = c.u;
+#endif
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ord2f(uint32_t u) {
+  uint32_t b = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(b);
+#else
+  union { float f; uint32_t u; } c; c.u = b; return c.f;
+#endif
+}
+
 // Number of kernels this library has launched in this process (every launch site bumps it; read through
 // npair_kernel_launches(): bench.py reports the per-step delta as gpu_launches).
 extern unsigned long long g_kernel_launches;

@@ -174,3 +174,10 @@ def test_pair_kernels_match_single_cta_bitwise(cuda, B, D, prec):
         ctx.close()
     for a, b in zip(res[0], res[1]):
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_mma_symmetry_self_check(cuda):
+    """npair_create's one-off device check behind the row-record exchange: a similarity matrix computed with every tile is bitwise
+    symmetric in each operand format (if it ever is not, world > 1 contexts use the reduce-scatter form)."""
+    for prec in PRECS:
+        assert capi.lib().npair_debug_mma_symmetric(prec) == 1, PREC_NAME[prec]
