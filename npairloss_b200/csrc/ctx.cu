@@ -529,6 +529,7 @@ static int validate(const npair_config* c, std::string* err) {
   return NPAIR_OK;
 }
 
+static inline bool is_rel_cfg_early(int m) { return m == NPAIR_RELATIVE_HARD || m == NPAIR_RELATIVE_EASY; }
 struct Sizes { long long N, Dp, Np, Qp, ldS; int ns; size_t total; };
 static Sizes sizes_of(const npair_config* c) {
   Sizes s;
@@ -552,6 +553,12 @@ static Sizes sizes_of(const npair_config* c) {
     int smax = 148 / (tiles > 0 ? tiles : 1); if (smax > 16) smax = 16;
     if (smax > 1) t += sizeof(float) * static_cast<size_t>(smax) * c->Q * c->D;
   }
+  if (tc && (is_rel_cfg_early(c->ap_method) && c->ap_region == NPAIR_GLOBAL || is_rel_cfg_early(c->an_method) && c->an_region == NPAIR_GLOBAL)) {
+    unsigned long long cap = static_cast<unsigned long long>(c->Q) * s.N / 8 + 4096;           // candidate lists of the GLOBAL radix select
+    if (cap > (32ull << 20)) cap = 32ull << 20;
+    t += 8ull * cap;
+  }
+  if (c->world > 1) t += sizeof(float) * (2ull * s.N * c->D + 2ull * s.N + 16ull * s.N) + (c->global_scope ? 8ull * c->world * 8192 : 0);   // exchange region
   t += 4ull * 21 * c->Q + 65536;                                                    // row arrays, records, scalars
   s.total = t;
   return s;

@@ -507,7 +507,8 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
   }
   if (EPI != EPI_OUT && p.fuse_thr) {
     // every CTA's statistics atomics are out; the last CTA to get here picks the thresholds for the whole block of rows
-    __shared__ int s_last_cta;
+    // (a static __shared__ flag would push static + dynamic shared memory past the 227 KB a CTA may ask for)
+    volatile int& s_last_cta = *reinterpret_cast<volatile int*>(aux + 192);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) s_last_cta = (atomicAdd(&p.bs->ticket2, 1u) == gridDim.x - 1) ? 1 : 0;

@@ -505,6 +505,19 @@ void launch_thresholds(RowArrays ra, int Q, int N, MiningParams mp, BlockScalars
 // --------------------------------------------------------------------------------------------
 #define NPAIR_SEL_BINS 2048
 
+// Histogram increment as ONE shared-memory reduction per lane.  A plain atomicAdd(&hist[d], 1) is rewritten by the compiler into a
+// loop over the warp's distinct addresses (leader election + ATOMS.POPC.INC per address): ~20 instructions per distinct bin, the
+// bulk of the select kernels' instruction count in the first round-2 version.  The hardware resolves same-address conflicts itself.
+__device__ __forceinline__ void smem_inc(unsigned int* p) {
+  asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(p))) : "memory");
+}
+__device__ __forceinline__ void smem_inc_off(unsigned int* base, uint32_t byte_off) {
+  asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(base)) + byte_off) : "memory");
+}
+__device__ __forceinline__ void smem_dec(unsigned int* p) {
+  asm volatile("red.shared.add.u32 [%0], -1;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(p))) : "memory");
+}
+
 // Sweep of one row: calls f(key, j, side) for every column j < N with side = 0 (same label as the row) or 1 (different);
 // the self pair is NOT excluded here.  16-byte loads of S (row stride is a multiple of 32 floats) and of the labels.
 template <class F>
@@ -636,7 +649,7 @@ __device__ __noinline__ uint32_t slow_select_row(const float* __restrict__ row, 
       if (j == self_col) continue;
       if ((lab_cols[j] == li) != (side == 0)) continue;
       const uint32_t key = f2ord(row[j]);
-      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & (nb - 1)], 1u);
+      if ((key & mask) == prefix) smem_inc(&hist[(key >> shift) & (nb - 1)]);
     }
     __syncwarp();
     unsigned int r2, pp;
@@ -648,7 +661,7 @@ __device__ __noinline__ uint32_t slow_select_row(const float* __restrict__ row, 
   return prefix;
 }
 
-__global__ void __launch_bounds__(32 * NPAIR_LSEL_WARPS) local_select_kernel(const float* __restrict__ S, long long ldS, int Q, int N,
+__global__ void __launch_bounds__(32 * NPAIR_LSEL_WARPS, 2) local_select_kernel(const float* __restrict__ S, long long ldS, int Q, int N,
                                                                               const float* __restrict__ lab_rows, const float* __restrict__ lab_cols,
                                                                               int self_offset, int side_mask /*1 AP, 2 AN*/, float sn_ap, float sn_an,
                                                                               RowArrays ra, BlockScalars* bs) {
@@ -683,7 +696,7 @@ __global__ void __launch_bounds__(32 * NPAIR_LSEL_WARPS) local_select_kernel(con
         const float ll[4] = {l[u].x, l[u].y, l[u].z, l[u].w};
         if (want_diff) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) atomicAdd(reinterpret_cast<unsigned int*>(reinterpret_cast<unsigned char*>(W.hist) + ((vv[c] >> 20) & 0xFFCu)), 1u);
+          for (int c = 0; c < 4; ++c) smem_inc_off(W.hist, (vv[c] >> 20) & 0xFFCu);
         }
         if (ll[0] == li || ll[1] == li || ll[2] == li || ll[3] == li) {
 #pragma unroll
@@ -694,7 +707,7 @@ __global__ void __launch_bounds__(32 * NPAIR_LSEL_WARPS) local_select_kernel(con
     }
     for (int j = n_vec + lane; j < N; j += 32) {                  // ragged tail / unaligned labels
       const uint32_t b = __float_as_uint(row[j]);
-      if (want_diff) atomicAdd(&W.hist[b >> 22], 1u);
+      if (want_diff) smem_inc(&W.hist[b >> 22]);
       if (lab_cols[j] == li && j != self_col) { const unsigned int k = atomicAdd(&W.n_same, 1u); if (k < NPAIR_LSEL_SCAP) W.same[k] = b; }
     }
     __syncwarp();
@@ -731,7 +744,7 @@ __global__ void __launch_bounds__(32 * NPAIR_LSEL_WARPS) local_select_kernel(con
         thr = clamp_thr(ord2f(slow_select_row(row, N, lab_cols, li, self_col, 1, static_cast<unsigned int>(pos), W.hist, lane)));
       } else {
         // excluded keys (same-label entries + the self pair) leave the histogram; then walk the bins in value order
-        for (unsigned int e = lane; e <= ns; e += 32) atomicSub(&W.hist[(e < ns ? W.same[e] : self_bits) >> 22], 1u);
+        for (unsigned int e = lane; e <= ns; e += 32) smem_dec(&W.hist[(e < ns ? W.same[e] : self_bits) >> 22]);
         __syncwarp();
         // permute into value order in place is not needed: lanes own 32 consecutive ORDER positions and read the raw bins they map to
         unsigned int mine = 0;
@@ -788,13 +801,13 @@ __global__ void __launch_bounds__(32 * NPAIR_LSEL_WARPS) local_select_kernel(con
             __syncwarp();
             for (unsigned int e = 0; e < cnt; ++e) {
               const uint32_t k = W.cand[e * 32 + lane] ^ flip;
-              if ((k & msk) == pre) atomicAdd(&W.hist[(k >> shifts[ps]) & (nb - 1)], 1u);
+              if ((k & msk) == pre) smem_inc(&W.hist[(k >> shifts[ps]) & (nb - 1)]);
             }
             __syncwarp();
             for (unsigned int e = lane; e <= ns; e += 32) {
               const uint32_t b = e < ns ? W.same[e] : self_bits;
               const uint32_t k = (b & 0x3FFFFFu) ^ flip;
-              if ((b >> 22) == raw && (k & msk) == pre) atomicSub(&W.hist[(k >> shifts[ps]) & (nb - 1)], 1u);
+              if ((b >> 22) == raw && (k & msk) == pre) smem_dec(&W.hist[(k >> shifts[ps]) & (nb - 1)]);
             }
             __syncwarp();
             unsigned int r2, p2;
@@ -915,7 +928,7 @@ __global__ void __launch_bounds__(512) global_select_kernel(const float* __restr
   auto take = [&](uint32_t bits, int side) {
     const uint32_t k = (bits & 0x1FFFFFu) ^ (side == 0 ? flip0 : flip1);
     if (pass == 2 && ((k >> 10) != (side == 0 ? mid0 : mid1))) return;
-    atomicAdd(&hist[side][(k >> shift) & dm], 1u);
+    smem_inc(&hist[side][(k >> shift) & dm]);
     if (side == 0 ? comp0 : comp1) {
       const unsigned int slot = atomicAdd(&s_nst[side], 1u);
       if (slot < NPAIR_GSEL_STAGE) stage[side][slot] = k;
@@ -955,7 +968,7 @@ __global__ void __launch_bounds__(512) global_select_kernel(const float* __restr
           if (sweep1) {
             if (pass == 0) {
 #pragma unroll
-              for (int c = 0; c < 4; ++c) atomicAdd(reinterpret_cast<unsigned int*>(reinterpret_cast<unsigned char*>(hist[1]) + ((vv[c] >> 19) & 0x1FFCu)), 1u);
+              for (int c = 0; c < 4; ++c) smem_inc_off(hist[1], (vv[c] >> 19) & 0x1FFCu);
             } else if ((vv[0] >> 21) == raw1 || (vv[1] >> 21) == raw1 || (vv[2] >> 21) == raw1 || (vv[3] >> 21) == raw1) {
 #pragma unroll
               for (int c = 0; c < 4; ++c) if ((vv[c] >> 21) == raw1) take(vv[c], 1);
@@ -967,7 +980,7 @@ __global__ void __launch_bounds__(512) global_select_kernel(const float* __restr
             if (j4 + c >= N || j4 + c == self_col) continue;                    // the self pair is in neither list (.cu:54)
             const int side = (ll[c] == li) ? 0 : 1;
             if (!(side == 0 ? sweep0 : sweep1)) continue;
-            if (pass == 0) atomicAdd(&hist[side][vv[c] >> 21], 1u);
+            if (pass == 0) smem_inc(&hist[side][vv[c] >> 21]);
             else if ((vv[c] >> 21) == (side == 0 ? raw0 : raw1)) take(vv[c], side);
           }
         }
@@ -1000,7 +1013,7 @@ __global__ void __launch_bounds__(512) global_select_kernel(const float* __restr
       const uint32_t* cl = gb.cand + static_cast<size_t>(side) * gb.cap;
       for (unsigned int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
         const uint32_t k = cl[e];
-        if ((k >> 10) == mid) atomicAdd(&hist[side][k & dm], 1u);
+        if ((k >> 10) == mid) smem_inc(&hist[side][k & dm]);
       }
     }
   }

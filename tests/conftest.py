@@ -17,3 +17,20 @@ def oracle():
     from oracle import oracle_lib
     oracle_lib.build()
     return oracle_lib
+
+
+def pytest_collection_modifyitems(config, items):
+    """`-m gpu` on a machine without a CUDA device: skip instead of erroring inside every test."""
+    if not any("gpu" in it.keywords for it in items):
+        return
+    try:
+        import torch
+        has = torch.cuda.is_available()
+    except Exception:
+        has = False
+    if has:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device (the product path has no CPU fallback)")
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)

@@ -56,3 +56,23 @@ def test_no_cpu_fallback():
     with pytest.raises(capi.NpairError) as e:
         capi.Context(capi.make_config(8, 4))
     assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+
+
+def test_config_defaults_cover_the_abi2_extensions():
+    """npair_config_default: proto defaults (caffe.proto:4-7,19-22) and every ABI-2 extension switched off."""
+    import ctypes as C
+    from npairloss_b200 import capi
+    cfg = capi.NpairConfig()
+    C.memset(C.byref(cfg), 0xFF, C.sizeof(cfg))
+    capi.lib().npair_config_default(C.byref(cfg), 120, 1024)
+    assert (cfg.Q, cfg.D, cfg.world, cfg.rank, cfg.num_tops) == (120, 1024, 1, 0, 5)
+    assert (cfg.margin_ident, cfg.margin_diff, cfg.identsn, cfg.diffsn) == (0.0, 0.0, -1.0, -1.0)
+    assert (cfg.ap_region, cfg.ap_method, cfg.an_region, cfg.an_method) == (1, 2, 1, 2)
+    assert (cfg.global_scope, cfg.normalize_input, cfg.grad_chunk_cols, cfg.flags) == (0, 0, 0, 0)
+    assert C.sizeof(cfg) == 21 * 4
+    # argument validation of the extensions (no device needed: validation comes first)
+    L = capi.lib()
+    for field, bad in (("global_scope", 2), ("normalize_input", -1), ("grad_chunk_cols", 100)):
+        c2 = capi.make_config(64, 32, **{field: bad})
+        assert L.npair_workspace_bytes(C.byref(c2)) == 0, field
+    assert L.npair_workspace_bytes(C.byref(capi.make_config(64, 32, normalize_input=1))) > L.npair_workspace_bytes(C.byref(capi.make_config(64, 32)))
