@@ -95,7 +95,8 @@ enum {
   NPAIR_FLAG_SIM_1CTA = 2,        /* similarity GEMM without CTA pairs                                                       */
   NPAIR_FLAG_GRAD_1CTA = 4,       /* gradient GEMM without CTA pairs                                                         */
   NPAIR_FLAG_NCCL_RECORDS = 8,    /* world > 1: exchange the row records with ncclAllGather instead of NVLink peer stores    */
-  NPAIR_FLAG_NCCL_FEATURES = 16   /* world > 1: gather the features with ncclAllGather instead of NVLink peer loads          */
+  NPAIR_FLAG_NCCL_FEATURES = 16,  /* world > 1: gather the features with ncclAllGather instead of NVLink peer loads          */
+  NPAIR_FLAG_LSEL_WARP = 32       /* LOCAL RELATIVE_* select: warp-per-row kernel also for rows that fit the block-per-row one */
 };
 
 enum { NPAIR_BWD_AUTO = 0, NPAIR_BWD_REDUCE_SCATTER = 1 };

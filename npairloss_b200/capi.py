@@ -26,7 +26,7 @@ class NpairConfig(C.Structure):
                 ("global_scope", C.c_int32), ("normalize_input", C.c_int32), ("grad_chunk_cols", C.c_int32), ("flags", C.c_int32)]
 
 
-FLAG_NO_FUSED_GRAD, FLAG_SIM_1CTA, FLAG_GRAD_1CTA, FLAG_NCCL_RECORDS, FLAG_NCCL_FEATURES = 1, 2, 4, 8, 16
+FLAG_NO_FUSED_GRAD, FLAG_SIM_1CTA, FLAG_GRAD_1CTA, FLAG_NCCL_RECORDS, FLAG_NCCL_FEATURES, FLAG_LSEL_WARP = 1, 2, 4, 8, 16, 32
 
 
 EXPORTS = ["npair_config_default", "npair_workspace_bytes", "npair_nccl_unique_id", "npair_create", "npair_create_with_comm",

@@ -1013,10 +1013,10 @@ static int forward_impl(npair_ctx* c, const float* d_feat, const float* d_label,
   // ---- operand preparation: |x| sum (top asum, .cu:400), power-of-two pre-scale, split to tensor-core pieces ----
   {
     PhaseTimer pt(c, 1, st);
-    launch_prep_reduce(d_feat, static_cast<long long>(Q) * D, c->x_total, static_cast<long long>(N) * D, c->partial,
-                       c->prec == PREC_FP16X2 ? 1 : 0, c->ra, Q, c->bs, st);
     // Xs (the un-concatenated K-major pieces) is only read by the single-pass bf16 similarity GEMM and the SIMT backend
     uint16_t* xs_dst = (c->XcatA && c->cfg.gemm_backend == NPAIR_GEMM_TCGEN05) ? nullptr : c->Xs;
+    launch_prep_reduce(d_feat, static_cast<long long>(Q) * D, c->x_total, static_cast<long long>(N) * D, c->partial,
+                       c->prec == PREC_FP16X2 ? 1 : 0, c->ra, Q, c->bs, st);
     launch_split(c->x_total, N, D, c->prec, c->bs, xs_dst, c->Dp, c->XsT, c->Np, c->XlT, c->Qp, self_off, Q, c->XcatA, c->XcatB, c->Dp, st);
   }
   // ---- S = X_local . X_total^T (.cu:218) with fused masks + row statistics (.cu:44-66, :225-265) ----
@@ -1075,7 +1075,7 @@ static int forward_impl(npair_ctx* c, const float* d_feat, const float* d_label,
         }
       }
     }
-    if (local_mask) launch_local_select(c->S, c->ldS, Q, N, d_label, c->lab_total, self_off, local_mask, mp.identsn, mp.diffsn, c->ra, c->bs, c->sms, st);
+    if (local_mask) launch_local_select(c->S, c->ldS, Q, N, d_label, c->lab_total, self_off, local_mask, mp.identsn, mp.diffsn, c->ra, c->bs, c->sms, (c->cfg.flags & NPAIR_FLAG_LSEL_WARP) != 0, st);
   }
   }
   // ---- selection + counts + exp + masked sums + log + retrieval in one pass (.cu:343-398) ----

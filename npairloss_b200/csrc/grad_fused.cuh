@@ -115,11 +115,13 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, 
                : "memory");
 }
 
-// End of the accumulation chunk that starts at K block c0 of the range [kb0, kb1).  The FIRST chunk of a tile is shortened by a
-// per-cluster amount so that the clusters do not all drain at the same moment (bursts of 128 KB of L2 reductions per SM).
-__device__ __forceinline__ int chunk_end(int c0, int kb0, int kb1, int ch, int worker) {
+// End of the accumulation chunk that starts at K block c0 of the range [kb0, kb1).  The FIRST chunk of a tile is shortened by an
+// amount that depends on the tile (`key`: its 256-row block, column block and split -- NOT on which CTA computes it, so the
+// summation order, hence every bit of the result, is independent of the grid and of the 1-CTA / CTA-pair variant): neighbouring
+// tiles do not all drain at the same moment (bursts of 128 KB of L2 reductions per SM).
+__device__ __forceinline__ int chunk_end(int c0, int kb0, int kb1, int ch, int key) {
   if (ch <= 0) return kb1;
-  if (c0 == kb0) { const int first = max(1, (((worker & 7) + 1) * ch) >> 3); return min(kb1, kb0 + first); }
+  if (c0 == kb0) { const int first = max(1, (((key & 7) + 1) * ch) >> 3); return min(kb1, kb0 + first); }
   return min(kb1, c0 + ch);
 }
 
@@ -232,11 +234,12 @@ fused_grad_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_consta
       uint32_t gen = 0;                          // accumulator generations (one per chunk), drained by warps 2, 3, 20, 21
       for (int tile = worker; tile < num_tiles; tile += num_workers) {
         const uint32_t d_tmem = tmem_base;
-        const int split = tile % p.splits;
+        const int mn = tile / p.splits, split = tile - mn * p.splits;
+        const int ckey = ((mn / p.tiles_n) >> (NCTA == 1 ? 1 : 0)) + mn % p.tiles_n + split;
         const int kb0 = split * p.kb_per_split, kb1 = min(p.num_kblocks, kb0 + p.kb_per_split);
         const int ch = p.chunk_kb;
         for (int c0 = kb0, c1; c0 < kb1; c0 = c1, ++gen) {
-          c1 = chunk_end(c0, kb0, kb1, ch, worker);
+          c1 = chunk_end(c0, kb0, kb1, ch, ckey);
           ptx::mbar_wait(&tempty_bar[0], (gen & 1u) ^ 1u);
           ptx::tc_fence_after();
           for (int kb = c0; kb < c1; ++kb) {
@@ -365,7 +368,7 @@ fused_grad_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_consta
       float* obase = p.splits > 1 ? p.part + static_cast<long long>(split) * p.Q * p.ldo : p.out;
       const float beta = p.splits > 1 ? 0.f : p.beta;
       for (int c0 = kb0, c1; c0 < kb1; c0 = c1, ++gen) {
-        c1 = chunk_end(c0, kb0, kb1, p.chunk_kb, worker);
+        c1 = chunk_end(c0, kb0, kb1, p.chunk_kb, ((mn / p.tiles_n) >> (NCTA == 1 ? 1 : 0)) + n_blk + split);
         const bool first = (c0 == kb0);          // first chunk of the tile stores (+ beta * out), later chunks add (fp32 RN)
         ptx::mbar_wait(&tfull_bar[0], gen & 1u);
         ptx::tc_fence_after();

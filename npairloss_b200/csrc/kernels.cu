@@ -123,8 +123,9 @@ __device__ __forceinline__ bool sel_an(float s, float tn, int m) {   // .cu:100-
 // --------------------------------------------------------------------------------------------
 // One kernel: per-block partial |x| sums (local rows) and max|x| (all rows), the reset of the per-row statistics, and --
 // in the last block to finish (ticket) -- the final asum, the power-of-two operand scale and the reset of the step state.
-__global__ void __launch_bounds__(256) prep_reduce_kernel(const float* __restrict__ xl, long long nl, const float* __restrict__ xt, long long ntot,
-                                                          float* __restrict__ partial, int want_scale, RowArrays ra, int Q, BlockScalars* bs) {
+// Returns true in the block that finished last (it has written the step's scalars to *bs).
+__device__ __forceinline__ bool prep_reduce_body(const float* __restrict__ xl, long long nl, const float* __restrict__ xt, long long ntot,
+                                                 float* __restrict__ partial, int want_scale, RowArrays ra, int Q, BlockScalars* bs) {
   __shared__ float s_sum[8], s_max[8];
   __shared__ int s_last;
   float sum = 0.f, mx = 0.f;
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(256) prep_reduce_kernel(const float* __restric
     s_last = (atomicAdd(&bs->ticket0, 1u) == gridDim.x - 1) ? 1 : 0;
   }
   __syncthreads();
-  if (!s_last) return;
+  if (!s_last) return false;
   __threadfence();
   __shared__ double s_dsum[8];
   double dsum = 0.0; mx = 0.f;
@@ -212,6 +213,11 @@ __global__ void __launch_bounds__(256) prep_reduce_kernel(const float* __restric
     bs->cand_n[0] = 0; bs->cand_n[1] = 0;
     bs->n_same = 0; bs->n_diff = 0;
   }
+  return true;
+}
+__global__ void __launch_bounds__(256) prep_reduce_kernel(const float* __restrict__ xl, long long nl, const float* __restrict__ xt, long long ntot,
+                                                          float* __restrict__ partial, int want_scale, RowArrays ra, int Q, BlockScalars* bs) {
+  prep_reduce_body(xl, nl, xt, ntot, partial, want_scale, ra, Q, bs);
 }
 void launch_prep_reduce(const float* x_local, long long n_local, const float* x_total, long long n_total, float* partial,
                         int want_scale, RowArrays ra, int Q, BlockScalars* bs, cudaStream_t st) {
@@ -282,28 +288,42 @@ void launch_absmax_asum(const float* x_local, long long n_local, const float* x_
 // Block = 256 threads, tile = 32 rows (n) x 64 features (d).  Thread (nl = t/8, dg = t%8) converts 8 consecutive features of
 // one row: two 16-byte loads, one 16-byte store per piece / section; the transposed pieces go through a shared tile so
 // that they, too, are written as 16-byte row segments.
-template <int PREC>
-__global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ x, int N, int D, const BlockScalars* __restrict__ bs,
-                                                    uint16_t* __restrict__ Xs, long long ldXs, uint16_t* __restrict__ XsT, long long ldXsT,
-                                                    uint16_t* __restrict__ XlT, long long ldXlT, int row0, int Q,
-                                                    uint16_t* __restrict__ XcatA, uint16_t* __restrict__ XcatB, long long Dp) {
-  constexpr int NS = (PREC == PREC_BF16) ? 1 : (PREC == PREC_FP16X2 ? 2 : 3);
-  __shared__ __align__(16) uint16_t tile[NS][64][40];      // [piece][d][n], row padded to 80 bytes (16-byte aligned, spreads banks)
-  const float sc = (PREC == PREC_FP16X2) ? bs->x_scale : 1.f;
-  const int n0 = blockIdx.y * 32, d0 = blockIdx.x * 64;
+struct SplitArgs {
+  const float* x; int N, D;
+  uint16_t* Xs; long long ldXs; uint16_t* XsT; long long ldXsT; uint16_t* XlT; long long ldXlT; int row0, Q;
+  uint16_t *XcatA, *XcatB; long long Dp;
+};
+// The 8 features thread t of a block converts in tile (tile_d, tile_n): two 16-byte loads (issued early by the fused kernel).
+__device__ __forceinline__ void split_load(const SplitArgs& a, int tile_d, int tile_n, float (&v)[8]) {
+  const float* __restrict__ x = a.x; const int N = a.N, D = a.D;
   const int t = threadIdx.x, nl = t >> 3, dg = t & 7;
-  const int n = n0 + nl, d = d0 + 8 * dg;
-  uint16_t p[8][3];
-  float v[8];
+  const int n = tile_n * 32 + nl, d = tile_d * 64 + 8 * dg;
   const bool rowok = n < N;
   if (rowok && d + 7 < D && (D & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {   // 16-byte loads need an aligned base
-    const float4 a = *reinterpret_cast<const float4*>(x + static_cast<long long>(n) * D + d);
+    const float4 a4 = *reinterpret_cast<const float4*>(x + static_cast<long long>(n) * D + d);
     const float4 b4 = *reinterpret_cast<const float4*>(x + static_cast<long long>(n) * D + d + 4);
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b4.x; v[5] = b4.y; v[6] = b4.z; v[7] = b4.w;
+    v[0] = a4.x; v[1] = a4.y; v[2] = a4.z; v[3] = a4.w; v[4] = b4.x; v[5] = b4.y; v[6] = b4.z; v[7] = b4.w;
   } else {
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] = (rowok && d + e < D) ? x[static_cast<long long>(n) * D + d + e] : 0.f;
   }
+}
+// One 32-row x 64-feature tile (tile_n, tile_d) by one block of 256 threads from the values split_load fetched.  `buf` alternates
+// between consecutive tiles of a block: the transposition tile is double-buffered, so ONE barrier per tile is enough.
+template <int PREC>
+__device__ __forceinline__ void split_tile(const SplitArgs& a, float sc, int tile_d, int tile_n, const float (&v)[8], int buf) {
+  const int N = a.N, D = a.D;
+  uint16_t* __restrict__ Xs = a.Xs; const long long ldXs = a.ldXs; uint16_t* __restrict__ XsT = a.XsT; const long long ldXsT = a.ldXsT;
+  uint16_t* __restrict__ XlT = a.XlT; const long long ldXlT = a.ldXlT; const int row0 = a.row0, Q = a.Q;
+  uint16_t* __restrict__ XcatA = a.XcatA; uint16_t* __restrict__ XcatB = a.XcatB; const long long Dp = a.Dp;
+  constexpr int NS = (PREC == PREC_BF16) ? 1 : (PREC == PREC_FP16X2 ? 2 : 3);
+  __shared__ __align__(16) uint16_t tile2[2][NS][64][40];  // [buffer][piece][d][n], row padded to 80 bytes (16-byte aligned, spreads banks)
+  uint16_t (*tile)[64][40] = tile2[buf];
+  const int n0 = tile_n * 32, d0 = tile_d * 64;
+  const int t = threadIdx.x, nl = t >> 3, dg = t & 7;
+  const int n = n0 + nl, d = d0 + 8 * dg;
+  uint16_t p[8][3];
+  const bool rowok = n < N;
 #pragma unroll
   for (int e = 0; e < 8; ++e) split3<PREC>(v[e] * sc, p[e][0], p[e][1], p[e][2]);
   uint4 pk[3];
@@ -372,13 +392,23 @@ __global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ x,
     }
   }
 }
+template <int PREC>
+__global__ void __launch_bounds__(256) split_kernel(SplitArgs a, const BlockScalars* __restrict__ bs) {
+  float v[8];
+  split_load(a, blockIdx.x, blockIdx.y, v);
+  split_tile<PREC>(a, (PREC == PREC_FP16X2) ? bs->x_scale : 1.f, blockIdx.x, blockIdx.y, v, 0);
+}
+// Measured and dropped (round 2): reduce + grid-wide release/acquire + split in ONE cooperative launch (prep_fused_kernel) took
+// 31.4 us against 29.4 us for the two launches below -- the blocks spend ~6 us spinning for the last block's scalars, more than the
+// launch gap they save (ncu: CCTL.IVALL 38 k times, barrier stall 12 per issue).
 void launch_split(const float* x_total, int N, int D, int prec, const BlockScalars* bs, uint16_t* Xs, long long ldXs,
                   uint16_t* XsT, long long ldXsT, uint16_t* XlT, long long ldXlT, int row0_local, int Q,
                   uint16_t* XcatA, uint16_t* XcatB, long long Dp, cudaStream_t st) {
   dim3 grid((D + 63) / 64, (N + 31) / 32);
-  if (prec == PREC_BF16) split_kernel<PREC_BF16><<<grid, 256, 0, st>>>(x_total, N, D, bs, Xs, ldXs, XsT, ldXsT, XlT, ldXlT, row0_local, Q, XcatA, XcatB, Dp);
-  else if (prec == PREC_FP16X2) split_kernel<PREC_FP16X2><<<grid, 256, 0, st>>>(x_total, N, D, bs, Xs, ldXs, XsT, ldXsT, XlT, ldXlT, row0_local, Q, XcatA, XcatB, Dp);
-  else split_kernel<PREC_BF16X3><<<grid, 256, 0, st>>>(x_total, N, D, bs, Xs, ldXs, XsT, ldXsT, XlT, ldXlT, row0_local, Q, XcatA, XcatB, Dp);
+  const SplitArgs a{x_total, N, D, Xs, ldXs, XsT, ldXsT, XlT, ldXlT, row0_local, Q, XcatA, XcatB, Dp};
+  if (prec == PREC_BF16) split_kernel<PREC_BF16><<<grid, 256, 0, st>>>(a, bs);
+  else if (prec == PREC_FP16X2) split_kernel<PREC_FP16X2><<<grid, 256, 0, st>>>(a, bs);
+  else split_kernel<PREC_BF16X3><<<grid, 256, 0, st>>>(a, bs);
   count_launch();
 }
 
@@ -823,8 +853,255 @@ __global__ void __launch_bounds__(32 * NPAIR_LSEL_WARPS, 2) local_select_kernel(
     }
   }
 }
+
+// ---- LOCAL, rows of up to 8192 columns: ONE BLOCK per row, the row stays in registers ----
+// The warp-per-row kernel above is bound by its instruction count and by its few warps in flight (ncu: 56 M warp instructions, 29 %
+// issue slots with 16 warps per SM).  This kernel holds a row in the registers of 256 threads (8 independent 16-byte loads each, S is
+// read ONCE) and bins by VALUE with three instructions per entry:
+//   pass 0   label test: entries with the row's label (the self pair among them) go to the short same-label list and are replaced by
+//            NaN in the registers -- fminf / fmaxf skip NaN, so the value range [lo, hi] of the entries that stay needs no branch
+//   pass 1   bin*4 = mantissa of fmaf(s, 4*2048/(hi-lo), 2^23 + 4 - lo*that): one FFMA, one AND, one shared-memory reduction.  The map
+//            is monotone in s, so the wanted rank lies in the bin where the running count crosses it; bins hold a few dozen entries and
+//            lanes rarely collide.  NaN lands in bin 4095, which nobody reads.
+//   pick     the bin's entries (same registers, same three instructions) -> ordered keys in shared memory, ranked by counting
+//            (<= 256 of them).  A fuller bin (outliers stretching the range, masses of duplicates), or a range the float map cannot
+//            resolve, is refined from the registers instead, 11 bits of the ORDERED KEY at a time.
+// The next row's loads are issued as soon as the registers are free, before the pick.  (Measured: keeping TWO rows in registers, the
+// next row's loads a whole iteration ahead at 2 blocks per SM, is slower: 153 against 140 us.)
+#define NPAIR_LSB_THREADS 256
+#define NPAIR_LSB_VPT 8                    // 16-byte groups per thread: 256 * 8 * 4 = 8192 columns
+#define NPAIR_LSB_BINS 2048
+#define NPAIR_LSB_HIST 2304                // bins the find walks: 1 + 2048 + slack (the value map is shifted up by one bin); multiple of 256
+#define NPAIR_LSB_CCAP 256                 // bin population ranked by counting
+#ifndef NPAIR_LSB_MINB
+#define NPAIR_LSB_MINB 3                   // resident blocks per SM (80 registers)
+#endif
+struct LselBlock {
+  unsigned int hist[4096];                 // [0, NPAIR_LSB_HIST) are cleared and read; 4095 collects the NaN (excluded) entries
+  uint32_t cand[NPAIR_LSB_CCAP];
+  uint32_t same[NPAIR_LSEL_SCAP];
+  unsigned int n_same, n_cand;
+  unsigned int warp_tot[NPAIR_LSB_THREADS / 32];
+  unsigned int out[3];                     // find: {bin, rank inside the bin, population}
+  float red_min[NPAIR_LSB_THREADS / 32], red_max[NPAIR_LSB_THREADS / 32];
+  uint32_t red_klo[NPAIR_LSB_THREADS / 32], red_khi[NPAIR_LSB_THREADS / 32];
+};
+// rank r within hist[0 .. PER * 256) in index order; every thread sums PER consecutive bins.  Two barriers; the result is in B.out
+// afterwards (bin == PER * 256: rank out of range).
+template <int PER>
+__device__ __forceinline__ void block_find_bin_u32(LselBlock& B, unsigned int r) {
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  unsigned int h[PER], mine = 0;
+#pragma unroll
+  for (int q = 0; q < PER; ++q) { h[q] = B.hist[tid * PER + q]; mine += h[q]; }
+  unsigned int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  if (lane == 31) B.warp_tot[w] = incl;
+  if (tid == 0) B.out[0] = static_cast<unsigned int>(PER * NPAIR_LSB_THREADS);
+  __syncthreads();
+  unsigned int before = incl - mine;
+#pragma unroll
+  for (int k = 0; k < NPAIR_LSB_THREADS / 32; ++k) before += (k < w) ? B.warp_tot[k] : 0u;
+  if (mine && r >= before && r < before + mine) {                  // exactly one thread
+    unsigned int cum = before;
+    int b = 0;
+#pragma unroll
+    for (int q = 0; q < PER - 1; ++q) { if (b == q && cum + h[q] <= r) { cum += h[q]; b = q + 1; } }
+    unsigned int hb = h[0];
+#pragma unroll
+    for (int q = 1; q < PER; ++q) hb = (b == q) ? h[q] : hb;
+    B.out[0] = static_cast<unsigned int>(tid * PER + b); B.out[1] = r - cum; B.out[2] = hb;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ uint4 ldg_stream_u4(const float* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+// byte offset (bin * 4) of an entry in the histogram: monotone in f; NaN -> 0x3FFC
+__device__ __forceinline__ uint32_t lsb_off(uint32_t bits, float s4, float c0) { return __float_as_uint(__fmaf_rn(__uint_as_float(bits), s4, c0)) & 0x3FFCu; }
+
+__global__ void __launch_bounds__(NPAIR_LSB_THREADS, NPAIR_LSB_MINB) local_select_block_kernel(const float* __restrict__ S, long long ldS, int Q, int N,
+                                                                                   const float* __restrict__ lab_rows, const float* __restrict__ lab_cols,
+                                                                                   int self_offset, int side_mask /*1 AP, 2 AN*/, float sn_ap, float sn_an,
+                                                                                   RowArrays ra, BlockScalars* bs) {
+  __shared__ __align__(16) LselBlock B;
+  constexpr uint32_t kNaN = 0x7FFFFFFFu;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const bool want_same = side_mask & 1, want_diff = side_mask & 2;
+  // whole 4-column groups come through 16-byte loads (rows start 128-byte aligned: ldS is a multiple of 32); the last N % 4 columns
+  // sit in one extra register of threads 0..2
+  const int n4 = N & ~3;
+  const bool has_tail = tid < N - n4;
+  uint32_t v[4 * NPAIR_LSB_VPT + 1];       // [32] = the tail column (NaN where there is none)
+  int i = blockIdx.x;
+  auto load_row = [&](int r) {
+    const float* row = S + static_cast<long long>(r) * ldS;
+#pragma unroll
+    for (int u = 0; u < NPAIR_LSB_VPT; ++u) {
+      const int jj = (u * NPAIR_LSB_THREADS + tid) * 4;
+      uint4 t = make_uint4(kNaN, kNaN, kNaN, kNaN);
+      if (jj < n4) t = ldg_stream_u4(row + jj);
+      v[4 * u] = t.x; v[4 * u + 1] = t.y; v[4 * u + 2] = t.z; v[4 * u + 3] = t.w;
+    }
+    v[4 * NPAIR_LSB_VPT] = has_tail ? __float_as_uint(row[n4 + tid]) : kNaN;
+  };
+  if (i < Q) load_row(i);
+  for (; i < Q; i += gridDim.x) {
+    const float li = lab_rows[i];
+    const int self_col = i + self_offset;
+    const int cs = ra.cnt_same[i];
+    for (int b = tid * 4; b < NPAIR_LSB_HIST; b += NPAIR_LSB_THREADS * 4) *reinterpret_cast<uint4*>(&B.hist[b]) = make_uint4(0u, 0u, 0u, 0u);
+    if (tid == 0) { B.n_same = 0; B.n_cand = 0; }
+    __syncthreads();          // publishes the reset (the previous row's readers are behind the loop-end barrier)
+    // ---------------- pass 0: labels -> same-label list, NaN in the registers; value range of the entries that stay ----------------
+    float mn = FLT_MAX, mx = -FLT_MAX;
+#pragma unroll
+    for (int u = 0; u < NPAIR_LSB_VPT; ++u) {
+      const int jj = (u * NPAIR_LSB_THREADS + tid) * 4;
+      if (jj < n4) {
+        const float4 l = __ldg(reinterpret_cast<const float4*>(lab_cols + jj));
+        const float ll[4] = {l.x, l.y, l.z, l.w};
+        if (l.x == li || l.y == li || l.z == li || l.w == li) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (ll[c] == li) {
+              if (jj + c != self_col) { const unsigned int k = atomicAdd(&B.n_same, 1u); if (k < NPAIR_LSEL_SCAP) B.same[k] = v[4 * u + c]; }
+              v[4 * u + c] = kNaN;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { mn = fminf(mn, __uint_as_float(v[4 * u + c])); mx = fmaxf(mx, __uint_as_float(v[4 * u + c])); }
+      }
+    }
+    if (has_tail) {
+      const int j = n4 + tid;
+      if (lab_cols[j] == li) {
+        if (j != self_col) { const unsigned int k = atomicAdd(&B.n_same, 1u); if (k < NPAIR_LSEL_SCAP) B.same[k] = v[4 * NPAIR_LSB_VPT]; }
+        v[4 * NPAIR_LSB_VPT] = kNaN;
+      }
+      mn = fminf(mn, __uint_as_float(v[4 * NPAIR_LSB_VPT])); mx = fmaxf(mx, __uint_as_float(v[4 * NPAIR_LSB_VPT]));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+    if (lane == 0) { B.red_min[w] = mn; B.red_max[w] = mx; }
+    __syncthreads();
+    const unsigned int ns = B.n_same;                              // == cs
+    float lo = B.red_min[0], hi = B.red_max[0];
+#pragma unroll
+    for (int k = 1; k < NPAIR_LSB_THREADS / 32; ++k) { lo = fminf(lo, B.red_min[k]); hi = fmaxf(hi, B.red_max[k]); }
+    bool slow_ap = false;
+    unsigned long long pos_ap = 0, pos_an = 0;
+    // ---------------- AP side: the same-label list is short; warp 0 ranks it by counting ----------------
+    if (want_same) {
+      if (cs == 0) { if (tid == 0) { atomicOr(&bs->err, DERR_EMPTY_LIST); ra.posi_thr[i] = 0.f; } }
+      else if (!pos_index(sn_ap, static_cast<unsigned long long>(cs), pos_ap)) { if (tid == 0) { atomicOr(&bs->err, DERR_POS_RANGE); ra.posi_thr[i] = 0.f; } }
+      else if (ns > NPAIR_LSEL_SCAP) slow_ap = true;
+      else if (w == 0) {
+        for (unsigned int e = lane; e < ns; e += 32) {
+          const uint32_t key = f2ord(__uint_as_float(B.same[e]));
+          unsigned int rk = 0;
+          for (unsigned int t = 0; t < ns; ++t) { const uint32_t kt = f2ord(__uint_as_float(B.same[t])); rk += (kt < key || (kt == key && t < e)) ? 1u : 0u; }
+          if (rk == static_cast<unsigned int>(pos_ap)) ra.posi_thr[i] = clamp_thr(ord2f(key));               // .cu:288
+        }
+      }
+    }
+    // ---------------- AN side (every condition below is block-uniform) ----------------
+    bool have_an = false, refine = false, by_bin = false;
+    float s4 = 0.f, c0 = 0.f;
+    unsigned int rank = 0;
+    uint32_t boff = 0;
+    if (want_diff) {
+      const unsigned long long size = static_cast<unsigned long long>(N - 1 - cs);
+      if (size == 0) { if (tid == 0) { atomicOr(&bs->err, DERR_EMPTY_LIST); ra.nega_thr[i] = 0.f; } }
+      else if (!pos_index(sn_an, size, pos_an)) { if (tid == 0) { atomicOr(&bs->err, DERR_POS_RANGE); ra.nega_thr[i] = 0.f; } }
+      else have_an = true;
+    }
+    if (have_an) {
+      rank = static_cast<unsigned int>(pos_an);
+      // the value map: usable when it sends lo to bin >= 1 and hi to a bin the find walks (always, unless the range is empty or outside
+      // what fp32 can scale -- then the key digits do the whole job)
+      s4 = __fdiv_rn(4.f * NPAIR_LSB_BINS, hi - lo);
+      c0 = __fmaf_rn(-lo, s4, 8388612.f);                           // 2^23 + 4: one bin of head room below lo
+      const uint32_t o_lo = __float_as_uint(__fmaf_rn(lo, s4, c0)), o_hi = __float_as_uint(__fmaf_rn(hi, s4, c0));
+      const bool map_ok = hi > lo && o_lo >= 0x4B000000u && o_hi >= o_lo && o_hi < 0x4B000000u + 4u * (NPAIR_LSB_HIST - 1);
+      if (!map_ok) refine = true;
+      else {
+#pragma unroll
+        for (int e = 0; e < 4 * NPAIR_LSB_VPT + 1; ++e) smem_inc_off(B.hist, lsb_off(v[e], s4, c0));
+        __syncthreads();
+        block_find_bin_u32<NPAIR_LSB_HIST / NPAIR_LSB_THREADS>(B, rank);
+        boff = B.out[0] << 2; rank = B.out[1];
+        if (B.out[2] > NPAIR_LSB_CCAP) { refine = true; by_bin = true; }
+        else {
+#pragma unroll
+          for (int e = 0; e < 4 * NPAIR_LSB_VPT + 1; ++e)
+            if (lsb_off(v[e], s4, c0) == boff) B.cand[atomicAdd(&B.n_cand, 1u)] = f2ord(__uint_as_float(v[e]));
+        }
+      }
+      if (refine) {
+        // Rare: the entries still in play (all of them, or one crowded bin) are narrowed by 11 bits of their ORDERED KEY per round, from
+        // the registers: [klo, khi] always contains the wanted entry and `rank` counts inside it.
+        uint32_t klo = 0xFFFFFFFFu, khi = 0u;
+        auto in_play = [&](uint32_t bits) { return bits != kNaN && (!by_bin || lsb_off(bits, s4, c0) == boff); };
+#pragma unroll
+        for (int e = 0; e < 4 * NPAIR_LSB_VPT + 1; ++e)
+          if (in_play(v[e])) { const uint32_t k = f2ord(__uint_as_float(v[e])); klo = min(klo, k); khi = max(khi, k); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { klo = min(klo, __shfl_xor_sync(0xffffffffu, klo, o)); khi = max(khi, __shfl_xor_sync(0xffffffffu, khi, o)); }
+        __syncthreads();                                            // readers of red_* / out of the steps above are done
+        if (lane == 0) { B.red_klo[w] = klo; B.red_khi[w] = khi; }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < NPAIR_LSB_THREADS / 32; ++k) { klo = min(klo, B.red_klo[k]); khi = max(khi, B.red_khi[k]); }
+        for (int round = 0; round < 4 && khi != klo; ++round) {
+          const uint32_t range = khi - klo;
+          const int shift = max(0, 32 - __clz(range) - 11);       // (range >> shift) < 2048
+          for (int b = tid * 4; b < NPAIR_LSB_HIST; b += NPAIR_LSB_THREADS * 4) *reinterpret_cast<uint4*>(&B.hist[b]) = make_uint4(0u, 0u, 0u, 0u);
+          __syncthreads();
+#pragma unroll
+          for (int e = 0; e < 4 * NPAIR_LSB_VPT + 1; ++e)
+            if (in_play(v[e])) { const uint32_t k = f2ord(__uint_as_float(v[e])); if (k >= klo && k <= khi) smem_inc(&B.hist[(k - klo) >> shift]); }
+          __syncthreads();
+          block_find_bin_u32<NPAIR_LSB_HIST / NPAIR_LSB_THREADS>(B, rank);
+          rank = B.out[1];
+          klo += B.out[0] << shift;
+          khi = min(khi, klo + ((shift ? (1u << shift) : 1u) - 1u));
+        }
+        if (tid == 0) ra.nega_thr[i] = clamp_thr(ord2f(klo));                                               // .cu:319
+      }
+    }
+    // ---------------- the registers are free: the next row streams in while this row's pick runs ----------------
+    const float* row = S + static_cast<long long>(i) * ldS;
+    if (i + static_cast<int>(gridDim.x) < Q) load_row(i + static_cast<int>(gridDim.x));
+    if (have_an && !refine) {
+      __syncthreads();
+      const unsigned int nc = B.n_cand;                            // <= NPAIR_LSB_CCAP = blockDim
+      if (tid < static_cast<int>(nc)) {
+        const uint32_t key = B.cand[tid];
+        unsigned int rk = 0;
+        for (unsigned int t = 0; t < nc; ++t) { const uint32_t kt = B.cand[t]; rk += (kt < key || (kt == key && static_cast<int>(t) < tid)) ? 1u : 0u; }
+        if (rk == rank) ra.nega_thr[i] = clamp_thr(ord2f(key));                                             // .cu:319
+      }
+    }
+    if (slow_ap) {                                                 // more than 128 same-label entries: warp 0 redoes the side with plain sweeps
+      __syncthreads();
+      if (w == 0) { const float t = clamp_thr(ord2f(slow_select_row(row, N, lab_cols, li, self_col, 0, static_cast<unsigned int>(pos_ap), B.hist, lane))); if (lane == 0) ra.posi_thr[i] = t; }
+    }
+    __syncthreads();
+  }
+}
 void launch_local_select(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
-                         int self_offset, int side_mask, float sn_ap, float sn_an, RowArrays ra, BlockScalars* bs, int sms, cudaStream_t st) {
+                         int self_offset, int side_mask, float sn_ap, float sn_an, RowArrays ra, BlockScalars* bs, int sms, bool force_warp_kernel, cudaStream_t st) {
+  if (!force_warp_kernel && N <= NPAIR_LSB_THREADS * NPAIR_LSB_VPT * 4 && (reinterpret_cast<uintptr_t>(lab_cols) & 15) == 0 && (ldS & 3) == 0) {
+    int grid = sms * NPAIR_LSB_MINB; if (grid > Q) grid = Q;
+    local_select_block_kernel<<<grid, NPAIR_LSB_THREADS, 0, st>>>(S, ldS, Q, N, lab_rows, lab_cols, self_offset, side_mask, sn_ap, sn_an, ra, bs);
+    count_launch();
+    return;
+  }
   const int smem = static_cast<int>(sizeof(LselWarp)) * NPAIR_LSEL_WARPS;
   static bool attr_set = false;
   if (!attr_set) { cudaFuncSetAttribute(local_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
@@ -1068,7 +1345,7 @@ __global__ void __launch_bounds__(512) global_decide_kernel(const float* __restr
 void launch_global_select_pass(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
                                int self_offset, int side_mask, int pass, RowArrays ra, unsigned long long* hist, uint32_t* cand,
                                unsigned int cand_cap, int world_scope, BlockScalars* bs, int sms, cudaStream_t st) {
-  int grid = sms * 4; if (grid > Q) grid = Q;
+  int grid = sms * NPAIR_LSB_MINB; if (grid > Q) grid = Q;
   GlobalSelectBufs gb; gb.hist = hist; gb.cand = cand; gb.cap = cand_cap; gb.world_scope = world_scope;
   global_select_kernel<<<grid, 512, 0, st>>>(S, ldS, Q, N, lab_rows, lab_cols, self_offset, side_mask, pass, gb, ra, bs);
   count_launch();
@@ -1324,6 +1601,7 @@ void launch_lse_rows(const float* S, long long ldS, int Q, int N, const float* l
   // few rows per rank (anchor sharding over many GPUs): several warps share a row so that every SM still holds ~32 warps
   int wpr = 1;
   while (wpr < 8 && static_cast<long long>(Q) * wpr < 4096 && N / (2 * wpr) >= 512) wpr *= 2;
+  // (measured: splitting rows over two warps at Q = 8192 to even out the 2.31 waves of one-warp-per-row blocks is slower, 80.6 vs 77 us)
   if (wpr > 1) {
     const int rows_per_blk = 8 / wpr;
     const int grid = (Q + rows_per_blk - 1) / rows_per_blk;

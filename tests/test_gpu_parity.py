@@ -112,6 +112,42 @@ def test_odd_shapes_and_usage_block(cuda, oracle, shape, mining_name):
     check_parity(oracle, x, lab, Q, world, mining, capi.PREC_FP32_FP16X2, capi.GEMM_TCGEN05, tag=f"{shape} {mining_name}")
 
 
+@pytest.mark.parametrize("flags", [0, capi.FLAG_LSEL_WARP])
+@pytest.mark.parametrize("shape,ipc,sn", [((701, 1, 96), 3, (-0.3, -0.3)), ((512, 2, 64), 40, (-0.6, -0.05)), ((300, 1, 200), 150, (-0.2, -0.97)),
+                                          ((1024, 1, 128), 4, (1.0, 5.0)), ((258, 1, 64), 129, (-0.5, -0.5))])
+def test_local_relative_select_kernels(cuda, oracle, shape, ipc, sn, flags):
+    """LOCAL RELATIVE_* on both sides through both per-row select kernels (block-per-row with the row in registers: rows of up to
+    8192 columns; warp-per-row: npair_config.flags & NPAIR_FLAG_LSEL_WARP, and longer rows): few and many images per class (same-label
+    lists beyond the 128-entry fast path), fractional and absolute positions, ragged row lengths.  Thresholds are bit-exact (level 2 of
+    check_parity compares the selection-dependent results with the oracle run on the GPU's own similarities)."""
+    from gpu_harness import check_parity
+    Q, world, D = shape
+    x, lab = synth.make_inputs(Q * world, D, seed=Q + D + ipc, imgs_per_class=ipc, noise=1.5)
+    for apM, anM in ((capi.RELATIVE_HARD, capi.RELATIVE_HARD), (capi.RELATIVE_EASY, capi.RELATIVE_EASY)):
+        mining = dict(margin_ident=0.01, margin_diff=-0.02, identsn=sn[0], diffsn=sn[1], ap_region=synth.LOCAL, ap_method=apM,
+                      an_region=synth.LOCAL, an_method=anM)
+        check_parity(oracle, x, lab, Q, world, mining, capi.PREC_FP32_FP16X2, capi.GEMM_TCGEN05, tag=f"lsel {shape} ipc{ipc} sn{sn} f{flags} m{apM}",
+                     flags=flags)
+
+
+@pytest.mark.parametrize("flags", [0, capi.FLAG_LSEL_WARP])
+def test_local_relative_select_crowded_bins(cuda, oracle, flags):
+    """Rows whose similarities crowd into one value bin: 300 exact copies of one embedding spread over different classes (equal keys)
+    and 400 copies with 1e-6 noise (distinct keys, one bin): the block-per-row kernel's key-digit refinement; also one row of all-equal
+    similarities apart from the copies (D = 1 direction)."""
+    from gpu_harness import check_parity
+    B, D = 1024, 64
+    x, lab = synth.make_inputs(B, D, seed=4242, imgs_per_class=2, noise=1.5)
+    rng = np.random.default_rng(7)
+    idx = rng.permutation(B)
+    x[idx[:300]] = x[idx[0]]
+    x[idx[300:700]] = x[idx[300]] + 1e-6 * rng.standard_normal((400, D)).astype(np.float32)
+    for sn in ((-0.3, -0.3), (-0.5, -0.62), (0.0, 40.0)):
+        mining = dict(margin_ident=0.0, margin_diff=0.0, identsn=sn[0], diffsn=sn[1], ap_region=synth.LOCAL, ap_method=capi.RELATIVE_HARD,
+                      an_region=synth.LOCAL, an_method=capi.RELATIVE_HARD)
+        check_parity(oracle, x, lab, B, 1, mining, capi.PREC_FP32_FP16X2, capi.GEMM_TCGEN05, tag=f"crowded sn{sn} f{flags}", flags=flags)
+
+
 def test_num_tops_layout(cuda, oracle):
     from gpu_harness import gpu_step_world
     Q, D = 64, 32
