@@ -26,9 +26,13 @@ from __future__ import annotations
 
 import os
 
-# the CPU arm's OpenMP threads stay on their cores (set before anything loads libgomp)
-os.environ.setdefault("OMP_PROC_BIND", "close")
-os.environ.setdefault("OMP_PLACES", "cores")
+# The CPU arm's OpenMP threads stay on their cores (set before anything loads libgomp).  ONLY in a single-process run: with
+# OMP_PROC_BIND set libgomp also binds the INITIAL thread to the first place, so under torchrun every rank's main thread landed on
+# core 0 and the eight busy-polling ranks took turns on it -- 32.5 ms per step at N = 8 whatever the configuration (round 2, first
+# 8-GPU run; profiles/r02_experiments.md).  Sharded runs never set it; their reference arm (rank 0 only) runs unpinned.
+if int(os.environ.get("WORLD_SIZE", "1")) == 1:
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PLACES", "cores")
 
 import argparse  # noqa: E402
 import ctypes as C  # noqa: E402
@@ -256,7 +260,15 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a B200 (the product path has no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    host_affinity = None
     if world > 1:
+        # one busy-polling host thread per rank: make sure an inherited OMP_PROC_BIND / taskset has not parked all ranks on one core
+        try:
+            if len(os.sched_getaffinity(0)) < world:
+                os.sched_setaffinity(0, range(os.cpu_count()))
+            host_affinity = len(os.sched_getaffinity(0))
+        except (AttributeError, OSError):
+            pass
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     assert B % world == 0
@@ -610,6 +622,7 @@ def main():
                "config": {"workload": f"{name}: B={B}, D={D}, {B // 2} classes x 2, {mining_desc}, loss_weight 1",
                           "global_batch": B, "feature_dim": D, "rows_per_rank": Q, "sharding": f"anchor-sharded x{world}",
                           "precision": precision, "noise": noise, "seed": seed, "cfg_flags": args.cfg_flags,
+                          "host_cpus_allowed_per_rank": host_affinity,
                           "exchange": (None if world == 1 else ("NCCL all-gathers" if args.cfg_flags & 24 == 24 else "peer-memory pushes over NVLink (cudaIpc), NCCL only for bootstrap")),
                           "step_call": "npair_forward_backward (one host sync)" if args.fused_step else "npair_forward + npair_backward",
                           "l2": (f"flushed: a {2 * L2_BYTES >> 20} MB device buffer is rewritten before every timed step (per-rank S = "

@@ -6,6 +6,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <sched.h>
 #include <cudaTypedefs.h>
 #include <dlfcn.h>
 
@@ -1129,6 +1130,7 @@ static int forward_impl(npair_ctx* c, const float* d_feat, const float* d_label,
     while (*seqp != c->tops_seq) {
       if (++spins > (1ull << 28)) { CUDA_TRY(c, cudaStreamSynchronize(st)); if (*seqp != c->tops_seq) { c->err = "the forward kernels finished without publishing their results"; return NPAIR_E_CUDA; } break; }
       __builtin_ia32_pause();
+      if ((spins & 0x3FFull) == 0) sched_yield();   // ranks that share a core (fewer cores than ranks, an inherited binding) take turns quickly
     }
     __sync_synchronize();
   }

@@ -1345,7 +1345,7 @@ __global__ void __launch_bounds__(512) global_decide_kernel(const float* __restr
 void launch_global_select_pass(const float* S, long long ldS, int Q, int N, const float* lab_rows, const float* lab_cols,
                                int self_offset, int side_mask, int pass, RowArrays ra, unsigned long long* hist, uint32_t* cand,
                                unsigned int cand_cap, int world_scope, BlockScalars* bs, int sms, cudaStream_t st) {
-  int grid = sms * NPAIR_LSB_MINB; if (grid > Q) grid = Q;
+  int grid = sms * 4; if (grid > Q) grid = Q;
   GlobalSelectBufs gb; gb.hist = hist; gb.cand = cand; gb.cap = cand_cap; gb.world_scope = world_scope;
   global_select_kernel<<<grid, 512, 0, st>>>(S, ldS, Q, N, lab_rows, lab_cols, self_offset, side_mask, pass, gb, ra, bs);
   count_launch();
@@ -1439,6 +1439,23 @@ __global__ void __launch_bounds__(256, NPAIR_LSE_MINB) lse_rows_kernel(const flo
   float A = 0.f, T = 0.f; int c = 0;
   float m2 = 0.f, thr_p = 0.f, thr_n = 0.f, li = 0.f; int cs = 0;
   if (i < Q) {
+    // the first block of this warp's segment is requested before anything else: the per-row set-up below (dependent loads of the row
+    // statistics, the retrieval cut's expf search) then runs under the DRAM latency instead of in front of it
+    constexpr int U = NPAIR_LSE_U;
+    const float* row = S + static_cast<long long>(i) * ldS;
+    // this warp's segment [c_lo, c_hi) of the row: multiples of 512 columns
+    const int seg = ((N + wpr - 1) / wpr + 128 * U - 1) / (128 * U) * (128 * U);
+    const int c_lo = min(N, part * seg), c_hi = min(N, c_lo + seg);
+    const int n_full = c_lo + (c_hi - c_lo) / (128 * U) * (128 * U);
+    const float4* srow4 = reinterpret_cast<const float4*>(row + c_lo) + lane;
+    const float4* lab4 = reinterpret_cast<const float4*>(lab_cols + c_lo) + lane;
+    const bool lab_aligned = (reinterpret_cast<uintptr_t>(lab_cols) & 15) == 0;
+    const bool fast = lab_aligned && c_lo < n_full;
+    float4 v[U], vn[U];
+    if (fast) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) v[u] = ldg_stream(srow4 + 32 * u);
+    }
     li = lab_rows[i];
     const int self_col = i + self_offset;
     const float max_all = ord2f(ra.st_maxall[i]);
@@ -1453,23 +1470,11 @@ __global__ void __launch_bounds__(256, NPAIR_LSE_MINB) lse_rows_kernel(const flo
     thr_p = ap_thr(tp, mp.ap_method); thr_n = an_thr(tn, mp.an_method);
     cs = ra.cnt_same[i];
     const float scut = cs > 0 ? retrieval_cut(ord2f(ra.st_maxw[i]), max_all, lane) : INFINITY;
-    const float* row = S + static_cast<long long>(i) * ldS;
     // ---- full 512-column blocks: unguarded 128-bit loads (4 in flight per lane for S, 4 for the labels) ----
-    constexpr int U = NPAIR_LSE_U;
-    // this warp's segment [c_lo, c_hi) of the row: multiples of 512 columns
-    const int seg = ((N + wpr - 1) / wpr + 128 * U - 1) / (128 * U) * (128 * U);
-    const int c_lo = min(N, part * seg), c_hi = min(N, c_lo + seg);
-    const int n_full = c_lo + (c_hi - c_lo) / (128 * U) * (128 * U);
-    const float4* srow4 = reinterpret_cast<const float4*>(row + c_lo) + lane;
-    const float4* lab4 = reinterpret_cast<const float4*>(lab_cols + c_lo) + lane;
-    const bool lab_aligned = (reinterpret_cast<uintptr_t>(lab_cols) & 15) == 0;
     int base = c_lo;
-    if (lab_aligned && base < n_full) {
+    if (fast) {
       // software pipeline: the 16-byte loads of block k+1 (streamed past the L1: every byte of S is used once) are in flight while
       // block k is evaluated; the labels (32 KB shared by every row) come from the L1 when they are needed
-      float4 v[U], vn[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) v[u] = ldg_stream(srow4 + 32 * u);
       for (; base < n_full; base += 128 * U, srow4 += 32 * U, lab4 += 32 * U) {
         const bool more = base + 128 * U < n_full;
         if (more) {
@@ -1561,9 +1566,20 @@ __global__ void __launch_bounds__(256, NPAIR_LSE_MINB) lse_rows_kernel(const flo
   __shared__ double s_l[8];
   __shared__ int s_h[3][8];
   double ls = 0.0; int h[3] = {0, 0, 0};
-  for (int r = threadIdx.x; r < Q; r += blockDim.x) {
-    ls += __ldcg(&ra.logv[r]);
-    h[0] += __ldcg(&ra.hits[r]); h[1] += __ldcg(&ra.hits[Q + r]); h[2] += __ldcg(&ra.hits[2 * Q + r]);
+  // FU rows per thread and trip, all 4*FU loads issued before the first use: with one row per trip this tail was a chain of 32 L2
+  // latencies at Q = 8192 (~20 us of the row pass).  The per-thread summation order (r ascending) is unchanged.
+  constexpr int FU = 8;
+  for (int r0 = threadIdx.x; r0 < Q; r0 += FU * blockDim.x) {
+    float lv[FU]; int h0[FU], h1[FU], h2[FU];
+#pragma unroll
+    for (int u = 0; u < FU; ++u) {
+      const int r = r0 + u * blockDim.x;
+      const bool ok = r < Q;
+      lv[u] = ok ? __ldcg(&ra.logv[r]) : 0.f;
+      h0[u] = ok ? __ldcg(&ra.hits[r]) : 0; h1[u] = ok ? __ldcg(&ra.hits[Q + r]) : 0; h2[u] = ok ? __ldcg(&ra.hits[2 * Q + r]) : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < FU; ++u) { ls += lv[u]; h[0] += h0[u]; h[1] += h1[u]; h[2] += h2[u]; }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {

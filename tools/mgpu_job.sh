@@ -6,7 +6,7 @@ port=29700
 for cfg in $CFGS; do
 port=$((port+1))
 echo "== bench $cfg N=$N"
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $port bench.py --gpus $N --config $cfg --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/bench_r2_${cfg}_n$N.json 2> gpurun_out/bench_r2_${cfg}_n$N.err
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $port bench.py --gpus $N --config $cfg --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/bench_r2_${cfg}_n$N.json 2> gpurun_out/bench_r2_${cfg}_n$N.err
 python - <<PY
 import json
 try:
