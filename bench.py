@@ -9,8 +9,9 @@ over one batch of synthetic L2-normalised embeddings (B/2 classes x 2 images, SU
 over the N ranks (strong scaling: Q = B/N rows per rank against all B columns).  --config picks one of BASELINE.json's named
 configurations (HL = the headline metric, usage-block mining of usage/def.prototxt:137-146).
 
-  value    : whole-job samples/sec with the inputs resident in HBM, through the C ABI (npair_forward + npair_backward: includes
-             the feature exchange, the row-record exchange and the five host scalars), CUDA-event timed, max over ranks.
+  value    : whole-job samples/sec with the inputs resident in HBM, through the C ABI (npair_forward_backward: both passes enqueued,
+             one wait for the five host scalars; includes the feature exchange and the row-record exchange), CUDA-event timed, max
+             over ranks.  step_call_other: the same through npair_forward + npair_backward (--two-call makes that the headline).
   e2e      : the same metric through the reference-facing plugin surface (the Caffe-style layer in npairloss_b200/caffe_shim)
              with HOST bottoms: every timed step copies that step's batch host->device from pinned memory (on a copy stream,
              double-buffered like Caffe's prefetching data layers) and reads the five tops device->host.  e2e_serial is the same
@@ -235,7 +236,8 @@ def main():
     # both sides, diffsn -0.3: a radix select per row and side, costliest) are the two other settings it asks to be reported
     ap.add_argument("--mining", default="config", choices=["config", "usage", "rand", "relative"])
     ap.add_argument("--no-extras", action="store_true", help="skip the other_minings / e2e variants / parity_check legs")
-    ap.add_argument("--fused-step", action="store_true", help="device-resident step through npair_forward_backward (one host sync)")
+    ap.add_argument("--two-call", action="store_true", help="device-resident step through npair_forward + npair_backward (the host returns to the "
+                    "caller between the passes) instead of npair_forward_backward; the other form is always reported as `step_call_other`")
     ap.add_argument("--no-flush", action="store_true", help="diagnostic: never flush the L2 between steps (sharded runs)")
     ap.add_argument("--cfg-flags", type=int, default=0, help="npair_config.flags (NPAIR_FLAG_*), e.g. 24 = exchange through NCCL instead of peer memory")
     ap.add_argument("--grad-chunk", type=int, default=0, help="npair_config.grad_chunk_cols (0 = library default)")
@@ -305,13 +307,17 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_device(c=None):
+    def step_two_call(c=None):
         c = c or ctx
-        if args.fused_step:
-            return c.forward_backward(d_x, d_l, 1.0, d_g)
         tops = c.forward(d_x, d_l)
         c.backward(1.0, d_g)
         return tops
+
+    def step_fused(c=None):
+        return (c or ctx).forward_backward(d_x, d_l, 1.0, d_g)
+
+    step_device = step_two_call if args.two_call else step_fused
+    step_other = step_fused if args.two_call else step_two_call
 
     # L2 rule: the step's working set is dominated by the Q x N fp32 similarity block.  When it is larger than twice the 126 MB
     # L2 nothing survives from one step to the next (N = 1: 268 MB); otherwise (sharded runs) a 252 MB device buffer is rewritten
@@ -320,15 +326,16 @@ def main():
     need_flush = 4 * Q * N < 2 * L2_BYTES and not args.no_flush
     flush_buf = torch.empty(2 * L2_BYTES, dtype=torch.uint8, device=dev) if need_flush else None
 
-    def timed_steps(c, steps):
+    def timed_steps(c, steps, fn=None):
         """ms per step (this rank), kernel launches inside the region."""
+        fn = fn or step_device
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         if not need_flush:
             e0.record(stream)
             l0 = capi.kernel_launches()
             for _ in range(steps):
-                step_device(c)
+                fn(c)
             nl = capi.kernel_launches() - l0
             e1.record(stream)
             barrier()
@@ -338,7 +345,7 @@ def main():
         for ea, eb in pairs:
             flush_buf.fill_(1)                 # same stream as the step: ordered before it, evicts the whole L2
             ea.record(stream)
-            step_device(c)
+            fn(c)
             eb.record(stream)
         nl = capi.kernel_launches() - l0
         barrier()
@@ -372,6 +379,10 @@ def main():
         clocks["note"] = "sampled with nvidia-smi -lms 25 from warm-up through the timed region and an untimed continuation of the same load"
     ms_step = max_over_ranks(ms_mine)
     value = B / (ms_step * 1e-3)
+    # the other form of the step call, timed the same way (flush rule included)
+    for _ in range(3):
+        step_other()
+    ms_other = max_over_ranks(timed_steps(ctx, args.steps, step_other)[0])
     tops = step_device()
     torch.cuda.synchronize()
     grad_dev = d_g.cpu().numpy()
@@ -391,9 +402,10 @@ def main():
             barrier()
             return max_over_ranks(e0.elapsed_time(e1) / steps)
         ms_nf = plain_loop(lambda: step_device(), args.steps)
-        ms_fu = plain_loop(lambda: ctx.forward_backward(d_x, d_l, 1.0, d_g), args.steps)
-        variants = {"no_l2_flush": {"ms_per_step": ms_nf, "value": B / (ms_nf * 1e-3), "note": "npair_forward + npair_backward back to back, one event pair around the loop, L2 not flushed"},
-                    "fused_call_no_l2_flush": {"ms_per_step": ms_fu, "value": B / (ms_fu * 1e-3), "note": "npair_forward_backward: the backward is enqueued behind the forward, one host synchronisation per step"}}
+        ms_ot = plain_loop(lambda: step_other(), args.steps)
+        variants = {"no_l2_flush": {"ms_per_step": ms_nf, "value": B / (ms_nf * 1e-3), "note": "the headline step call back to back, one event pair around the loop, L2 not flushed"},
+                    "other_call_no_l2_flush": {"ms_per_step": ms_ot, "value": B / (ms_ot * 1e-3),
+                                               "note": ("npair_forward_backward" if args.two_call else "npair_forward + npair_backward (the host returns to the caller between the passes)")}}
 
     # ---------------- end-to-end through the plugin surface with host buffers ----------------
     # The Caffe-style layer (npairloss_b200/caffe_shim) on HOST blobs: a data layer hands a new batch through mutable_cpu_data()
@@ -624,12 +636,14 @@ def main():
                           "precision": precision, "noise": noise, "seed": seed, "cfg_flags": args.cfg_flags,
                           "host_cpus_allowed_per_rank": host_affinity,
                           "exchange": (None if world == 1 else ("NCCL all-gathers" if args.cfg_flags & 24 == 24 else "peer-memory pushes over NVLink (cudaIpc), NCCL only for bootstrap")),
-                          "step_call": "npair_forward_backward (one host sync)" if args.fused_step else "npair_forward + npair_backward",
+                          "step_call": "npair_forward + npair_backward" if args.two_call else "npair_forward_backward (both passes enqueued, one wait for the five tops)",
                           "l2": (f"flushed: a {2 * L2_BYTES >> 20} MB device buffer is rewritten before every timed step (per-rank S = "
                                  f"{4 * Q * N / 1e6:.0f} MB fp32 would otherwise stay in the 126 MB L2); steps timed one by one, flush excluded"
                                  if need_flush else
                                  f"not flushed: per-step working set (S {4 * Q * N / 1e6:.0f} MB fp32 + operand pieces) is more than twice the 126 MB L2")},
                "clocks": clocks, "roofline": roofline, "roofline_other": roofline_other, "phase_ms": phase_ms, "hbm_kernels": hbm,
+               "step_call_other": {"call": ("npair_forward_backward" if args.two_call else "npair_forward + npair_backward"), "ms_per_step": ms_other,
+                                   "value": B / (ms_other * 1e-3), "note": "the other form of the step call, timed like the headline"},
                "other_minings": other, "sharded_variants": variants, "parity_check": parity, "cpu_baseline": cpu, "e2e": e2e, **e2e_variants,
                "gpu_launches": launches_timed,
                "tops": {"loss": tops[0], "top1": tops[1], "top5": tops[2], "top10": tops[3], "feature_asum": tops[4]}}

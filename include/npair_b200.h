@@ -132,8 +132,9 @@ int npair_forward(npair_ctx* ctx, const float* d_feat, const float* d_label, flo
 int npair_backward(npair_ctx* ctx, float loss_weight, float* d_feat_diff, void* stream);
 
 /* npair_forward + npair_backward with a single host synchronisation: the backward is enqueued behind the forward's kernels (the
- * loss weight -- top[0]'s diff, reference .cu:435 -- is a constant of the net), then the call waits for the five tops.  Same
- * results; saves the host round trip during which the GPU idles.  On a forward error the gradient buffer is unspecified. */
+ * loss weight -- top[0]'s diff, reference .cu:435 -- is a constant of the net), then the call waits for the five tops ONLY: like
+ * npair_backward, the gradient is complete in stream order, not when the call returns.  Same results; saves the host round trip
+ * during which the GPU idles.  On a forward error the gradient buffer is unspecified. */
 int npair_forward_backward(npair_ctx* ctx, const float* d_feat, const float* d_label, float loss_weight, float* d_feat_diff,
                            float tops_host[5], void* stream);
 

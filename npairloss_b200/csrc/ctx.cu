@@ -942,6 +942,22 @@ static MiningParams mining_of(const npair_config& c) {
 static inline bool is_rel_m(int m) { return m == NPAIR_RELATIVE_HARD || m == NPAIR_RELATIVE_EASY; }
 static inline bool sn_max(float sn) { return sn >= 0.f && static_cast<int>(sn) == 0; }
 
+// The reference blocks after its forward (host reads of loss / asum, .cu:384,400).  The five tops land in mapped pinned memory followed by
+// this forward's sequence number: polling that word returns a few microseconds earlier than a stream synchronisation and does not
+// wait for anything enqueued behind the row pass (the row-record push, a backward).  A fault in a kernel never writes the number:
+// after ~2 s fall back to the synchronisation, which reports the error.
+static int wait_tops(npair_ctx* c, cudaStream_t st) {
+  volatile unsigned int* seqp = reinterpret_cast<volatile unsigned int*>(c->tops_pinned) + 6;
+  unsigned long long spins = 0;
+  while (*seqp != c->tops_seq) {
+    if (++spins > (1ull << 28)) { CUDA_TRY(c, cudaStreamSynchronize(st)); if (*seqp != c->tops_seq) { c->err = "the forward kernels finished without publishing their results"; return NPAIR_E_CUDA; } break; }
+    __builtin_ia32_pause();
+    if ((spins & 0x3FFull) == 0) sched_yield();   // ranks that share a core (fewer cores than ranks, an inherited binding) take turns quickly
+  }
+  __sync_synchronize();
+  return NPAIR_OK;
+}
+
 static int forward_impl(npair_ctx* c, const float* d_feat, const float* d_label, float tops_host[5], cudaStream_t st);
 
 int npair_forward(npair_ctx* c, const float* d_feat, const float* d_label, float tops_host[5], void* stream) {
@@ -1120,20 +1136,7 @@ static int forward_impl(npair_ctx* c, const float* d_feat, const float* d_label,
   }
   CUDA_TRY(c, cudaGetLastError());
   if (c->defer_sync) return NPAIR_OK;              // npair_forward_backward enqueues the backward first, then waits once
-  // The reference also blocks here (host reads of loss / asum, .cu:384,400).  The five tops land in mapped pinned memory followed by
-  // this forward's sequence number: polling that word returns a few microseconds earlier than a stream synchronisation and does not
-  // wait for the row-record push behind the row pass.  A fault in a kernel never writes the number: after ~2 s fall back to the
-  // synchronisation, which reports the error.
-  {
-    volatile unsigned int* seqp = reinterpret_cast<volatile unsigned int*>(c->tops_pinned) + 6;
-    unsigned long long spins = 0;
-    while (*seqp != c->tops_seq) {
-      if (++spins > (1ull << 28)) { CUDA_TRY(c, cudaStreamSynchronize(st)); if (*seqp != c->tops_seq) { c->err = "the forward kernels finished without publishing their results"; return NPAIR_E_CUDA; } break; }
-      __builtin_ia32_pause();
-      if ((spins & 0x3FFull) == 0) sched_yield();   // ranks that share a core (fewer cores than ranks, an inherited binding) take turns quickly
-    }
-    __sync_synchronize();
-  }
+  { const int wrc = wait_tops(c, st); if (wrc != NPAIR_OK) return wrc; }
   const int derr = reinterpret_cast<int*>(c->tops_pinned)[5];
   if (derr & DERR_EMPTY_LIST) { c->err = "an empty same/diff list was indexed (undefined behaviour in the reference, .cu:296/:327/:288)"; return NPAIR_E_EMPTY_LIST; }
   if (derr & DERR_POS_RANGE) { c->err = "identsn/diffsn select a position outside the list (undefined behaviour in the reference, .cu:285-288)"; return NPAIR_E_POS_RANGE; }
@@ -1184,7 +1187,8 @@ int npair_forward_backward(npair_ctx* c, const float* d_feat, const float* d_lab
   c->fwd_done = true;                                  // enqueued; confirmed (or revoked) after the synchronisation below
   rc = backward_impl(c, loss_weight, d_diff, nullptr, nullptr, st);
   if (rc != NPAIR_OK) { c->fwd_done = false; return rc; }
-  CUDA_TRY(c, cudaStreamSynchronize(st));
+  // wait for the forward's tops only: the gradient kernels keep running while the caller prepares (and enqueues) its next step
+  { const int wrc = wait_tops(c, st); if (wrc != NPAIR_OK) { c->fwd_done = false; return wrc; } }
   const int derr = reinterpret_cast<int*>(c->tops_pinned)[5];
   if (derr) c->fwd_done = false;
   if (derr & DERR_EMPTY_LIST) { c->err = "an empty same/diff list was indexed (undefined behaviour in the reference, .cu:296/:327/:288)"; return NPAIR_E_EMPTY_LIST; }

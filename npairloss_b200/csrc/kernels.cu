@@ -1617,7 +1617,13 @@ void launch_lse_rows(const float* S, long long ldS, int Q, int N, const float* l
   // few rows per rank (anchor sharding over many GPUs): several warps share a row so that every SM still holds ~32 warps
   int wpr = 1;
   while (wpr < 8 && static_cast<long long>(Q) * wpr < 4096 && N / (2 * wpr) >= 512) wpr *= 2;
+  // measured on one rank's strip of a sharded HL job (tests/tune_rank.py, N = 8192): Q = 1024: 2 warps per row 18.6 us, 4: 22.7, 8: 25.5;
+  // Q = 2048: 2: 29.8, 8: 37.1 -- beyond two warps the per-warp set-up outweighs the fuller SMs
+  if (Q >= 1024 && wpr > 2) wpr = 2;
   // (measured: splitting rows over two warps at Q = 8192 to even out the 2.31 waves of one-warp-per-row blocks is slower, 80.6 vs 77 us)
+#ifdef NPAIR_LSE_WPR_FORCE      // tuning builds only
+  wpr = NPAIR_LSE_WPR_FORCE;
+#endif
   if (wpr > 1) {
     const int rows_per_blk = 8 / wpr;
     const int grid = (Q + rows_per_blk - 1) / rows_per_blk;

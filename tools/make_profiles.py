@@ -9,6 +9,10 @@ M = {"dur": "gpu__time_duration.sum", "rd": "dram__bytes_read.sum", "wr": "dram_
      "tensor": "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "issue": "smsp__issue_active.avg.pct_of_peak_sustained_active",
      "warps": "sm__warps_active.avg.pct_of_peak_sustained_active", "inst": "smsp__inst_executed.sum", "dram_pct": "dram__throughput.avg.pct_of_peak_sustained_elapsed",
      "l2req": "lts__t_requests_srcunit_tex.sum", "regs": "launch__registers_per_thread", "grid": "launch__grid_size", "block": "launch__block_size"}
+try:
+    PEAK_GBS = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs']
+except Exception:
+    PEAK_GBS = 6650.0
 UNIT = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0, "us": 1.0, "ms": 1e3, "ns": 1e-3, "s": 1e6}
 
 
@@ -44,13 +48,13 @@ for tag in ("main", "lsel", "gsel"):
             allrows.append(d)
 lines = [f"# ncu --set full captures, round {R[1:]} (B = 8192, D = 512, fp16x2; `tools/profile_job.sh`, `--clock-control none`)", "",
          "Durations under ncu are cold-cache and serialised; the live per-phase CUDA-event times are in the bench lines.", "",
-         "| capture | kernel | grid x block | regs | duration µs | DRAM read MB | DRAM write MB | DRAM GB/s | DRAM % of peak | tensor pipe active % | issue active % | warps active % | warp instr (M) | L2 requests (M) |",
+         "| capture | kernel | grid x block | regs | duration µs | DRAM read MB | DRAM write MB | DRAM GB/s | DRAM % of the measured copy peak | tensor pipe active % | issue active % | warps active % | warp instr (M) | L2 requests (M) |",
          "|---|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
 traffic = {}
 for d in allrows:
     gbs = (d["rd"] + d["wr"]) / (d["dur"] * 1e-6) / 1e9 if d.get("dur") else 0
     lines.append(f"| {d['capture']} | `{short(d['kernel'])}` | {int(d['grid'])} x {int(d['block'])} | {int(d['regs'])} | {d['dur']:.1f} | {d['rd'] / 1e6:.1f} | {d['wr'] / 1e6:.1f} | "
-                 f"{gbs:.0f} | {d.get('dram_pct') or 0:.1f} | {d.get('tensor') or 0:.1f} | {d.get('issue') or 0:.1f} | {d.get('warps') or 0:.1f} | {(d.get('inst') or 0) / 1e6:.1f} | {(d.get('l2req') or 0) / 1e6:.2f} |")
+                 f"{gbs:.0f} | {100.0 * gbs / PEAK_GBS:.1f} | {d.get('tensor') or 0:.1f} | {d.get('issue') or 0:.1f} | {d.get('warps') or 0:.1f} | {(d.get('inst') or 0) / 1e6:.1f} | {(d.get('l2req') or 0) / 1e6:.2f} |")
     traffic.setdefault(d["capture"], []).append({"kernel": short(d["kernel"]), "dram_bytes": d["rd"] + d["wr"], "dram_read": d["rd"], "dram_write": d["wr"], "duration_us": d["dur"]})
 open(os.path.join(ROOT, "profiles", f"{R}_ncu_summary.md"), "w").write("\n".join(lines) + "\n")
 kern = {}
